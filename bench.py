@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark of the fused render path (BASELINE.json: primary rays/s, 4096-ray / 64+64-sample / 5-exposure).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one forward pass of the hot path over one synthetic batch: 4096 primary rays -> 5 exposures (20480
+sub-rays) -> coarse pass (64 samples) -> hierarchical sampling -> fine pass (128 samples) -> composited colours.
+N > 1 (torchrun): every rank renders its own 4096-ray batch (weak scaling, no data-path collective); value = all
+rays / max-over-ranks time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, N_EXPOSURE, NC, NI = 4096, 5, 64, 64
+AABB = ((-1.5, -1.5, -1.0), (1.5, 1.5, 1.0))
+COARSE_VOX, FINE_VOX = 16777248, 134217984          # configs/.../tx_blurfactory_*.txt:66,74
+H = W = 400
+FOCAL = 400.0
+
+# algorithmic work, MACs
+MAC_COARSE_SAMPLE = 17152                            # basis 3072 + sigma_net 7104 + color_net 6976
+MAC_FINE_SAMPLE = 171520                             # sigma_net 65536 + color_net 105984
+MAC_BASIS = 3072
+
+
+def flops_per_subray(nc=NC, ni=NI):
+    return 2 * (nc * MAC_COARSE_SAMPLE + 3 * MAC_BASIS * ni + (nc + ni) * MAC_FINE_SAMPLE)
+
+
+def flops_fine_kernel_per_subray(nc=NC, ni=NI):
+    return 2 * (3 * MAC_BASIS * ni + (nc + ni) * MAC_FINE_SAMPLE)
+
+
+def grid_size(n_voxels):
+    """voxnerf.py:87-92."""
+    import torch
+    amin, amax = torch.tensor(AABB[0]), torch.tensor(AABB[1])
+    voxel = ((amax - amin).prod() / n_voxels).pow(1 / 3)
+    return ((amax - amin) / voxel).long().tolist()
+
+
+def make_params(device, seed=0):
+    """Random-init parameters with the reference's names, shapes and init scales (voxnerf.py:104-118, nn.Linear)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    P = {}
+
+    def lin(name, out_c, in_c):
+        bound = 1.0 / (in_c ** 0.5)
+        P[name] = ((torch.rand(out_c, in_c, generator=g) * 2 - 1) * bound).to(device)
+
+    for pre, nvox, hid, geo in (("mlp_coarse.", COARSE_VOX, 64, 15), ("mlp_fine.", FINE_VOX, 256, 128)):
+        gs = grid_size(nvox)
+        gd = torch.Generator(device=device).manual_seed(seed + (1 if hid == 64 else 2))
+        for i, (m, v) in enumerate((((0, 1), 2), ((0, 2), 1), ((1, 2), 0))):
+            c = (64, 16, 16)[i]
+            P[pre + f"app_plane.{i}"] = 0.1 * torch.randn((1, c, gs[m[1]], gs[m[0]]), generator=gd, device=device)
+            P[pre + f"app_line.{i}"] = 0.1 * torch.randn((1, c, gs[v], 1), generator=gd, device=device)
+        lin(pre + "basis_mat.weight", 32, 96)
+        lin(pre + "sigma_net.0.weight", hid, (32 if hid == 64 else 64) + 63)
+        lin(pre + "sigma_net.1.weight", 1 + geo, hid)
+        lin(pre + "color_net.0.weight", hid, geo + 27)
+        lin(pre + "color_net.1.weight", hid, hid)
+        lin(pre + "color_net.2.weight", 3, hid)
+    return P
+
+
+def make_rays(n, seed):
+    """SURVEY 8(d) synthetic sub-rays [n*E, 3, 2]: camera looking down -z; the E exposures of a primary ray are
+    small rigid perturbations of it (what the RBK kernel produces)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 1, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])
+    d = torch.cat([torch.randn(n, 1, 2, generator=g) * 0.3, -torch.ones(n, 1, 1)], -1)
+    o = o + 0.01 * torch.randn(n, N_EXPOSURE, 3, generator=g)
+    d = d + 0.01 * torch.randn(n, N_EXPOSURE, 3, generator=g)
+    return torch.stack([o, d], -1).reshape(n * N_EXPOSURE, 3, 2)
+
+
+def build_ray_batch(rays):
+    """render() prologue (renderer.py:423-446, utils/rays.py:104-145) in torch -- host-side input preparation."""
+    import torch
+    o, d = rays[..., 0], rays[..., 1]
+    viewdirs = d / torch.norm(d, dim=-1, keepdim=True)
+    near = 1.0
+    t = -(near + o[..., 2]) / d[..., 2]
+    o = o + t[..., None] * d
+    ox_oz, oy_oz = o[..., 0] / o[..., 2], o[..., 1] / o[..., 2]
+    o0 = -1. / (W / (2. * FOCAL)) * ox_oz
+    o1 = -1. / (H / (2. * FOCAL)) * oy_oz
+    o2 = 1. + 2. * near / o[..., 2]
+    d0 = -1. / (W / (2. * FOCAL)) * (d[..., 0] / d[..., 2] - ox_oz)
+    d1 = -1. / (H / (2. * FOCAL)) * (d[..., 1] / d[..., 2] - oy_oz)
+    d2 = 1 - o2
+    on, dn = torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+    return torch.cat([on, dn, torch.zeros_like(dn[..., :1]), torch.ones_like(dn[..., :1]), viewdirs], -1).float().contiguous()
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(P_cpu, rays_cpu, threads):
+    """One bounded CPU step of the reference algorithm (oracle port; the reference is Python and cannot travel)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import evdeblur_oracle as oc
+    torch.set_num_threads(threads)
+    cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
+    with torch.no_grad():
+        rb = oc.build_ray_batch(H, W, FOCAL, rays_cpu)
+        t0 = time.perf_counter()
+        out = oc.render_rays(P_cpu, cfg, rb, NC, NI)
+        dt = time.perf_counter() - t0
+    return dt, out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores, bounded sample per step."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_rays = 256
+    P = make_params("cpu")
+    rays = make_rays(sample_rays, seed=100)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _ = cpu_reference_step(P, rays, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / max(len(times), 1)
+    val = sample_rays / (ms / 1e3)
+    line = {"impl": "reference", "metric": "primary_rays_per_sec_fwd", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config("fp32", sample=f"{sample_rays} primary rays x {N_EXPOSURE} exposures per step"),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample_rays} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, full-size VM grids"},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(precision, **extra):
+    cfg = {"workload": f"blurfactory c2f render fwd: {N_RAYS} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, "
+                       f"PDRF coarse {grid_size(COARSE_VOX)} / fine {grid_size(FINE_VOX)} VM grids",
+           "rays": N_RAYS, "exposures": N_EXPOSURE, "samples": [NC, NI], "precision": precision,
+           "perturb": 0, "l2": "flushed between timed steps (256 MiB write)"}
+    cfg.update(extra)
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from evdeblurnerf_b200 import RenderEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = make_params(dev)
+    eng = RenderEngine(P, *AABB, precision=args.precision)
+    rays_host = make_rays(N_RAYS, seed=1000 + rank)
+    rb_host = build_ray_batch(rays_host).pin_memory()
+    rb_dev = rb_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_host = torch.empty((N_RAYS * N_EXPOSURE, 3), dtype=torch.float32).pin_memory()
+
+    def step(rb):
+        return eng.render_rays(rb, NC, N_importance=NI, is_train=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(rb_dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, L2 flushed before each, CUDA events around each step -----------------------
+    sampler = ClockSampler(local)
+    eng.profile = {}
+    ev = []
+    barrier()
+    sampler.start()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(rb_dev)
+        e.record()
+        ev.append((s, e))
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
+    kern_ms = {k: sum(s.elapsed_time(e) for s, e in v) / len(v) for k, v in eng.profile.items()}
+    eng.profile = None
+
+    # ---- end to end through the public API: pinned host rays -> H2D -> render -> D2H colours, every step ------------
+    ev2 = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rb = rb_host.to(dev, non_blocking=True)
+        out = step(rb)
+        out_host.copy_(out["rgb_map"], non_blocking=True)
+        e.record()
+        ev2.append((s, e))
+    barrier()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = world * N_RAYS / (ms_per_step / 1e3)
+    e2e_value = world * N_RAYS / (e2e_ms / args.steps / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
+    R = N_RAYS * N_EXPOSURE
+    fine_ms = kern_ms.get("fine", float("nan"))
+    achieved = flops_fine_kernel_per_subray() * R / (fine_ms / 1e3) / 1e12
+    line = {
+        "metric": "primary_rays_per_sec_fwd", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args.precision),
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rb_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+        "kernels_ms": kern_ms,
+        "roofline": {"bound": "tensor", "kernel": "edn_render_fine_fwd", "achieved": achieved, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "flops_per_launch": flops_fine_kernel_per_subray() * R, "ms_per_launch": fine_ms,
+                     "whole_step_tflops": flops_per_subray() * R / (ms_per_step / 1e3) / 1e12},
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 256
+        Pc = {k: v.cpu() for k, v in P.items()}
+        rays_c = make_rays(sample, seed=100)
+        best, t_spent = None, 0.0
+        for i in range(4):
+            dt, _ = cpu_reference_step(Pc, rays_c, threads)
+            t_spent += dt
+            if i > 0:
+                best = dt if best is None else min(best, dt)
+            if t_spent > 25.0 and best is not None:
+                break
+        line["cpu_baseline"] = {"value": sample / best, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": f"{sample} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, same VM grids; "
+                                          f"best of {i} after 1 warm-up"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

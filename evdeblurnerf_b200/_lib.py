@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI in include/evdeblur_b200.h (libevdeblur_b200.so, built in-tree by csrc/build.py).
+
+There is no CPU fallback: importing the package works without the library (so that host-side logic can be tested on a
+CPU box), but every compute entry point raises if the library is missing or CUDA is unavailable.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libevdeblur_b200.so")
+
+EDN_F32, EDN_BF16 = 0, 1
+FLAG_LINDISP, FLAG_TRAIN, FLAG_RELU_RGB = 1, 2, 4
+
+c_float_p = C.c_void_p   # device pointers travel as plain integers
+
+
+class VmGrid(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("line", C.c_void_p * 3), ("plane_h", C.c_int32 * 3),
+                ("plane_w", C.c_int32 * 3), ("line_len", C.c_int32 * 3), ("n_comp", C.c_int32 * 3),
+                ("dtype", C.c_int32), ("basis_t", C.c_void_p), ("aabb_min", C.c_float * 3),
+                ("aabb_max", C.c_float * 3)]
+
+
+class FieldMlp(C.Structure):
+    _fields_ = [("sigma0_t", C.c_void_p), ("sigma1_t", C.c_void_p), ("sigma1_v", C.c_void_p),
+                ("color0_t", C.c_void_p), ("color1_t", C.c_void_p), ("color2_t", C.c_void_p),
+                ("color0_b", C.c_void_p), ("color1_b", C.c_void_p), ("color2_b", C.c_void_p),
+                ("hidden", C.c_int32), ("geo_feat", C.c_int32)]
+
+
+# name -> (restype, argtypes); must list every symbol include/evdeblur_b200.h declares (tests/test_abi.py checks)
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES = {
+    "edn_last_error": (C.c_char_p, []),
+    "edn_abi_version": (C.c_int, []),
+    "edn_pack_vm_plane": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "edn_vm_sample": (C.c_int, [C.POINTER(VmGrid), _P, _P, _I64, _P]),
+    "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
+                                        _P, _P, _P, _P, _P, _P, _P]),
+    "edn_sample_pdf_merge": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "edn_render_fine_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _I64,
+                                      _I32, _I32, _F, _I32, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Returns the loaded CDLL; raises NativeLibraryError when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python evdeblurnerf_b200/csrc/build.py` "
+            f"(or __graft_entry__.build()). evdeblurnerf_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().edn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) tensor or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "edn: tensor must be contiguous"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,118 @@
+/* evdeblur_b200.h -- C ABI of the B200-native EvDeblurNeRF render / blur-loss hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer on the current CUDA device
+ * unless the parameter name ends in `_host`.  Every entry point returns 0 on success, a negative EDN_E_* code
+ * otherwise (edn_last_error() gives the text) and enqueues its work on `stream` (a cudaStream_t passed as void*;
+ * NULL = legacy default stream) without synchronising.
+ *
+ * The reference (uzh-rpg/EvDeblurNeRF @ 4111020) has no FFI: its "operator interface" is the Python method surface
+ * listed in SURVEY.md section 8(b).  Each entry point below names the reference file:line it replaces; the Python
+ * mirror of that surface (same names / argument meaning) lives in evdeblurnerf_b200/ and binds these symbols with
+ * ctypes (INTEGRATION.md shows the binding a reference maintainer would add).
+ */
+#ifndef EVDEBLUR_B200_H_
+#define EVDEBLUR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDN_ABI_VERSION 1
+
+enum {
+  EDN_OK = 0,
+  EDN_E_INVALID = -1,   /* bad argument (shape / dim not supported, null pointer) */
+  EDN_E_CUDA = -2,      /* a CUDA runtime call failed */
+  EDN_E_UNSUPPORTED = -3
+};
+
+enum { EDN_F32 = 0, EDN_BF16 = 1 };
+
+/* flags for the render entry points */
+enum {
+  EDN_FLAG_LINDISP = 1,       /* renderer.py:166-167 */
+  EDN_FLAG_TRAIN = 2,         /* module.training: disables the rmnearplane mask (voxnerf.py:181) */
+  EDN_FLAG_RELU_RGB = 4       /* CRR coarse field: rgb_activate='relu' on top of the sigmoid (voxnerf.py:266) */
+};
+
+/* VM-decomposed feature grid of one PDRF field (networks/pdrf/voxnerf.py:99-118, 132-151).
+ * Planes / lines are in RENDER LAYOUT: channel-last, plane i = [H_i][W_i][C_i], line i = [L_i][C_i]
+ * (edn_pack_vm_plane converts from the reference's [1,C,H,W] parameters). */
+typedef struct edn_vm_grid {
+  const void* plane[3];
+  const void* line[3];
+  int32_t plane_h[3];      /* gridSize[matMode[i][1]] */
+  int32_t plane_w[3];      /* gridSize[matMode[i][0]] */
+  int32_t line_len[3];     /* gridSize[vecMode[i]]    */
+  int32_t n_comp[3];       /* must be {64,16,16}      */
+  int32_t dtype;           /* EDN_F32 | EDN_BF16      */
+  const float* basis_t;    /* basis_mat.weight transposed: [96][32] fp32 */
+  float aabb_min[3];
+  float aabb_max[3];
+} edn_vm_grid;
+
+/* One PDRF field's MLP weights, TRANSPOSED ([in][out], out contiguous) and zero padded as stated.
+ * coarse (CRR): sigma0_t [96][64] (row 95 zero), sigma1_t [64][16], color0_t [42][64], color1_t [64][64], color2_t [64][4]
+ * fine   (FVR): sigma0_t [128][256] (row 127 zero), sigma1_t [256][128] (the geo_feat columns 1..128 of sigma_net.1),
+ *               sigma1_v [256] (its sigma column 0), color0_t [155][256], color1_t [256][256], color2_t [256][4]
+ * color*_b: bias vectors or NULL (--rgb_add_bias, voxnerf.py:80). */
+typedef struct edn_field_mlp {
+  const float* sigma0_t;
+  const float* sigma1_t;
+  const float* sigma1_v;   /* fine only; NULL for the coarse field */
+  const float* color0_t;
+  const float* color1_t;
+  const float* color2_t;
+  const float* color0_b;
+  const float* color1_b;
+  const float* color2_b;
+  int32_t hidden;          /* 64 (coarse) | 256 (fine) */
+  int32_t geo_feat;        /* 15 (coarse) | 128 (fine) */
+} edn_field_mlp;
+
+const char* edn_last_error(void);
+int edn_abi_version(void);
+
+/* [1,C,H,W] fp32 (reference parameter layout, voxnerf.py:107-117) -> channel-last [H][W][C] fp32 or bf16. */
+int edn_pack_vm_plane(const float* src_chw, void* dst_hwc, int32_t C, int32_t H, int32_t W, int32_t dst_dtype,
+                      void* stream);
+
+/* VoxelNeRFBase.sample (voxnerf.py:203-208, 132-151): pts [n,3] -> feat [n,32].  Unit-test / drop-in entry. */
+int edn_vm_sample(const edn_vm_grid* grid, const float* pts, float* feat, int64_t n, void* stream);
+
+/* Coarse pass of NeRFAll.render_rays (renderer.py:157-188): sample placement, VM lookup, PE, CRR field
+ * (voxnerf.py:210-259) and sigma->alpha compositing (voxnerf.py:153-201), fused.
+ *   ray_batch [R][11] = o,d,near,far,viewdirs (renderer.py:443-446)
+ *   t_vals [n_samples]        = linspace(0,1,n_samples)
+ *   t_rand [R][n_samples]     or NULL (perturb == 0)            (renderer.py:176)
+ *   noise  [R][n_samples-1]   or NULL (already * raw_noise_std)  (voxnerf.py:175)
+ * outputs: z_vals [R][S], weights [R][S], rgb [R][3], depth [R], acc [R];
+ *          feat [R][S][15] or NULL (feature_map, voxnerf.py:221); ft_coarse [R][S][32] or NULL. */
+int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_mlp* mlp, const float* ray_batch,
+                          const float* t_vals, const float* t_rand, const float* noise, int64_t n_rays,
+                          int32_t n_samples, int32_t flags, float rmnearplane, float* z_vals, float* weights,
+                          float* rgb, float* depth, float* acc, float* feat, void* stream);
+
+/* sample_pdf (utils/rays.py:149-193) as called at renderer.py:199-203 + merge/sort (renderer.py:205) + z_std (:250).
+ *   u_det [n_importance] = linspace(0,1,n_importance) (perturb == 0) or NULL;  u_rand [R][n_importance] or NULL.
+ * outputs: z_samples [R][Ni], inds [R][Ni] int64 or NULL, z_vals [R][Nc+Ni] sorted (stable), order [R][Nc+Ni] int64
+ * or NULL, z_std [R] or NULL.  cdf accumulated sequentially in fp64 and rounded (== torch CPU cumsum). */
+int edn_sample_pdf_merge(const float* z_vals0, const float* weights0, const float* u_det, const float* u_rand,
+                         int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples, int64_t* inds,
+                         float* z_vals, int64_t* order, float* z_std, void* stream);
+
+/* Fine pass of render_rays (renderer.py:190-217): VM lookup of both grids at the merged samples, PE, FVR field,
+ * compositing.  precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path.
+ *   z_vals [R][S] sorted merged depths;  noise [R][S-1] or NULL.
+ * outputs: weights [R][S], rgb [R][3], depth [R], acc [R], feat [R][S][128] or NULL (depth_feature for AWP). */
+int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_fine, const edn_field_mlp* mlp,
+                        const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays,
+                        int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* weights,
+                        float* rgb, float* depth, float* acc, float* feat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVDEBLUR_B200_H_ */
