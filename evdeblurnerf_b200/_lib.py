@@ -26,7 +26,7 @@ class FieldMlp(C.Structure):
     _fields_ = [("sigma0_t", C.c_void_p), ("sigma1_t", C.c_void_p), ("sigma1_v", C.c_void_p),
                 ("color0_t", C.c_void_p), ("color1_t", C.c_void_p), ("color2_t", C.c_void_p),
                 ("color0_b", C.c_void_p), ("color1_b", C.c_void_p), ("color2_b", C.c_void_p),
-                ("hidden", C.c_int32), ("geo_feat", C.c_int32)]
+                ("hidden", C.c_int32), ("geo_feat", C.c_int32), ("tc_blob", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/evdeblur_b200.h declares (tests/test_abi.py checks)
@@ -39,6 +39,8 @@ SIGNATURES = {
     "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
                                         _P, _P, _P, _P, _P, _P, _P]),
     "edn_sample_pdf_merge": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "edn_fine_tc_blob_bytes": (C.c_int64, []),
+    "edn_pack_fine_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P]),
     "edn_render_fine_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _I64,
                                       _I32, _I32, _F, _I32, _P, _P, _P, _P, _P, _P]),
 }

@@ -1,0 +1,24 @@
+// Launch arguments shared by the fp32 (fine_f32.cu) and tcgen05 (fine_tc.cu) fine-pass kernels.
+#pragma once
+#include "common.cuh"
+
+namespace edn {
+
+struct FineArgs {
+  GridDev gc, gf;
+  edn_field_mlp mlp;
+  const float* ray_batch;
+  const float* z_vals;
+  const float* noise;
+  int64_t n_rays;
+  int S;
+  int flags;
+  float rmnearplane;
+  float* weights;
+  float* rgb;
+  float* depth;
+  float* acc;
+  float* feat;
+};
+
+}  // namespace edn

@@ -4,6 +4,7 @@
 // color_net 155->256->256->3, sigmoid, compositing.  One CTA renders one ray at a time in 64-sample row tiles;
 // activations stay in shared memory, weights stream from L2 in 16-row K chunks (cp.async double buffer).
 #include "common.cuh"
+#include "fine_args.cuh"
 
 namespace edn {
 
@@ -28,22 +29,6 @@ struct FineSmem {
   static constexpr int total = rgb + 3 * kMaxS;
 };
 
-struct FineArgs {
-  GridDev gc, gf;
-  edn_field_mlp mlp;
-  const float* ray_batch;
-  const float* z_vals;
-  const float* noise;
-  int64_t n_rays;
-  int S;
-  int flags;
-  float rmnearplane;
-  float* weights;
-  float* rgb;
-  float* depth;
-  float* acc;
-  float* feat;
-};
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -105,7 +105,19 @@ class PackedField:
         m.color0_b = ptr(b0)
         m.color1_b = ptr(b1)
         m.color2_b = ptr(b2)
+        m.tc_blob = None
         self.mlp = m
+        self.basis_t = basis_t
+
+    def pack_tensor_core_operands(self, coarse_field):
+        """bf16 UMMA operand blob of the fine field + both basis_mat's (edn_pack_fine_tc); tcgen05 path only."""
+        lib = _lib.load()
+        n = int(lib.edn_fine_tc_blob_bytes())
+        blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
+        check(lib.edn_pack_fine_tc(C.byref(self.mlp), ptr(coarse_field.basis_t), ptr(self.basis_t), ptr(blob), stream_ptr()),
+              "edn_pack_fine_tc")
+        self.keep.append(blob)
+        self.mlp.tc_blob = blob.data_ptr()
 
 
 class RenderEngine:
@@ -148,6 +160,8 @@ class RenderEngine:
         self.fine = None
         if "mlp_fine.sigma_net.0.weight" in P:
             self.fine = PackedField(P, "mlp_fine.", self.aabb_min, self.aabb_max, False, grid_dtype)
+            if self.prec_code == EDN_BF16:
+                self.fine.pack_tensor_core_operands(self.coarse)
 
     def _linspace(self, n):
         # computed by torch on the CPU (bit-identical to the reference's torch.linspace), cached on the device

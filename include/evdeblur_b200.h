@@ -70,6 +70,7 @@ typedef struct edn_field_mlp {
   const float* color2_b;
   int32_t hidden;          /* 64 (coarse) | 256 (fine) */
   int32_t geo_feat;        /* 15 (coarse) | 128 (fine) */
+  const void* tc_blob;     /* bf16 tensor-core operand blob written by edn_pack_fine_tc (EDN_BF16 precision) or NULL */
 } edn_field_mlp;
 
 const char* edn_last_error(void);
@@ -102,6 +103,12 @@ int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_mlp* mlp, con
 int edn_sample_pdf_merge(const float* z_vals0, const float* weights0, const float* u_det, const float* u_rand,
                          int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples, int64_t* inds,
                          float* z_vals, int64_t* order, float* z_std, void* stream);
+
+/* Size in bytes of the tensor-core operand blob of the fine field, and its packer: every K=16 slice of every layer
+ * (and of the two basis_mat's) as a bf16 UMMA K-major core-matrix tile, in the order the fine kernel streams them. */
+int64_t edn_fine_tc_blob_bytes(void);
+int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, void* blob,
+                     void* stream);
 
 /* Fine pass of render_rays (renderer.py:190-217): VM lookup of both grids at the merged samples, PE, FVR field,
  * compositing.  precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path.

@@ -158,8 +158,9 @@ def vm_grid_size(aabb_min, aabb_max, n_voxels):
     return ((amax - amin) / voxel).long().tolist()
 
 
-def vm_sample(P, prefix, pts, aabb_min, aabb_max):
-    """`VoxelNeRFBase.sample` with F.grid_sample exactly as the reference issues it. pts [R,S,3] -> [R,S,app_dim]."""
+def vm_products(P, prefix, pts, aabb_min, aabb_max):
+    """compute_appfeature up to (plane (.) line), voxnerf.py:132-149, with F.grid_sample exactly as the reference
+    issues it.  pts [..., 3] -> [n, 96]."""
     amin, amax = torch.as_tensor(aabb_min, dtype=torch.float32), torch.as_tensor(aabb_max, dtype=torch.float32)
     inv = 2.0 / (amax - amin)
     xyz = (pts.reshape(-1, 3) - amin) * inv - 1
@@ -169,8 +170,12 @@ def vm_sample(P, prefix, pts, aabb_min, aabb_max):
         cl = torch.stack((torch.zeros_like(xyz[..., 0]), xyz[..., VECMODE[i]]), -1).view(1, -1, 1, 2)
         feats_p.append(F.grid_sample(P[prefix + f"app_plane.{i}"], cp, align_corners=True).view(-1, xyz.shape[0]))
         feats_l.append(F.grid_sample(P[prefix + f"app_line.{i}"], cl, align_corners=True).view(-1, xyz.shape[0]))
-    prod = (torch.cat(feats_p) * torch.cat(feats_l)).T
-    out = F.linear(prod, P[prefix + "basis_mat.weight"])
+    return (torch.cat(feats_p) * torch.cat(feats_l)).T
+
+
+def vm_sample(P, prefix, pts, aabb_min, aabb_max):
+    """`VoxelNeRFBase.sample` (voxnerf.py:203-208). pts [R,S,3] -> [R,S,app_dim]."""
+    out = F.linear(vm_products(P, prefix, pts, aabb_min, aabb_max), P[prefix + "basis_mat.weight"])
     return out.reshape(pts.shape[0], pts.shape[1], -1)
 
 

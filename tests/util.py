@@ -73,3 +73,53 @@ def random_params(seed, coarse_grid=(18, 18, 12), fine_grid=(36, 36, 24), device
         lin(pre + "color_net.1.weight", hid, hid)
         lin(pre + "color_net.2.weight", 3, hid)
     return {k: v.to(device) for k, v in P.items()}
+
+
+def oracle_fine_at(P, ray_batch, z_all, noise=None, is_train=True, rmnearplane=0):
+    """Oracle fine stage (renderer.py:206-217) evaluated at GIVEN merged depths: sample_pdf is ill-conditioned in the
+    last bits of weights0 (t = (u - cdf_b) / denom with denom down to 1e-5), so the fine pass is checked tightly at the
+    depths the CUDA path itself produced, and the sampler separately (bit-exact on identical weights)."""
+    import evdeblur_oracle as oc
+    o, d, vd = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, -3:]
+    pts = o[:, None, :] + d[:, None, :] * z_all[..., None]
+    ft = torch.cat([oc.vm_sample(P, "mlp_coarse.", pts, *AABB), oc.vm_sample(P, "mlp_fine.", pts, *AABB)], -1)
+    rgb, depth, acc, w, feat = oc.field_forward(P, "mlp_fine.", pts, vd, ft, z_all, d, noise, is_train, rmnearplane,
+                                                rgb_act="none")
+    return {"rgb_map": rgb, "depth_map": depth, "acc_map": acc, "weights": w, "depth_feature": feat}
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearplane=0):
+    """Torch fp32 reference of the tcgen05 fine pass with its operand roundings made explicit: VM planes, the
+    plane (.) line products, every MMA A operand (features, PE, activations) and every weight matrix are rounded to
+    bf16; accumulation, biases, sigma, sigmoid and compositing stay fp32.  The view-direction part of color_net.0 is an
+    fp32 per-ray bias.  Against this reference the CUDA kernel differs by accumulation order only."""
+    import evdeblur_oracle as oc
+    import torch.nn.functional as F
+    o, d, vd = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, -3:]
+    R, S = z_all.shape
+    pts = o[:, None, :] + d[:, None, :] * z_all[..., None]
+    Pb = {k: (_bf(v) if ("app_plane" in k or "app_line" in k) else v) for k, v in P.items()}
+    fts = []
+    for pre in ("mlp_coarse.", "mlp_fine."):
+        g = _bf(oc.vm_products(Pb, pre, pts, *AABB))
+        fts.append(_bf(F.linear(g, _bf(P[pre + "basis_mat.weight"]))))
+    x = torch.cat(fts + [_bf(oc.posenc(pts.reshape(-1, 3), 10))], -1)
+    pre = "mlp_fine."
+    h1 = _bf(torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"]))))
+    w1 = _bf(P[pre + "sigma_net.1.weight"])
+    sigma = F.linear(h1, w1[:1])
+    geo = F.linear(h1, w1[1:])
+    w3 = P[pre + "color_net.0.weight"]
+    bias_ray = F.linear(oc.posenc(vd, 4), w3[:, 128:], P.get(pre + "color_net.0.bias"))          # [R,256] fp32
+    h3 = F.linear(_bf(geo), _bf(w3[:, :128])) + bias_ray[:, None, :].expand(R, S, 256).reshape(R * S, 256)
+    h3 = _bf(torch.relu(h3))
+    h4 = _bf(torch.relu(F.linear(h3, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias"))))
+    rgb = torch.sigmoid(F.linear(h4, _bf(P[pre + "color_net.2.weight"]), P.get(pre + "color_net.2.bias")))
+    raw = torch.cat([sigma, rgb], -1).reshape(R, S, 4)
+    rgb_map, _, acc, w, depth = oc.raw2outputs(raw, z_all, d, noise, is_train, rmnearplane)
+    return {"rgb_map": rgb_map, "depth_map": depth, "acc_map": acc, "weights": w, "depth_feature": geo.reshape(R, S, -1),
+            "sigma": sigma.reshape(R, S)}
