@@ -163,6 +163,23 @@ class RenderEngine:
             if self.prec_code == EDN_BF16:
                 self.fine.pack_tensor_core_operands(self.coarse)
 
+    @staticmethod
+    def _empty_result(dev, Nc, Ni, retraw, want_feat):
+        f32 = dict(dtype=torch.float32, device=dev)
+        S = Nc + Ni
+        ret = {"rgb_map": torch.empty((0, 3), **f32), "depth_map": torch.empty((0,), **f32), "acc_map": torch.empty((0,), **f32)}
+        if retraw:
+            ret["z_vals"], ret["weights"] = torch.empty((0, S), **f32), torch.empty((0, S), **f32)
+        if Ni > 0:
+            ret.update(rgb0=torch.empty((0, 3), **f32), depth0=torch.empty((0,), **f32), acc0=torch.empty((0,), **f32),
+                       z_std=torch.empty((0,), **f32))
+            if retraw:
+                ret["z_vals0"], ret["weights0"] = torch.empty((0, Nc), **f32), torch.empty((0, Nc), **f32)
+        if want_feat:
+            ret["depth_feature"] = torch.empty((0, S, 128 if Ni > 0 else 15), **f32)
+            ret["z_vals"] = torch.empty((0, S), **f32)
+        return ret
+
     def _linspace(self, n):
         # computed by torch on the CPU (bit-identical to the reference's torch.linspace), cached on the device
         if n not in self._lin:
@@ -212,6 +229,8 @@ class RenderEngine:
         lib = _lib.load()
         rb = ray_batch.float().contiguous()
         R, dev = rb.shape[0], rb.device
+        if R == 0:
+            return self._empty_result(dev, int(N_samples), int(N_importance), retraw, use_awp and not force_naive and not inference)
         rand = dict(rand or {})
         Nc, Ni = int(N_samples), int(N_importance)
         flags = (FLAG_LINDISP if lindisp else 0) | (FLAG_TRAIN if is_train else 0)
