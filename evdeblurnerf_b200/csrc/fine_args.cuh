@@ -19,6 +19,7 @@ struct FineArgs {
   float* depth;
   float* acc;
   float* feat;
+  long long* trace;   // dev tooling (EDN_TC_TRACE=1): per-phase clock64 stamps of CTA 0, NULL otherwise
 };
 
 }  // namespace edn

@@ -305,6 +305,7 @@ extern "C" int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_
   a.mlp = *mlp;
   a.ray_batch = ray_batch; a.z_vals = z_vals; a.noise = noise; a.n_rays = n_rays; a.S = n_samples; a.flags = flags;
   a.rmnearplane = rmnearplane; a.weights = weights; a.rgb = rgb; a.depth = depth; a.acc = acc; a.feat = feat;
+  a.trace = nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == EDN_F32) return launch_fine_f32(a, grid_fine->dtype, st);
   if (precision == EDN_BF16) return launch_fine_tc(a, grid_fine->dtype, st);

@@ -1,14 +1,21 @@
 // Fine pass of render_rays on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 operands / fp32 accumulation.
 // Replaces networks/renderer.py:190-217 + networks/pdrf/voxnerf.py:203-259,153-201 for the FVR field.
 //
-// One CTA renders one ray (M = 128 merged samples = one UMMA M tile) at a time; two CTAs are co-resident per SM so
-// that one CTA's gather / epilogue overlaps the other's MMAs.  Per ray:
-//   rows  (warps 0-3, thread = sample row): PE -> A[:,64:128]; cooperative VM gather of both grids -> two 128x96 bf16
-//         tiles;  after each layer: TMEM -> registers -> bias/ReLU -> bf16 -> A operand of the next layer;  finally
+// One persistent CTA per SM renders TWO rays at a time (two row groups of 128 threads; one ray = 128 merged samples
+// = one UMMA M tile) so that one ray's epilogue / gather overlaps the other ray's MMAs:
+//   rows  (warps 0-7, thread = sample row, group = warp / 4): PE -> A[:,64:128]; cooperative VM gather of both grids
+//         -> two 128x96 bf16 tiles;  after each layer: TMEM -> registers -> bias/ReLU -> bf16 -> A operand of the next
+//         layer; sigma (256->1) and rgb (256->3) are fp32 dot products folded into the epilogues;  finally
 //         sigma->alpha compositing with a warp-shuffle transmittance scan.
-//   mma   (warp 4, one thread): streams every K=16 weight slice through a 5-stage shared-memory ring with bulk async
-//         copies (TMA engine) and issues tcgen05.mma: basis_mat x2 (N=32), sigma_net 128->256->144(=128 geo + sigma),
-//         color_net 128(+per-ray view-dir bias)->256->256->16(=rgb).  Accumulators live in 256 TMEM columns.
+//   load  (warp 10, one thread): streams the layer weights (320 KB per ray pair, 16 KB stages) through a 4-stage
+//         shared-memory ring with bulk async copies (TMA engine); a stage is refilled once BOTH rays' MMAs on it retired.
+//   mma   (warps 8 and 9, one thread each, one per ray): wait for the ray's A operand and the ring stage, issue
+//         tcgen05.mma: basis_mat x2 (N=32, resident B), sigma_net 128->256->128(geo), color_net 128(+view-dir
+//         bias)->256->256, and commit to the stage-release / accumulator-ready mbarriers.  2 x 256 TMEM columns.
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -20,80 +27,73 @@ namespace {
 
 using namespace tc;
 
-constexpr int kRowThreads = 128;
-constexpr int kThreads = 160;
-constexpr int kNst = 5;                 // weight ring stages
-constexpr int kStageBytes = 8192;       // one K=16 slice of an N=256 layer
-constexpr int kABytes = 65536;          // 128 rows x 256 K bf16
-constexpr int kChunkA = 2048;           // bytes of one 8-wide K chunk of a 128-row tile
-constexpr uint32_t kTmemCols = 256;
-constexpr int kChunksPerRay = 12 + 8 + 16 + 8 + 16 + 16;   // 76 MMA steps per ray
-constexpr int kN2 = 144;                // sigma_net.1: 128 geo columns + sigma (col 128) + 15 zero columns
-constexpr int kN5 = 16;                 // color_net.2: rgb in columns 0..2
+constexpr int kGroupThreads = 128;
+constexpr int kRowWarps = 8;
+constexpr int kThreads = kRowWarps * 32 + 96;   // 8 row warps + 2 MMA issuer warps + 1 weight-stream warp
+constexpr int kNst = 4;                  // weight ring stages
+constexpr int kStageBytes = 16384;
+constexpr int kABytes = 65536;           // per ray: 128 rows x 256 K bf16
+constexpr int kChunkA = 2048;            // bytes of one 8-wide K chunk of a 128-row tile
+constexpr int kBasisBytes = 2 * 6 * 1024;  // two basis_mat's, 6 K-steps x (N=32 x 16 x 2 B)
+constexpr uint32_t kTmemCols = 512;
+constexpr int kRingStagesPerRay = 20;    // 320 KB / 16 KB
+constexpr int kStepsPerRay = 2 + kRingStagesPerRay;
+constexpr int64_t kBlobBytes = kBasisBytes + (int64_t)kRingStagesPerRay * kStageBytes;
 
-enum : uint8_t { kFirst = 1, kLast = 2 };
-
-struct Chunk {
-  uint32_t goff;     // byte offset of the weight slice in the blob
-  uint32_t a_off;    // byte offset of the A K-step inside the A buffer
-  uint16_t bytes;
-  uint16_t n;
-  uint16_t d_col;
-  uint8_t accum;
-  uint8_t flags;
+struct StepDesc {
+  uint8_t kind;      // 0 = basis coarse tile, 1 = basis fine tile, 2 = ring stage
+  uint8_t n_mmas;
+  uint16_t n;        // UMMA N
+  uint16_t a_k0;     // first A K-step (16 columns each) of this stage
+  uint8_t first;     // first step of a layer: wait for the rows' A operand
+  uint8_t last;      // last step of a layer: commit the accumulator barrier
 };
-__constant__ Chunk c_sched[kChunksPerRay];
+__constant__ StepDesc c_steps[kStepsPerRay];
 
-struct LayerDef { int K, N; };
-// blob order: basis_coarse, basis_fine, sigma0, sigma1, color0, color1, color2
-constexpr LayerDef kLayers[7] = {{96, 32}, {96, 32}, {128, 256}, {256, kN2}, {128, 256}, {256, 256}, {256, kN5}};
-
-std::vector<Chunk> build_schedule(int64_t* blob_bytes, int64_t layer_off[7]) {
-  std::vector<Chunk> v;
-  uint32_t goff = 0;
-  const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
-  for (int L = 0; L < 7; ++L) {
-    layer_off[L] = goff;
-    const int steps = kLayers[L].K / 16, N = kLayers[L].N;
-    for (int j = 0; j < steps; ++j) {
-      Chunk c{};
-      c.goff = goff;
-      c.bytes = (uint16_t)(N * 32);
-      c.n = (uint16_t)N;
-      c.accum = j > 0;
-      c.flags = 0;
-      if (L == 0) { c.a_off = (16 + 2 * j) * kChunkA; c.d_col = 0; if (j == 0) c.flags |= kFirst; }
-      else if (L == 1) { c.a_off = fine_tile_chunks[j] * kChunkA; c.d_col = 32; if (j == steps - 1) c.flags |= kLast; }
-      else { c.a_off = 2 * j * kChunkA; c.d_col = 0; if (j == 0) c.flags |= kFirst; if (j == steps - 1) c.flags |= kLast; }
-      v.push_back(c);
-      goff += c.bytes;
-    }
-  }
-  *blob_bytes = goff;
+std::vector<StepDesc> build_steps() {
+  std::vector<StepDesc> v;
+  v.push_back({0, 6, 32, 0, 1, 0});
+  v.push_back({1, 6, 32, 0, 0, 1});
+  auto layer = [&](int K, int N) {
+    const int kstep_bytes = N * 32, per_stage = kStageBytes / kstep_bytes, stages = (K / 16) / per_stage;
+    for (int s = 0; s < stages; ++s)
+      v.push_back({2, (uint8_t)per_stage, (uint16_t)N, (uint16_t)(s * per_stage), (uint8_t)(s == 0), (uint8_t)(s == stages - 1)});
+  };
+  layer(128, 256);   // sigma_net.0
+  layer(256, 128);   // sigma_net.1 (geo columns)
+  layer(128, 256);   // color_net.0 (geo part)
+  layer(256, 256);   // color_net.1
   return v;
 }
 
-struct Misc {
-  uint64_t bar_a, bar_acc, full[kNst], empty[kNst];
-  uint32_t tmem_base, pad[3];
-  float z[kRowThreads];
-  float sig[kRowThreads];
-  float bias[256];
+struct alignas(16) GroupMisc {
+  float z[kGroupThreads];
+  alignas(16) float bias[256];
   float red[4][8];
   float wtot[4];
 };
-constexpr int kSmemBytes = kABytes + kNst * kStageBytes + (int)sizeof(Misc);
+struct Misc {
+  uint64_t bar_a[2], bar_acc[2], full[kNst], empty[kNst], bar_basis;
+  GridDev grids[2];          // [0] coarse, [1] fine
+  uint32_t tmem_base, pad[3];
+  alignas(16) float wsig[256];           // sigma_net.1 row 0 (sigma head)
+  alignas(16) float wrgb[256][4];        // color_net.2 transposed (rgb head)
+  alignas(16) float bias1[256];          // color_net.1 bias (zeros without --rgb_add_bias)
+  GroupMisc grp[2];
+};
+static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 && offsetof(Misc, bias1) % 16 == 0 &&
+              offsetof(Misc, grp) % 16 == 0 && offsetof(GroupMisc, bias) % 16 == 0, "float4 alignment");
+constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kBasisBytes + (int)sizeof(Misc);
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // ---- weight packing -----------------------------------------------------------------------------------------------
 // dst element (n, k) of a [K][N] layer -> bf16 index (k/16)*(N*16) + ((k%16)/8)*(N*8) + n*8 + k%8
-__global__ void pack_layer_kernel(const float* __restrict__ wt, int ld, int k_valid, int n_valid, const float* __restrict__ vec,
-                                  int vec_col, int K, int N, __nv_bfloat16* __restrict__ dst) {
+__global__ void pack_layer_kernel(const float* __restrict__ wt, int ld, int k_valid, int n_valid, int K, int N,
+                                  __nv_bfloat16* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   const int k = i / N, n = i - k * N;
-  float v = 0.f;
-  if (k < k_valid && n < n_valid) v = wt[(size_t)k * ld + n];
-  else if (vec && n == vec_col && k < k_valid) v = vec[k];
+  const float v = (k < k_valid && n < n_valid) ? wt[(size_t)k * ld + n] : 0.f;
   dst[(size_t)(k / 16) * (N * 16) + ((k % 16) / 8) * (N * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
 }
 
@@ -107,107 +107,170 @@ __device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
   *c = __cosf(r);
 }
 
-template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
-template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+// Raw 16-byte channel chunk of a bf16 texel row / 2 x 16 bytes of an fp32 one.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
-
-// 8 channels [c8*8, c8*8+8) of component `comp` at one point: (bilinear plane) * (linear line) -> 16 bytes of bf16
-template <typename T>
-__device__ __forceinline__ uint4 gather8(const T* __restrict__ plane, const T* __restrict__ line, int C, int c8,
-                                         const Taps2& pt, const Taps1& lt) {
-  float pv[4][8], lv[2][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) load8<T>(plane + (size_t)pt.off[k] * C + c8 * 8, pv[k]);
-#pragma unroll
-  for (int k = 0; k < 2; ++k) load8<T>(line + (size_t)lt.off[k] * C + c8 * 8, lv[k]);
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float p = pv[0][i] * pt.w[0];
-    p = fmaf(pv[1][i], pt.w[1], p); p = fmaf(pv[2][i], pt.w[2], p); p = fmaf(pv[3][i], pt.w[3], p);
-    const float l = fmaf(lv[1][i], lt.w[1], lv[0][i] * lt.w[0]);
-    o[i] = p * l;
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
-  return make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-}
+};
+template <> struct Raw8<float> {
+  float4 lo, hi;
+  __device__ __forceinline__ void load(const float* p) {
+    lo = __ldg(reinterpret_cast<const float4*>(p)); hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  }
+};
 
-// Cooperative gather of one grid for the 32 points of this warp: lane (q = lane/8, j = lane%8) serves point 8*gi+j.
+// One gather task = 8 channels of one VM component at one point: 4 plane taps + 2 line taps (issue), then
+// (bilinear plane) * (linear line) -> 16 bytes of bf16 (finish).  Issue and finish are split so that several tasks'
+// loads are in flight together.
 template <typename T>
-__device__ __forceinline__ void gather_grid(const GridDev& g, bool fine_tile, uint8_t* As, const float* z_s, int warp, int lane,
-                                            const float o[3], const float d[3]) {
+struct GatherTask {
+  Raw8<T> pv[4], lv[2];
+  float pw[4], lw[2];
+  __device__ __forceinline__ void issue(const T* __restrict__ plane, const T* __restrict__ line, int C, int c8,
+                                        const Taps2& pt, const Taps1& lt) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pv[k].load(plane + (size_t)pt.off[k] * C + c8 * 8); pw[k] = pt.w[k]; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { lv[k].load(line + (size_t)lt.off[k] * C + c8 * 8); lw[k] = lt.w[k]; }
+  }
+  __device__ __forceinline__ void finish(uint8_t* dst) const {
+    float p[8], l[8], t[8];
+    pv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = t[i] * pw[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      pv[k].get(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fmaf(t[i], pw[k], p[i]);
+    }
+    lv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = t[i] * lw[0];
+    lv[1].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
+    st_shared_v4(dst, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+  }
+};
+
+// Cooperative gather of both grids for the 32 points of this warp.  Lane (q = lane/8, j = lane%8) serves point 8*gi+j
+// and reads 16-byte channel chunks, so every warp-wide load covers whole 32 B sectors of 8 texels.  Per (grid, gi)
+// iteration a lane runs 3 tasks (component 0 chunks q and q+4, and chunk q&1 of component 1 + q/2) with all 18 loads
+// issued before the first use.  Tile placement inside the ray's A buffer (2 KB chunks): coarse tile -> chunks 16..27,
+// fine tile -> 28..31,0..7.
+template <typename T>
+__device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As, const float* z_s, int gwarp, int lane,
+                                             const float o[3], const float d[3]) {
   const int q = lane >> 3;
-#pragma unroll 2
-  for (int gi = 0; gi < 4; ++gi) {
-    const int pt = warp * 32 + gi * 8 + (lane & 7);
+#pragma unroll 1
+  for (int itg = 0; itg < 8; ++itg) {
+    const int fine_tile = itg >> 2, gi = itg & 3;
+    const GridDev& g = grids_s[fine_tile];
+    const int pt = gwarp * 32 + gi * 8 + (lane & 7);
     const float zv = z_s[pt];
     float p[3], n[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
     normalize_pt(g, p, n);
     uint8_t* row = As + pt * 16;
-    {  // component 0: plane (x,y) 64 channels, line z; this lane does channel chunks q and q+4
-      Taps2 t2; Taps1 t1;
-      plane_taps(n[0], n[1], g.ph[0], g.pw[0], t2);
-      line_taps(n[2], g.ll[0], t1);
+    GatherTask<T> t0, t1, t2;
+    {  // component 0: plane (x,y) 64 channels, line z
+      Taps2 pt2; Taps1 lt1;
+      plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
+      line_taps(n[2], g.ll[0], lt1);
       const T* pl = reinterpret_cast<const T*>(g.plane[0]);
       const T* ln = reinterpret_cast<const T*>(g.line[0]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int cc = 4 * h + q;
-        const uint4 v = gather8<T>(pl, ln, 64, cc, t2, t1);
-        const int chunk = fine_tile ? (cc < 4 ? 28 + cc : cc - 4) : 16 + cc;
-        st_shared_v4(row + chunk * kChunkA, v.x, v.y, v.z, v.w);
-      }
+      t0.issue(pl, ln, 64, q, pt2, lt1);
+      t1.issue(pl, ln, 64, q + 4, pt2, lt1);
     }
     {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
-      const int comp = 1 + (q >> 1), c8 = q & 1;
-      Taps2 t2; Taps1 t1;
-      plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], t2);
-      line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], t1);
-      const uint4 v = gather8<T>(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, c8, t2, t1);
-      const int cc = 8 + q;
-      const int chunk = fine_tile ? cc - 4 : 16 + cc;
-      st_shared_v4(row + chunk * kChunkA, v.x, v.y, v.z, v.w);
+      const int comp = 1 + (q >> 1);
+      Taps2 pt2; Taps1 lt1;
+      plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], pt2);
+      line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
+      t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
     }
+    const int c0 = fine_tile ? 28 + q : 16 + q;            // channel chunk q
+    const int c1 = fine_tile ? q : 20 + q;                 // channel chunk q + 4
+    const int c2 = fine_tile ? 4 + q : 24 + q;             // channel chunk 8 + q
+    t0.finish(row + c0 * kChunkA);
+    t1.finish(row + c1 * kChunkA);
+    t2.finish(row + c2 * kChunkA);
   }
 }
 
-// TMEM columns [col0, col0+32) of this thread's row -> (+bias) -> (ReLU) -> bf16 -> A chunks col0/8 .. col0/8+3
-template <bool RELU>
-__device__ __forceinline__ void epilogue32(uint32_t taddr_row, int col0, uint8_t* a_row, const float* bias_s,
-                                           const float* __restrict__ bias_g, float* __restrict__ gout) {
-  uint32_t v[32];
-  tmem_ld32(taddr_row + col0, v);
-  tmem_ld_wait();
+enum EpiMode { kEpiPlain = 0, kEpiRelu = 1, kEpiReluSigma = 2, kEpiReluRgb = 3 };
+
+// 32 accumulator columns of this thread's row:  x = acc (+ bias);  optional fp32 copy to global;  ReLU;  fp32 dot
+// products with the sigma / rgb head;  bf16 -> A operand chunks (except kEpiReluRgb: only the rgb head is produced).
+__device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0, int mode, uint8_t* a_row,
+                                               const float* bias_s, float* __restrict__ gout, const float* wsig,
+                                               const float (*wrgb)[4], float* head) {
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    f[i] = __uint_as_float(v[i]);
-    if (bias_s) f[i] += bias_s[col0 + i];
-    if (bias_g) f[i] += __ldg(bias_g + col0 + i);
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (bias_s) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
+      f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+    }
   }
   if (gout) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(gout + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
   }
+  if (mode != kEpiPlain) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t pk[4];
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (mode == kEpiReluSigma) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float x0 = f[8 * j + 2 * e], x1 = f[8 * j + 2 * e + 1];
-      if (RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-      pk[e] = pack_bf16x2(x0, x1);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(wsig + col0 + i);
+      s0 = fmaf(f[i], w.x, s0); s1 = fmaf(f[i + 1], w.y, s1); s0 = fmaf(f[i + 2], w.z, s0); s1 = fmaf(f[i + 3], w.w, s1);
     }
-    st_shared_v4(a_row + (col0 / 8 + j) * kChunkA, pk[0], pk[1], pk[2], pk[3]);
+    head[0] += s0 + s1;
+  }
+  if (mode == kEpiReluRgb) {
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(&wrgb[col0 + i][0]);
+      r0 = fmaf(f[i], w.x, r0); r1 = fmaf(f[i], w.y, r1); r2 = fmaf(f[i], w.z, r2);
+    }
+    head[0] += r0; head[1] += r1; head[2] += r2;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(a_row + (col0 / 8 + j) * kChunkA, pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+  }
+}
+
+// Layer epilogue over `ncols` (multiple of 64) accumulator columns; ONE copy of the code for all layers (the kernel is
+// instruction-cache sensitive), two tcgen05.ld's in flight per iteration.
+__device__ __noinline__ void layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int ncols, int mode, const float* bias_s,
+                                            float* __restrict__ gout, const float* wsig, const float (*wrgb)[4], float* head) {
+#pragma unroll 1
+  for (int col0 = 0; col0 < ncols; col0 += 64) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(taddr_row + col0, v0);
+    tmem_ld32(taddr_row + col0 + 32, v1);
+    tmem_ld_wait();
+    epilogue_block(v0, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
+    epilogue_block(v1, col0 + 32, mode, a_row, bias_s, gout, wsig, wrgb, head);
   }
 }
 
@@ -218,86 +281,138 @@ __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 2) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* As = smem;
-  uint8_t* Ws = smem + kABytes;
-  Misc* m = reinterpret_cast<Misc*>(smem + kABytes + kNst * kStageBytes);
+  uint8_t* As = smem;                                   // [2][64 KB]
+  uint8_t* Ws = smem + 2 * kABytes;                     // ring
+  uint8_t* Bs = Ws + kNst * kStageBytes;                // resident basis_mat operands
+  Misc* m = reinterpret_cast<Misc*>(Bs + kBasisBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&m->bar_a, kRowThreads);
-    mbar_init(&m->bar_acc, 1);
-    for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[s], 1); mbar_init(&m->empty[s], 1); }
+    for (int q = 0; q < 2; ++q) { mbar_init(&m->bar_a[q], kGroupThreads); mbar_init(&m->bar_acc[q], 1); }
+    for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[s], 1); mbar_init(&m->empty[s], 2); }
+    mbar_init(&m->bar_basis, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&m->tmem_base, kTmemCols);
+  if (warp == kRowWarps) tmem_alloc(&m->tmem_base, kTmemCols);
+  for (int i = tid; i < 256; i += kThreads) {
+    m->wsig[i] = __ldg(a.mlp.sigma1_v + i);
+    m->bias1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m->wrgb[i][j] = __ldg(a.mlp.color2_t + i * 4 + j);
+  }
+  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = m->tmem_base;
-  const int64_t n_my = (a.n_rays > (int64_t)blockIdx.x) ? (a.n_rays - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_pairs_total = (a.n_rays + 1) / 2;
+  const int64_t n_my = (n_pairs_total > (int64_t)blockIdx.x) ? (n_pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int S = a.S;
 
-  if (warp == 4) {
-    // =================================== MMA + weight-stream warp =====================================================
-    if (lane == 0) {
-      const uint32_t a_base = smem_u32(As), w_base = smem_u32(Ws);
-      const uint64_t total = (uint64_t)n_my * kChunksPerRay;
-      uint64_t g = 0, g_issue = 0;
-      uint32_t pa = 0;
+  if (warp == kRowWarps + 2) {
+    // =================================== weight-stream producer warp ==================================================
+    if (lane == 0 && n_my > 0) {
+      const uint8_t* stream = blob + kBasisBytes;
+      mbar_expect_tx(&m->bar_basis, kBasisBytes);
+      bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis);
+      const uint32_t total_ring = (uint32_t)n_my * kRingStagesPerRay;
+      for (uint32_t g = 0; g < total_ring; ++g) {
+        const int s = g % kNst;
+        const uint32_t use = g / kNst;
+        if (use > 0) mbar_wait(&m->empty[s], (use - 1) & 1);      // both rays' MMAs on the previous tenant completed
+        mbar_expect_tx(&m->full[s], kStageBytes);
+        bulk_g2s(Ws + s * kStageBytes, stream + (size_t)(g % kRingStagesPerRay) * kStageBytes, kStageBytes, &m->full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kRowWarps) {
+    // =================================== MMA issuer warp of ray group q (one thread) ===================================
+    const int q = warp - kRowWarps;
+    if (lane == 0 && n_my > 0) {
+      const uint32_t aq = smem_u32(As) + q * kABytes, w_base = smem_u32(Ws), b_base = smem_u32(Bs);
+      const uint32_t d_tmem = tmem + q * 256;
+      const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
+      uint32_t pa = 0, g = 0;
+      mbar_wait(&m->bar_basis, 0);
       for (int64_t it = 0; it < n_my; ++it) {
-        for (int c = 0; c < kChunksPerRay; ++c, ++g) {
-          while (g_issue < total && g_issue < g + kNst) {     // keep the ring full without blocking ahead of need
-            const int s = (int)(g_issue % kNst);
-            const uint64_t use = g_issue / kNst;
-            if (use > 0) {
-              const uint32_t par = (uint32_t)((use - 1) & 1);
-              if (g_issue == g) mbar_wait(&m->empty[s], par);
-              else if (!mbar_test_wait(&m->empty[s], par)) break;
+#pragma unroll 1
+        for (int step = 0; step < kStepsPerRay; ++step) {
+          const StepDesc sd = c_steps[step];
+          if (sd.first) { mbar_wait(&m->bar_a[q], pa); pa ^= 1; }
+          if (sd.kind == 2) {
+            const int s = g % kNst;
+            mbar_wait(&m->full[s], (g / kNst) & 1);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_bf16(128, sd.n);
+            const uint32_t kstep_bytes = (uint32_t)sd.n * 32u;
+            for (int i = 0; i < sd.n_mmas; ++i) {
+              const uint32_t kst = sd.a_k0 + i;
+              const uint64_t adesc = make_smem_desc(aq + kst * 2 * kChunkA, kChunkA, 128);
+              const uint64_t bdesc = make_smem_desc(w_base + s * kStageBytes + i * kstep_bytes, (uint32_t)sd.n * 16u, 128);
+              mma_bf16_ss(d_tmem, adesc, bdesc, idesc, kst > 0);
             }
-            const Chunk& ci = c_sched[g_issue % kChunksPerRay];
-            mbar_expect_tx(&m->full[s], ci.bytes);
-            bulk_g2s(Ws + s * kStageBytes, blob + ci.goff, ci.bytes, &m->full[s]);
-            ++g_issue;
+            mma_commit(&m->empty[s]);
+            ++g;
+          } else {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_bf16(128, 32);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const int chunk = sd.kind == 0 ? 16 + 2 * j : fine_tile_chunks[j];
+              const uint64_t adesc = make_smem_desc(aq + chunk * kChunkA, kChunkA, 128);
+              const uint64_t bdesc = make_smem_desc(b_base + (sd.kind * 6 + j) * 1024, 32 * 16, 128);
+              mma_bf16_ss(d_tmem + sd.kind * 32, adesc, bdesc, idesc, j > 0);
+            }
           }
-          const Chunk& ch = c_sched[c];
-          if (ch.flags & kFirst) { mbar_wait(&m->bar_a, pa); pa ^= 1; }
-          const int s = (int)(g % kNst);
-          mbar_wait(&m->full[s], (uint32_t)((g / kNst) & 1));
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(a_base + ch.a_off, kChunkA, 128);
-          const uint64_t bdesc = make_smem_desc(w_base + s * kStageBytes, (uint32_t)ch.n * 16u, 128);
-          mma_bf16_ss(tmem + ch.d_col, adesc, bdesc, make_idesc_bf16(128, ch.n), ch.accum);
-          mma_commit(&m->empty[s]);
-          if (ch.flags & kLast) mma_commit(&m->bar_acc);
+          if (sd.last) mma_commit(&m->bar_acc[q]);
         }
       }
     }
     __syncwarp();
   } else {
     // =================================== row warps: thread = sample row ===============================================
-    const int r = tid;
-    uint8_t* a_row = As + r * 16;
-    const uint32_t taddr_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const int q = warp >> 2, gwarp = warp & 3;
+    const int r = tid & (kGroupThreads - 1);
+    uint8_t* Aq = As + q * kABytes;
+    uint8_t* a_row = Aq + r * 16;
+    GroupMisc* gm = &m->grp[q];
+    const uint32_t taddr_row = tmem + ((uint32_t)(gwarp * 32) << 16) + q * 256;
     uint32_t pacc = 0;
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
+    const int bar_id = 1 + q;
+    auto stamp = [&](int64_t it, int k) {
+      if (a.trace && blockIdx.x == 0 && r == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
+    };
     for (int64_t it = 0; it < n_my; ++it) {
-      const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
+      stamp(it, 0);
+      const int64_t ray_raw = 2 * ((int64_t)blockIdx.x + it * gridDim.x) + q;
+      const bool live = ray_raw < a.n_rays;             // odd ray count: the last pair's second ray is a masked duplicate
+      const int64_t ray = live ? ray_raw : a.n_rays - 1;
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
       const float zv = a.z_vals[ray * S + min(r, S - 1)];
-      m->z[r] = zv;
+      gm->z[r] = zv;
       {  // ---- PE(pts) -> A columns 64..127 (chunks 8..15); column 127 is the zero pad of K = 127 -> 128 -------------
+        // sin/cos of the base frequency by range-reduced MUFU, higher octaves by the double-angle recurrence
+        // (abs error <= 2^9 * 1e-7, far below the bf16 resolution of the MMA operand)
         float pe[64];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) pe[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+        for (int i = 0; i < 3; ++i) {
+          pe[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+          fast_sincos(pe[i], &pe[3 + i], &pe[6 + i]);
+        }
 #pragma unroll
-        for (int f = 0; f < kPeFreqPts; ++f) {
+        for (int f = 1; f < kPeFreqPts; ++f) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) fast_sincos(pe[i] * (float)(1 << f), &pe[3 + 6 * f + i], &pe[6 + 6 * f + i]);
+          for (int i = 0; i < 3; ++i) {
+            const float sp = pe[3 + 6 * (f - 1) + i], cp = pe[6 + 6 * (f - 1) + i];
+            pe[3 + 6 * f + i] = 2.0f * sp * cp;
+            pe[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+          }
         }
         pe[63] = 0.f;
 #pragma unroll
@@ -305,79 +420,77 @@ __global__ void __launch_bounds__(kThreads, 2) fine_fwd_tc_kernel(const FineArgs
           st_shared_v4(a_row + (8 + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
                        pack_bf16x2(pe[8 * j + 4], pe[8 * j + 5]), pack_bf16x2(pe[8 * j + 6], pe[8 * j + 7]));
       }
-      {  // ---- per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir) (fp32, exact sincos) --------------------
+      {  // ---- per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir), fp32 ------------------------------------
         const float vd[3] = {__ldg(rb + 8), __ldg(rb + 9), __ldg(rb + 10)};
         float ped[kPeDir];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ped[i] = vd[i];
+        for (int i = 0; i < 3; ++i) { ped[i] = vd[i]; fast_sincos(vd[i], &ped[3 + i], &ped[6 + i]); }
 #pragma unroll
-        for (int f = 0; f < kPeFreqDir; ++f) {
+        for (int f = 1; f < kPeFreqDir; ++f) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) sincosf(vd[i] * (float)(1 << f), &ped[3 + 6 * f + i], &ped[6 + 6 * f + i]);
+          for (int i = 0; i < 3; ++i) {
+            const float sp = ped[3 + 6 * (f - 1) + i], cp = ped[6 + 6 * (f - 1) + i];
+            ped[3 + 6 * f + i] = 2.0f * sp * cp;
+            ped[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+          }
         }
-#pragma unroll
+#pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          const int col = r + half * kRowThreads;
+          const int col = r + half * kGroupThreads;
           float b = a.mlp.color0_b ? __ldg(a.mlp.color0_b + col) : 0.f;
           const float* w = a.mlp.color0_t + (size_t)128 * 256 + col;
 #pragma unroll
           for (int j = 0; j < kPeDir; ++j) b = fmaf(__ldg(w + j * 256), ped[j], b);
-          m->bias[col] = b;
+          gm->bias[col] = b;
         }
       }
-      named_bar_sync(1, kRowThreads);      // z[] (and bias[]) visible to all row warps
+      named_bar_sync(bar_id, kGroupThreads);      // z[] (and bias[]) visible to the whole group
+      stamp(it, 1);
       // ---- VM gather of both grids -> two 128 x 96 bf16 tiles ----------------------------------------------------------
-      gather_grid<T>(a.gc, false, As, m->z, warp, lane, o, d);
-      gather_grid<T>(a.gf, true, As, m->z, warp, lane, o, d);
-      rows_signal_a(&m->bar_a);
+      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d);
+      rows_signal_a(&m->bar_a[q]);
+      stamp(it, 2);
       // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-      epilogue32<false>(taddr_row, 0, a_row, nullptr, nullptr, nullptr);
-      epilogue32<false>(taddr_row, 32, a_row, nullptr, nullptr, nullptr);
-      rows_signal_a(&m->bar_a);
-      // ---- sigma_net.0 -> ReLU ---------------------------------------------------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) epilogue32<true>(taddr_row, c0, a_row, nullptr, nullptr, nullptr);
-      rows_signal_a(&m->bar_a);
-      // ---- sigma_net.1 -> geo (128, linear) + sigma ---------------------------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-      {
-        float* gout = (a.feat && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) epilogue32<false>(taddr_row, c0, a_row, nullptr, nullptr, gout);
-        uint32_t v[16];
-        tmem_ld16(taddr_row + 128, v);
-        tmem_ld_wait();
-        m->sig[r] = __uint_as_float(v[0]);
-      }
-      rows_signal_a(&m->bar_a);
+      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+      stamp(it, 3);
+      layer_epilogue(taddr_row, a_row, 64, kEpiPlain, nullptr, nullptr, m->wsig, m->wrgb, nullptr);
+      rows_signal_a(&m->bar_a[q]);
+      stamp(it, 4);
+      // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0) -------------------------------------------
+      float sig_raw[1] = {0.f};
+      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+      stamp(it, 5);
+      layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, nullptr, nullptr, m->wsig, m->wrgb, sig_raw);
+      rows_signal_a(&m->bar_a[q]);
+      stamp(it, 6);
+      // ---- sigma_net.1 -> geo (128, linear) ------------------------------------------------------------------------------
+      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+      stamp(it, 7);
+      layer_epilogue(taddr_row, a_row, 128, kEpiPlain, nullptr,
+                     (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, m->wsig, m->wrgb, nullptr);
+      rows_signal_a(&m->bar_a[q]);
+      stamp(it, 8);
       // ---- color_net.0 (+ per-ray view-dir bias) -> ReLU ------------------------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) epilogue32<true>(taddr_row, c0, a_row, m->bias, nullptr, nullptr);
-      rows_signal_a(&m->bar_a);
-      // ---- color_net.1 -> ReLU -------------------------------------------------------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) epilogue32<true>(taddr_row, c0, a_row, nullptr, a.mlp.color1_b, nullptr);
-      rows_signal_a(&m->bar_a);
-      // ---- color_net.2 -> sigmoid, then compositing (voxnerf.py:153-201) ---------------------------------------------------
-      mbar_wait(&m->bar_acc, pacc); pacc ^= 1; tc_fence_after();
-      float col[3];
-      {
-        uint32_t v[16];
-        tmem_ld16(taddr_row, v);
-        tmem_ld_wait();
+      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+      stamp(it, 9);
+      layer_epilogue(taddr_row, a_row, 256, kEpiRelu, gm->bias, nullptr, m->wsig, m->wrgb, nullptr);
+      rows_signal_a(&m->bar_a[q]);
+      stamp(it, 10);
+      // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2) -> sigmoid -----------------------------------------
+      float col[3] = {0.f, 0.f, 0.f};
+      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+      stamp(it, 11);
+      layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, m->bias1, nullptr, m->wsig, m->wrgb, col);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) col[i] = sigmoidf_(__uint_as_float(v[i]) + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
-      }
+      for (int i = 0; i < 3; ++i) col[i] = sigmoidf_(col[i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+      stamp(it, 12);
+      // ---- compositing (voxnerf.py:153-201) -----------------------------------------------------------------------------------
       float alpha = 0.f;
       if (r < S - 1) {
         const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-        const float znext = m->z[r + 1];
+        const float znext = gm->z[r + 1];
         const float dist = __fmul_rn(znext - zv, dnorm);
-        float sg = m->sig[r];
+        float sg = sig_raw[0];
         if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + r);
         sg = fmaxf(sg, 0.f);
         if (mask_near && !(znext > near_thr)) sg = 0.f;
@@ -393,11 +506,11 @@ __global__ void __launch_bounds__(kThreads, 2) fine_fwd_tc_kernel(const FineArgs
       }
       float Tr = __shfl_up_sync(0xffffffffu, t, 1);
       if (lane == 0) Tr = 1.0f;
-      if (lane == 31) m->wtot[warp] = t;
-      named_bar_sync(1, kRowThreads);
-      for (int w2 = 0; w2 < warp; ++w2) Tr *= m->wtot[w2];
+      if (lane == 31) gm->wtot[gwarp] = t;
+      named_bar_sync(bar_id, kGroupThreads);
+      for (int w2 = 0; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
       const float wgt = alpha * Tr;
-      if (r < S) a.weights[ray * S + r] = wgt;
+      if (live && r < S) a.weights[ray * S + r] = wgt;
       float red[5] = {wgt * col[0], wgt * col[1], wgt * col[2], wgt * zv, wgt};
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -406,45 +519,63 @@ __global__ void __launch_bounds__(kThreads, 2) fine_fwd_tc_kernel(const FineArgs
       }
       if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) m->red[warp][i] = red[i];
+        for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
       }
-      named_bar_sync(1, kRowThreads);
-      if (r < 5) {
-        const float v = m->red[0][r] + m->red[1][r] + m->red[2][r] + m->red[3][r];
+      named_bar_sync(bar_id, kGroupThreads);
+      if (live && r < 5) {
+        const float v = gm->red[0][r] + gm->red[1][r] + gm->red[2][r] + gm->red[3][r];
         if (r < 3) a.rgb[ray * 3 + r] = v; else if (r == 3) a.depth[ray] = v; else a.acc[ray] = v;
       }
-      named_bar_sync(1, kRowThreads);      // red[] / wtot[] / z[] free for the next ray
+      named_bar_sync(bar_id, kGroupThreads);      // red[] / wtot[] / z[] free for the next ray
+      stamp(it, 13);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kRowWarps) tmem_dealloc(tmem, kTmemCols);
 }
 
-int ensure_schedule(int64_t* blob_bytes, int64_t layer_off[7]) {
+int ensure_schedule() {
   static bool uploaded = false;
-  static int64_t bytes = 0, offs[7];
   if (!uploaded) {
-    std::vector<Chunk> v = build_schedule(&bytes, offs);
-    if ((int)v.size() != kChunksPerRay) { set_error("fine_tc: schedule size mismatch"); return EDN_E_INVALID; }
-    EDN_CUDA_OK(cudaMemcpyToSymbol(c_sched, v.data(), sizeof(Chunk) * v.size()));
+    std::vector<StepDesc> v = build_steps();
+    if ((int)v.size() != kStepsPerRay) { set_error("fine_tc: schedule size mismatch (%d)", (int)v.size()); return EDN_E_INVALID; }
+    EDN_CUDA_OK(cudaMemcpyToSymbol(c_steps, v.data(), sizeof(StepDesc) * v.size()));
     uploaded = true;
   }
-  if (blob_bytes) *blob_bytes = bytes;
-  if (layer_off) for (int i = 0; i < 7; ++i) layer_off[i] = offs[i];
   return 0;
 }
 
 }  // namespace
 
 int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
-  EDN_REQUIRE(a.S >= 2 && a.S <= kRowThreads, "edn_render_fine_fwd(bf16): n_samples must be in [2,128], got %d", a.S);
+  EDN_REQUIRE(a.S >= 2 && a.S <= kGroupThreads, "edn_render_fine_fwd(bf16): n_samples must be in [2,128], got %d", a.S);
   EDN_REQUIRE(a.mlp.tc_blob != nullptr, "edn_render_fine_fwd(bf16): edn_field_mlp.tc_blob is NULL (call edn_pack_fine_tc)");
-  int rc = ensure_schedule(nullptr, nullptr);
+  int rc = ensure_schedule();
   if (rc) return rc;
-  const int64_t max_ctas = 2 * (int64_t)num_sms();
-  const unsigned gx = (unsigned)(a.n_rays < max_ctas ? a.n_rays : max_ctas);
+  const int64_t n_pairs = (a.n_rays + 1) / 2;
+  const unsigned gx = (unsigned)(n_pairs < (int64_t)num_sms() ? n_pairs : (int64_t)num_sms());
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
+  const char* tr = getenv("EDN_TC_TRACE");
+  if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
+    FineArgs b = a;
+    long long* buf = nullptr;
+    EDN_CUDA_OK(cudaMallocManaged(&buf, 8 * 16 * sizeof(long long)));
+    memset(buf, 0, 8 * 16 * sizeof(long long));
+    b.trace = buf;
+    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob);
+    EDN_CUDA_OK(cudaGetLastError());
+    EDN_CUDA_OK(cudaStreamSynchronize(st));
+    static const char* names[14] = {"start", "pe+bias", "gather", "w.basis", "e.ft", "w.L1", "e.L1", "w.L2", "e.L2", "w.L3", "e.L3", "w.L4", "e.L4", "composite"};
+    for (int i = 0; i < 8; ++i) {
+      fprintf(stderr, "[trace it=%d q=%d] t0=%lld :", 8 + i / 2, i % 2, buf[i * 16] - buf[0]);
+      for (int k = 1; k < 14; ++k) fprintf(stderr, " %s=%lld", names[k], buf[i * 16 + k] - buf[i * 16 + k - 1]);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(buf);
+    return EDN_OK;
+  }
   if (grid_dtype == EDN_BF16) {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
@@ -458,11 +589,7 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
 
 }  // namespace edn
 
-extern "C" int64_t edn_fine_tc_blob_bytes(void) {
-  int64_t bytes = 0, offs[7];
-  edn::build_schedule(&bytes, offs);
-  return bytes;
-}
+extern "C" int64_t edn_fine_tc_blob_bytes(void) { return edn::kBlobBytes; }
 
 extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, void* blob,
                                 void* stream) {
@@ -470,21 +597,21 @@ extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_c
   EDN_REQUIRE(mlp && basis_t_coarse && basis_t_fine && blob, "edn_pack_fine_tc: null pointer");
   EDN_REQUIRE(mlp->hidden == 256 && mlp->geo_feat == 128 && mlp->sigma0_t && mlp->sigma1_t && mlp->sigma1_v && mlp->color0_t &&
               mlp->color1_t && mlp->color2_t, "edn_pack_fine_tc: needs the fine field (hidden=256, geo_feat=128)");
-  int64_t bytes, off[7];
-  int rc = ensure_schedule(&bytes, off);
-  if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* b = reinterpret_cast<uint8_t*>(blob);
-  struct Src { const float* wt; int ld, kv, nv; const float* vec; int vec_col; };
-  const Src src[7] = {{basis_t_coarse, 32, 96, 32, nullptr, -1}, {basis_t_fine, 32, 96, 32, nullptr, -1},
-                      {mlp->sigma0_t, 256, 128, 256, nullptr, -1}, {mlp->sigma1_t, 128, 256, 128, mlp->sigma1_v, 128},
-                      {mlp->color0_t, 256, 128, 256, nullptr, -1}, {mlp->color1_t, 256, 256, 256, nullptr, -1},
-                      {mlp->color2_t, 4, 256, 3, nullptr, -1}};
-  for (int L = 0; L < 7; ++L) {
-    const int K = kLayers[L].K, N = kLayers[L].N, total = K * N;
-    pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].vec, src[L].vec_col, K, N,
-                                                           reinterpret_cast<__nv_bfloat16*>(b + off[L]));
+  // blob = [basis coarse 6 KB][basis fine 6 KB][sigma0 64 KB][sigma1(geo) 64 KB][color0(geo rows) 64 KB][color1 128 KB]
+  struct Src { const float* wt; int ld, kv, nv, K, N; };
+  const Src src[6] = {{basis_t_coarse, 32, 96, 32, 96, 32}, {basis_t_fine, 32, 96, 32, 96, 32},
+                      {mlp->sigma0_t, 256, 128, 256, 128, 256}, {mlp->sigma1_t, 128, 256, 128, 256, 128},
+                      {mlp->color0_t, 256, 128, 256, 128, 256}, {mlp->color1_t, 256, 256, 256, 256, 256}};
+  size_t off = 0;
+  for (int L = 0; L < 6; ++L) {
+    const int total = src[L].K * src[L].N;
+    pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].K, src[L].N,
+                                                           reinterpret_cast<__nv_bfloat16*>(b + off));
+    off += (size_t)total * 2;
   }
+  EDN_REQUIRE((int64_t)off == kBlobBytes, "edn_pack_fine_tc: blob size mismatch");
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

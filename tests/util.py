@@ -94,8 +94,8 @@ def _bf(x):
 
 def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearplane=0):
     """Torch fp32 reference of the tcgen05 fine pass with its operand roundings made explicit: VM planes, the
-    plane (.) line products, every MMA A operand (features, PE, activations) and every weight matrix are rounded to
-    bf16; accumulation, biases, sigma, sigmoid and compositing stay fp32.  The view-direction part of color_net.0 is an
+    plane (.) line products, every MMA A operand (features, PE, activations) and every MMA weight matrix are rounded to
+    bf16; accumulation, biases, the sigma / rgb heads (fp32 dot products in the epilogues), sigmoid and compositing stay fp32.  The view-direction part of color_net.0 is an
     fp32 per-ray bias.  Against this reference the CUDA kernel differs by accumulation order only."""
     import evdeblur_oracle as oc
     import torch.nn.functional as F
@@ -109,16 +109,17 @@ def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearpla
         fts.append(_bf(F.linear(g, _bf(P[pre + "basis_mat.weight"]))))
     x = torch.cat(fts + [_bf(oc.posenc(pts.reshape(-1, 3), 10))], -1)
     pre = "mlp_fine."
-    h1 = _bf(torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"]))))
-    w1 = _bf(P[pre + "sigma_net.1.weight"])
-    sigma = F.linear(h1, w1[:1])
-    geo = F.linear(h1, w1[1:])
+    h1_f32 = torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"])))
+    h1 = _bf(h1_f32)
+    w1 = P[pre + "sigma_net.1.weight"]
+    sigma = F.linear(h1_f32, w1[:1])            # sigma head: fp32 dot product in the layer epilogue
+    geo = F.linear(h1, _bf(w1[1:]))
     w3 = P[pre + "color_net.0.weight"]
     bias_ray = F.linear(oc.posenc(vd, 4), w3[:, 128:], P.get(pre + "color_net.0.bias"))          # [R,256] fp32
     h3 = F.linear(_bf(geo), _bf(w3[:, :128])) + bias_ray[:, None, :].expand(R, S, 256).reshape(R * S, 256)
     h3 = _bf(torch.relu(h3))
-    h4 = _bf(torch.relu(F.linear(h3, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias"))))
-    rgb = torch.sigmoid(F.linear(h4, _bf(P[pre + "color_net.2.weight"]), P.get(pre + "color_net.2.bias")))
+    h4 = torch.relu(F.linear(h3, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias")))
+    rgb = torch.sigmoid(F.linear(h4, P[pre + "color_net.2.weight"], P.get(pre + "color_net.2.bias")))   # fp32 rgb head
     raw = torch.cat([sigma, rgb], -1).reshape(R, S, 4)
     rgb_map, _, acc, w, depth = oc.raw2outputs(raw, z_all, d, noise, is_train, rmnearplane)
     return {"rgb_map": rgb_map, "depth_map": depth, "acc_map": acc, "weights": w, "depth_feature": geo.reshape(R, S, -1),
