@@ -37,7 +37,9 @@ SIGNATURES = {
     "edn_pack_vm_plane": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "edn_vm_sample": (C.c_int, [C.POINTER(VmGrid), _P, _P, _I64, _P]),
     "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
-                                        _P, _P, _P, _P, _P, _P, _P]),
+                                        _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "edn_coarse_tc_blob_bytes": (C.c_int64, []),
+    "edn_pack_coarse_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P]),
     "edn_sample_pdf_merge": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "edn_fine_tc_blob_bytes": (C.c_int64, []),
     "edn_pack_fine_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P]),

@@ -5,6 +5,7 @@
 // acc[out] += W^T[k][out] * x_k with the transposed weights broadcast from shared memory (LDS.128), so the input
 // vector is never materialised and the per-thread state is the output accumulators only.
 #include "common.cuh"
+#include "coarse_args.cuh"
 
 namespace edn {
 
@@ -32,24 +33,6 @@ struct CoarseSmemLayout {
   static constexpr int total = w + kCoarseThreads;
 };
 
-struct CoarseArgs {
-  GridDev grid;
-  edn_field_mlp mlp;
-  const float* ray_batch;
-  const float* t_vals;
-  const float* t_rand;
-  const float* noise;
-  int64_t n_rays;
-  int n_samples;
-  int flags;
-  float rmnearplane;
-  float* z_vals;
-  float* weights;
-  float* rgb;
-  float* depth;
-  float* acc;
-  float* feat;
-};
 
 template <int N>
 __device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restrict__ w_row, float x) {
@@ -64,20 +47,6 @@ __device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restric
 
 __device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n, float fill_if_null) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src ? __ldg(src + i) : fill_if_null;
-}
-
-__device__ __forceinline__ float place_sample(const CoarseArgs& a, int64_t ray, int s, float near, float far) {
-  const int S = a.n_samples;
-  auto zt = [&](int i) -> float {
-    const float t = __ldg(a.t_vals + i);
-    if (!(a.flags & EDN_FLAG_LINDISP)) return __fadd_rn(__fmul_rn(near, 1.0f - t), __fmul_rn(far, t));
-    return 1.0f / __fadd_rn(__fmul_rn(1.0f / near, 1.0f - t), __fmul_rn(1.0f / far, t));
-  };
-  const float z = zt(s);
-  if (!a.t_rand) return z;
-  const float lower = (s == 0) ? z : 0.5f * __fadd_rn(z, zt(s - 1));
-  const float upper = (s == S - 1) ? z : 0.5f * __fadd_rn(zt(s + 1), z);
-  return __fadd_rn(lower, __fmul_rn(upper - lower, __ldg(a.t_rand + ray * S + s)));
 }
 
 template <typename T>
@@ -220,8 +189,9 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_fwd_kernel(const Coa
 
 extern "C" int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_mlp* mlp, const float* ray_batch,
                                      const float* t_vals, const float* t_rand, const float* noise, int64_t n_rays,
-                                     int32_t n_samples, int32_t flags, float rmnearplane, float* z_vals,
-                                     float* weights, float* rgb, float* depth, float* acc, float* feat, void* stream) {
+                                     int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision,
+                                     float* z_vals, float* weights, float* rgb, float* depth, float* acc, float* feat,
+                                     void* stream) {
   using namespace edn;
   EDN_REQUIRE(mlp && ray_batch && t_vals && z_vals && weights && rgb && depth && acc, "edn_render_coarse_fwd: null pointer");
   EDN_REQUIRE(n_rays >= 0, "edn_render_coarse_fwd: n_rays < 0");
@@ -237,11 +207,13 @@ extern "C" int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_ml
   a.ray_batch = ray_batch; a.t_vals = t_vals; a.t_rand = t_rand; a.noise = noise;
   a.n_rays = n_rays; a.n_samples = n_samples; a.flags = flags; a.rmnearplane = rmnearplane;
   a.z_vals = z_vals; a.weights = weights; a.rgb = rgb; a.depth = depth; a.acc = acc; a.feat = feat;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == EDN_BF16) return launch_coarse_tc(a, grid->dtype, st);
+  EDN_REQUIRE(precision == EDN_F32, "edn_render_coarse_fwd: bad precision %d", precision);
   const int rpb = kCoarseThreads / n_samples;
   const int64_t n_groups = (n_rays + rpb - 1) / rpb;
   const int grid_x = (int)(n_groups < (int64_t)num_sms() ? n_groups : (int64_t)num_sms());
   const size_t smem = CoarseSmemLayout::total * sizeof(float);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (grid->dtype == EDN_F32) {
     EDN_CUDA_OK(cudaFuncSetAttribute(coarse_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     coarse_fwd_kernel<float><<<grid_x, kCoarseThreads, smem, st>>>(a);

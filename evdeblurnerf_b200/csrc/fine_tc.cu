@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "fine_args.cuh"
 #include "tc_common.cuh"
+#include "tc_rows.cuh"
 
 namespace edn {
 namespace {
@@ -33,7 +34,6 @@ constexpr int kThreads = kRowWarps * 32 + 96;   // 8 row warps + 2 MMA issuer wa
 constexpr int kNst = 4;                  // weight ring stages
 constexpr int kStageBytes = 16384;
 constexpr int kABytes = 65536;           // per ray: 128 rows x 256 K bf16
-constexpr int kChunkA = 2048;            // bytes of one 8-wide K chunk of a 128-row tile
 constexpr int kBasisBytes = 2 * 6 * 1024;  // two basis_mat's, 6 K-steps x (N=32 x 16 x 2 B)
 constexpr uint32_t kTmemCols = 512;
 constexpr int kRingStagesPerRay = 20;    // 320 KB / 16 KB
@@ -85,83 +85,6 @@ static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 &
               offsetof(Misc, grp) % 16 == 0 && offsetof(GroupMisc, bias) % 16 == 0, "float4 alignment");
 constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kBasisBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
-
-// ---- weight packing -----------------------------------------------------------------------------------------------
-// dst element (n, k) of a [K][N] layer -> bf16 index (k/16)*(N*16) + ((k%16)/8)*(N*8) + n*8 + k%8
-__global__ void pack_layer_kernel(const float* __restrict__ wt, int ld, int k_valid, int n_valid, int K, int N,
-                                  __nv_bfloat16* __restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K * N) return;
-  const int k = i / N, n = i - k * N;
-  const float v = (k < k_valid && n < n_valid) ? wt[(size_t)k * ld + n] : 0.f;
-  dst[(size_t)(k / 16) * (N * 16) + ((k % 16) / 8) * (N * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
-}
-
-// ---- small device helpers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
-  // Cody-Waite reduction to [-pi, pi] then MUFU; abs error ~5e-7, far below bf16 resolution of the MMA operand
-  const float k = rintf(x * 0.15915494309189535f);
-  float r = fmaf(-k, 6.28125f, x);
-  r = fmaf(-k, 1.9353071795864769e-3f, r);
-  *s = __sinf(r);
-  *c = __cosf(r);
-}
-
-// Raw 16-byte channel chunk of a bf16 texel row / 2 x 16 bytes of an fp32 one.
-template <typename T> struct Raw8;
-template <> struct Raw8<__nv_bfloat16> {
-  uint4 r;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
-  __device__ __forceinline__ void get(float (&v)[8]) const {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-  }
-};
-template <> struct Raw8<float> {
-  float4 lo, hi;
-  __device__ __forceinline__ void load(const float* p) {
-    lo = __ldg(reinterpret_cast<const float4*>(p)); hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  }
-  __device__ __forceinline__ void get(float (&v)[8]) const {
-    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-  }
-};
-
-// One gather task = 8 channels of one VM component at one point: 4 plane taps + 2 line taps (issue), then
-// (bilinear plane) * (linear line) -> 16 bytes of bf16 (finish).  Issue and finish are split so that several tasks'
-// loads are in flight together.
-template <typename T>
-struct GatherTask {
-  Raw8<T> pv[4], lv[2];
-  float pw[4], lw[2];
-  __device__ __forceinline__ void issue(const T* __restrict__ plane, const T* __restrict__ line, int C, int c8,
-                                        const Taps2& pt, const Taps1& lt) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { pv[k].load(plane + (size_t)pt.off[k] * C + c8 * 8); pw[k] = pt.w[k]; }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) { lv[k].load(line + (size_t)lt.off[k] * C + c8 * 8); lw[k] = lt.w[k]; }
-  }
-  __device__ __forceinline__ void finish(uint8_t* dst) const {
-    float p[8], l[8], t[8];
-    pv[0].get(t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = t[i] * pw[0];
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-      pv[k].get(t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) p[i] = fmaf(t[i], pw[k], p[i]);
-    }
-    lv[0].get(t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) l[i] = t[i] * lw[0];
-    lv[1].get(t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
-    st_shared_v4(dst, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-  }
-};
 
 // Cooperative gather of both grids for the 32 points of this warp.  Lane (q = lane/8, j = lane%8) serves point 8*gi+j
 // and reads 16-byte channel chunks, so every warp-wide load covers whole 32 B sectors of 8 texels.  Per (grid, gi)
@@ -607,7 +530,7 @@ extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_c
   size_t off = 0;
   for (int L = 0; L < 6; ++L) {
     const int total = src[L].K * src[L].N;
-    pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].K, src[L].N,
+    tc::pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].K, src[L].N, 0,
                                                            reinterpret_cast<__nv_bfloat16*>(b + off));
     off += (size_t)total * 2;
   }

@@ -1,0 +1,93 @@
+// Row-side building blocks shared by the tensor-core render kernels (fine_tc.cu, coarse_tc.cu): fast sin/cos for
+// the bf16 PE operand, the cooperative VM gather task, and the UMMA weight-slice packer.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace edn {
+namespace tc {
+
+constexpr int kChunkA = 2048;            // bytes of one 8-wide K chunk of a 128-row bf16 operand tile
+
+// ---- weight packing -----------------------------------------------------------------------------------------------
+// dst element (n, k) of a [K][N] layer -> bf16 index (k/16)*(N*16) + ((k%16)/8)*(N*8) + n*8 + k%8
+// col_rot: output column n reads source column (n + col_rot) % N (used to move the sigma column last).
+static __global__ void pack_layer_kernel(const float* __restrict__ wt, int ld, int k_valid, int n_valid, int K, int N, int col_rot,
+                                         __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int k = i / N, n = i - k * N;
+  const int ns = (n + col_rot) % N;
+  const float v = (k < k_valid && ns < n_valid) ? wt[(size_t)k * ld + ns] : 0.f;
+  dst[(size_t)(k / 16) * (N * 16) + ((k % 16) / 8) * (N * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
+}
+
+// ---- small device helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+  // Cody-Waite reduction to [-pi, pi] then MUFU; abs error ~5e-7, far below bf16 resolution of the MMA operand
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.28125f, x);
+  r = fmaf(-k, 1.9353071795864769e-3f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
+// Raw 16-byte channel chunk of a bf16 texel row / 2 x 16 bytes of an fp32 one.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+template <> struct Raw8<float> {
+  float4 lo, hi;
+  __device__ __forceinline__ void load(const float* p) {
+    lo = __ldg(reinterpret_cast<const float4*>(p)); hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  }
+};
+
+// One gather task = 8 channels of one VM component at one point: 4 plane taps + 2 line taps (issue), then
+// (bilinear plane) * (linear line) -> 16 bytes of bf16 (finish).  Issue and finish are split so that several tasks'
+// loads are in flight together.
+template <typename T>
+struct GatherTask {
+  Raw8<T> pv[4], lv[2];
+  float pw[4], lw[2];
+  __device__ __forceinline__ void issue(const T* __restrict__ plane, const T* __restrict__ line, int C, int c8,
+                                        const Taps2& pt, const Taps1& lt) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pv[k].load(plane + (size_t)pt.off[k] * C + c8 * 8); pw[k] = pt.w[k]; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { lv[k].load(line + (size_t)lt.off[k] * C + c8 * 8); lw[k] = lt.w[k]; }
+  }
+  __device__ __forceinline__ void finish(uint8_t* dst) const {
+    float p[8], l[8], t[8];
+    pv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = t[i] * pw[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      pv[k].get(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fmaf(t[i], pw[k], p[i]);
+    }
+    lv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = t[i] * lw[0];
+    lv[1].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
+    st_shared_v4(dst, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+  }
+};
+
+
+}  // namespace tc
+}  // namespace edn

@@ -109,13 +109,18 @@ class PackedField:
         self.mlp = m
         self.basis_t = basis_t
 
-    def pack_tensor_core_operands(self, coarse_field):
-        """bf16 UMMA operand blob of the fine field + both basis_mat's (edn_pack_fine_tc); tcgen05 path only."""
+    def pack_tensor_core_operands(self, coarse_field=None):
+        """bf16 UMMA operand blob (edn_pack_fine_tc: fine field + both basis_mat's; edn_pack_coarse_tc: coarse field)."""
         lib = _lib.load()
-        n = int(lib.edn_fine_tc_blob_bytes())
-        blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
-        check(lib.edn_pack_fine_tc(C.byref(self.mlp), ptr(coarse_field.basis_t), ptr(self.basis_t), ptr(blob), stream_ptr()),
-              "edn_pack_fine_tc")
+        if self.coarse:
+            n = int(lib.edn_coarse_tc_blob_bytes())
+            blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
+            check(lib.edn_pack_coarse_tc(C.byref(self.mlp), ptr(self.basis_t), ptr(blob), stream_ptr()), "edn_pack_coarse_tc")
+        else:
+            n = int(lib.edn_fine_tc_blob_bytes())
+            blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
+            check(lib.edn_pack_fine_tc(C.byref(self.mlp), ptr(coarse_field.basis_t), ptr(self.basis_t), ptr(blob), stream_ptr()),
+                  "edn_pack_fine_tc")
         self.keep.append(blob)
         self.mlp.tc_blob = blob.data_ptr()
 
@@ -157,6 +162,8 @@ class RenderEngine:
         P = {k: (v if v.is_cuda else v.to(self.device)) for k, v in params.items() if isinstance(v, torch.Tensor)}
         grid_dtype = self.prec_code
         self.coarse = PackedField(P, "mlp_coarse.", self.aabb_min, self.aabb_max, True, grid_dtype)
+        if self.prec_code == EDN_BF16:
+            self.coarse.pack_tensor_core_operands()
         self.fine = None
         if "mlp_fine.sigma_net.0.weight" in P:
             self.fine = PackedField(P, "mlp_fine.", self.aabb_min, self.aabb_max, False, grid_dtype)
@@ -179,6 +186,10 @@ class RenderEngine:
             ret["depth_feature"] = torch.empty((0, S, 128 if Ni > 0 else 15), **f32)
             ret["z_vals"] = torch.empty((0, S), **f32)
         return ret
+
+    def _coarse_precision(self, n_samples):
+        # the tensor-core coarse kernel tiles 128 rows = floor(128 / n_samples) rays; other sample counts use the SIMT kernel
+        return EDN_BF16 if (self.prec_code == EDN_BF16 and 32 <= n_samples <= 128) else EDN_F32
 
     def _linspace(self, n):
         # computed by torch on the CPU (bit-identical to the reference's torch.linspace), cached on the device
@@ -254,7 +265,8 @@ class RenderEngine:
         tv = self._linspace(Nc)
         check(self._launch("coarse", lambda: lib.edn_render_coarse_fwd(
             C.byref(self.coarse.grid), C.byref(self.coarse.mlp), ptr(rb), ptr(tv), ptr(t_rand), ptr(noise0), R, Nc,
-            flags | FLAG_RELU_RGB, self.rmnearplane, ptr(z0), ptr(w0), ptr(rgb0), ptr(depth0), ptr(acc0), ptr(feat0),
+            flags | FLAG_RELU_RGB, self.rmnearplane, self._coarse_precision(Nc), ptr(z0), ptr(w0), ptr(rgb0), ptr(depth0),
+            ptr(acc0), ptr(feat0),
             stream_ptr())), "edn_render_coarse_fwd")
         if Ni <= 0:
             ret = {"rgb_map": rgb0, "depth_map": depth0, "acc_map": acc0}

@@ -70,7 +70,7 @@ typedef struct edn_field_mlp {
   const float* color2_b;
   int32_t hidden;          /* 64 (coarse) | 256 (fine) */
   int32_t geo_feat;        /* 15 (coarse) | 128 (fine) */
-  const void* tc_blob;     /* bf16 tensor-core operand blob written by edn_pack_fine_tc (EDN_BF16 precision) or NULL */
+  const void* tc_blob;     /* bf16 tensor-core operand blob (edn_pack_fine_tc / edn_pack_coarse_tc) or NULL */
 } edn_field_mlp;
 
 const char* edn_last_error(void);
@@ -89,12 +89,17 @@ int edn_vm_sample(const edn_vm_grid* grid, const float* pts, float* feat, int64_
  *   t_vals [n_samples]        = linspace(0,1,n_samples)
  *   t_rand [R][n_samples]     or NULL (perturb == 0)            (renderer.py:176)
  *   noise  [R][n_samples-1]   or NULL (already * raw_noise_std)  (voxnerf.py:175)
+ * precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path (32 <= n_samples <= 128).
  * outputs: z_vals [R][S], weights [R][S], rgb [R][3], depth [R], acc [R];
- *          feat [R][S][15] or NULL (feature_map, voxnerf.py:221); ft_coarse [R][S][32] or NULL. */
+ *          feat [R][S][15] or NULL (feature_map, voxnerf.py:221). */
 int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_mlp* mlp, const float* ray_batch,
                           const float* t_vals, const float* t_rand, const float* noise, int64_t n_rays,
-                          int32_t n_samples, int32_t flags, float rmnearplane, float* z_vals, float* weights,
-                          float* rgb, float* depth, float* acc, float* feat, void* stream);
+                          int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* z_vals,
+                          float* weights, float* rgb, float* depth, float* acc, float* feat, void* stream);
+
+/* bf16 UMMA operand blob of the coarse field (EDN_BF16 precision of edn_render_coarse_fwd): size and packer. */
+int64_t edn_coarse_tc_blob_bytes(void);
+int edn_pack_coarse_tc(const edn_field_mlp* mlp, const float* basis_t, void* blob, void* stream);
 
 /* sample_pdf (utils/rays.py:149-193) as called at renderer.py:199-203 + merge/sort (renderer.py:205) + z_std (:250).
  *   u_det [n_importance] = linspace(0,1,n_importance) (perturb == 0) or NULL;  u_rand [R][n_importance] or NULL.

@@ -7,7 +7,8 @@ import pytest
 import torch
 
 import evdeblur_oracle as oc
-from util import AABB, CFG, FOCAL, H, W, assert_close, emulated_bf16_fine, oracle_fine_at, random_params, small_params, synthetic_rays
+from util import (AABB, CFG, FOCAL, H, W, assert_close, emulated_bf16_coarse, emulated_bf16_fine, oracle_fine_at,
+                  random_params, small_params, synthetic_rays)
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +23,37 @@ def engines():
     P, _ = small_params()
     Pc = {k: v.cuda() for k, v in P.items()}
     return P, RenderEngine(Pc, *AABB, precision="bf16"), RenderEngine(Pc, *AABB, precision="fp32")
+
+
+def test_tc_coarse_matches_emulated_reference(engines):
+    P, eng, _ = engines
+    rays, _ = synthetic_rays(150, seed=33)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays)
+    out = eng.render_rays(rb.cuda(), 64, retraw=True, use_awp=True)          # coarse only, feature_map requested
+    emu = emulated_bf16_coarse(P, rb, 64)
+    assert torch.equal(out["z_vals"].cpu(), emu["z_vals"])                    # placement stays bit-exact
+    assert_close(out["depth_feature"], emu["feature"], "geo", rtol=2e-2, atol=5e-3)
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
+    ref = oc.render_rays(P, CFG, rb, 64, 0)
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(out[k], ref[k], "fp32 " + k, rtol=0, atol=ORACLE_ATOL)
+
+
+@pytest.mark.parametrize("nc,R", [(32, 41), (64, 7), (96, 10), (128, 5), (48, 9)])
+def test_tc_coarse_ragged(nc, R):
+    from evdeblurnerf_b200 import RenderEngine
+    P = random_params(13)
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="bf16")
+    rays, _ = synthetic_rays(R, seed=nc)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays)
+    g = torch.Generator().manual_seed(nc)
+    t_rand, noise = torch.rand(R, nc, generator=g), torch.randn(R, nc - 1, generator=g)
+    out = eng.render_rays(rb.cuda(), nc, retraw=True, perturb=1., raw_noise_std=1., rand={"t_rand": t_rand.cuda(), "noise0": noise.cuda()})
+    emu = emulated_bf16_coarse(P, rb, nc, t_rand=t_rand, noise=noise)
+    assert torch.equal(out["z_vals"].cpu(), emu["z_vals"])
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
 
 
 def test_tc_fine_matches_emulated_reference(engines):

@@ -124,3 +124,31 @@ def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearpla
     rgb_map, _, acc, w, depth = oc.raw2outputs(raw, z_all, d, noise, is_train, rmnearplane)
     return {"rgb_map": rgb_map, "depth_map": depth, "acc_map": acc, "weights": w, "depth_feature": geo.reshape(R, S, -1),
             "sigma": sigma.reshape(R, S)}
+
+
+def emulated_bf16_coarse(P, ray_batch, n_samples, t_rand=None, noise=None, is_train=True, rmnearplane=0):
+    """Torch fp32 reference of the tcgen05 coarse pass with its bf16 operand roundings made explicit (same
+    conventions as emulated_bf16_fine; sigma comes out of the sigma_net.1 MMA, the rgb head is an fp32 dot product)."""
+    import evdeblur_oracle as oc
+    import torch.nn.functional as F
+    o, d, vd = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, -3:]
+    z = oc.place_samples(ray_batch[:, 6:7], ray_batch[:, 7:8], n_samples, False, t_rand)
+    R, S = z.shape
+    pts = o[:, None, :] + d[:, None, :] * z[..., None]
+    pre = "mlp_coarse."
+    Pb = {k: (_bf(v) if ("app_plane" in k or "app_line" in k) else v) for k, v in P.items()}
+    g = _bf(oc.vm_products(Pb, pre, pts, *AABB))
+    ft = _bf(F.linear(g, _bf(P[pre + "basis_mat.weight"])))
+    x = torch.cat([ft, _bf(oc.posenc(pts.reshape(-1, 3), 10))], -1)
+    h1 = _bf(torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"]))))
+    o16 = F.linear(h1, _bf(P[pre + "sigma_net.1.weight"]))
+    sigma, geo = o16[:, :1], o16[:, 1:]
+    w3 = P[pre + "color_net.0.weight"]
+    bias_ray = F.linear(oc.posenc(vd, 4), w3[:, 15:], P.get(pre + "color_net.0.bias"))
+    c0 = F.linear(_bf(geo), _bf(w3[:, :15])) + bias_ray[:, None, :].expand(R, S, 64).reshape(R * S, 64)
+    c0 = _bf(torch.relu(c0))
+    c1 = torch.relu(F.linear(c0, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias")))
+    rgb = torch.sigmoid(F.linear(c1, P[pre + "color_net.2.weight"], P.get(pre + "color_net.2.bias")))
+    raw = torch.cat([sigma, rgb], -1).reshape(R, S, 4)
+    rgb_map, _, acc, w, depth = oc.raw2outputs(raw, z, d, noise, is_train, rmnearplane, rgb_act="relu")
+    return {"rgb_map": rgb_map, "depth_map": depth, "acc_map": acc, "weights": w, "z_vals": z, "feature": geo.reshape(R, S, -1)}
