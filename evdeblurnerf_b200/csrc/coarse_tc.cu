@@ -316,20 +316,21 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
           col[0] = fmaf(f[i], w.x, col[0]); col[1] = fmaf(f[i], w.y, col[1]); col[2] = fmaf(f[i], w.z, col[2]);
         }
       }
-      gm->sig[r] = sig_raw;
+      {  // ---- compositing (voxnerf.py:153-201): alpha per row in parallel, then one thread per ray in sample order ---------
+        const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+        const bool is_last = (s == S - 1);
+        const float z_next = gm->z[min(r + 1, kGroupThreads - 1)];
+        const float nz = (a.noise && !is_last) ? __ldg(a.noise + ray * (S - 1) + s) : 0.f;
+        gm->sig[r] = alpha_of_sample(sig_raw, zv, z_next, nz, dnorm, mask_near, a.rmnearplane / 128.0f, is_last);
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) gm->rgb[3 * r + i] = sigmoidf_(col[i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
       named_bar_sync(bar_id, kGroupThreads);
-      // ---- compositing: one thread per ray, sequential like torch.cumprod (voxnerf.py:153-201) -----------------------------------
       if (r < rpt) {
         const int64_t r2 = tile * rpt + r;
         if (r2 < a.n_rays) {
-          const float* rb2 = a.ray_batch + r2 * 11;
-          const float dx = __ldg(rb2 + 3), dy = __ldg(rb2 + 4), dz = __ldg(rb2 + 5);
-          const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
           float out[5];
-          composite_ray(gm->sig + r * S, gm->rgb + 3 * r * S, gm->z + r * S, a.noise ? a.noise + r2 * (S - 1) : nullptr, S, dnorm,
-                        mask_near, a.rmnearplane / 128.0f, (a.flags & EDN_FLAG_RELU_RGB) != 0, gm->w + r * S, out);
+          composite_from_alpha(gm->sig + r * S, gm->rgb + 3 * r * S, gm->z + r * S, S, (a.flags & EDN_FLAG_RELU_RGB) != 0, gm->w + r * S, out);
           a.rgb[r2 * 3 + 0] = out[0]; a.rgb[r2 * 3 + 1] = out[1]; a.rgb[r2 * 3 + 2] = out[2];
           a.depth[r2] = out[3];
           a.acc[r2] = out[4];

@@ -221,6 +221,35 @@ __device__ __forceinline__ void composite_ray(const float* __restrict__ sig_s, c
   out[0] = r; out[1] = gg; out[2] = b; out[3] = dep; out[4] = acc;
 }
 
+// Two-phase variant used by the tensor-core kernels: every row thread computes its own alpha in parallel ...
+__device__ __forceinline__ float alpha_of_sample(float sig_raw, float z, float z_next, float noise, float dnorm, bool mask_near,
+                                                 float near_thr, bool is_last) {
+  if (is_last) return 1.0f;                                 // voxnerf.py:189
+  const float dist = __fmul_rn(z_next - z, dnorm);
+  float sg = fmaxf(sig_raw + noise, 0.0f);
+  if (mask_near && !(z_next > near_thr)) sg = 0.0f;
+  return 1.0f - expf(-__fmul_rn(sg, dist));
+}
+// ... and ONE thread per ray runs the (cheap) sequential transmittance product and the ray sums, in sample order.
+__device__ __forceinline__ void composite_from_alpha(const float* __restrict__ alpha_s, const float* __restrict__ rgb_s /*[S][3]*/,
+                                                     const float* __restrict__ z_s, int S, bool relu_rgb, float* __restrict__ w_s,
+                                                     float out[5]) {
+  float T = 1.0f, r = 0.f, gg = 0.f, b = 0.f, dep = 0.f, acc = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) {
+    const float alpha = alpha_s[s];
+    const float w = alpha * T;
+    w_s[s] = w;
+    float cr = rgb_s[3 * s + 0], cg = rgb_s[3 * s + 1], cb = rgb_s[3 * s + 2];
+    if (relu_rgb) { cr = fmaxf(cr, 0.f); cg = fmaxf(cg, 0.f); cb = fmaxf(cb, 0.f); }
+    r = fmaf(w, cr, r); gg = fmaf(w, cg, gg); b = fmaf(w, cb, b);
+    dep = fmaf(w, z_s[s], dep);
+    acc += w;
+    T = T * (1.0f - alpha);
+  }
+  out[0] = r; out[1] = gg; out[2] = b; out[3] = dep; out[4] = acc;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace edn

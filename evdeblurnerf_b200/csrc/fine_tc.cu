@@ -75,7 +75,7 @@ struct alignas(16) GroupMisc {
 struct Misc {
   uint64_t bar_a[2], bar_acc[2], full[kNst], empty[kNst], bar_basis;
   GridDev grids[2];          // [0] coarse, [1] fine
-  uint32_t tmem_base, pad[3];
+  uint32_t tmem_base, skew_flag, pad[2];
   alignas(16) float wsig[256];           // sigma_net.1 row 0 (sigma head)
   alignas(16) float wrgb[256][4];        // color_net.2 transposed (rgb head)
   alignas(16) float bias1[256];          // color_net.1 bias (zeros without --rgb_add_bias)
@@ -153,6 +153,13 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(gout + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
   }
+  if (mode == kEpiRelu) {          // ReLU fused into the bf16 conversion
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(a_row + (col0 / 8 + j) * kChunkA, pack_relu_bf16x2(f[8 * j], f[8 * j + 1]), pack_relu_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                   pack_relu_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_relu_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+    return;
+  }
   if (mode != kEpiPlain) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -204,7 +211,7 @@ __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob, const int skew) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB]
   uint8_t* Ws = smem + 2 * kABytes;                     // ring
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[s], 1); mbar_init(&m->empty[s], 2); }
     mbar_init(&m->bar_basis, 1);
     fence_barrier_init();
+    m->skew_flag = 0;
   }
   if (warp == kRowWarps) tmem_alloc(&m->tmem_base, kTmemCols);
   for (int i = tid; i < 256; i += kThreads) {
@@ -306,6 +314,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
     const int bar_id = 1 + q;
+    if (q == 1 && skew) {   // start the second ray one layer late so that its MMAs fall into the first ray's epilogues
+      uint32_t spins = 0;
+      while (*reinterpret_cast<volatile uint32_t*>(&m->skew_flag) == 0) { if (++spins > (1u << 26)) __trap(); }
+    }
     auto stamp = [&](int64_t it, int k) {
       if (a.trace && blockIdx.x == 0 && r == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
     };
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       stamp(it, 5);
       layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, nullptr, nullptr, m->wsig, m->wrgb, sig_raw);
       rows_signal_a(&m->bar_a[q]);
+      if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 6);
       // ---- sigma_net.1 -> geo (128, linear) ------------------------------------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
@@ -403,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       float col[3] = {0.f, 0.f, 0.f};
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 11);
-      layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, m->bias1, nullptr, m->wsig, m->wrgb, col);
+      layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, a.mlp.color1_b ? m->bias1 : nullptr, nullptr, m->wsig, m->wrgb, col);
 #pragma unroll
       for (int i = 0; i < 3; ++i) col[i] = sigmoidf_(col[i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
       stamp(it, 12);
@@ -479,6 +492,8 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   const int64_t n_pairs = (a.n_rays + 1) / 2;
   const unsigned gx = (unsigned)(n_pairs < (int64_t)num_sms() ? n_pairs : (int64_t)num_sms());
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
+  const char* sk = getenv("EDN_TC_SKEW");
+  const int skew = (sk && sk[0] == '0') ? 0 : 1;
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;
@@ -487,7 +502,7 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
     memset(buf, 0, 8 * 16 * sizeof(long long));
     b.trace = buf;
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob);
+    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob, skew);
     EDN_CUDA_OK(cudaGetLastError());
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     static const char* names[14] = {"start", "pe+bias", "gather", "w.basis", "e.ft", "w.L1", "e.L1", "w.L2", "e.L2", "w.L3", "e.L3", "w.L4", "e.L4", "composite"};
@@ -501,10 +516,10 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   }
   if (grid_dtype == EDN_BF16) {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
+    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob, skew);
   } else {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
+    fine_fwd_tc_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, blob, skew);
   }
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
