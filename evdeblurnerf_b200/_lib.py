@@ -29,6 +29,20 @@ class FieldMlp(C.Structure):
                 ("hidden", C.c_int32), ("geo_feat", C.c_int32), ("tc_blob", C.c_void_p)]
 
 
+class RbkParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("img_embed", "r_branch_w", "r_branch_b", "v_branch_w", "v_branch_b", "w_branch_w",
+                                           "w_branch_b", "r_linear_w", "r_linear_b", "v_linear_w", "v_linear_b", "w_linear_w",
+                                           "w_linear_b")] + [("num_motion", C.c_int32), ("n_img", C.c_int32),
+                                                             ("rv_window", C.c_float)]
+
+
+class CrfParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3")] + [
+        ("extra_features", C.c_int32), ("gamma", C.c_float)]
+
+
+CRF_GAMMA, CRF_LEARN, CRF_SKIP_LEARN, CRF_LUMA = 1, 2, 4, 8
+
 # name -> (restype, argtypes); must list every symbol include/evdeblur_b200.h declares (tests/test_abi.py checks)
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -45,6 +59,15 @@ SIGNATURES = {
     "edn_pack_fine_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P]),
     "edn_render_fine_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _I64,
                                       _I32, _I32, _F, _I32, _P, _P, _P, _P, _P, _P]),
+    "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
+    "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
+    "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),
+    "edn_crf_fwd": (C.c_int, [C.POINTER(CrfParams), _P, _P, _I32, _I32, _I64, _P, _P]),
+    "edn_egm_loss_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _F, _P, _P]),
+    "edn_img2mse": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "edn_tv_loss_app": (C.c_int, [C.POINTER(C.c_void_p * 3), C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int32 * 3),
+                                  C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _P, _P, _P]),
+    "edn_edi_prior": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _I32, _I32, _I32, _F, _F, _P, _P, _P]),
 }
 
 _lib = None

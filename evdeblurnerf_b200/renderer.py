@@ -1,0 +1,214 @@
+"""Host mirror of the reference renderer façade `NeRFAll` (networks/renderer.py:14-626), mode = c2f, kernel_type = RBK.
+
+Same method names, argument order and return structure as the reference so that `run_nerf.py`'s call sites
+(`nerf(H, W, K, chunk, rays=..., rays_info=..., **render_kwargs)`) keep working; every arithmetic
+step is a kernel of libevdeblur_b200.so.  Round-1 scope: forward passes (training-branch forward and eval render);
+parameters are read from a reference `state_dict()` (SURVEY Appendix A names).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RbkParams, check, ptr, stream_ptr
+from .engine import RenderEngine
+from .losses import tv_loss_app
+
+
+class RigidBlurringModel:
+    """networks/dpnerf/blurmodel.py:8-173 (feat_ch = 0, depth-1 branches, use_origin = True: every shipped config)."""
+
+    def __init__(self, params, num_motion, rv_window=0.1, prefix="kernelsnet."):
+        self.num_motion, self.rv_window, self.prefix = int(num_motion), float(rv_window), prefix
+        self.keep = []
+        p = RbkParams()
+
+        def g(name):
+            t = params[prefix + name].detach().to(torch.float32).contiguous()
+            if not t.is_cuda:
+                raise RuntimeError("RigidBlurringModel parameters must be CUDA tensors")
+            self.keep.append(t)
+            return t
+
+        emb = g("view_embed_module.img_embed")
+        if emb.shape[1] != 32:
+            raise RuntimeError("unsupported view-latent width %d (expected 32)" % emb.shape[1])
+        p.img_embed, p.n_img = emb.data_ptr(), emb.shape[0]
+        for h in ("r", "v", "w"):
+            w, b = g(f"{h}_branch.0.weight"), g(f"{h}_branch.0.bias")
+            if tuple(w.shape) != (32, 32) or (prefix + f"{h}_branch.1.weight") in params:
+                raise RuntimeError("unsupported RBK branch shape (expected one 32x32 layer per head)")
+            setattr(p, f"{h}_branch_w", w.data_ptr())
+            setattr(p, f"{h}_branch_b", b.data_ptr())
+            w, b = g(f"{h}_linear.weight"), g(f"{h}_linear.bias")
+            exp_out = (self.num_motion + 1) if h == "w" else 3 * self.num_motion
+            if tuple(w.shape) != (exp_out, 32):
+                raise RuntimeError(f"unsupported {h}_linear shape {tuple(w.shape)} for num_motion={self.num_motion}")
+            setattr(p, f"{h}_linear_w", w.data_ptr())
+            setattr(p, f"{h}_linear_b", b.data_ptr())
+        p.num_motion, p.rv_window = self.num_motion, self.rv_window
+        self.p = p
+
+    def warp(self, H, W, focal, rays, images_idx, near=0., far=1., ndc=True, want_new_rays=True, want_ray_batch=True):
+        """Fused forward + render() prologue -> dict(new_rays [N,E,3,2], weight [N,E], img_embed [N,32], ray_batch [N*E,11])."""
+        r = rays.detach().to(torch.float32).contiguous()
+        idx = images_idx.reshape(-1).to(torch.int64).contiguous()
+        N, E, dev = r.shape[0], self.num_motion + 1, r.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = {"weight": torch.empty((N, E), **f32), "img_embed": torch.empty((N, 32), **f32),
+               "new_rays": torch.empty((N, E, 3, 2), **f32) if want_new_rays else None,
+               "ray_batch": torch.empty((N * E, 11), **f32) if want_ray_batch else None}
+        check(_lib.load().edn_rbk_warp_ndc_fwd(C.byref(self.p), ptr(r), ptr(idx), N, int(H), int(W), float(focal), float(near),
+                                               float(far), 1 if ndc else 0, ptr(out["new_rays"]), ptr(out["weight"]),
+                                               ptr(out["img_embed"]), ptr(out["ray_batch"]), stream_ptr()), "edn_rbk_warp_ndc_fwd")
+        return out
+
+    def __call__(self, H, W, K, rays, rays_info, feats=None, return_img_embed=False):
+        """Reference signature (blurmodel.py:129): -> (new_rays, weight, align_loss=None, extras)."""
+        o = self.warp(H, W, float(K[0][0]), rays, rays_info["images_idx"], want_ray_batch=False)
+        extras = {"img_embed": o["img_embed"]} if return_img_embed else {}
+        return o["new_rays"], o["weight"], None, extras
+
+    @staticmethod
+    def rbk_weighted_sum(rgb, depth, acc, extras, ccw):
+        """blurmodel.py:112-127: reduce [N*E, ...] -> [N, ...] with weights ccw [N,E] for rgb, depth, acc and every extra."""
+        N, E = ccw.shape
+        ws = lambda x: weighted_sum(x, ccw)
+        out_extras = {k: (ws(v) if (isinstance(v, torch.Tensor) and v.shape[:1] == (N * E,)) else v) for k, v in extras.items()}
+        return ws(rgb), ws(depth), ws(acc), out_extras
+
+
+def weighted_sum(x, ccw):
+    """x [N*E, ...] , ccw [N,E] -> [N, ...]."""
+    N, E = ccw.shape
+    xf = x.detach().to(torch.float32).contiguous()
+    Cn = max(1, xf.numel() // max(1, N * E))
+    out = torch.empty((N,) + tuple(xf.shape[1:]), dtype=torch.float32, device=xf.device)
+    check(_lib.load().edn_weighted_sum(ptr(xf), ptr(ccw.detach().float().contiguous()), ptr(out), N, E, Cn, stream_ptr()),
+          "edn_weighted_sum")
+    return out
+
+
+def build_ray_batch(H, W, focal, rays, near=0., far=1., ndc=True):
+    """render() prologue (renderer.py:423-446): rays [R,3,2] -> ray_batch [R,11]."""
+    r = rays.detach().to(torch.float32).contiguous().reshape(-1, 3, 2)
+    out = torch.empty((r.shape[0], 11), dtype=torch.float32, device=r.device)
+    check(_lib.load().edn_build_ray_batch(ptr(r), r.shape[0], int(H), int(W), float(focal), float(near), float(far),
+                                          1 if ndc else 0, ptr(out), stream_ptr()), "edn_build_ray_batch")
+    return out
+
+
+class NeRFAll:
+    """Drop-in for the reference façade (mode = c2f, kernel_type = RBK or none).  `params`: reference state_dict."""
+
+    def __init__(self, params, aabb_min, aabb_max, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False):
+        if use_awp:
+            raise NotImplementedError("kernel_use_awp: the AWP branch (networks/dpnerf/awp.py) is not built yet")
+        self.params = {k: v for k, v in params.items() if isinstance(v, torch.Tensor)}
+        self.engine = RenderEngine(self.params, aabb_min, aabb_max, precision=precision, rmnearplane=render_rmnearplane)
+        self.kernelsnet = None
+        if "kernelsnet.r_linear.weight" in self.params:
+            self.kernelsnet = RigidBlurringModel(self.params, kernel_ptnum - 1)
+        self.mode, self.kernel_type, self.use_awp = "c2f", "RBK", False
+        self.training = True
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    # ---- renderer.py:129 ----------------------------------------------------------------------------------------------
+    def render_rays(self, ray_batch, N_samples, retraw=False, lindisp=False, perturb=0., N_importance=0, white_bkgd=False,
+                    raw_noise_std=0., pytest=False, force_naive=False, inference=False, **extra):
+        return self.engine.render_rays(ray_batch, N_samples, retraw=retraw, lindisp=lindisp, perturb=perturb,
+                                       N_importance=N_importance, white_bkgd=white_bkgd, raw_noise_std=raw_noise_std,
+                                       pytest=pytest, force_naive=force_naive, inference=inference, is_train=self.training,
+                                       use_awp=self.use_awp, **extra)
+
+    def _render_batch(self, ray_batch, rays_shape, **kwargs):
+        all_ret = self.render_rays(ray_batch, **kwargs)     # no chunk loop: the fused kernels keep no per-sample activations
+        for k in all_ret:
+            all_ret[k] = all_ret[k].reshape(list(rays_shape) + list(all_ret[k].shape[1:]))
+        k_extract = ["rgb_map", "depth_map", "acc_map"]
+        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+    # ---- renderer.py:399 ----------------------------------------------------------------------------------------------
+    def render(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False, c2w_staticcam=None,
+               **kwargs):
+        if c2w is not None or c2w_staticcam is not None:
+            raise NotImplementedError("render(c2w=...) : use render_path for full images")
+        rb = build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc)
+        return self._render_batch(rb, rays.shape[:-2], **kwargs)
+
+    # ---- renderer.py:266 ----------------------------------------------------------------------------------------------
+    def forward(self, H, W, K, chunk=1024 * 32, rays=None, rays_info=None, poses=None, **kwargs):
+        if not self.training:
+            assert poses is not None, "Please specify poses when in the eval model"
+            return self.render_path(H, W, K, chunk, poses, **kwargs)
+        assert rays is not None, "Please specify rays when in the training mode"
+        force_baseline = kwargs.pop("force_naive", True)
+        return_pts0_rgb = kwargs.pop("return_pts0_rgb", False)
+        N_importance = kwargs.get("N_importance", 0)
+        ndc, near, far = kwargs.pop("ndc", True), kwargs.pop("near", 0.), kwargs.pop("far", 1.)
+        kwargs.pop("use_viewdirs", None)
+        other_loss, other_tensors = {}, {}
+        if self.kernelsnet is not None and not force_baseline:
+            k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, rays_info["images_idx"], near, far, ndc, want_new_rays=False)
+            weight1 = k["weight"]
+            N, E = weight1.shape
+            rgb, depth, acc, extras = self._render_batch(k["ray_batch"], (N * E,), **kwargs)
+            rgb_pts = rgb.reshape(N, E, 3)
+            rgb_b = weighted_sum(rgb, weight1)
+            rgb1 = None
+            if N_importance > 0:
+                rgb1_pts = extras["rgb0"].reshape(N, E, 3)
+                rgb1 = weighted_sum(extras["rgb0"], weight1)
+            other_loss["TV"] = self.tv_loss(N_importance > 0)
+            if return_pts0_rgb:
+                other_tensors["stage1_rgb_pts0"] = rgb_pts[:, 0]
+                if N_importance > 0:
+                    other_tensors["stage1_rgb1_pts0"] = rgb1_pts[:, 0]
+            return rgb_b, rgb1, other_loss, other_tensors
+        rgb, depth, acc, extras = self.render(H, W, K, chunk, rays, ndc=ndc, near=near, far=far, **kwargs)
+        other_tensors["stage1_rgb_pts0"] = rgb
+        if N_importance > 0:
+            other_tensors["stage1_rgb1_pts0"] = extras["rgb0"]
+        other_loss["TV"] = self.tv_loss(N_importance > 0)
+        return rgb, extras.get("rgb0"), other_loss, other_tensors
+
+    __call__ = forward
+
+    def tv_loss(self, with_fine=True):
+        """renderer.py:361-365: (TV_loss_app(coarse) [+ TV_loss_app(fine)]) * 5."""
+        tv = tv_loss_app(self.params, "mlp_coarse.")
+        if with_fine:
+            tv = tv + tv_loss_app(self.params, "mlp_fine.")
+        return tv * 5
+
+    # ---- renderer.py:594 + utils/rays.py:8-22 ---------------------------------------------------------------------------
+    def render_path(self, H, W, K, chunk, render_poses, render_kwargs=None, render_factor=0, **kwargs):
+        if render_factor != 0:
+            H, W = H // render_factor, W // render_factor
+        kw = dict(render_kwargs or {})
+        kw.update(kwargs)
+        ndc, near, far = kw.pop("ndc", True), kw.pop("near", 0.), kw.pop("far", 1.)
+        kw.pop("use_viewdirs", None)
+        kw.setdefault("inference", True)
+        rgbs, depths = [], []
+        dev = self.engine.device
+        for c2w in render_poses:
+            c2w = torch.as_tensor(c2w, dtype=torch.float32, device=dev)
+            # get_rays (utils/rays.py:8-22): host-side ray generation, "next" scope of SURVEY 8(f)
+            i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="xy")
+            dirs = torch.stack([(i + (0.5 - float(K[0][2]))) / float(K[0][0]), -(j + (0.5 - float(K[1][2]))) / float(K[1][1]),
+                                -torch.ones_like(i)], -1)            # HALF_PIX = 0.5 (utils/rays.py:5)
+            rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+            rays_o = c2w[:3, -1].expand(rays_d.shape)
+            rays = torch.stack([rays_o, rays_d], -1).reshape(-1, 3, 2)
+            rb = build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc)
+            rgb, depth, acc, _ = self._render_batch(rb, (H, W), **kw)
+            rgbs.append(rgb)
+            depths.append(depth)
+        return torch.stack(rgbs, 0), torch.stack(depths, 0)

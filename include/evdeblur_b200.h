@@ -124,6 +124,82 @@ int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_
                         int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* weights,
                         float* rgb, float* depth, float* acc, float* feat, void* stream);
 
+/* ---- blur kernel + render() prologue ------------------------------------------------------------------------------ */
+
+/* DP-NeRF rigid blur kernel weights (nn.Linear layout [out][in], fp32), names as in the reference state_dict
+ * (SURVEY Appendix A): kernelsnet.view_embed_module.img_embed [n_img][32], {r,v,w}_branch.0 [32][32]+[32],
+ * r_linear / v_linear [3*num_motion][32]+[3*num_motion], w_linear [num_motion+1][32]+[num_motion+1]. */
+typedef struct edn_rbk_params {
+  const float* img_embed;
+  const float* r_branch_w; const float* r_branch_b;
+  const float* v_branch_w; const float* v_branch_b;
+  const float* w_branch_w; const float* w_branch_b;
+  const float* r_linear_w; const float* r_linear_b;
+  const float* v_linear_w; const float* v_linear_b;
+  const float* w_linear_w; const float* w_linear_b;
+  int32_t num_motion;      /* kernel_ptnum - 1 */
+  int32_t n_img;
+  float rv_window;         /* 0.1 */
+} edn_rbk_params;
+
+/* RigidBlurringModel.forward + rbk_warp (dpnerf/blurmodel.py:129-173, 51-82; utils/rigid_warping.py:18-49, 72-154) fused
+ * with the render() prologue (renderer.py:423-446) and get_ndc_rays (utils/rays.py:104-145).
+ *   rays [N][3][2], images_idx [N] int64
+ * outputs: new_rays [N][E][3][2] or NULL, weight [N][E], img_embed [N][32] or NULL, ray_batch [N*E][11] or NULL. */
+int edn_rbk_warp_ndc_fwd(const edn_rbk_params* p, const float* rays, const int64_t* images_idx, int64_t n_rays,
+                         int32_t H, int32_t W, float focal, float near, float far, int32_t ndc, float* new_rays,
+                         float* weight, float* img_embed, float* ray_batch, void* stream);
+
+/* render() prologue alone (renderer.py:423-446): rays [R][3][2] -> ray_batch [R][11]. */
+int edn_build_ray_batch(const float* rays, int64_t n_rays, int32_t H, int32_t W, float focal, float near, float far,
+                        int32_t ndc, float* ray_batch, void* stream);
+
+/* ---- loss path ------------------------------------------------------------------------------------------------------ */
+
+/* rbk_weighted_sum (dpnerf/blurmodel.py:112-127): x [N*E][C], w [N][E] -> out [N][C]. */
+int edn_weighted_sum(const float* x, const float* w, float* out, int64_t n, int32_t n_exposure, int64_t channels,
+                     void* stream);
+
+enum { EDN_CRF_GAMMA = 1, EDN_CRF_LEARN = 2, EDN_CRF_SKIP_LEARN = 4, EDN_CRF_LUMA = 8 };
+
+/* CRF residual MLP (tonemapping.py:7-57): linear.0 [16][1+extra], linear.2 [16][16], linear.4 [16][16], linear.6 [1][16]. */
+typedef struct edn_crf_params {
+  const float* w0; const float* b0;
+  const float* w1; const float* b1;
+  const float* w2; const float* b2;
+  const float* w3; const float* b3;
+  int32_t extra_features;
+  float gamma;
+} edn_crf_params;
+
+/* CRF.forward + TonemappingTransform.encode_rgb / encode_luma (tonemapping.py:59-93, 111-139).
+ *   x [M][3]; feat [M][F] (feat_per_channel = 0), [M][3][F] (= 1) or NULL (zero padded, tonemapping.py:83-86)
+ *   flags: EDN_CRF_GAMMA (map_type contains 'gamma'), EDN_CRF_LEARN (map_type == 'learn'), EDN_CRF_SKIP_LEARN,
+ *          EDN_CRF_LUMA (rec601 luma, out [M][1]; otherwise out [M][3]). */
+int edn_crf_fwd(const edn_crf_params* p, const float* x, const float* feat, int32_t feat_per_channel, int32_t flags,
+                int64_t m, float* out, void* stream);
+
+/* egm_loss (utils/events.py:260-284): luma_* [M][channels], bii [M], color_mask [M][3] uint8 one-hot or NULL,
+ * color_weight [3] or NULL -> out [1]. */
+int edn_egm_loss_fwd(const float* luma_start, const float* luma_end, const float* bii, const uint8_t* color_mask,
+                     const float* color_weight, int32_t channels, int64_t m, float log_eps, float* out, void* stream);
+
+/* img2mse (utils/metrics.py:7): mean((x - y)^2) over n elements -> out [1]. */
+int edn_img2mse(const float* x, const float* y, int64_t n, float* out, void* stream);
+
+/* VoxelNeRFBase.TV_loss_app (voxnerf.py:126-130, 306-324) on the reference-layout ([1,C,H,W] fp32) planes / lines of one
+ * field.  workspace: 12 doubles.  out [1] = sum_i 1e-2 TV(plane_i) + 1e-3 TV(line_i). */
+int edn_tv_loss_app(const float* const planes_chw[3], const float* const lines_chw[3], const int32_t plane_h[3],
+                    const int32_t plane_w[3], const int32_t line_len[3], const int32_t n_comp[3], double* workspace,
+                    float* out, void* stream);
+
+/* EDI prior for one frame (utils/edi.py:7-95, data/loader_events.py:99-131): events ev_x / ev_y / ev_p (p > 0 = positive),
+ * n_seg (even) sub-interval index ranges [seg_start[j], seg_end[j]) (device int64), blurry [H][W][C].
+ * workspace / output bii [n_seg][H][W] (brightness increment images), sharp [H][W][C]. */
+int edn_edi_prior(const float* ev_x, const float* ev_y, const float* ev_p, const int64_t* seg_start, const int64_t* seg_end,
+                  int32_t n_seg, int64_t max_seg_events, const float* blurry, int32_t H, int32_t W, int32_t C, float c_pos,
+                  float c_neg, float* bii, float* sharp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
