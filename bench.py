@@ -24,6 +24,8 @@ AABB = ((-1.5, -1.5, -1.0), (1.5, 1.5, 1.0))
 COARSE_VOX, FINE_VOX = 16777248, 134217984          # configs/.../tx_blurfactory_*.txt:66,74
 H = W = 400
 FOCAL = 400.0
+N_IMGS = 30
+KMAT = [[FOCAL, 0.0, 200.0], [0.0, FOCAL, 200.0], [0.0, 0.0, 1.0]]
 
 # algorithmic work, MACs
 MAC_COARSE_SAMPLE = 17152                            # basis 3072 + sigma_net 7104 + color_net 6976
@@ -70,38 +72,26 @@ def make_params(device, seed=0):
         lin(pre + "color_net.0.weight", hid, geo + 27)
         lin(pre + "color_net.1.weight", hid, hid)
         lin(pre + "color_net.2.weight", 3, hid)
+    # DP-NeRF rigid blur kernel (dpnerf/blurmodel.py:38-45); latents / r,v heads randomised so that the warp is non-trivial
+    pre = "kernelsnet."
+    P[pre + "view_embed_module.img_embed"] = (0.5 * torch.randn(N_IMGS, 32, generator=g)).to(device)
+    for h in ("r", "v", "w"):
+        lin(pre + f"{h}_branch.0.weight", 32, 32)
+        P[pre + f"{h}_branch.0.bias"] = torch.zeros(32, device=device)
+    for h, n_out in (("r", 3 * (N_EXPOSURE - 1)), ("v", 3 * (N_EXPOSURE - 1)), ("w", N_EXPOSURE)):
+        P[pre + f"{h}_linear.weight"] = (0.05 * torch.randn(n_out, 32, generator=g)).to(device)
+        P[pre + f"{h}_linear.bias"] = torch.zeros(n_out, device=device)
     return P
 
 
 def make_rays(n, seed):
-    """SURVEY 8(d) synthetic sub-rays [n*E, 3, 2]: camera looking down -z; the E exposures of a primary ray are
-    small rigid perturbations of it (what the RBK kernel produces)."""
+    """SURVEY 8(d) synthetic primary rays [n,3,2] (camera looking down -z so that NDC is well posed) + image ids [n,1]."""
     import torch
     g = torch.Generator().manual_seed(seed)
-    o = torch.randn(n, 1, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])
-    d = torch.cat([torch.randn(n, 1, 2, generator=g) * 0.3, -torch.ones(n, 1, 1)], -1)
-    o = o + 0.01 * torch.randn(n, N_EXPOSURE, 3, generator=g)
-    d = d + 0.01 * torch.randn(n, N_EXPOSURE, 3, generator=g)
-    return torch.stack([o, d], -1).reshape(n * N_EXPOSURE, 3, 2)
-
-
-def build_ray_batch(rays):
-    """render() prologue (renderer.py:423-446, utils/rays.py:104-145) in torch -- host-side input preparation."""
-    import torch
-    o, d = rays[..., 0], rays[..., 1]
-    viewdirs = d / torch.norm(d, dim=-1, keepdim=True)
-    near = 1.0
-    t = -(near + o[..., 2]) / d[..., 2]
-    o = o + t[..., None] * d
-    ox_oz, oy_oz = o[..., 0] / o[..., 2], o[..., 1] / o[..., 2]
-    o0 = -1. / (W / (2. * FOCAL)) * ox_oz
-    o1 = -1. / (H / (2. * FOCAL)) * oy_oz
-    o2 = 1. + 2. * near / o[..., 2]
-    d0 = -1. / (W / (2. * FOCAL)) * (d[..., 0] / d[..., 2] - ox_oz)
-    d1 = -1. / (H / (2. * FOCAL)) * (d[..., 1] / d[..., 2] - oy_oz)
-    d2 = 1 - o2
-    on, dn = torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
-    return torch.cat([on, dn, torch.zeros_like(dn[..., :1]), torch.ones_like(dn[..., :1]), viewdirs], -1).float().contiguous()
+    o = torch.randn(n, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])
+    d = torch.cat([torch.randn(n, 2, generator=g) * 0.3, -torch.ones(n, 1)], -1)
+    idx = torch.randint(0, N_IMGS, (n, 1), generator=g)
+    return torch.stack([o, d], -1).contiguous(), idx
 
 
 class ClockSampler:
@@ -140,17 +130,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step(P_cpu, rays_cpu, threads):
-    """One bounded CPU step of the reference algorithm (oracle port; the reference is Python and cannot travel)."""
+def cpu_reference_step(P_cpu, rays_cpu, idx_cpu, threads):
+    """One bounded CPU step of the reference algorithm (oracle port; the reference is Python and cannot travel):
+    blur-kernel warp -> NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import evdeblur_oracle as oc
     torch.set_num_threads(threads)
     cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
     with torch.no_grad():
-        rb = oc.build_ray_batch(H, W, FOCAL, rays_cpu)
         t0 = time.perf_counter()
-        out = oc.render_rays(P_cpu, cfg, rb, NC, NI)
+        out = oc.forward_train(P_cpu, cfg, H, W, FOCAL, rays_cpu, idx_cpu, N_EXPOSURE, NC, NI, use_awp=False)
         dt = time.perf_counter() - t0
     return dt, out
 
@@ -162,12 +152,12 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_rays = 256
+    sample_rays = 512
     P = make_params("cpu")
-    rays = make_rays(sample_rays, seed=100)
+    rays, idx = make_rays(sample_rays, seed=100)
     times = []
     for i in range(args.warmup + args.steps):
-        dt, _ = cpu_reference_step(P, rays, threads)
+        dt, _ = cpu_reference_step(P, rays, idx, threads)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / max(len(times), 1)
@@ -183,7 +173,8 @@ def run_reference(args):
 
 
 def workload_config(precision, **extra):
-    cfg = {"workload": f"blurfactory c2f render fwd: {N_RAYS} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, "
+    cfg = {"workload": f"blurfactory c2f render fwd (RBK warp + NDC -> coarse -> sample_pdf -> fine -> exposure blend): "
+                       f"{N_RAYS} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, "
                        f"PDRF coarse {grid_size(COARSE_VOX)} / fine {grid_size(FINE_VOX)} VM grids",
            "rays": N_RAYS, "exposures": N_EXPOSURE, "samples": [NC, NI], "precision": precision,
            "perturb": 0, "l2": "flushed between timed steps (256 MiB write)"}
@@ -197,7 +188,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -206,7 +197,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from evdeblurnerf_b200 import RenderEngine
+    from evdeblurnerf_b200 import NeRFAll
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,15 +208,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     P = make_params(dev)
-    eng = RenderEngine(P, *AABB, precision=args.precision)
-    rays_host = make_rays(N_RAYS, seed=1000 + rank)
-    rb_host = build_ray_batch(rays_host).pin_memory()
-    rb_dev = rb_host.to(dev)
+    nerf = NeRFAll(P, *AABB, kernel_ptnum=N_EXPOSURE, precision=args.precision).eval()
+    eng = nerf.engine
+    rays_host, idx_host = make_rays(N_RAYS, seed=1000 + rank)
+    rays_host, idx_host = rays_host.pin_memory(), idx_host.pin_memory()
+    rays_dev, idx_dev = rays_host.to(dev), idx_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out_host = torch.empty((N_RAYS * N_EXPOSURE, 3), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory()
 
-    def step(rb):
-        return eng.render_rays(rb, NC, N_importance=NI, is_train=False)
+    def step(rays, idx):
+        # public API call of one render: NeRFAll.render_blurred == the render part of NeRFAll.forward (training branch)
+        return nerf.render_blurred(H, W, KMAT, rays, idx, N_samples=NC, N_importance=NI, perturb=0., raw_noise_std=0.)
 
     def barrier():
         if world > 1:
@@ -233,7 +226,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(rb_dev)
+        step(rays_dev, idx_dev)
     torch.cuda.synchronize()
 
     # ---- device-resident timing: K steps, L2 flushed before each, CUDA events around each step -----------------------
@@ -247,7 +240,7 @@ def main():
         flush.fill_(1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        step(rb_dev)
+        step(rays_dev, idx_dev)
         e.record()
         ev.append((s, e))
     barrier()
@@ -264,9 +257,10 @@ def main():
         flush.fill_(1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        rb = rb_host.to(dev, non_blocking=True)
-        out = step(rb)
-        out_host.copy_(out["rgb_map"], non_blocking=True)
+        r_d = rays_host.to(dev, non_blocking=True)
+        i_d = idx_host.to(dev, non_blocking=True)
+        rgb, _ = step(r_d, i_d)
+        out_host.copy_(rgb, non_blocking=True)
         e.record()
         ev2.append((s, e))
     barrier()
@@ -299,9 +293,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(args.precision),
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rb_host.numel() * 4,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rays_host.numel() * 4 + idx_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 6 * args.steps,   # rbk_warp_ndc, coarse, sample_pdf_merge, fine, 2 x weighted_sum
         "clocks": clocks,
         "kernels_ms": kern_ms,
         "roofline": {"bound": "tensor", "kernel": "edn_render_fine_fwd", "achieved": achieved, "peak": peak_tf,
@@ -312,12 +306,12 @@ def main():
     }
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = 256
+        sample = 512
         Pc = {k: v.cpu() for k, v in P.items()}
-        rays_c = make_rays(sample, seed=100)
+        rays_c, idx_c = make_rays(sample, seed=100)
         best, t_spent = None, 0.0
         for i in range(4):
-            dt, _ = cpu_reference_step(Pc, rays_c, threads)
+            dt, _ = cpu_reference_step(Pc, rays_c, idx_c, threads)
             t_spent += dt
             if i > 0:
                 best = dt if best is None else min(best, dt)

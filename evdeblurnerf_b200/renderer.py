@@ -180,6 +180,15 @@ class NeRFAll:
 
     __call__ = forward
 
+    def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):
+        """The render part of the training forward (renderer.py:303-343 without the loss terms): blur-kernel warp ->
+        NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum.  Returns (rgb [N,3], rgb0 [N,3] | None)."""
+        k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, images_idx, near, far, ndc, want_new_rays=False)
+        out = self.render_rays(k["ray_batch"], **kwargs)
+        rgb = weighted_sum(out["rgb_map"], k["weight"])
+        rgb0 = weighted_sum(out["rgb0"], k["weight"]) if "rgb0" in out else None
+        return rgb, rgb0
+
     def tv_loss(self, with_fine=True):
         """renderer.py:361-365: (TV_loss_app(coarse) [+ TV_loss_app(fine)]) * 5."""
         tv = tv_loss_app(self.params, "mlp_coarse.")
