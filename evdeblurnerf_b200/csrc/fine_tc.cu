@@ -7,8 +7,10 @@
 //         -> two 128x96 bf16 tiles;  after each layer: TMEM -> registers -> bias/ReLU -> bf16 -> A operand of the next
 //         layer; sigma (256->1) and rgb (256->3) are fp32 dot products folded into the epilogues;  finally
 //         sigma->alpha compositing with a warp-shuffle transmittance scan.
-//   load  (warp 10, one thread): streams the layer weights (320 KB per ray pair, 16 KB stages) through a 4-stage
-//         shared-memory ring with bulk async copies (TMA engine); a stage is refilled once BOTH rays' MMAs on it retired.
+//   load  (warps 10 and 11, one thread each, one per ray): stream the layer weights (320 KB per ray, 16 KB stages, L2
+//         resident) through the ray group's private 2-stage shared-memory ring with bulk async copies (TMA engine).
+//         Private rings cost 2x the L2->smem weight traffic of a shared ring but let the two groups drift apart, so one
+//         group's gather / epilogue overlaps the other's MMAs (a shared ring forces lock-step: measured in r1).
 //   mma   (warps 8 and 9, one thread each, one per ray): wait for the ray's A operand and the ring stage, issue
 //         tcgen05.mma: basis_mat x2 (N=32, resident B), sigma_net 128->256->128(geo), color_net 128(+view-dir
 //         bias)->256->256, and commit to the stage-release / accumulator-ready mbarriers.  2 x 256 TMEM columns.
@@ -30,8 +32,8 @@ using namespace tc;
 
 constexpr int kGroupThreads = 128;
 constexpr int kRowWarps = 8;
-constexpr int kThreads = kRowWarps * 32 + 96;   // 8 row warps + 2 MMA issuer warps + 1 weight-stream warp
-constexpr int kNst = 4;                  // weight ring stages
+constexpr int kThreads = kRowWarps * 32 + 128;  // 8 row warps + 2 MMA issuer warps + 2 weight-stream warps
+constexpr int kNst = 2;                  // weight ring stages PER RAY GROUP (private rings: the groups must not run in lock-step)
 constexpr int kStageBytes = 16384;
 constexpr int kABytes = 65536;           // per ray: 128 rows x 256 K bf16
 constexpr int kBasisBytes = 2 * 6 * 1024;  // two basis_mat's, 6 K-steps x (N=32 x 16 x 2 B)
@@ -73,7 +75,7 @@ struct alignas(16) GroupMisc {
   float wtot[4];
 };
 struct Misc {
-  uint64_t bar_a[2], bar_acc[2], full[kNst], empty[kNst], bar_basis;
+  uint64_t bar_a[2], bar_acc[2], full[2][kNst], empty[2][kNst], bar_basis;
   GridDev grids[2];          // [0] coarse, [1] fine
   uint32_t tmem_base, skew_flag, pad[2];
   alignas(16) float wsig[256];           // sigma_net.1 row 0 (sigma head)
@@ -83,7 +85,7 @@ struct Misc {
 };
 static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 && offsetof(Misc, bias1) % 16 == 0 &&
               offsetof(Misc, grp) % 16 == 0 && offsetof(GroupMisc, bias) % 16 == 0, "float4 alignment");
-constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kBasisBytes + (int)sizeof(Misc);
+constexpr int kSmemBytes = 2 * kABytes + 2 * kNst * kStageBytes + kBasisBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // Cooperative gather of both grids for the 32 points of this warp.  Lane (q = lane/8, j = lane%8) serves point 8*gi+j
@@ -137,15 +139,15 @@ enum EpiMode { kEpiPlain = 0, kEpiRelu = 1, kEpiReluSigma = 2, kEpiReluRgb = 3 }
 // 32 accumulator columns of this thread's row:  x = acc (+ bias);  optional fp32 copy to global;  ReLU;  fp32 dot
 // products with the sigma / rgb head;  bf16 -> A operand chunks (except kEpiReluRgb: only the rgb head is produced).
 __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0, int mode, uint8_t* a_row,
-                                               const float* bias_s, float* __restrict__ gout, const float* wsig,
-                                               const float (*wrgb)[4], float* head) {
+                                               uint32_t bias_s, float* __restrict__ gout, uint32_t wsig, uint32_t wrgb,
+                                               float4& head) {   // bias_s / wsig / wrgb: shared-space addresses (0 = none)
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
   if (bias_s) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
+      const float4 b4 = ld_shared_f4(bias_s + (col0 + i) * 4);
       f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
     }
   }
@@ -168,19 +170,19 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(wsig + col0 + i);
+      const float4 w = ld_shared_f4(wsig + (col0 + i) * 4);
       s0 = fmaf(f[i], w.x, s0); s1 = fmaf(f[i + 1], w.y, s1); s0 = fmaf(f[i + 2], w.z, s0); s1 = fmaf(f[i + 3], w.w, s1);
     }
-    head[0] += s0 + s1;
+    head.x += s0 + s1;
   }
   if (mode == kEpiReluRgb) {
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(&wrgb[col0 + i][0]);
+      const float4 w = ld_shared_f4(wrgb + (col0 + i) * 16);
       r0 = fmaf(f[i], w.x, r0); r1 = fmaf(f[i], w.y, r1); r2 = fmaf(f[i], w.z, r2);
     }
-    head[0] += r0; head[1] += r1; head[2] += r2;
+    head.x += r0; head.y += r1; head.z += r2;
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -191,8 +193,9 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0
 
 // Layer epilogue over `ncols` (multiple of 64) accumulator columns; ONE copy of the code for all layers (the kernel is
 // instruction-cache sensitive), two tcgen05.ld's in flight per iteration.
-__device__ __noinline__ void layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int ncols, int mode, const float* bias_s,
-                                            float* __restrict__ gout, const float* wsig, const float (*wrgb)[4], float* head) {
+__device__ __noinline__ float4 layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int ncols, int mode, uint32_t bias_s,
+                                              float* __restrict__ gout, uint32_t wsig, uint32_t wrgb) {
+  float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int col0 = 0; col0 < ncols; col0 += 64) {
     uint32_t v0[32], v1[32];
@@ -202,6 +205,7 @@ __device__ __noinline__ void layer_epilogue(uint32_t taddr_row, uint8_t* a_row, 
     epilogue_block(v0, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
     epilogue_block(v1, col0 + 32, mode, a_row, bias_s, gout, wsig, wrgb, head);
   }
+  return head;
 }
 
 __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
@@ -211,17 +215,18 @@ __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob, const int skew) {
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB]
   uint8_t* Ws = smem + 2 * kABytes;                     // ring
-  uint8_t* Bs = Ws + kNst * kStageBytes;                // resident basis_mat operands
+  uint8_t* Bs = Ws + 2 * kNst * kStageBytes;            // resident basis_mat operands
   Misc* m = reinterpret_cast<Misc*>(Bs + kBasisBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int q = 0; q < 2; ++q) { mbar_init(&m->bar_a[q], kGroupThreads); mbar_init(&m->bar_acc[q], 1); }
-    for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[s], 1); mbar_init(&m->empty[s], 2); }
+    for (int q = 0; q < 2; ++q)
+      for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[q][s], 1); mbar_init(&m->empty[q][s], 1); }
     mbar_init(&m->bar_basis, 1);
     fence_barrier_init();
     m->skew_flag = 0;
@@ -242,19 +247,20 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   const int64_t n_my = (n_pairs_total > (int64_t)blockIdx.x) ? (n_pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int S = a.S;
 
-  if (warp == kRowWarps + 2) {
-    // =================================== weight-stream producer warp ==================================================
+  if (warp >= kRowWarps + 2) {
+    // =================================== weight-stream producer warp of ray group q ==================================
+    const int q = warp - (kRowWarps + 2);
     if (lane == 0 && n_my > 0) {
       const uint8_t* stream = blob + kBasisBytes;
-      mbar_expect_tx(&m->bar_basis, kBasisBytes);
-      bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis);
+      if (q == 0) { mbar_expect_tx(&m->bar_basis, kBasisBytes); bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis); }
+      uint8_t* ring = Ws + q * kNst * kStageBytes;
       const uint32_t total_ring = (uint32_t)n_my * kRingStagesPerRay;
       for (uint32_t g = 0; g < total_ring; ++g) {
         const int s = g % kNst;
         const uint32_t use = g / kNst;
-        if (use > 0) mbar_wait(&m->empty[s], (use - 1) & 1);      // both rays' MMAs on the previous tenant completed
-        mbar_expect_tx(&m->full[s], kStageBytes);
-        bulk_g2s(Ws + s * kStageBytes, stream + (size_t)(g % kRingStagesPerRay) * kStageBytes, kStageBytes, &m->full[s]);
+        if (use > 0) mbar_wait(&m->empty[q][s], (use - 1) & 1);   // the MMAs on the previous tenant completed
+        mbar_expect_tx(&m->full[q][s], kStageBytes);
+        bulk_g2s(ring + s * kStageBytes, stream + (size_t)(g % kRingStagesPerRay) * kStageBytes, kStageBytes, &m->full[q][s]);
       }
     }
     __syncwarp();
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     // =================================== MMA issuer warp of ray group q (one thread) ===================================
     const int q = warp - kRowWarps;
     if (lane == 0 && n_my > 0) {
-      const uint32_t aq = smem_u32(As) + q * kABytes, w_base = smem_u32(Ws), b_base = smem_u32(Bs);
+      const uint32_t aq = smem_u32(As) + q * kABytes, w_base = smem_u32(Ws) + q * kNst * kStageBytes, b_base = smem_u32(Bs);
       const uint32_t d_tmem = tmem + q * 256;
       const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
       uint32_t pa = 0, g = 0;
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
           if (sd.first) { mbar_wait(&m->bar_a[q], pa); pa ^= 1; }
           if (sd.kind == 2) {
             const int s = g % kNst;
-            mbar_wait(&m->full[s], (g / kNst) & 1);
+            mbar_wait(&m->full[q][s], (g / kNst) & 1);
             tc_fence_after();
             const uint32_t idesc = make_idesc_bf16(128, sd.n);
             const uint32_t kstep_bytes = (uint32_t)sd.n * 32u;
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
               const uint64_t bdesc = make_smem_desc(w_base + s * kStageBytes + i * kstep_bytes, (uint32_t)sd.n * 16u, 128);
               mma_bf16_ss(d_tmem, adesc, bdesc, idesc, kst > 0);
             }
-            mma_commit(&m->empty[s]);
+            mma_commit(&m->empty[q][s]);
             ++g;
           } else {
             tc_fence_after();
@@ -314,7 +320,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
     const int bar_id = 1 + q;
-    if (q == 1 && skew) {   // start the second ray one layer late so that its MMAs fall into the first ray's epilogues
+    const uint32_t s_wsig = smem_u32(m->wsig), s_wrgb = smem_u32(m->wrgb);
+    if (q == 1) {   // phase-shift the second ray group by ~half a ray so that its MMAs fall into the first group's gather / epilogues
       uint32_t spins = 0;
       while (*reinterpret_cast<volatile uint32_t*>(&m->skew_flag) == 0) { if (++spins > (1u << 26)) __trap(); }
     }
@@ -388,35 +395,34 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 3);
-      layer_epilogue(taddr_row, a_row, 64, kEpiPlain, nullptr, nullptr, m->wsig, m->wrgb, nullptr);
+      layer_epilogue(taddr_row, a_row, 64, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 4);
       // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0) -------------------------------------------
-      float sig_raw[1] = {0.f};
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 5);
-      layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, nullptr, nullptr, m->wsig, m->wrgb, sig_raw);
+      const float sig_raw = layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb).x;
       rows_signal_a(&m->bar_a[q]);
-      if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 6);
       // ---- sigma_net.1 -> geo (128, linear) ------------------------------------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 7);
-      layer_epilogue(taddr_row, a_row, 128, kEpiPlain, nullptr,
-                     (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, m->wsig, m->wrgb, nullptr);
+      layer_epilogue(taddr_row, a_row, 128, kEpiPlain, 0u,
+                     (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, s_wsig, s_wrgb);
       rows_signal_a(&m->bar_a[q]);
+      if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 8);
       // ---- color_net.0 (+ per-ray view-dir bias) -> ReLU ------------------------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 9);
-      layer_epilogue(taddr_row, a_row, 256, kEpiRelu, gm->bias, nullptr, m->wsig, m->wrgb, nullptr);
+      layer_epilogue(taddr_row, a_row, 256, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 10);
       // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2) -> sigmoid -----------------------------------------
-      float col[3] = {0.f, 0.f, 0.f};
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 11);
-      layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, a.mlp.color1_b ? m->bias1 : nullptr, nullptr, m->wsig, m->wrgb, col);
+      const float4 hd = layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, a.mlp.color1_b ? smem_u32(m->bias1) : 0u, nullptr, s_wsig, s_wrgb);
+      float col[3] = {hd.x, hd.y, hd.z};
 #pragma unroll
       for (int i = 0; i < 3; ++i) col[i] = sigmoidf_(col[i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
       stamp(it, 12);
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
         const float znext = gm->z[r + 1];
         const float dist = __fmul_rn(znext - zv, dnorm);
-        float sg = sig_raw[0];
+        float sg = sig_raw;
         if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + r);
         sg = fmaxf(sg, 0.f);
         if (mask_near && !(znext > near_thr)) sg = 0.f;
@@ -492,8 +498,6 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   const int64_t n_pairs = (a.n_rays + 1) / 2;
   const unsigned gx = (unsigned)(n_pairs < (int64_t)num_sms() ? n_pairs : (int64_t)num_sms());
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
-  const char* sk = getenv("EDN_TC_SKEW");
-  const int skew = (sk && sk[0] == '0') ? 0 : 1;
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;
@@ -502,7 +506,7 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
     memset(buf, 0, 8 * 16 * sizeof(long long));
     b.trace = buf;
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob, skew);
+    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob);
     EDN_CUDA_OK(cudaGetLastError());
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     static const char* names[14] = {"start", "pe+bias", "gather", "w.basis", "e.ft", "w.L1", "e.L1", "w.L2", "e.L2", "w.L3", "e.L3", "w.L4", "e.L4", "composite"};
@@ -516,10 +520,10 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   }
   if (grid_dtype == EDN_BF16) {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob, skew);
+    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
   } else {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, blob, skew);
+    fine_fwd_tc_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
   }
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
