@@ -4,7 +4,7 @@ Python here is the host-side mirror of the reference's operator surface (SURVEY.
 csrc/libevdeblur_b200.so through the C ABI declared in include/evdeblur_b200.h.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .engine import RenderEngine, PackedField  # noqa: F401
+from .engine import NerfRenderEngine, RenderEngine, PackedField  # noqa: F401
 from .renderer import NeRFAll, RigidBlurringModel, build_ray_batch, weighted_sum  # noqa: F401
 from .losses import TonemappingTransform, egm_loss, img2mse, tv_loss_app, edi_prior_image  # noqa: F401
 

@@ -41,7 +41,13 @@ class CrfParams(C.Structure):
         ("extra_features", C.c_int32), ("gamma", C.c_float)]
 
 
+class NerfMlp(C.Structure):
+    _fields_ = [("pts_t", C.c_void_p * 8), ("pts_b", C.c_void_p * 8)] + [(n, C.c_void_p) for n in (
+        "alpha_w", "alpha_b", "feature_t", "feature_b", "views_t", "views_b", "rgb_t", "rgb_b")]
+
+
 CRF_GAMMA, CRF_LEARN, CRF_SKIP_LEARN, CRF_LUMA = 1, 2, 4, 8
+FLAG_WHITE_BKGD = 8
 
 # name -> (restype, argtypes); must list every symbol include/evdeblur_b200.h declares (tests/test_abi.py checks)
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -59,6 +65,9 @@ SIGNATURES = {
     "edn_pack_fine_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P]),
     "edn_render_fine_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _I64,
                                       _I32, _I32, _F, _I32, _P, _P, _P, _P, _P, _P]),
+    "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
+    "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
     "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
     "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),

@@ -227,3 +227,27 @@ extern "C" int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_ml
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }
+
+namespace edn {
+__global__ void place_samples_kernel(const CoarseArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_rays * a.n_samples) return;
+  const int64_t ray = i / a.n_samples;
+  const int s = (int)(i - ray * a.n_samples);
+  a.z_vals[i] = place_sample(a, ray, s, __ldg(a.ray_batch + ray * 11 + 6), __ldg(a.ray_batch + ray * 11 + 7));
+}
+}  // namespace edn
+
+extern "C" int edn_place_samples(const float* ray_batch, const float* t_vals, const float* t_rand, int64_t n_rays, int32_t n_samples,
+                                 int32_t flags, float* z_vals, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(ray_batch && t_vals && z_vals && n_samples >= 1, "edn_place_samples: bad argument");
+  if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
+  CoarseArgs a{};
+  a.ray_batch = ray_batch; a.t_vals = t_vals; a.t_rand = t_rand; a.n_rays = n_rays; a.n_samples = n_samples; a.flags = flags;
+  a.z_vals = z_vals;
+  const int64_t n = n_rays * n_samples;
+  place_samples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}

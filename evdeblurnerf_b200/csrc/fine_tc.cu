@@ -192,18 +192,22 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0
 }
 
 // Layer epilogue over `ncols` (multiple of 64) accumulator columns; ONE copy of the code for all layers (the kernel is
-// instruction-cache sensitive), two tcgen05.ld's in flight per iteration.
+// instruction-cache sensitive).  Software pipelined: the tcgen05.ld of the next 32 columns is in flight while the
+// current 32 are processed.
 __device__ __noinline__ float4 layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int ncols, int mode, uint32_t bias_s,
                                               float* __restrict__ gout, uint32_t wsig, uint32_t wrgb) {
   float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr_row, va);
+  tmem_ld_wait();
 #pragma unroll 1
   for (int col0 = 0; col0 < ncols; col0 += 64) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32(taddr_row + col0, v0);
-    tmem_ld32(taddr_row + col0 + 32, v1);
+    tmem_ld32(taddr_row + col0 + 32, vb);
+    epilogue_block(va, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
     tmem_ld_wait();
-    epilogue_block(v0, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
-    epilogue_block(v1, col0 + 32, mode, a_row, bias_s, gout, wsig, wrgb, head);
+    if (col0 + 64 < ncols) tmem_ld32(taddr_row + col0 + 64, va);
+    epilogue_block(vb, col0 + 32, mode, a_row, bias_s, gout, wsig, wrgb, head);
+    tmem_ld_wait();
   }
   return head;
 }
@@ -277,10 +281,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
 #pragma unroll 1
         for (int step = 0; step < kStepsPerRay; ++step) {
           const StepDesc sd = c_steps[step];
-          if (sd.first) { mbar_wait(&m->bar_a[q], pa); pa ^= 1; }
           if (sd.kind == 2) {
             const int s = g % kNst;
-            mbar_wait(&m->full[q][s], (g / kNst) & 1);
+            mbar_wait(&m->full[q][s], (g / kNst) & 1);       // weights first: they landed long before the rows' A operand
+            if (sd.first) { mbar_wait(&m->bar_a[q], pa); pa ^= 1; }
             tc_fence_after();
             const uint32_t idesc = make_idesc_bf16(128, sd.n);
             const uint32_t kstep_bytes = (uint32_t)sd.n * 32u;
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
             mma_commit(&m->empty[q][s]);
             ++g;
           } else {
+            if (sd.first) { mbar_wait(&m->bar_a[q], pa); pa ^= 1; }
             tc_fence_after();
             const uint32_t idesc = make_idesc_bf16(128, 32);
 #pragma unroll

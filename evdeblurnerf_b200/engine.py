@@ -125,7 +125,16 @@ class PackedField:
         self.mlp.tc_blob = blob.data_ptr()
 
 
-class RenderEngine:
+class SamplerHost:
+    """Shared host pieces of the c2f and nerf-mode renderers: cached linspace vectors, profiling hooks, the sampler."""
+
+    def _init_host(self, device):
+        self.device = torch.device(device if device is not None else "cuda")
+        self._lin = {}
+        self.profile = None     # set to {} to collect (start, end) CUDA events per kernel (bench.py roofline leg)
+
+
+class RenderEngine(SamplerHost):
     """Fused c2f renderer over a reference `NeRFAll.state_dict()`-style parameter dict.
 
     precision: "fp32" -> fp32 SIMT kernels everywhere (parity mode, 1e-4 rel against the reference);
@@ -140,11 +149,9 @@ class RenderEngine:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
         self.precision = precision
         self.prec_code = EDN_F32 if precision == "fp32" else EDN_BF16
-        self.device = torch.device(device if device is not None else "cuda")
+        self._init_host(device)
         self.rmnearplane = float(rmnearplane)
         self.aabb_min, self.aabb_max = [float(x) for x in aabb_min], [float(x) for x in aabb_max]
-        self._lin = {}
-        self.profile = None     # set to {} to collect (start, end) CUDA events per kernel (bench.py roofline leg)
         self.repack(params)
 
     def _launch(self, name, fn):
@@ -308,3 +315,30 @@ class RenderEngine:
         if want_indices:
             ret["inds"], ret["order"], ret["z_samples"] = m["inds"], m["order"], m["z_samples"]
         return ret
+
+
+# the sampler / launch helpers do not depend on the VM fields: share them with the nerf-mode renderer
+SamplerHost._launch = RenderEngine._launch
+SamplerHost._linspace = RenderEngine._linspace
+SamplerHost.sample_pdf_merge = RenderEngine.sample_pdf_merge
+
+
+class NerfRenderEngine(SamplerHost):
+    """mode = nerf renderer over a reference state_dict (mlp_coarse.* / mlp_fine.* = networks/nerf.py::NeRF)."""
+
+    def __init__(self, params, rmnearplane=0, use_awp=False, device=None):
+        from .nerf_mode import NeRF
+        if not torch.cuda.is_available():
+            raise RuntimeError("evdeblurnerf_b200.NerfRenderEngine needs a CUDA device (no CPU fallback)")
+        _lib.load()
+        self._init_host(device)
+        P = {k: (v if v.is_cuda else v.to(self.device)) for k, v in params.items() if isinstance(v, torch.Tensor)}
+        ef = "before_linear" if use_awp else "after_linear"       # renderer.py:88-99
+        self.mlp_coarse = NeRF(P, "mlp_coarse.", ef, rmnearplane)
+        self.mlp_fine = NeRF(P, "mlp_fine.", ef, rmnearplane) if "mlp_fine.pts_linears.0.weight" in P else None
+
+    def render_rays(self, ray_batch, N_samples, **kw):
+        from .nerf_mode import render_rays_nerf
+        kw.pop("pytest", None)
+        kw.pop("want_indices", None)
+        return render_rays_nerf(self, self.mlp_coarse, self.mlp_fine, ray_batch, N_samples, **kw)

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import RbkParams, check, ptr, stream_ptr
-from .engine import RenderEngine
+from .engine import NerfRenderEngine, RenderEngine
 from .losses import tv_loss_app
 
 
@@ -99,17 +99,22 @@ def build_ray_batch(H, W, focal, rays, near=0., far=1., ndc=True):
 
 
 class NeRFAll:
-    """Drop-in for the reference façade (mode = c2f, kernel_type = RBK or none).  `params`: reference state_dict."""
+    """Drop-in for the reference façade (mode = c2f or nerf -- detected from the parameter names --, kernel_type = RBK or
+    none).  `params`: reference state_dict."""
 
     def __init__(self, params, aabb_min, aabb_max, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False):
         if use_awp:
             raise NotImplementedError("kernel_use_awp: the AWP branch (networks/dpnerf/awp.py) is not built yet")
         self.params = {k: v for k, v in params.items() if isinstance(v, torch.Tensor)}
-        self.engine = RenderEngine(self.params, aabb_min, aabb_max, precision=precision, rmnearplane=render_rmnearplane)
+        self.mode = "nerf" if "mlp_coarse.pts_linears.0.weight" in self.params else "c2f"
+        if self.mode == "nerf":
+            self.engine = NerfRenderEngine(self.params, rmnearplane=render_rmnearplane)
+        else:
+            self.engine = RenderEngine(self.params, aabb_min, aabb_max, precision=precision, rmnearplane=render_rmnearplane)
         self.kernelsnet = None
         if "kernelsnet.r_linear.weight" in self.params:
             self.kernelsnet = RigidBlurringModel(self.params, kernel_ptnum - 1)
-        self.mode, self.kernel_type, self.use_awp = "c2f", "RBK", False
+        self.kernel_type, self.use_awp = "RBK", False
         self.training = True
 
     def train(self, mode=True):
@@ -165,7 +170,8 @@ class NeRFAll:
             if N_importance > 0:
                 rgb1_pts = extras["rgb0"].reshape(N, E, 3)
                 rgb1 = weighted_sum(extras["rgb0"], weight1)
-            other_loss["TV"] = self.tv_loss(N_importance > 0)
+            if self.mode == "c2f":
+                other_loss["TV"] = self.tv_loss(N_importance > 0)
             if return_pts0_rgb:
                 other_tensors["stage1_rgb_pts0"] = rgb_pts[:, 0]
                 if N_importance > 0:
@@ -175,7 +181,8 @@ class NeRFAll:
         other_tensors["stage1_rgb_pts0"] = rgb
         if N_importance > 0:
             other_tensors["stage1_rgb1_pts0"] = extras["rgb0"]
-        other_loss["TV"] = self.tv_loss(N_importance > 0)
+        if self.mode == "c2f":
+            other_loss["TV"] = self.tv_loss(N_importance > 0)
         return rgb, extras.get("rgb0"), other_loss, other_tensors
 
     __call__ = forward
@@ -190,7 +197,9 @@ class NeRFAll:
         return rgb, rgb0
 
     def tv_loss(self, with_fine=True):
-        """renderer.py:361-365: (TV_loss_app(coarse) [+ TV_loss_app(fine)]) * 5."""
+        """renderer.py:361-365: (TV_loss_app(coarse) [+ TV_loss_app(fine)]) * 5 (mode = c2f only)."""
+        if self.mode != "c2f":
+            return None
         tv = tv_loss_app(self.params, "mlp_coarse.")
         if with_fine:
             tv = tv + tv_loss_app(self.params, "mlp_fine.")

@@ -34,7 +34,8 @@ enum { EDN_F32 = 0, EDN_BF16 = 1 };
 enum {
   EDN_FLAG_LINDISP = 1,       /* renderer.py:166-167 */
   EDN_FLAG_TRAIN = 2,         /* module.training: disables the rmnearplane mask (voxnerf.py:181) */
-  EDN_FLAG_RELU_RGB = 4       /* CRR coarse field: rgb_activate='relu' on top of the sigmoid (voxnerf.py:266) */
+  EDN_FLAG_RELU_RGB = 4,      /* CRR coarse field: rgb_activate='relu' on top of the sigmoid (voxnerf.py:266) */
+  EDN_FLAG_WHITE_BKGD = 8     /* nerf.py:126-127 */
 };
 
 /* VM-decomposed feature grid of one PDRF field (networks/pdrf/voxnerf.py:99-118, 132-151).
@@ -123,6 +124,35 @@ int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_
                         const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays,
                         int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* weights,
                         float* rgb, float* depth, float* acc, float* feat, void* stream);
+
+/* ---- mode = nerf ("run_network") -------------------------------------------------------------------------------------- */
+
+/* Vanilla NeRF field weights (networks/nerf.py:23-44), TRANSPOSED [in][out] fp32:
+ * pts_t[0] [64][256] (row 63 zero), pts_t[1..4,6,7] [256][256], pts_t[5] [320][256] = rows 0..62 PE part, row 63 zero,
+ * rows 64..319 h part (skip concat [input_pts, h], nerf.py:138-139); alpha_w [256]; feature_t [256][256];
+ * views_t [283][128] (rows 0..255 feature, 256..282 view-dir PE); rgb_t [128][4] (col 3 zero); rgb_b [3] or NULL. */
+typedef struct edn_nerf_mlp {
+  const float* pts_t[8];
+  const float* pts_b[8];
+  const float* alpha_w; const float* alpha_b;
+  const float* feature_t; const float* feature_b;
+  const float* views_t; const float* views_b;
+  const float* rgb_t; const float* rgb_b;
+} edn_nerf_mlp;
+
+/* NeRF.mlpforward + NeRF.eval (nerf.py:46-72, 131-162) at pts = o + d * z_vals: raw [R][S][4] = rgb(3), sigma;
+ * feature [R][S][256] or NULL (h when feature_after_linear = 0, feature_linear output otherwise). */
+int edn_nerf_mlp_fwd(const edn_nerf_mlp* mlp, const float* ray_batch, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                     int32_t feature_after_linear, float* raw, float* feature, void* stream);
+
+/* NeRF.raw2outputs (nerf.py:74-129). flags: EDN_FLAG_TRAIN, EDN_FLAG_WHITE_BKGD. */
+int edn_nerf_raw2outputs(const float* raw, const float* z_vals, const float* ray_batch, const float* noise, int64_t n_rays,
+                         int32_t n_samples, int32_t flags, float rmnearplane, float* weights, float* rgb, float* depth,
+                         float* acc, void* stream);
+
+/* Coarse sample placement alone (renderer.py:163-178), bit-exact: z_vals [R][n_samples]. */
+int edn_place_samples(const float* ray_batch, const float* t_vals, const float* t_rand, int64_t n_rays, int32_t n_samples,
+                      int32_t flags, float* z_vals, void* stream);
 
 /* ---- blur kernel + render() prologue ------------------------------------------------------------------------------ */
 
