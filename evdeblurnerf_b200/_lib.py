@@ -46,6 +46,13 @@ class NerfMlp(C.Structure):
         "alpha_w", "alpha_b", "feature_t", "feature_b", "views_t", "views_b", "rgb_t", "rgb_b")]
 
 
+class AwpParams(C.Structure):
+    _fields_ = [("sample_t", C.c_void_p * 4), ("sample_b", C.c_void_p * 4), ("motion_w", C.c_void_p * 2),
+                ("motion_b", C.c_void_p * 2)] + [(n, C.c_void_p) for n in (
+                    "mam_linear_t", "mam_linear_b", "line_conv_att", "conva", "convb", "convc", "convn", "convl", "convd_w",
+                    "bn_weight", "bn_bias", "w_linear_w", "w_linear_b")]
+
+
 CRF_GAMMA, CRF_LEARN, CRF_SKIP_LEARN, CRF_LUMA = 1, 2, 4, 8
 FLAG_WHITE_BKGD = 8
 
@@ -68,6 +75,8 @@ SIGNATURES = {
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "edn_awp_workspace_floats": (C.c_int64, [_I64, _I32, _I32]),
+    "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
     "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
     "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
     "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import RbkParams, check, ptr, stream_ptr
+from ._lib import AwpParams, RbkParams, check, ptr, stream_ptr
 from .engine import NerfRenderEngine, RenderEngine
 from .losses import tv_loss_app
 
@@ -78,6 +78,63 @@ class RigidBlurringModel:
         return ws(rgb), ws(depth), ws(acc), out_extras
 
 
+class AdaptiveWeightProposal:
+    """networks/dpnerf/awp.py:9-117 + mam.py (D_sam = 4, W_sam = 64, D_mot = 1, W_mot = 32, ray_dir_freq = 2, view latent 32:
+    the values run_nerf.py:203-212 passes for every shipped config).  Forward only, train-mode BatchNorm statistics."""
+
+    ccw_fine_scale = 0.05     # awp.py:22
+
+    def __init__(self, params, num_motion, prefix="awpnet.", bn_eps=1e-5):
+        self.E, self.bn_eps, self.keep = int(num_motion) + 1, float(bn_eps), []
+        p = AwpParams()
+
+        def g(name, transpose=False, shape=None):
+            t = params[prefix + name].detach().to(torch.float32)
+            if not t.is_cuda:
+                raise RuntimeError("AdaptiveWeightProposal parameters must be CUDA tensors")
+            if shape is not None and tuple(t.shape) != shape:
+                raise RuntimeError(f"unsupported shape for {prefix + name}: {tuple(t.shape)} (expected {shape})")
+            t = t.t() if transpose else t
+            t = t.contiguous()
+            self.keep.append(t)
+            return t.data_ptr()
+
+        for l in range(4):
+            p.sample_t[l] = g(f"sample_feature_embed_layer.{l}.weight", True, (64, 128) if l == 0 else (64, 64))
+            p.sample_b[l] = g(f"sample_feature_embed_layer.{l}.bias")
+        if (prefix + "sample_feature_embed_layer.4.weight") in params or (prefix + "motion_feature_embed_layer.2.weight") in params:
+            raise RuntimeError("unsupported AWP depth")
+        p.motion_w[0], p.motion_b[0] = g("motion_feature_embed_layer.0.weight", shape=(32, 111)), g("motion_feature_embed_layer.0.bias")
+        p.motion_w[1], p.motion_b[1] = g("motion_feature_embed_layer.1.weight", shape=(32, 32)), g("motion_feature_embed_layer.1.bias")
+        p.mam_linear_t, p.mam_linear_b = g("MAM.linear.weight", True, (32, 64)), g("MAM.linear.bias")
+        p.line_conv_att = g("MAM.Corr.line_conv_att.weight")
+        for n_, shp in (("conva", (16, 32, 1)), ("convb", (16, 32, 1)), ("convc", (16, 32, 1)), ("convn", (16, 16, 1)), ("convl", (16, 16, 1))):
+            setattr(p, n_, g(f"MAM.Corr.{n_}.weight", shape=shp))
+        p.convd_w = g("MAM.Corr.convd.0.weight", shape=(32, 32, 1))
+        p.bn_weight, p.bn_bias = g("MAM.Corr.convd.1.weight"), g("MAM.Corr.convd.1.bias")
+        p.w_linear_w, p.w_linear_b = g("w_linear.weight", shape=(self.E, 32)), g("w_linear.bias")
+        self.p = p
+
+    def __call__(self, depth_feature, z_vals, rays_d, view_feature):
+        """awp.py:79: depth_feature [N*E,S,128], z_vals [N*E,S], rays_d [N*E,3] (may be a strided view), view_feature [N,32]."""
+        df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
+        NE, S, Fd = df.shape
+        if Fd != 128:
+            raise RuntimeError("AWP: depth_feature must have 128 channels (mode = c2f)")
+        E = self.E
+        N = NE // E
+        rd = rays_d.detach().float()
+        if rd.stride(-1) != 1:
+            rd = rd.contiguous()
+        vf = view_feature.detach().float().contiguous()
+        lib = _lib.load()
+        ws = torch.empty((int(lib.edn_awp_workspace_floats(N, E, S)),), dtype=torch.float32, device=df.device)
+        ccw = torch.empty((N, E), dtype=torch.float32, device=df.device)
+        check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps, ptr(ws),
+                              ptr(ccw), stream_ptr()), "edn_awp_fwd")
+        return ccw
+
+
 def weighted_sum(x, ccw):
     """x [N*E, ...] , ccw [N,E] -> [N, ...]."""
     N, E = ccw.shape
@@ -87,6 +144,12 @@ def weighted_sum(x, ccw):
     check(_lib.load().edn_weighted_sum(ptr(xf), ptr(ccw.detach().float().contiguous()), ptr(out), N, E, Cn, stream_ptr()),
           "edn_weighted_sum")
     return out
+
+
+def normalize_ccw(ccw, scale):
+    """renderer.py:316-317: ccw + ccw * scale, renormalised over the exposures (row-wise, [N,E] is tiny: host tensor ops)."""
+    c = ccw + ccw * scale
+    return c / torch.sum(c, -1, keepdim=True)
 
 
 def build_ray_batch(H, W, focal, rays, near=0., far=1., ndc=True):
@@ -103,8 +166,6 @@ class NeRFAll:
     none).  `params`: reference state_dict."""
 
     def __init__(self, params, aabb_min, aabb_max, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False):
-        if use_awp:
-            raise NotImplementedError("kernel_use_awp: the AWP branch (networks/dpnerf/awp.py) is not built yet")
         self.params = {k: v for k, v in params.items() if isinstance(v, torch.Tensor)}
         self.mode = "nerf" if "mlp_coarse.pts_linears.0.weight" in self.params else "c2f"
         if self.mode == "nerf":
@@ -114,7 +175,10 @@ class NeRFAll:
         self.kernelsnet = None
         if "kernelsnet.r_linear.weight" in self.params:
             self.kernelsnet = RigidBlurringModel(self.params, kernel_ptnum - 1)
-        self.kernel_type, self.use_awp = "RBK", False
+        self.kernel_type, self.use_awp = "RBK", bool(use_awp)
+        self.awpnet = AdaptiveWeightProposal(self.params, kernel_ptnum - 1) if self.use_awp else None
+        if self.use_awp and self.mode != "c2f":
+            raise NotImplementedError("kernel_use_awp with mode = nerf (256-channel depth_feature) is not built")
         self.training = True
 
     def train(self, mode=True):
@@ -165,6 +229,12 @@ class NeRFAll:
             N, E = weight1.shape
             rgb, depth, acc, extras = self._render_batch(k["ray_batch"], (N * E,), **kwargs)
             rgb_pts = rgb.reshape(N, E, 3)
+            if self.use_awp:     # renderer.py:310-330
+                ccw = self.awpnet(extras["depth_feature"], extras["z_vals"], k["ray_batch"][:, 3:6], k["img_embed"])
+                ccw = normalize_ccw(ccw, self.awpnet.ccw_fine_scale)
+                other_tensors["rgb_awp"] = weighted_sum(rgb, ccw)
+                other_tensors["ccw_fine"] = ccw
+                other_tensors["stage1_img_embed"] = k["img_embed"]
             rgb_b = weighted_sum(rgb, weight1)
             rgb1 = None
             if N_importance > 0:

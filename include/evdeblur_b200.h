@@ -184,6 +184,31 @@ int edn_rbk_warp_ndc_fwd(const edn_rbk_params* p, const float* rays, const int64
 int edn_build_ray_batch(const float* rays, int64_t n_rays, int32_t H, int32_t W, float focal, float near, float far,
                         int32_t ndc, float* ray_batch, void* stream);
 
+/* ---- adaptive weight proposal -------------------------------------------------------------------------------------------- */
+
+/* AdaptiveWeightProposal weights (networks/dpnerf/awp.py:37-47, mam.py:13-65), fp32:
+ * sample_t[l] = sample_feature_embed_layer.l.weight TRANSPOSED ([128][64], then [64][64] x3), sample_b[l] [64];
+ * motion_w[l] = motion_feature_embed_layer.l.weight ([32][111], [32][32], nn.Linear layout), motion_b[l] [32];
+ * mam_linear_t = MAM.linear.weight transposed [64][32]; line_conv_att [32]; conva/convb/convc [16][32]; convn/convl [16][16];
+ * convd_w = MAM.Corr.convd.0.weight [32][32]; bn_weight / bn_bias = MAM.Corr.convd.1 [32]; w_linear [E][32] + [E]. */
+typedef struct edn_awp_params {
+  const float* sample_t[4]; const float* sample_b[4];
+  const float* motion_w[2]; const float* motion_b[2];
+  const float* mam_linear_t; const float* mam_linear_b;
+  const float* line_conv_att;
+  const float* conva; const float* convb; const float* convc; const float* convn; const float* convl;
+  const float* convd_w; const float* bn_weight; const float* bn_bias;
+  const float* w_linear_w; const float* w_linear_b;
+} edn_awp_params;
+
+/* AdaptiveWeightProposal.forward (awp.py:79-117) in train mode (BatchNorm1d uses batch statistics, mam.py:24-27):
+ * depth_feature [N*E][S][128], z_vals [N*E][S], rays_d rows of 3 floats with row stride rays_d_stride (e.g. ray_batch + 3,
+ * stride 11), view_feature [N][32] -> ccw [N][E].  workspace: edn_awp_workspace_floats() floats. */
+int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
+int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
+                int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
+                float bn_eps, float* workspace, float* ccw, void* stream);
+
 /* ---- loss path ------------------------------------------------------------------------------------------------------ */
 
 /* rbk_weighted_sum (dpnerf/blurmodel.py:112-127): x [N*E][C], w [N][E] -> out [N][C]. */

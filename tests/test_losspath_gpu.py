@@ -146,3 +146,30 @@ def test_render_path_eval(cuda_params):
     rb = oc.build_ray_batch(Hs, Ws, K[0][0], rays)
     ref = oc.render_rays(P, CFG, rb, 64, 64, is_train=False)
     assert_close(rgbs[0].reshape(-1, 3), ref["rgb_map"], "eval rgb", rtol=1e-4, atol=5e-4)
+
+
+def test_awp_forward_against_oracle(cuda_params):
+    """Row a11: AdaptiveWeightProposal.forward (train-mode BatchNorm) on the oracle's own depth_feature."""
+    from evdeblurnerf_b200.renderer import AdaptiveWeightProposal
+    P, _, Pg, _ = cuda_params
+    g = golden("case1_train48x5")
+    rb = oc.build_ray_batch(H, W, FOCAL, g["new_rays"].reshape(-1, 3, 2))
+    ref = oc.render_rays(P, CFG, rb, 64, 64, want_feature=True)
+    ccw_ref = oc.awp_forward(P, ref["depth_feature"], ref["z_vals"], rb[:, 3:6], g["img_embed"], 5)
+    awp = AdaptiveWeightProposal(Pg, 4)
+    ccw = awp(ref["depth_feature"].cuda(), ref["z_vals"].cuda(), rb.cuda()[:, 3:6], g["img_embed"].cuda())
+    assert_close(ccw, ccw_ref, "ccw", rtol=1e-4, atol=1e-6)
+    assert_close(ccw.sum(-1), torch.ones(48), "rows sum to 1", rtol=1e-5)
+
+
+def test_forward_train_with_awp_golden(cuda_params):
+    from evdeblurnerf_b200 import NeRFAll
+    _, _, Pg, _ = cuda_params
+    g = golden("case1_train48x5")
+    nerf = NeRFAll(Pg, *AABB, kernel_ptnum=5, precision="fp32", use_awp=True).train()
+    rgb, rgb1, other_loss, other = nerf(H, W, KMAT, chunk=32768, rays=g["rays"].cuda(), rays_info={"images_idx": g["images_idx"].cuda()},
+                                        force_naive=False, return_pts0_rgb=True, retraw=True, N_samples=64, N_importance=64,
+                                        perturb=0., raw_noise_std=0.)
+    assert_close(other["ccw_fine"], g["ccw_fine"], "ccw_fine", rtol=2e-4, atol=2e-5)
+    assert_close(other["rgb_awp"], g["rgb_awp"], "rgb_awp", rtol=1e-4, atol=2e-4)
+    assert_close(rgb, g["rgb"], "rgb", rtol=1e-4, atol=2e-4)
