@@ -38,9 +38,14 @@ constexpr int kStageBytes = 16384;
 constexpr int kABytes = 65536;           // per ray: 128 rows x 256 K bf16
 constexpr int kBasisBytes = 2 * 6 * 1024;  // two basis_mat's, 6 K-steps x (N=32 x 16 x 2 B)
 constexpr uint32_t kTmemCols = 512;
-constexpr int kRingStagesPerRay = 20;    // 320 KB / 16 KB
-constexpr int kStepsPerRay = 2 + kRingStagesPerRay;
-constexpr int64_t kBlobBytes = kBasisBytes + (int64_t)kRingStagesPerRay * kStageBytes;
+// Two layer schedules:
+//   full (depth_feature requested, AWP): basis x2 | sigma0 128->256 | sigma1 256->128 (geo) | color0 128->256 | color1 256->256
+//   lean (default): basis_mat folded into sigma_net.0 (K = 96+96+64 = 256) and sigma_net.1(geo) folded into color_net.0
+//        (both are linear maps without an activation in between): 3 layers of 256->256, 3 sync stages instead of 5.
+constexpr int kRingFull = 20, kRingLean = 24;            // 16 KB ring stages per ray
+constexpr int kStepsFull = 2 + kRingFull, kStepsLean = kRingLean;
+constexpr int64_t kOffFull = kBasisBytes, kOffLean = kOffFull + (int64_t)kRingFull * kStageBytes;
+constexpr int64_t kBlobBytes = kOffLean + (int64_t)kRingLean * kStageBytes;
 
 struct StepDesc {
   uint8_t kind;      // 0 = basis coarse tile, 1 = basis fine tile, 2 = ring stage
@@ -50,21 +55,30 @@ struct StepDesc {
   uint8_t first;     // first step of a layer: wait for the rows' A operand
   uint8_t last;      // last step of a layer: commit the accumulator barrier
 };
-__constant__ StepDesc c_steps[kStepsPerRay];
+__constant__ StepDesc c_steps[kStepsFull];
+__constant__ StepDesc c_steps_lean[kStepsLean];
 
-std::vector<StepDesc> build_steps() {
+std::vector<StepDesc> build_steps(bool lean) {
   std::vector<StepDesc> v;
-  v.push_back({0, 6, 32, 0, 1, 0});
-  v.push_back({1, 6, 32, 0, 0, 1});
+  if (!lean) {
+    v.push_back({0, 6, 32, 0, 1, 0});
+    v.push_back({1, 6, 32, 0, 0, 1});
+  }
   auto layer = [&](int K, int N) {
     const int kstep_bytes = N * 32, per_stage = kStageBytes / kstep_bytes, stages = (K / 16) / per_stage;
     for (int s = 0; s < stages; ++s)
       v.push_back({2, (uint8_t)per_stage, (uint16_t)N, (uint16_t)(s * per_stage), (uint8_t)(s == 0), (uint8_t)(s == stages - 1)});
   };
-  layer(128, 256);   // sigma_net.0
-  layer(256, 128);   // sigma_net.1 (geo columns)
-  layer(128, 256);   // color_net.0 (geo part)
-  layer(256, 256);   // color_net.1
+  if (lean) {
+    layer(256, 256);   // [g_coarse | g_fine | PE] -> sigma_net.0 with basis_mat folded in
+    layer(256, 256);   // color_net.0(geo part) o sigma_net.1(geo columns)
+    layer(256, 256);   // color_net.1
+  } else {
+    layer(128, 256);   // sigma_net.0
+    layer(256, 128);   // sigma_net.1 (geo columns)
+    layer(128, 256);   // color_net.0 (geo part)
+    layer(256, 256);   // color_net.1
+  }
   return v;
 }
 
@@ -95,7 +109,7 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 // fine tile -> 28..31,0..7.
 template <typename T>
 __device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As, const float* z_s, int gwarp, int lane,
-                                             const float o[3], const float d[3]) {
+                                             const float o[3], const float d[3], const bool lean) {
   const int q = lane >> 3;
 #pragma unroll 1
   for (int itg = 0; itg < 8; ++itg) {
@@ -125,9 +139,11 @@ __device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As
       line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
       t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
     }
-    const int c0 = fine_tile ? 28 + q : 16 + q;            // channel chunk q
-    const int c1 = fine_tile ? q : 20 + q;                 // channel chunk q + 4
-    const int c2 = fine_tile ? 4 + q : 24 + q;             // channel chunk 8 + q
+    // A-buffer chunk of channel chunk cc: lean: coarse cc, fine 12 + cc; full: coarse 16 + cc, fine 28..31,0..7
+    const int base = lean ? (fine_tile ? 12 : 0) : (fine_tile ? 28 : 16);
+    const int c0 = (base + q) & 31;                        // channel chunk q
+    const int c1 = (base + 4 + q) & 31;                    // channel chunk q + 4
+    const int c2 = (base + 8 + q) & 31;                    // channel chunk 8 + q
     t0.finish(row + c0 * kChunkA);
     t1.finish(row + c1 * kChunkA);
     t2.finish(row + c2 * kChunkA);
@@ -218,8 +234,10 @@ __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
   mbar_arrive(bar_a);
 }
 
-template <typename T>
+template <typename T, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
+  constexpr int kRingStagesPerRay = LEAN ? kRingLean : kRingFull;
+  constexpr int kStepsPerRay = LEAN ? kStepsLean : kStepsFull;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB]
   uint8_t* Ws = smem + 2 * kABytes;                     // ring
@@ -255,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     // =================================== weight-stream producer warp of ray group q ==================================
     const int q = warp - (kRowWarps + 2);
     if (lane == 0 && n_my > 0) {
-      const uint8_t* stream = blob + kBasisBytes;
-      if (q == 0) { mbar_expect_tx(&m->bar_basis, kBasisBytes); bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis); }
+      const uint8_t* stream = blob + (LEAN ? kOffLean : kOffFull);
+      if (q == 0 && !LEAN) { mbar_expect_tx(&m->bar_basis, kBasisBytes); bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis); }
       uint8_t* ring = Ws + q * kNst * kStageBytes;
       const uint32_t total_ring = (uint32_t)n_my * kRingStagesPerRay;
       for (uint32_t g = 0; g < total_ring; ++g) {
@@ -276,11 +294,11 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       const uint32_t d_tmem = tmem + q * 256;
       const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
       uint32_t pa = 0, g = 0;
-      mbar_wait(&m->bar_basis, 0);
+      if (!LEAN) mbar_wait(&m->bar_basis, 0);
       for (int64_t it = 0; it < n_my; ++it) {
 #pragma unroll 1
         for (int step = 0; step < kStepsPerRay; ++step) {
-          const StepDesc sd = c_steps[step];
+          const StepDesc sd = LEAN ? c_steps_lean[step] : c_steps[step];
           if (sd.kind == 2) {
             const int s = g % kNst;
             mbar_wait(&m->full[q][s], (g / kNst) & 1);       // weights first: they landed long before the rows' A operand
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         pe[63] = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          st_shared_v4(a_row + (8 + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
+          st_shared_v4(a_row + ((LEAN ? 24 : 8) + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
                        pack_bf16x2(pe[8 * j + 4], pe[8 * j + 5]), pack_bf16x2(pe[8 * j + 6], pe[8 * j + 7]));
       }
       {  // ---- per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir), fp32 ------------------------------------
@@ -394,27 +412,31 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       named_bar_sync(bar_id, kGroupThreads);      // z[] (and bias[]) visible to the whole group
       stamp(it, 1);
       // ---- VM gather of both grids -> two 128 x 96 bf16 tiles ----------------------------------------------------------
-      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d);
+      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN);
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 2);
-      // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ------------------------------------------------
-      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
-      stamp(it, 3);
-      layer_epilogue(taddr_row, a_row, 64, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
-      rows_signal_a(&m->bar_a[q]);
-      stamp(it, 4);
+      if (!LEAN) {
+        // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ----------------------------------------------
+        mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+        stamp(it, 3);
+        layer_epilogue(taddr_row, a_row, 64, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
+        rows_signal_a(&m->bar_a[q]);
+        stamp(it, 4);
+      }
       // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0) -------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 5);
       const float sig_raw = layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb).x;
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 6);
-      // ---- sigma_net.1 -> geo (128, linear) ------------------------------------------------------------------------------
-      mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
-      stamp(it, 7);
-      layer_epilogue(taddr_row, a_row, 128, kEpiPlain, 0u,
-                     (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, s_wsig, s_wrgb);
-      rows_signal_a(&m->bar_a[q]);
+      if (!LEAN) {
+        // ---- sigma_net.1 -> geo (128, linear) ----------------------------------------------------------------------------
+        mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
+        stamp(it, 7);
+        layer_epilogue(taddr_row, a_row, 128, kEpiPlain, 0u,
+                       (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, s_wsig, s_wrgb);
+        rows_signal_a(&m->bar_a[q]);
+      }
       if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 8);
       // ---- color_net.0 (+ per-ray view-dir bias) -> ReLU ------------------------------------------------------------------
@@ -485,12 +507,32 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
 int ensure_schedule() {
   static bool uploaded = false;
   if (!uploaded) {
-    std::vector<StepDesc> v = build_steps();
-    if ((int)v.size() != kStepsPerRay) { set_error("fine_tc: schedule size mismatch (%d)", (int)v.size()); return EDN_E_INVALID; }
+    std::vector<StepDesc> v = build_steps(false), vl = build_steps(true);
+    if ((int)v.size() != kStepsFull || (int)vl.size() != kStepsLean) { set_error("fine_tc: schedule size mismatch"); return EDN_E_INVALID; }
     EDN_CUDA_OK(cudaMemcpyToSymbol(c_steps, v.data(), sizeof(StepDesc) * v.size()));
+    EDN_CUDA_OK(cudaMemcpyToSymbol(c_steps_lean, vl.data(), sizeof(StepDesc) * vl.size()));
     uploaded = true;
   }
   return 0;
+}
+
+// C[M][N] = A[M][K] . B[K][N] (row-major fp32, leading dimensions lda / ldb / ldc): weight folding at pack time only
+__global__ void fold_matmul_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ Cm, int ldc,
+                                   int M, int K, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int mi = i / N, ni = i - mi * N;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(A[(size_t)mi * lda + k], B[(size_t)k * ldb + ni], acc);
+  Cm[(size_t)mi * ldc + ni] = acc;
+}
+
+template <typename T, bool LEAN>
+int launch_variant(const FineArgs& a, const uint8_t* blob, unsigned gx, cudaStream_t st) {
+  EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<T, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  fine_fwd_tc_kernel<T, LEAN><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
 }
 
 }  // namespace
@@ -503,6 +545,8 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   const int64_t n_pairs = (a.n_rays + 1) / 2;
   const unsigned gx = (unsigned)(n_pairs < (int64_t)num_sms() ? n_pairs : (int64_t)num_sms());
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
+  const char* fv = getenv("EDN_TC_FULL");                       // dev switch: force the unfolded schedule
+  const bool lean = (a.feat == nullptr) && !(fv && fv[0] == '1');   // depth_feature (geo) only exists in the full schedule
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;
@@ -510,52 +554,61 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
     EDN_CUDA_OK(cudaMallocManaged(&buf, 8 * 16 * sizeof(long long)));
     memset(buf, 0, 8 * 16 * sizeof(long long));
     b.trace = buf;
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(b, blob);
-    EDN_CUDA_OK(cudaGetLastError());
+    rc = lean ? launch_variant<__nv_bfloat16, true>(b, blob, gx, st) : launch_variant<__nv_bfloat16, false>(b, blob, gx, st);
+    if (rc) return rc;
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     static const char* names[14] = {"start", "pe+bias", "gather", "w.basis", "e.ft", "w.L1", "e.L1", "w.L2", "e.L2", "w.L3", "e.L3", "w.L4", "e.L4", "composite"};
     for (int i = 0; i < 8; ++i) {
-      fprintf(stderr, "[trace it=%d q=%d] t0=%lld :", 8 + i / 2, i % 2, buf[i * 16] - buf[0]);
-      for (int k = 1; k < 14; ++k) fprintf(stderr, " %s=%lld", names[k], buf[i * 16 + k] - buf[i * 16 + k - 1]);
+      fprintf(stderr, "[trace %s it=%d q=%d] t0=%lld :", lean ? "lean" : "full", 8 + i / 2, i % 2, buf[i * 16] - buf[0]);
+      long long prev = buf[i * 16];
+      for (int k = 1; k < 14; ++k) {
+        if (buf[i * 16 + k] == 0) continue;
+        fprintf(stderr, " %s=%lld", names[k], buf[i * 16 + k] - prev);
+        prev = buf[i * 16 + k];
+      }
       fprintf(stderr, "\n");
     }
     cudaFree(buf);
     return EDN_OK;
   }
-  if (grid_dtype == EDN_BF16) {
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
-  } else {
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
-  }
-  EDN_CUDA_OK(cudaGetLastError());
-  return EDN_OK;
+  if (grid_dtype == EDN_BF16)
+    return lean ? launch_variant<__nv_bfloat16, true>(a, blob, gx, st) : launch_variant<__nv_bfloat16, false>(a, blob, gx, st);
+  return lean ? launch_variant<float, true>(a, blob, gx, st) : launch_variant<float, false>(a, blob, gx, st);
 }
 
 }  // namespace edn
 
 extern "C" int64_t edn_fine_tc_blob_bytes(void) { return edn::kBlobBytes; }
 
-extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, void* blob,
-                                void* stream) {
+extern "C" int64_t edn_fine_tc_pack_workspace_floats(void) { return 2 * 256 * 256; }
+
+extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, float* workspace,
+                                void* blob, void* stream) {
   using namespace edn;
-  EDN_REQUIRE(mlp && basis_t_coarse && basis_t_fine && blob, "edn_pack_fine_tc: null pointer");
+  EDN_REQUIRE(mlp && basis_t_coarse && basis_t_fine && blob && workspace, "edn_pack_fine_tc: null pointer");
   EDN_REQUIRE(mlp->hidden == 256 && mlp->geo_feat == 128 && mlp->sigma0_t && mlp->sigma1_t && mlp->sigma1_v && mlp->color0_t &&
               mlp->color1_t && mlp->color2_t, "edn_pack_fine_tc: needs the fine field (hidden=256, geo_feat=128)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* b = reinterpret_cast<uint8_t*>(blob);
-  // blob = [basis coarse 6 KB][basis fine 6 KB][sigma0 64 KB][sigma1(geo) 64 KB][color0(geo rows) 64 KB][color1 128 KB]
+  // ---- folded layers of the lean schedule (fp32 products, rounded to bf16 once by the packer) -------------------------
+  float* f1 = workspace;              // [256][256]: rows 0..95 basis_c . sigma0[0:32], 96..191 basis_f . sigma0[32:64], 192..255 sigma0[64:128]
+  float* f23 = workspace + 256 * 256; // [256][256] = sigma1(geo) [256][128] . color0(geo rows) [128][256]
+  fold_matmul_kernel<<<(96 * 256 + 255) / 256, 256, 0, st>>>(basis_t_coarse, 32, mlp->sigma0_t, 256, f1, 256, 96, 32, 256);
+  fold_matmul_kernel<<<(96 * 256 + 255) / 256, 256, 0, st>>>(basis_t_fine, 32, mlp->sigma0_t + 32 * 256, 256, f1 + 96 * 256, 256, 96, 32, 256);
+  EDN_CUDA_OK(cudaMemcpyAsync(f1 + 192 * 256, mlp->sigma0_t + 64 * 256, sizeof(float) * 64 * 256, cudaMemcpyDeviceToDevice, st));
+  fold_matmul_kernel<<<(256 * 256 + 255) / 256, 256, 0, st>>>(mlp->sigma1_t, 128, mlp->color0_t, 256, f23, 256, 256, 128, 256);
+  // blob = [basis coarse 6 KB][basis fine 6 KB] | full: [sigma0 64 KB][sigma1(geo) 64 KB][color0(geo rows) 64 KB][color1 128 KB]
+  //        | lean: [fold1 128 KB][fold23 128 KB][color1 128 KB]
   struct Src { const float* wt; int ld, kv, nv, K, N; };
-  const Src src[6] = {{basis_t_coarse, 32, 96, 32, 96, 32}, {basis_t_fine, 32, 96, 32, 96, 32},
+  const Src src[9] = {{basis_t_coarse, 32, 96, 32, 96, 32}, {basis_t_fine, 32, 96, 32, 96, 32},
                       {mlp->sigma0_t, 256, 128, 256, 128, 256}, {mlp->sigma1_t, 128, 256, 128, 256, 128},
-                      {mlp->color0_t, 256, 128, 256, 128, 256}, {mlp->color1_t, 256, 256, 256, 256, 256}};
+                      {mlp->color0_t, 256, 128, 256, 128, 256}, {mlp->color1_t, 256, 256, 256, 256, 256},
+                      {f1, 256, 256, 256, 256, 256}, {f23, 256, 256, 256, 256, 256}, {mlp->color1_t, 256, 256, 256, 256, 256}};
   size_t off = 0;
-  for (int L = 0; L < 6; ++L) {
+  for (int L = 0; L < 9; ++L) {
     const int total = src[L].K * src[L].N;
     tc::pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].K, src[L].N, 0,
-                                                           reinterpret_cast<__nv_bfloat16*>(b + off));
+                                                               reinterpret_cast<__nv_bfloat16*>(b + off));
     off += (size_t)total * 2;
   }
   EDN_REQUIRE((int64_t)off == kBlobBytes, "edn_pack_fine_tc: blob size mismatch");

@@ -119,8 +119,9 @@ class PackedField:
         else:
             n = int(lib.edn_fine_tc_blob_bytes())
             blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
-            check(lib.edn_pack_fine_tc(C.byref(self.mlp), ptr(coarse_field.basis_t), ptr(self.basis_t), ptr(blob), stream_ptr()),
-                  "edn_pack_fine_tc")
+            ws = torch.empty((int(lib.edn_fine_tc_pack_workspace_floats()),), dtype=torch.float32, device=self.basis_t.device)
+            check(lib.edn_pack_fine_tc(C.byref(self.mlp), ptr(coarse_field.basis_t), ptr(self.basis_t), ptr(ws), ptr(blob),
+                                       stream_ptr()), "edn_pack_fine_tc")
         self.keep.append(blob)
         self.mlp.tc_blob = blob.data_ptr()
 

@@ -111,10 +111,13 @@ int edn_sample_pdf_merge(const float* z_vals0, const float* weights0, const floa
                          float* z_vals, int64_t* order, float* z_std, void* stream);
 
 /* Size in bytes of the tensor-core operand blob of the fine field, and its packer: every K=16 slice of every layer
- * (and of the two basis_mat's) as a bf16 UMMA K-major core-matrix tile, in the order the fine kernel streams them. */
+ * (and of the two basis_mat's) as a bf16 UMMA K-major core-matrix tile, in the order the fine kernel streams them -- for
+ * both schedules: "full" (layer by layer, emits depth_feature) and "lean" (basis_mat folded into sigma_net.0 and
+ * sigma_net.1's geo columns folded into color_net.0: linear maps composed in fp32 at pack time). */
 int64_t edn_fine_tc_blob_bytes(void);
-int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, void* blob,
-                     void* stream);
+int64_t edn_fine_tc_pack_workspace_floats(void);
+int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, float* workspace,
+                     void* blob, void* stream);
 
 /* Fine pass of render_rays (renderer.py:190-217): VM lookup of both grids at the merged samples, PE, FVR field,
  * compositing.  precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path.

@@ -71,6 +71,21 @@ def test_tc_fine_matches_emulated_reference(engines):
         assert_close(out[k], fin[k], "fp32 " + k, rtol=0, atol=ORACLE_ATOL)
 
 
+def test_tc_fine_lean_schedule_matches_emulated_reference(engines):
+    """Default (no depth_feature) path: basis_mat / sigma_net.1 folded into the neighbouring layers at pack time."""
+    P, eng, _ = engines
+    rays, _ = synthetic_rays(150, seed=34)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays)
+    out = eng.render_rays(rb.cuda(), 64, retraw=True, N_importance=64)
+    z = out["z_vals"].cpu()
+    emu = emulated_bf16_fine(P, rb, z, lean=True)
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
+    fin = oracle_fine_at(P, rb, z)
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(out[k], fin[k], "fp32 " + k, rtol=0, atol=ORACLE_ATOL)
+
+
 def test_tc_noise_and_eval_mask(engines):
     P, _, _ = engines
     from evdeblurnerf_b200 import RenderEngine
@@ -82,7 +97,7 @@ def test_tc_noise_and_eval_mask(engines):
             "noise0": torch.randn(40, 63, generator=g), "noise1": torch.randn(40, 127, generator=g)}
     out = eng.render_rays(rb.cuda(), 64, retraw=True, N_importance=64, perturb=1., raw_noise_std=1.,
                           rand={k: v.cuda() for k, v in rand.items()}, is_train=False)
-    emu = emulated_bf16_fine(P, rb, out["z_vals"].cpu(), noise=rand["noise1"], is_train=False, rmnearplane=40)
+    emu = emulated_bf16_fine(P, rb, out["z_vals"].cpu(), noise=rand["noise1"], is_train=False, rmnearplane=40, lean=True)
     for k in ("weights", "rgb_map", "depth_map", "acc_map"):
         assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
 
@@ -95,7 +110,7 @@ def test_tc_ragged_sample_counts(nc, ni, R):
     rays, _ = synthetic_rays(R, seed=nc + ni)
     rb = oc.build_ray_batch(H, W, FOCAL, rays)
     out = eng.render_rays(rb.cuda(), nc, retraw=True, N_importance=ni)
-    emu = emulated_bf16_fine(P, rb, out["z_vals"].cpu())
+    emu = emulated_bf16_fine(P, rb, out["z_vals"].cpu(), lean=True)
     for k in ("weights", "rgb_map", "depth_map", "acc_map"):
         assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
 
@@ -119,6 +134,6 @@ def test_tc_full_size_properties():
     # the bf16 coarse pass shares the fp32 coarse kernel only through bf16 planes, so compare image-level statistics
     err = (out["rgb_map"] - ref["rgb_map"]).abs()
     assert float(err.mean()) < 1e-2 and float(err.max()) < 0.15
-    emu = emulated_bf16_fine(P, rb[:48].cpu(), z[:48].cpu())
+    emu = emulated_bf16_fine(P, rb[:48].cpu(), z[:48].cpu(), lean=True)
     for k in ("weights", "rgb_map"):
         assert_close(out[k][:48], emu[k], k, rtol=0, atol=EMU_ATOL)

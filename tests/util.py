@@ -92,7 +92,7 @@ def _bf(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearplane=0):
+def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearplane=0, lean=False):
     """Torch fp32 reference of the tcgen05 fine pass with its operand roundings made explicit: VM planes, the
     plane (.) line products, every MMA A operand (features, PE, activations) and every MMA weight matrix are rounded to
     bf16; accumulation, biases, the sigma / rgb heads (fp32 dot products in the epilogues), sigmoid and compositing stay fp32.  The view-direction part of color_net.0 is an
@@ -103,20 +103,29 @@ def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearpla
     R, S = z_all.shape
     pts = o[:, None, :] + d[:, None, :] * z_all[..., None]
     Pb = {k: (_bf(v) if ("app_plane" in k or "app_line" in k) else v) for k, v in P.items()}
-    fts = []
+    fts, gs = [], []
     for pre in ("mlp_coarse.", "mlp_fine."):
         g = _bf(oc.vm_products(Pb, pre, pts, *AABB))
+        gs.append(g)
         fts.append(_bf(F.linear(g, _bf(P[pre + "basis_mat.weight"]))))
-    x = torch.cat(fts + [_bf(oc.posenc(pts.reshape(-1, 3), 10))], -1)
+    pe = _bf(oc.posenc(pts.reshape(-1, 3), 10))
     pre = "mlp_fine."
-    h1_f32 = torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"])))
+    w0 = P[pre + "sigma_net.0.weight"]
+    if lean:   # "lean" schedule: basis_mat folded into sigma_net.0 in fp32, the product rounded to bf16 once
+        w0f = torch.cat([w0[:, :32] @ P["mlp_coarse.basis_mat.weight"], w0[:, 32:64] @ P["mlp_fine.basis_mat.weight"], w0[:, 64:]], 1)
+        h1_f32 = torch.relu(F.linear(torch.cat(gs + [pe], -1), _bf(w0f)))
+    else:
+        h1_f32 = torch.relu(F.linear(torch.cat(fts + [pe], -1), _bf(w0)))
     h1 = _bf(h1_f32)
     w1 = P[pre + "sigma_net.1.weight"]
     sigma = F.linear(h1_f32, w1[:1])            # sigma head: fp32 dot product in the layer epilogue
     geo = F.linear(h1, _bf(w1[1:]))
     w3 = P[pre + "color_net.0.weight"]
     bias_ray = F.linear(oc.posenc(vd, 4), w3[:, 128:], P.get(pre + "color_net.0.bias"))          # [R,256] fp32
-    h3 = F.linear(_bf(geo), _bf(w3[:, :128])) + bias_ray[:, None, :].expand(R, S, 256).reshape(R * S, 256)
+    if lean:   # sigma_net.1 (geo columns) folded into color_net.0
+        h3 = F.linear(h1, _bf(w3[:, :128] @ w1[1:])) + bias_ray[:, None, :].expand(R, S, 256).reshape(R * S, 256)
+    else:
+        h3 = F.linear(_bf(geo), _bf(w3[:, :128])) + bias_ray[:, None, :].expand(R, S, 256).reshape(R * S, 256)
     h3 = _bf(torch.relu(h3))
     h4 = torch.relu(F.linear(h3, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias")))
     rgb = torch.sigmoid(F.linear(h4, P[pre + "color_net.2.weight"], P.get(pre + "color_net.2.bias")))   # fp32 rgb head
