@@ -83,6 +83,7 @@ std::vector<StepDesc> build_steps(bool lean) {
 }
 
 struct alignas(16) GroupMisc {
+  float tcarry, pad_[3];
   float z[kGroupThreads];
   alignas(16) float bias[256];
   float red[4][8];
@@ -268,6 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   const int64_t n_pairs_total = (a.n_rays + 1) / 2;
   const int64_t n_my = (n_pairs_total > (int64_t)blockIdx.x) ? (n_pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int S = a.S;
+  const int tpr = (S + kGroupThreads - 1) / kGroupThreads;   // 128-row tiles per ray (rays longer than 128 samples span several)
+  const int64_t n_it = n_my * tpr;
 
   if (warp >= kRowWarps + 2) {
     // =================================== weight-stream producer warp of ray group q ==================================
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       const uint8_t* stream = blob + (LEAN ? kOffLean : kOffFull);
       if (q == 0 && !LEAN) { mbar_expect_tx(&m->bar_basis, kBasisBytes); bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis); }
       uint8_t* ring = Ws + q * kNst * kStageBytes;
-      const uint32_t total_ring = (uint32_t)n_my * kRingStagesPerRay;
+      const uint32_t total_ring = (uint32_t)n_it * kRingStagesPerRay;
       for (uint32_t g = 0; g < total_ring; ++g) {
         const int s = g % kNst;
         const uint32_t use = g / kNst;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
       uint32_t pa = 0, g = 0;
       if (!LEAN) mbar_wait(&m->bar_basis, 0);
-      for (int64_t it = 0; it < n_my; ++it) {
+      for (int64_t it = 0; it < n_it; ++it) {
 #pragma unroll 1
         for (int step = 0; step < kStepsPerRay; ++step) {
           const StepDesc sd = LEAN ? c_steps_lean[step] : c_steps[step];
@@ -351,16 +354,21 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     auto stamp = [&](int64_t it, int k) {
       if (a.trace && blockIdx.x == 0 && r == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
     };
-    for (int64_t it = 0; it < n_my; ++it) {
+    float run_sum = 0.f;                    // thread r < 5: running ray sum (rgb, depth, acc) across the tiles of a ray
+    int tile = -1;
+    int64_t ray_raw = 2 * (int64_t)blockIdx.x + q - 2 * (int64_t)gridDim.x;
+    for (int64_t it = 0; it < n_it; ++it) {
       stamp(it, 0);
-      const int64_t ray_raw = 2 * ((int64_t)blockIdx.x + it * gridDim.x) + q;
+      if (++tile == tpr || it == 0) { tile = 0; ray_raw += 2 * (int64_t)gridDim.x; }
+      const int rg = tile * kGroupThreads + r;          // sample index of this row within the ray
       const bool live = ray_raw < a.n_rays;             // odd ray count: the last pair's second ray is a masked duplicate
       const int64_t ray = live ? ray_raw : a.n_rays - 1;
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
-      const float zv = a.z_vals[ray * S + min(r, S - 1)];
+      const float zv = a.z_vals[ray * S + min(rg, S - 1)];
       gm->z[r] = zv;
+      if (tile == 0 && r == 0) gm->tcarry = 1.0f;
       {  // ---- PE(pts) -> A columns 64..127 (chunks 8..15); column 127 is the zero pad of K = 127 -> 128 -------------
         // sin/cos of the base frequency by range-reduced MUFU, higher octaves by the double-angle recurrence
         // (abs error <= 2^9 * 1e-7, far below the bf16 resolution of the MMA operand)
@@ -434,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 7);
         layer_epilogue(taddr_row, a_row, 128, kEpiPlain, 0u,
-                       (a.feat && live && r < S) ? a.feat + ((size_t)ray * S + r) * 128 : nullptr, s_wsig, s_wrgb);
+                       (a.feat && live && rg < S) ? a.feat + ((size_t)ray * S + rg) * 128 : nullptr, s_wsig, s_wrgb);
         rows_signal_a(&m->bar_a[q]);
       }
       if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
@@ -455,16 +463,16 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       stamp(it, 12);
       // ---- compositing (voxnerf.py:153-201) -----------------------------------------------------------------------------------
       float alpha = 0.f;
-      if (r < S - 1) {
+      if (rg < S - 1) {
         const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-        const float znext = gm->z[r + 1];
+        const float znext = (r + 1 < kGroupThreads) ? gm->z[r + 1] : a.z_vals[ray * S + rg + 1];
         const float dist = __fmul_rn(znext - zv, dnorm);
         float sg = sig_raw;
-        if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + r);
+        if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + rg);
         sg = fmaxf(sg, 0.f);
         if (mask_near && !(znext > near_thr)) sg = 0.f;
         alpha = 1.0f - expf(-__fmul_rn(sg, dist));
-      } else if (r == S - 1) {
+      } else if (rg == S - 1) {
         alpha = 1.0f;
       }
       float t = 1.0f - alpha;                 // inclusive product scan of (1 - alpha) over the warp
@@ -477,9 +485,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       if (lane == 0) Tr = 1.0f;
       if (lane == 31) gm->wtot[gwarp] = t;
       named_bar_sync(bar_id, kGroupThreads);
+      Tr *= gm->tcarry;                       // transmittance accumulated over the previous tiles of this ray
       for (int w2 = 0; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
       const float wgt = alpha * Tr;
-      if (live && r < S) a.weights[ray * S + r] = wgt;
+      if (live && rg < S) a.weights[ray * S + rg] = wgt;
       float red[5] = {wgt * col[0], wgt * col[1], wgt * col[2], wgt * zv, wgt};
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -491,10 +500,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
       }
       named_bar_sync(bar_id, kGroupThreads);
-      if (live && r < 5) {
-        const float v = gm->red[0][r] + gm->red[1][r] + gm->red[2][r] + gm->red[3][r];
-        if (r < 3) a.rgb[ray * 3 + r] = v; else if (r == 3) a.depth[ray] = v; else a.acc[ray] = v;
+      if (r < 5) {
+        if (tile == 0) run_sum = 0.f;
+        run_sum += gm->red[0][r] + gm->red[1][r] + gm->red[2][r] + gm->red[3][r];
+        if (live && tile == tpr - 1) {
+          if (r < 3) a.rgb[ray * 3 + r] = run_sum; else if (r == 3) a.depth[ray] = run_sum; else a.acc[ray] = run_sum;
+        }
       }
+      if (r == 5) gm->tcarry = gm->tcarry * gm->wtot[0] * gm->wtot[1] * gm->wtot[2] * gm->wtot[3];
       named_bar_sync(bar_id, kGroupThreads);      // red[] / wtot[] / z[] free for the next ray
       stamp(it, 13);
     }
@@ -538,7 +551,7 @@ int launch_variant(const FineArgs& a, const uint8_t* blob, unsigned gx, cudaStre
 }  // namespace
 
 int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
-  EDN_REQUIRE(a.S >= 2 && a.S <= kGroupThreads, "edn_render_fine_fwd(bf16): n_samples must be in [2,128], got %d", a.S);
+  EDN_REQUIRE(a.S >= 2, "edn_render_fine_fwd(bf16): n_samples must be >= 2, got %d", a.S);
   EDN_REQUIRE(a.mlp.tc_blob != nullptr, "edn_render_fine_fwd(bf16): edn_field_mlp.tc_blob is NULL (call edn_pack_fine_tc)");
   int rc = ensure_schedule();
   if (rc) return rc;

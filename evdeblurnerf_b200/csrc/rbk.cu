@@ -188,8 +188,9 @@ extern "C" int edn_rbk_warp_ndc_fwd(const edn_rbk_params* p, const float* rays, 
   EDN_REQUIRE(p && rays && images_idx && weight, "edn_rbk_warp_ndc_fwd: null pointer");
   EDN_REQUIRE(p->num_motion >= 0 && p->num_motion < kMaxE, "edn_rbk_warp_ndc_fwd: num_motion must be in [0,%d)", kMaxE);
   EDN_REQUIRE(p->img_embed && p->r_branch_w && p->r_branch_b && p->v_branch_w && p->v_branch_b && p->w_branch_w && p->w_branch_b &&
-              p->r_linear_w && p->r_linear_b && p->v_linear_w && p->v_linear_b && p->w_linear_w && p->w_linear_b,
-              "edn_rbk_warp_ndc_fwd: null kernel-net weight");
+              p->w_linear_w && p->w_linear_b, "edn_rbk_warp_ndc_fwd: null kernel-net weight");
+  EDN_REQUIRE(p->num_motion == 0 || (p->r_linear_w && p->r_linear_b && p->v_linear_w && p->v_linear_b),
+              "edn_rbk_warp_ndc_fwd: null r/v head weight");
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
   RbkArgs a{*p, rays, images_idx, n_rays, H, W, focal, near, far, ndc, new_rays, weight, img_embed, ray_batch};
   const int M = p->num_motion, E = M + 1;

@@ -195,6 +195,10 @@ class RenderEngine(SamplerHost):
             ret["z_vals"] = torch.empty((0, S), **f32)
         return ret
 
+    def _fine_precision(self, n_total):
+        # the tensor-core fine kernel maps a ray to ceil(S / 128) UMMA M tiles (e.g. 96 + 96 samples = 128 + 64 rows)
+        return self.prec_code
+
     def _coarse_precision(self, n_samples):
         # the tensor-core coarse kernel tiles 128 rows = floor(128 / n_samples) rays; other sample counts use the SIMT kernel
         return EDN_BF16 if (self.prec_code == EDN_BF16 and 32 <= n_samples <= 128) else EDN_F32
@@ -303,7 +307,7 @@ class RenderEngine(SamplerHost):
         feat1 = torch.empty((R, S, 128), **f32) if want_feat else None
         check(self._launch("fine", lambda: lib.edn_render_fine_fwd(
             C.byref(self.coarse.grid), C.byref(self.fine.grid), C.byref(self.fine.mlp), ptr(rb), ptr(m["z_vals"]),
-            ptr(noise1), R, S, flags, self.rmnearplane, self.prec_code, ptr(w1), ptr(rgb1), ptr(depth1), ptr(acc1),
+            ptr(noise1), R, S, flags, self.rmnearplane, self._fine_precision(S), ptr(w1), ptr(rgb1), ptr(depth1), ptr(acc1),
             ptr(feat1), stream_ptr())), "edn_render_fine_fwd")
         ret = {"rgb_map": rgb1, "depth_map": depth1, "acc_map": acc1}
         if retraw:

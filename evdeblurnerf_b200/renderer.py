@@ -260,6 +260,9 @@ class NeRFAll:
     def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):
         """The render part of the training forward (renderer.py:303-343 without the loss terms): blur-kernel warp ->
         NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum.  Returns (rgb [N,3], rgb0 [N,3] | None)."""
+        if self.kernelsnet is None:           # kernel_type = none: one exposure per ray, no blending
+            out = self.render_rays(build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc), **kwargs)
+            return out["rgb_map"], out.get("rgb0")
         k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, images_idx, near, far, ndc, want_new_rays=False)
         out = self.render_rays(k["ray_batch"], **kwargs)
         rgb = weighted_sum(out["rgb_map"], k["weight"])

@@ -102,7 +102,7 @@ def test_tc_noise_and_eval_mask(engines):
         assert_close(out[k], emu[k], k, rtol=0, atol=EMU_ATOL)
 
 
-@pytest.mark.parametrize("nc,ni,R", [(32, 32, 37), (64, 17, 9), (64, 64, 1)])
+@pytest.mark.parametrize("nc,ni,R", [(32, 32, 37), (64, 17, 9), (64, 64, 1), (96, 96, 21), (128, 128, 5), (64, 70, 4)])
 def test_tc_ragged_sample_counts(nc, ni, R):
     from evdeblurnerf_b200 import RenderEngine
     P = random_params(9)
