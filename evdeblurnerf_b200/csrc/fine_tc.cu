@@ -3,15 +3,16 @@
 //
 // One persistent CTA per SM renders TWO rays at a time (two row groups of 128 threads; one ray = 128 merged samples
 // = one UMMA M tile) so that one ray's epilogue / gather overlaps the other ray's MMAs:
-//   rows  (warps 0-7, thread = sample row, group = warp / 4): PE -> A[:,64:128]; cooperative VM gather of both grids
-//         -> two 128x96 bf16 tiles;  after each layer: TMEM -> registers -> bias/ReLU -> bf16 -> A operand of the next
-//         layer; sigma (256->1) and rgb (256->3) are fp32 dot products folded into the epilogues;  finally
-//         sigma->alpha compositing with a warp-shuffle transmittance scan.
-//   load  (warps 10 and 11, one thread each, one per ray): stream the layer weights (320 KB per ray, 16 KB stages, L2
+//   rows  (warps 0-15, TWO threads per sample row, group = warp / 8): PE -> A; cooperative VM gather (half 0: coarse grid,
+//         half 1: fine grid) -> two 128x96 bf16 tiles;  after each layer: TMEM -> registers -> bias/ReLU -> bf16 -> A
+//         operand of the next layer, each half of a row handling half of the columns; sigma (256->1) and rgb (256->3) are
+//         fp32 dot products folded into the epilogues;  finally sigma->alpha compositing with a warp-shuffle scan.
+//         The row code is instruction-latency bound per warp, hence 16 row warps (640 threads x 96 registers).
+//   load  (warps 18 and 19, one thread each, one per ray): stream the layer weights (320 KB per ray, 16 KB stages, L2
 //         resident) through the ray group's private 2-stage shared-memory ring with bulk async copies (TMA engine).
 //         Private rings cost 2x the L2->smem weight traffic of a shared ring but let the two groups drift apart, so one
 //         group's gather / epilogue overlaps the other's MMAs (a shared ring forces lock-step: measured in r1).
-//   mma   (warps 8 and 9, one thread each, one per ray): wait for the ray's A operand and the ring stage, issue
+//   mma   (warps 16 and 17, one thread each, one per ray): wait for the ray's A operand and the ring stage, issue
 //         tcgen05.mma: basis_mat x2 (N=32, resident B), sigma_net 128->256->128(geo), color_net 128(+view-dir
 //         bias)->256->256, and commit to the stage-release / accumulator-ready mbarriers.  2 x 256 TMEM columns.
 #include <cstddef>
@@ -30,9 +31,10 @@ namespace {
 
 using namespace tc;
 
-constexpr int kGroupThreads = 128;
-constexpr int kRowWarps = 8;
-constexpr int kThreads = kRowWarps * 32 + 128;  // 8 row warps + 2 MMA issuer warps + 2 weight-stream warps
+constexpr int kRows = 128;               // sample rows of one ray tile = one UMMA M tile
+constexpr int kGroupThreads = 256;       // TWO threads per sample row (halves h = 0 / 1 split the gather grids and the columns)
+constexpr int kRowWarps = 16;            // 2 ray groups x 8 warps
+constexpr int kThreads = kRowWarps * 32 + 128;  // + 2 MMA issuer warps + 2 weight-stream warps = 640
 constexpr int kNst = 2;                  // weight ring stages PER RAY GROUP (private rings: the groups must not run in lock-step)
 constexpr int kStageBytes = 16384;
 constexpr int kABytes = 65536;           // per ray: 128 rows x 256 K bf16
@@ -84,8 +86,9 @@ std::vector<StepDesc> build_steps(bool lean) {
 
 struct alignas(16) GroupMisc {
   float tcarry, pad_[3];
-  float z[kGroupThreads];
+  float z[kRows];
   alignas(16) float bias[256];
+  alignas(16) float headp[2][kRows][4];   // per column-half partial sigma (x) / rgb (xyz) heads
   float red[4][8];
   float wtot[4];
 };
@@ -103,18 +106,16 @@ static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 &
 constexpr int kSmemBytes = 2 * kABytes + 2 * kNst * kStageBytes + kBasisBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-// Cooperative gather of both grids for the 32 points of this warp.  Lane (q = lane/8, j = lane%8) serves point 8*gi+j
-// and reads 16-byte channel chunks, so every warp-wide load covers whole 32 B sectors of 8 texels.  Per (grid, gi)
-// iteration a lane runs 3 tasks (component 0 chunks q and q+4, and chunk q&1 of component 1 + q/2) with all 18 loads
-// issued before the first use.  Tile placement inside the ray's A buffer (2 KB chunks): coarse tile -> chunks 16..27,
-// fine tile -> 28..31,0..7.
+// Cooperative gather of ONE grid (fine_tile = 0 coarse / 1 fine) for the 32 points of this warp.  Lane (q = lane/8,
+// j = lane%8) serves point 8*gi+j and reads 16-byte channel chunks, so every warp-wide load covers whole 32 B sectors of
+// 8 texels.  Per gi iteration a lane runs 3 tasks (component 0 chunks q and q+4 with 12 loads in flight, then chunk q&1
+// of component 1 + q/2).
 template <typename T>
 __device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As, const float* z_s, int gwarp, int lane,
-                                             const float o[3], const float d[3], const bool lean) {
+                                             const float o[3], const float d[3], const bool lean, const int fine_tile) {
   const int q = lane >> 3;
 #pragma unroll 1
-  for (int itg = 0; itg < 8; ++itg) {
-    const int fine_tile = itg >> 2, gi = itg & 3;
+  for (int gi = 0; gi < 4; ++gi) {
     const GridDev& g = grids_s[fine_tile];
     const int pt = gwarp * 32 + gi * 8 + (lane & 7);
     const float zv = z_s[pt];
@@ -123,8 +124,10 @@ __device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As
     for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
     normalize_pt(g, p, n);
     uint8_t* row = As + pt * 16;
-    GatherTask<T> t0, t1, t2;
-    {  // component 0: plane (x,y) 64 channels, line z
+    // A-buffer chunk of channel chunk cc: lean: coarse cc, fine 12 + cc; full: coarse 16 + cc, fine 28..31,0..7
+    const int base = lean ? (fine_tile ? 12 : 0) : (fine_tile ? 28 : 16);
+    {  // component 0: plane (x,y) 64 channels, line z: channel chunks q and q + 4, 12 loads in flight
+      GatherTask<T> t0, t1;
       Taps2 pt2; Taps1 lt1;
       plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
       line_taps(n[2], g.ll[0], lt1);
@@ -132,22 +135,18 @@ __device__ __forceinline__ void gather_tiles(const GridDev* grids_s, uint8_t* As
       const T* ln = reinterpret_cast<const T*>(g.line[0]);
       t0.issue(pl, ln, 64, q, pt2, lt1);
       t1.issue(pl, ln, 64, q + 4, pt2, lt1);
+      t0.finish(row + ((base + q) & 31) * kChunkA);
+      t1.finish(row + ((base + 4 + q) & 31) * kChunkA);
     }
     {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
+      GatherTask<T> t2;
       const int comp = 1 + (q >> 1);
       Taps2 pt2; Taps1 lt1;
       plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], pt2);
       line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
       t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
+      t2.finish(row + ((base + 8 + q) & 31) * kChunkA);
     }
-    // A-buffer chunk of channel chunk cc: lean: coarse cc, fine 12 + cc; full: coarse 16 + cc, fine 28..31,0..7
-    const int base = lean ? (fine_tile ? 12 : 0) : (fine_tile ? 28 : 16);
-    const int c0 = (base + q) & 31;                        // channel chunk q
-    const int c1 = (base + 4 + q) & 31;                    // channel chunk q + 4
-    const int c2 = (base + 8 + q) & 31;                    // channel chunk 8 + q
-    t0.finish(row + c0 * kChunkA);
-    t1.finish(row + c1 * kChunkA);
-    t2.finish(row + c2 * kChunkA);
   }
 }
 
@@ -208,23 +207,17 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], int col0
   }
 }
 
-// Layer epilogue over `ncols` (multiple of 64) accumulator columns; ONE copy of the code for all layers (the kernel is
-// instruction-cache sensitive).  Software pipelined: the tcgen05.ld of the next 32 columns is in flight while the
-// current 32 are processed.
-__device__ __noinline__ float4 layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int ncols, int mode, uint32_t bias_s,
+// Layer epilogue over accumulator columns [col_begin, col_begin + ncols) (multiples of 32) of this thread's row; ONE
+// copy of the code for all layers (the kernel is instruction-cache sensitive).
+__device__ __noinline__ float4 layer_epilogue(uint32_t taddr_row, uint8_t* a_row, int col_begin, int ncols, int mode, uint32_t bias_s,
                                               float* __restrict__ gout, uint32_t wsig, uint32_t wrgb) {
   float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t va[32], vb[32];
-  tmem_ld32(taddr_row, va);
-  tmem_ld_wait();
 #pragma unroll 1
-  for (int col0 = 0; col0 < ncols; col0 += 64) {
-    tmem_ld32(taddr_row + col0 + 32, vb);
-    epilogue_block(va, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
+  for (int col0 = col_begin; col0 < col_begin + ncols; col0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr_row + col0, v);
     tmem_ld_wait();
-    if (col0 + 64 < ncols) tmem_ld32(taddr_row + col0 + 64, va);
-    epilogue_block(vb, col0 + 32, mode, a_row, bias_s, gout, wsig, wrgb, head);
-    tmem_ld_wait();
+    epilogue_block(v, col0, mode, a_row, bias_s, gout, wsig, wrgb, head);
   }
   return head;
 }
@@ -269,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   const int64_t n_pairs_total = (a.n_rays + 1) / 2;
   const int64_t n_my = (n_pairs_total > (int64_t)blockIdx.x) ? (n_pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int S = a.S;
-  const int tpr = (S + kGroupThreads - 1) / kGroupThreads;   // 128-row tiles per ray (rays longer than 128 samples span several)
+  const int tpr = (S + kRows - 1) / kRows;                   // 128-row tiles per ray (rays longer than 128 samples span several)
   const int64_t n_it = n_my * tpr;
 
   if (warp >= kRowWarps + 2) {
@@ -335,9 +328,11 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     }
     __syncwarp();
   } else {
-    // =================================== row warps: thread = sample row ===============================================
-    const int q = warp >> 2, gwarp = warp & 3;
-    const int r = tid & (kGroupThreads - 1);
+    // =================================== row warps: TWO threads per sample row ===========================================
+    // group q = warp / 8; half = (warp / 4) & 1 selects the VM grid to gather (0 coarse, 1 fine) and the column half of
+    // every epilogue; both halves of a row read the same TMEM lane (lane quarter = warp % 4).
+    const int q = warp >> 3, half = (warp >> 2) & 1, gwarp = warp & 3;
+    const int r = gwarp * 32 + lane;
     uint8_t* Aq = As + q * kABytes;
     uint8_t* a_row = Aq + r * 16;
     GroupMisc* gm = &m->grp[q];
@@ -345,31 +340,32 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     uint32_t pacc = 0;
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
-    const int bar_id = 1 + q;
+    const int bar_id = 1 + q, bar_half = 3 + q;
     const uint32_t s_wsig = smem_u32(m->wsig), s_wrgb = smem_u32(m->wrgb);
     if (q == 1) {   // phase-shift the second ray group by ~half a ray so that its MMAs fall into the first group's gather / epilogues
       uint32_t spins = 0;
       while (*reinterpret_cast<volatile uint32_t*>(&m->skew_flag) == 0) { if (++spins > (1u << 26)) __trap(); }
     }
     auto stamp = [&](int64_t it, int k) {
-      if (a.trace && blockIdx.x == 0 && r == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
+      if (a.trace && blockIdx.x == 0 && r == 0 && half == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
     };
-    float run_sum = 0.f;                    // thread r < 5: running ray sum (rgb, depth, acc) across the tiles of a ray
+    float run_sum = 0.f;                    // half 0, thread r < 5: running ray sum (rgb, depth, acc) across the tiles of a ray
     int tile = -1;
     int64_t ray_raw = 2 * (int64_t)blockIdx.x + q - 2 * (int64_t)gridDim.x;
     for (int64_t it = 0; it < n_it; ++it) {
       stamp(it, 0);
       if (++tile == tpr || it == 0) { tile = 0; ray_raw += 2 * (int64_t)gridDim.x; }
-      const int rg = tile * kGroupThreads + r;          // sample index of this row within the ray
+      const int rg = tile * kRows + r;                  // sample index of this row within the ray
       const bool live = ray_raw < a.n_rays;             // odd ray count: the last pair's second ray is a masked duplicate
       const int64_t ray = live ? ray_raw : a.n_rays - 1;
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
       const float zv = a.z_vals[ray * S + min(rg, S - 1)];
-      gm->z[r] = zv;
-      if (tile == 0 && r == 0) gm->tcarry = 1.0f;
-      {  // ---- PE(pts) -> A columns 64..127 (chunks 8..15); column 127 is the zero pad of K = 127 -> 128 -------------
+      if (half == 0) {
+        gm->z[r] = zv;
+        if (tile == 0 && r == 0) gm->tcarry = 1.0f;
+        // ---- PE(pts) -> 64 A columns (full: chunks 8..15, lean: 24..31); the last column is the zero pad of K = 127 -> 128.
         // sin/cos of the base frequency by range-reduced MUFU, higher octaves by the double-angle recurrence
         // (abs error <= 2^9 * 1e-7, far below the bf16 resolution of the MMA operand)
         float pe[64];
@@ -392,8 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         for (int j = 0; j < 8; ++j)
           st_shared_v4(a_row + ((LEAN ? 24 : 8) + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
                        pack_bf16x2(pe[8 * j + 4], pe[8 * j + 5]), pack_bf16x2(pe[8 * j + 6], pe[8 * j + 7]));
-      }
-      {  // ---- per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir), fp32 ------------------------------------
+      } else if (tile == 0) {
+        // ---- per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir), fp32; thread r -> columns r and r + 128 ----
         const float vd[3] = {__ldg(rb + 8), __ldg(rb + 9), __ldg(rb + 10)};
         float ped[kPeDir];
 #pragma unroll
@@ -408,8 +404,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
           }
         }
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int col = r + half * kGroupThreads;
+        for (int hc = 0; hc < 2; ++hc) {
+          const int col = r + hc * kRows;
           float b = a.mlp.color0_b ? __ldg(a.mlp.color0_b + col) : 0.f;
           const float* w = a.mlp.color0_t + (size_t)128 * 256 + col;
 #pragma unroll
@@ -419,96 +415,109 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       }
       named_bar_sync(bar_id, kGroupThreads);      // z[] (and bias[]) visible to the whole group
       stamp(it, 1);
-      // ---- VM gather of both grids -> two 128 x 96 bf16 tiles ----------------------------------------------------------
-      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN);
+      // ---- VM gather: half 0 gathers the coarse grid, half 1 the fine grid -> two 128 x 96 bf16 tiles ------------------
+      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 2);
       if (!LEAN) {
         // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ----------------------------------------------
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 3);
-        layer_epilogue(taddr_row, a_row, 64, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
+        layer_epilogue(taddr_row, a_row, 32 * half, 32, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
         rows_signal_a(&m->bar_a[q]);
         stamp(it, 4);
       }
-      // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0) -------------------------------------------
+      // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0; partial per column half) -----------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 5);
-      const float sig_raw = layer_epilogue(taddr_row, a_row, 256, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb).x;
+      {
+        const float4 hd = layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb);
+        gm->headp[half][r][3] = hd.x;
+      }
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 6);
       if (!LEAN) {
         // ---- sigma_net.1 -> geo (128, linear) ----------------------------------------------------------------------------
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 7);
-        layer_epilogue(taddr_row, a_row, 128, kEpiPlain, 0u,
+        layer_epilogue(taddr_row, a_row, 64 * half, 64, kEpiPlain, 0u,
                        (a.feat && live && rg < S) ? a.feat + ((size_t)ray * S + rg) * 128 : nullptr, s_wsig, s_wrgb);
         rows_signal_a(&m->bar_a[q]);
       }
-      if (q == 0 && it == 0 && r == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
+      if (q == 0 && it == 0 && r == 0 && half == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 8);
       // ---- color_net.0 (+ per-ray view-dir bias) -> ReLU ------------------------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 9);
-      layer_epilogue(taddr_row, a_row, 256, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
+      layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
       rows_signal_a(&m->bar_a[q]);
       stamp(it, 10);
-      // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2) -> sigmoid -----------------------------------------
+      // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2; partial per column half) --------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 11);
-      const float4 hd = layer_epilogue(taddr_row, a_row, 256, kEpiReluRgb, a.mlp.color1_b ? smem_u32(m->bias1) : 0u, nullptr, s_wsig, s_wrgb);
-      float col[3] = {hd.x, hd.y, hd.z};
-#pragma unroll
-      for (int i = 0; i < 3; ++i) col[i] = sigmoidf_(col[i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+      {
+        const float4 hd = layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiReluRgb, a.mlp.color1_b ? smem_u32(m->bias1) : 0u, nullptr,
+                                         s_wsig, s_wrgb);
+        gm->headp[half][r][0] = hd.x; gm->headp[half][r][1] = hd.y; gm->headp[half][r][2] = hd.z;
+      }
+      tc_fence_before();
+      named_bar_sync(bar_id, kGroupThreads);      // both halves' head partials visible; all TMEM reads of this tile done
       stamp(it, 12);
-      // ---- compositing (voxnerf.py:153-201) -----------------------------------------------------------------------------------
-      float alpha = 0.f;
-      if (rg < S - 1) {
-        const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-        const float znext = (r + 1 < kGroupThreads) ? gm->z[r + 1] : a.z_vals[ray * S + rg + 1];
-        const float dist = __fmul_rn(znext - zv, dnorm);
-        float sg = sig_raw;
-        if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + rg);
-        sg = fmaxf(sg, 0.f);
-        if (mask_near && !(znext > near_thr)) sg = 0.f;
-        alpha = 1.0f - expf(-__fmul_rn(sg, dist));
-      } else if (rg == S - 1) {
-        alpha = 1.0f;
-      }
-      float t = 1.0f - alpha;                 // inclusive product scan of (1 - alpha) over the warp
+      if (half == 0) {
+        // ---- compositing (voxnerf.py:153-201), one thread per sample row --------------------------------------------------
+        float col[3];
 #pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const float y = __shfl_up_sync(0xffffffffu, t, dlt);
-        if (lane >= dlt) t *= y;
-      }
-      float Tr = __shfl_up_sync(0xffffffffu, t, 1);
-      if (lane == 0) Tr = 1.0f;
-      if (lane == 31) gm->wtot[gwarp] = t;
-      named_bar_sync(bar_id, kGroupThreads);
-      Tr *= gm->tcarry;                       // transmittance accumulated over the previous tiles of this ray
-      for (int w2 = 0; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
-      const float wgt = alpha * Tr;
-      if (live && rg < S) a.weights[ray * S + rg] = wgt;
-      float red[5] = {wgt * col[0], wgt * col[1], wgt * col[2], wgt * zv, wgt};
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], off);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
-      }
-      named_bar_sync(bar_id, kGroupThreads);
-      if (r < 5) {
-        if (tile == 0) run_sum = 0.f;
-        run_sum += gm->red[0][r] + gm->red[1][r] + gm->red[2][r] + gm->red[3][r];
-        if (live && tile == tpr - 1) {
-          if (r < 3) a.rgb[ray * 3 + r] = run_sum; else if (r == 3) a.depth[ray] = run_sum; else a.acc[ray] = run_sum;
+        for (int i = 0; i < 3; ++i)
+          col[i] = sigmoidf_(gm->headp[0][r][i] + gm->headp[1][r][i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+        const float sig_raw = gm->headp[0][r][3] + gm->headp[1][r][3];
+        float alpha = 0.f;
+        if (rg < S - 1) {
+          const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+          const float znext = (r + 1 < kRows) ? gm->z[r + 1] : a.z_vals[ray * S + rg + 1];
+          const float dist = __fmul_rn(znext - zv, dnorm);
+          float sg = sig_raw;
+          if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + rg);
+          sg = fmaxf(sg, 0.f);
+          if (mask_near && !(znext > near_thr)) sg = 0.f;
+          alpha = 1.0f - expf(-__fmul_rn(sg, dist));
+        } else if (rg == S - 1) {
+          alpha = 1.0f;
         }
+        float t = 1.0f - alpha;                 // inclusive product scan of (1 - alpha) over the warp
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float y = __shfl_up_sync(0xffffffffu, t, dlt);
+          if (lane >= dlt) t *= y;
+        }
+        float Tr = __shfl_up_sync(0xffffffffu, t, 1);
+        if (lane == 0) Tr = 1.0f;
+        if (lane == 31) gm->wtot[gwarp] = t;
+        named_bar_sync(bar_half, kRows);
+        Tr *= gm->tcarry;                       // transmittance accumulated over the previous tiles of this ray
+        for (int w2 = 0; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
+        const float wgt = alpha * Tr;
+        if (live && rg < S) a.weights[ray * S + rg] = wgt;
+        float red[5] = {wgt * col[0], wgt * col[1], wgt * col[2], wgt * zv, wgt};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
+        }
+        named_bar_sync(bar_half, kRows);
+        if (r < 5) {
+          if (tile == 0) run_sum = 0.f;
+          run_sum += gm->red[0][r] + gm->red[1][r] + gm->red[2][r] + gm->red[3][r];
+          if (live && tile == tpr - 1) {
+            if (r < 3) a.rgb[ray * 3 + r] = run_sum; else if (r == 3) a.depth[ray] = run_sum; else a.acc[ray] = run_sum;
+          }
+        }
+        if (r == 5) gm->tcarry = gm->tcarry * gm->wtot[0] * gm->wtot[1] * gm->wtot[2] * gm->wtot[3];
       }
-      if (r == 5) gm->tcarry = gm->tcarry * gm->wtot[0] * gm->wtot[1] * gm->wtot[2] * gm->wtot[3];
-      named_bar_sync(bar_id, kGroupThreads);      // red[] / wtot[] / z[] free for the next ray
+      named_bar_sync(bar_id, kGroupThreads);      // red[] / wtot[] / z[] / headp[] free for the next ray
       stamp(it, 13);
     }
   }
