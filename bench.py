@@ -287,6 +287,18 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
     R = N_RAYS * N_EXPOSURE
     fine_ms = kern_ms.get("fine", float("nan"))
+    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of the fine kernel from the committed ncu --set full capture
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r1_tc_kernels_ncu_summary.txt")).read().split("=" * 100)
+        blk = next(b for b in txt if "fine_fwd_tc_kernel" in b)
+        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum ", "dram__bytes_write.sum "):
+            ln = next(l for l in blk.splitlines() if l.startswith(key)).split()
+            tot += float(ln[1]) * unit[ln[2]]
+        traffic = tot if args.precision == "bf16" else None
+    except Exception:
+        traffic = None
     achieved = flops_fine_kernel_per_subray() * R / (fine_ms / 1e3) / 1e12
     line = {
         "metric": "primary_rays_per_sec_fwd", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -299,7 +311,8 @@ def main():
         "clocks": clocks,
         "kernels_ms": kern_ms,
         "roofline": {"bound": "tensor", "kernel": "edn_render_fine_fwd", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                     "peak_source": peak_src,
                      "flops_per_launch": flops_fine_kernel_per_subray() * R, "ms_per_launch": fine_ms,
                      "whole_step_tflops": flops_per_subray() * R / (ms_per_step / 1e3) / 1e12},
         "wall_s_timed_region": t_wall,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "edn_last_error": (C.c_char_p, []),
     "edn_abi_version": (C.c_int, []),
     "edn_pack_vm_plane": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "edn_fill_random": (C.c_int, [_P, _I64, C.c_uint64, C.c_uint32, _I32, _F, _P]),
     "edn_vm_sample": (C.c_int, [C.POINTER(VmGrid), _P, _P, _I64, _P]),
     "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
                                         _I32, _P, _P, _P, _P, _P, _P, _P]),

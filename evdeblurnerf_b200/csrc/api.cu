@@ -98,3 +98,55 @@ extern "C" int edn_vm_sample(const edn_vm_grid* grid, const float* pts, float* f
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }
+
+// ---- counter-based RNG for the stratified jitter / pdf samples / density noise (renderer.py:176, rays.py:162,
+//      voxnerf.py:175).  Philox4x32-10 keyed by (seed, stream); element i draws from counter i: reproducible for a
+//      given seed independent of launch geometry, no generator state on the host. --------------------------------------
+namespace edn {
+namespace {
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__global__ void fill_random_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t stream_id, int normal, float scale) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // 4 outputs per thread
+  if (i4 * 4 >= n) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i4, (uint32_t)(i4 >> 32), stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float v[4];
+  if (!normal) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (float)(r[j] >> 8) * (1.0f / 16777216.0f) * scale;      // [0, 1): 24 random bits
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {                                                              // Box-Muller
+      const float u1 = ((float)(r[j] >> 8) + 1.0f) * (1.0f / 16777216.0f);                        // (0, 1]
+      const float u2 = (float)(r[j + 1] >> 8) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      v[j] = rad * cs * scale; v[j + 1] = rad * sn * scale;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) out[i4 * 4 + j] = v[j];
+}
+}  // namespace
+}  // namespace edn
+
+extern "C" int edn_fill_random(float* out, int64_t n, uint64_t seed, uint32_t stream_id, int32_t normal, float scale, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(out && n >= 0, "edn_fill_random: bad argument");
+  if (n == 0) return EDN_OK;
+  const int64_t threads = (n + 3) / 4;
+  fill_random_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n, seed, stream_id, normal, scale);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}

@@ -129,7 +129,20 @@ class PackedField:
 class SamplerHost:
     """Shared host pieces of the c2f and nerf-mode renderers: cached linspace vectors, profiling hooks, the sampler."""
 
+    def seed(self, seed):
+        """Seed of the in-library Philox generator used for perturb / raw_noise_std draws; every render call advances a
+        call counter, so draws differ between calls and are reproducible for a given (seed, call order)."""
+        self._seed, self._calls = int(seed) & ((1 << 64) - 1), 0
+
+    def _random(self, shape, stream_id, normal=False, scale=1.0):
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        sid = (self._calls * 8 + stream_id) & 0xFFFFFFFF
+        check(_lib.load().edn_fill_random(ptr(out), out.numel(), self._seed, sid, 1 if normal else 0, float(scale), stream_ptr()),
+              "edn_fill_random")
+        return out
+
     def _init_host(self, device):
+        self.seed(0)
         self.device = torch.device(device if device is not None else "cuda")
         self._lin = {}
         self.profile = None     # set to {} to collect (start, end) CUDA events per kernel (bench.py roofline leg)
@@ -243,8 +256,9 @@ class RenderEngine(SamplerHost):
 
         Extra keyword arguments (not in the reference): `is_train` (= module.training), `use_awp` (= self.use_awp),
         `rand` = dict of injected random tensors {t_rand [R,Nc], u [R,Ni], noise0 [R,Nc-1], noise1 [R,Nc+Ni-1]} (noise
-        already scaled by raw_noise_std) -- when absent and perturb / raw_noise_std are non-zero they are drawn with
-        torch's CUDA generator in the reference's order (renderer.py:176, voxnerf.py:175, rays.py:162, voxnerf.py:175).
+        already scaled by raw_noise_std) -- when absent and perturb / raw_noise_std are non-zero they are drawn by the
+        library's counter-based Philox generator (edn_fill_random; seed with `engine.seed(s)`), one stream per draw site
+        (renderer.py:176, voxnerf.py:175, rays.py:162, voxnerf.py:175).
         """
         _require_cuda(ray_batch, "ray_batch")
         if ray_batch.shape[-1] != 11:
@@ -260,13 +274,14 @@ class RenderEngine(SamplerHost):
         f32 = dict(dtype=torch.float32, device=dev)
 
         t_rand = noise0 = None
+        self._calls += 1
         if perturb > 0.:
-            t_rand = rand["t_rand"] if "t_rand" in rand else torch.rand((R, Nc), **f32)
+            t_rand = rand["t_rand"] if "t_rand" in rand else self._random((R, Nc), 0)
             t_rand = t_rand.float().contiguous()
         if "noise0" in rand:
             noise0 = rand["noise0"].float().contiguous()
         elif raw_noise_std > 0.:
-            noise0 = (torch.randn((R, Nc - 1), **f32) * raw_noise_std).contiguous()
+            noise0 = self._random((R, Nc - 1), 1, normal=True, scale=raw_noise_std)
         z0 = torch.empty((R, Nc), **f32)
         w0 = torch.empty((R, Nc), **f32)
         rgb0 = torch.empty((R, 3), **f32)
@@ -292,14 +307,14 @@ class RenderEngine(SamplerHost):
             raise RuntimeError("render_rays: N_importance > 0 needs mlp_fine.* parameters")
         u = None
         if perturb > 0.:
-            u = rand["u"] if "u" in rand else torch.rand((R, Ni), **f32)
+            u = rand["u"] if "u" in rand else self._random((R, Ni), 2)
         m = self.sample_pdf_merge(z0, w0, Ni, u=u, want_indices=want_indices)
         S = Nc + Ni
         noise1 = None
         if "noise1" in rand:
             noise1 = rand["noise1"].float().contiguous()
         elif raw_noise_std > 0.:
-            noise1 = (torch.randn((R, S - 1), **f32) * raw_noise_std).contiguous()
+            noise1 = self._random((R, S - 1), 3, normal=True, scale=raw_noise_std)
         w1 = torch.empty((R, S), **f32)
         rgb1 = torch.empty((R, 3), **f32)
         depth1 = torch.empty((R,), **f32)

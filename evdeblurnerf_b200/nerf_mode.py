@@ -79,8 +79,9 @@ def render_rays_nerf(engine, mlp_coarse, mlp_fine, ray_batch, N_samples, retraw=
     Nc, Ni = int(N_samples), int(N_importance)
     f32 = dict(dtype=torch.float32, device=dev)
     t_rand = None
+    engine._calls += 1
     if perturb > 0.:
-        t_rand = (rand["t_rand"] if "t_rand" in rand else torch.rand((R, Nc), **f32)).float().contiguous()
+        t_rand = (rand["t_rand"] if "t_rand" in rand else engine._random((R, Nc), 0)).float().contiguous()
     z0 = torch.empty((R, Nc), **f32)
     check(_lib.load().edn_place_samples(ptr(rb), ptr(engine._linspace(Nc)), ptr(t_rand), R, Nc, FLAG_LINDISP if lindisp else 0, ptr(z0),
                                         stream_ptr()), "edn_place_samples")
@@ -89,7 +90,7 @@ def render_rays_nerf(engine, mlp_coarse, mlp_fine, ray_batch, N_samples, retraw=
     def noise(n, key):
         if key in rand:
             return rand[key]
-        return torch.randn((R, n), **f32) * raw_noise_std if raw_noise_std > 0. else None
+        return engine._random((R, n), 1 if key == "noise0" else 3, normal=True, scale=raw_noise_std) if raw_noise_std > 0. else None
 
     raw0, feat0 = mlp_coarse.mlpforward_at(rb, z0, want_feat and Ni == 0)
     rgb0, depth0, acc0, w0 = mlp_coarse.raw2outputs(raw0, z0, rb, noise(Nc - 1, "noise0"), white_bkgd, is_train)
@@ -97,7 +98,7 @@ def render_rays_nerf(engine, mlp_coarse, mlp_fine, ray_batch, N_samples, retraw=
     if retraw:
         ret["z_vals"], ret["weights"] = z0, w0
     if Ni > 0:
-        u = (rand["u"] if "u" in rand else torch.rand((R, Ni), **f32)) if perturb > 0. else None
+        u = (rand["u"] if "u" in rand else engine._random((R, Ni), 2)) if perturb > 0. else None
         m = engine.sample_pdf_merge(z0, w0, Ni, u=u, want_indices=False)
         raw1, feat1 = mlp_fine.mlpforward_at(rb, m["z_vals"], want_feat)
         rgb1, depth1, acc1, w1 = mlp_fine.raw2outputs(raw1, m["z_vals"], rb, noise(Nc + Ni - 1, "noise1"), white_bkgd, is_train)

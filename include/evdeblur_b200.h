@@ -81,6 +81,11 @@ int edn_abi_version(void);
 int edn_pack_vm_plane(const float* src_chw, void* dst_hwc, int32_t C, int32_t H, int32_t W, int32_t dst_dtype,
                       void* stream);
 
+/* Counter-based RNG (Philox4x32-10) for the render path's random draws: stratified jitter t_rand (renderer.py:176), pdf
+ * samples u (utils/rays.py:162) -- uniform [0,1) -- and the density noise randn * raw_noise_std (voxnerf.py:175, normal = 1,
+ * scale = raw_noise_std).  Element i depends only on (seed, stream_id, i). */
+int edn_fill_random(float* out, int64_t n, uint64_t seed, uint32_t stream_id, int32_t normal, float scale, void* stream);
+
 /* VoxelNeRFBase.sample (voxnerf.py:203-208, 132-151): pts [n,3] -> feat [n,32].  Unit-test / drop-in entry. */
 int edn_vm_sample(const edn_vm_grid* grid, const float* pts, float* feat, int64_t n, void* stream);
 

@@ -206,3 +206,35 @@ def test_full_size_properties():
     fin = oracle_fine_at(P, rb[:64].cpu(), out["z_vals"][:64].cpu())
     for k in ("rgb_map", "depth_map", "weights"):
         assert_close(out[k][:64], fin[k], k, rtol=1e-4, atol=2e-5)
+
+
+def test_philox_random_draws(engine):
+    """In-library RNG for perturb / raw_noise_std: range, moments, reproducibility, stream independence."""
+    engine.seed(123)
+    engine._calls = 5
+    u = engine._random((400, 257), 0)
+    n = engine._random((400, 257), 1, normal=True, scale=2.0)
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 5e-3 and abs(float(u.var()) - 1 / 12) < 2e-3
+    assert abs(float(n.mean())) < 2e-2 and abs(float(n.std()) - 2.0) < 2e-2
+    assert abs(float(((n / 2.0) ** 4).mean()) - 3.0) < 0.15                       # kurtosis of a normal
+    engine.seed(123); engine._calls = 5
+    assert torch.equal(u, engine._random((400, 257), 0))                           # reproducible
+    assert not torch.equal(u, engine._random((400, 257), 2))                       # streams differ
+    engine.seed(124); engine._calls = 5
+    assert not torch.equal(u, engine._random((400, 257), 0))                       # seeds differ
+    assert abs(float(torch.corrcoef(torch.stack([u.flatten()[:-1], u.flatten()[1:]]))[0, 1])) < 1e-2
+
+
+def test_perturbed_render_is_reproducible_and_valid(engine):
+    rays, _ = synthetic_rays(64, seed=9)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays).cuda()
+    engine.seed(7)
+    a = engine.render_rays(rb, 64, retraw=True, N_importance=64, perturb=1., raw_noise_std=1.)
+    engine.seed(7)
+    b = engine.render_rays(rb, 64, retraw=True, N_importance=64, perturb=1., raw_noise_std=1.)
+    c = engine.render_rays(rb, 64, retraw=True, N_importance=64, perturb=1., raw_noise_std=1.)
+    assert torch.equal(a["rgb_map"], b["rgb_map"]) and not torch.equal(a["rgb_map"], c["rgb_map"])
+    z = a["z_vals"]
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and bool((a["z_vals0"][:, 1:] > a["z_vals0"][:, :-1]).all())
+    assert_close(a["weights"].sum(-1), a["acc_map"], "acc", rtol=1e-5, atol=1e-6)
