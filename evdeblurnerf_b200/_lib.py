@@ -67,7 +67,8 @@ SIGNATURES = {
     "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
                                         _I32, _P, _P, _P, _P, _P, _P, _P]),
     "edn_coarse_tc_blob_bytes": (C.c_int64, []),
-    "edn_pack_coarse_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P]),
+    "edn_coarse_tc_pack_workspace_floats": (C.c_int64, []),
+    "edn_pack_coarse_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P]),
     "edn_sample_pdf_merge": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "edn_fine_tc_blob_bytes": (C.c_int64, []),
     "edn_fine_tc_pack_workspace_floats": (C.c_int64, []),

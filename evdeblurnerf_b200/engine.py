@@ -115,7 +115,8 @@ class PackedField:
         if self.coarse:
             n = int(lib.edn_coarse_tc_blob_bytes())
             blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)
-            check(lib.edn_pack_coarse_tc(C.byref(self.mlp), ptr(self.basis_t), ptr(blob), stream_ptr()), "edn_pack_coarse_tc")
+            ws = torch.empty((int(lib.edn_coarse_tc_pack_workspace_floats()),), dtype=torch.float32, device=self.basis_t.device)
+            check(lib.edn_pack_coarse_tc(C.byref(self.mlp), ptr(self.basis_t), ptr(ws), ptr(blob), stream_ptr()), "edn_pack_coarse_tc")
         else:
             n = int(lib.edn_fine_tc_blob_bytes())
             blob = torch.empty((n,), dtype=torch.uint8, device=self.basis_t.device)

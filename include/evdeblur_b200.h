@@ -105,7 +105,8 @@ int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_mlp* mlp, con
 
 /* bf16 UMMA operand blob of the coarse field (EDN_BF16 precision of edn_render_coarse_fwd): size and packer. */
 int64_t edn_coarse_tc_blob_bytes(void);
-int edn_pack_coarse_tc(const edn_field_mlp* mlp, const float* basis_t, void* blob, void* stream);
+int64_t edn_coarse_tc_pack_workspace_floats(void);
+int edn_pack_coarse_tc(const edn_field_mlp* mlp, const float* basis_t, float* workspace, void* blob, void* stream);
 
 /* sample_pdf (utils/rays.py:149-193) as called at renderer.py:199-203 + merge/sort (renderer.py:205) + z_std (:250).
  *   u_det [n_importance] = linspace(0,1,n_importance) (perturb == 0) or NULL;  u_rand [R][n_importance] or NULL.

@@ -29,8 +29,8 @@ def test_tc_coarse_matches_emulated_reference(engines):
     P, eng, _ = engines
     rays, _ = synthetic_rays(150, seed=33)
     rb = oc.build_ray_batch(H, W, FOCAL, rays)
-    out = eng.render_rays(rb.cuda(), 64, retraw=True, use_awp=True)          # coarse only, feature_map requested
-    emu = emulated_bf16_coarse(P, rb, 64)
+    out = eng.render_rays(rb.cuda(), 64, retraw=True, use_awp=True)          # coarse only, feature_map requested -> full schedule
+    emu = emulated_bf16_coarse(P, rb, 64, lean=False)
     assert torch.equal(out["z_vals"].cpu(), emu["z_vals"])                    # placement stays bit-exact
     assert_close(out["depth_feature"], emu["feature"], "geo", rtol=2e-2, atol=5e-3)
     for k in ("weights", "rgb_map", "depth_map", "acc_map"):
@@ -38,6 +38,11 @@ def test_tc_coarse_matches_emulated_reference(engines):
     ref = oc.render_rays(P, CFG, rb, 64, 0)
     for k in ("weights", "rgb_map", "depth_map", "acc_map"):
         assert_close(out[k], ref[k], "fp32 " + k, rtol=0, atol=ORACLE_ATOL)
+    lean = eng.render_rays(rb.cuda(), 64, retraw=True)                          # default: lean (folded) schedule
+    emu_l = emulated_bf16_coarse(P, rb, 64, lean=True)
+    for k in ("weights", "rgb_map", "depth_map", "acc_map"):
+        assert_close(lean[k], emu_l[k], "lean " + k, rtol=0, atol=EMU_ATOL)
+        assert_close(lean[k], ref[k], "lean fp32 " + k, rtol=0, atol=ORACLE_ATOL)
 
 
 @pytest.mark.parametrize("nc,R", [(32, 41), (64, 7), (96, 10), (128, 5), (48, 9)])

@@ -135,7 +135,7 @@ def emulated_bf16_fine(P, ray_batch, z_all, noise=None, is_train=True, rmnearpla
             "sigma": sigma.reshape(R, S)}
 
 
-def emulated_bf16_coarse(P, ray_batch, n_samples, t_rand=None, noise=None, is_train=True, rmnearplane=0):
+def emulated_bf16_coarse(P, ray_batch, n_samples, t_rand=None, noise=None, is_train=True, rmnearplane=0, lean=True):
     """Torch fp32 reference of the tcgen05 coarse pass with its bf16 operand roundings made explicit (same
     conventions as emulated_bf16_fine; sigma comes out of the sigma_net.1 MMA, the rgb head is an fp32 dot product)."""
     import evdeblur_oracle as oc
@@ -147,14 +147,23 @@ def emulated_bf16_coarse(P, ray_batch, n_samples, t_rand=None, noise=None, is_tr
     pre = "mlp_coarse."
     Pb = {k: (_bf(v) if ("app_plane" in k or "app_line" in k) else v) for k, v in P.items()}
     g = _bf(oc.vm_products(Pb, pre, pts, *AABB))
-    ft = _bf(F.linear(g, _bf(P[pre + "basis_mat.weight"])))
-    x = torch.cat([ft, _bf(oc.posenc(pts.reshape(-1, 3), 10))], -1)
-    h1 = _bf(torch.relu(F.linear(x, _bf(P[pre + "sigma_net.0.weight"]))))
-    o16 = F.linear(h1, _bf(P[pre + "sigma_net.1.weight"]))
-    sigma, geo = o16[:, :1], o16[:, 1:]
-    w3 = P[pre + "color_net.0.weight"]
+    pe = _bf(oc.posenc(pts.reshape(-1, 3), 10))
+    w0, w1, w3 = P[pre + "sigma_net.0.weight"], P[pre + "sigma_net.1.weight"], P[pre + "color_net.0.weight"]
     bias_ray = F.linear(oc.posenc(vd, 4), w3[:, 15:], P.get(pre + "color_net.0.bias"))
-    c0 = F.linear(_bf(geo), _bf(w3[:, :15])) + bias_ray[:, None, :].expand(R, S, 64).reshape(R * S, 64)
+    if lean:   # default schedule: basis_mat folded into sigma_net.0, sigma_net.1's geo rows folded into color_net.0, fp32 sigma head
+        w0f = torch.cat([w0[:, :32] @ P[pre + "basis_mat.weight"], w0[:, 32:]], 1)
+        h1_f32 = torch.relu(F.linear(torch.cat([g, pe], -1), _bf(w0f)))
+        h1 = _bf(h1_f32)
+        sigma = F.linear(h1_f32, w1[:1])
+        geo = F.linear(h1, w1[1:])
+        c0 = F.linear(h1, _bf(w3[:, :15] @ w1[1:]))
+    else:
+        ft = _bf(F.linear(g, _bf(P[pre + "basis_mat.weight"])))
+        h1 = _bf(torch.relu(F.linear(torch.cat([ft, pe], -1), _bf(w0))))
+        o16 = F.linear(h1, _bf(w1))
+        sigma, geo = o16[:, :1], o16[:, 1:]
+        c0 = F.linear(_bf(geo), _bf(w3[:, :15]))
+    c0 = c0 + bias_ray[:, None, :].expand(R, S, 64).reshape(R * S, 64)
     c0 = _bf(torch.relu(c0))
     c1 = torch.relu(F.linear(c0, _bf(P[pre + "color_net.1.weight"]), P.get(pre + "color_net.1.bias")))
     rgb = torch.sigmoid(F.linear(c1, P[pre + "color_net.2.weight"], P.get(pre + "color_net.2.bias")))
