@@ -29,6 +29,16 @@ class FieldMlp(C.Structure):
                 ("hidden", C.c_int32), ("geo_feat", C.c_int32), ("tc_blob", C.c_void_p)]
 
 
+class FieldWeights(C.Structure):
+    _fields_ = [("basis", C.c_void_p * 2)] + [(n, C.c_void_p) for n in (
+        "sigma0", "sigma1", "color0", "color1", "color2", "color0_b", "color1_b", "color2_b")] + [
+        ("hidden", C.c_int32), ("geo_feat", C.c_int32), ("n_grids", C.c_int32)]
+
+
+class VmGridGrad(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("line", C.c_void_p * 3)]
+
+
 class RbkParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("img_embed", "r_branch_w", "r_branch_b", "v_branch_w", "v_branch_b", "w_branch_w",
                                            "w_branch_b", "r_linear_w", "r_linear_b", "v_linear_w", "v_linear_b", "w_linear_w",
@@ -75,6 +85,11 @@ SIGNATURES = {
     "edn_pack_fine_tc": (C.c_int, [C.POINTER(FieldMlp), _P, _P, _P, _P, _P]),
     "edn_render_fine_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _I64,
                                       _I32, _I32, _F, _I32, _P, _P, _P, _P, _P, _P]),
+    "edn_field_bwd_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I64, _I32]),
+    "edn_render_field_bwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldWeights), _P, _P, _P, _I64, _I32,
+                                       _I32, _P, _P, _P, _P, _P, C.POINTER(FieldWeights), C.POINTER(VmGridGrad),
+                                       C.POINTER(VmGridGrad), _P, _P, _I64, _P]),
+    "edn_unpack_vm_plane_grad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),

@@ -50,6 +50,27 @@ __global__ void pack_plane_kernel(const float* __restrict__ src, T* __restrict__
   }
 }
 
+// [H*W][C] -> (+)= [C][H*W]: gradient planes back to the reference parameter layout.
+__global__ void unpack_plane_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t HW, int accumulate) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? src[p * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const int64_t p = p0 + threadIdx.x;
+    if (c < C && p < HW) {
+      float* d = dst + (int64_t)c * HW + p;
+      *d = accumulate ? *d + tile[threadIdx.x][j] : tile[threadIdx.x][j];
+    }
+  }
+}
+
 template <typename T>
 __global__ void vm_sample_kernel(const GridDev g, const float* __restrict__ pts, float* __restrict__ feat, int64_t n) {
   __shared__ __align__(16) float basis_s[kAppComp * kAppDim];
@@ -79,6 +100,17 @@ extern "C" int edn_pack_vm_plane(const float* src_chw, void* dst_hwc, int32_t C,
   if (dst_dtype == EDN_F32) pack_plane_kernel<float><<<grid, block, 0, st>>>(src_chw, (float*)dst_hwc, C, HW);
   else if (dst_dtype == EDN_BF16) pack_plane_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src_chw, (__nv_bfloat16*)dst_hwc, C, HW);
   else { set_error("edn_pack_vm_plane: bad dtype %d", dst_dtype); return EDN_E_INVALID; }
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
+
+extern "C" int edn_unpack_vm_plane_grad(const float* src_hwc, float* dst_chw, int32_t C, int32_t H, int32_t W, int32_t accumulate,
+                                        void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(src_hwc && dst_chw && C > 0 && H > 0 && W > 0, "edn_unpack_vm_plane_grad: bad argument");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+  unpack_plane_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_hwc, dst_chw, C, HW, accumulate);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

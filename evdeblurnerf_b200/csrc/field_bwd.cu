@@ -1,0 +1,546 @@
+// Backward of one PDRF field's render pass (the autograd backward of VoxelNeRFBase.sample + forward + raw2outputs,
+// networks/pdrf/voxnerf.py:132-259, at the sample depths the forward pass placed; renderer.py:183-217).
+//
+// Design: the forward kernels keep every per-sample activation on chip, so nothing is saved for backward.  This pass
+// recomputes the activations of a chunk of rays into an HBM workspace as plain row-major matrices and walks the chain
+// backwards.  Every contraction here is a plain tall GEMM (M = samples of the chunk, up to 2^19 rows; N, K <= 256) -- the
+// weight gradient dW = dY^T X reduces over all samples -- and goes to cuBLAS; everything that is not a GEMM is a hand-written
+// kernel in this file: VM plane (.) line products and their scatter-add backward (vector red.global.add.v4.f32 into
+// channel-last gradient planes), positional encodings and their backward, ReLU masks, the sigma->alpha compositing backward
+// (a division-free suffix recursion, exact when a sample saturates alpha = 1) and the per-ray reduction onto the ray batch.
+//
+// Buffers per sample m of a chunk (fp32, row-major):
+//   P_g [96]   plane (.) line products of grid g            X0 [ldX] = [ft_0 (32) | ft_1 (32) | PE(pts) (63) | 0]
+//   H1  [hid]  relu(sigma_net.0)                            SG [ldS] = [sigma | geo_feat | PE(viewdir) (27) | 0]
+//   H2, H3 [hid] relu(color_net.0/1)                        RGB [4]  = color_net.2 pre-activation
+#include <cublas_v2.h>
+
+#include "common.cuh"
+
+namespace edn {
+namespace {
+
+constexpr int kQuads = kAppComp / 4;          // 24 channel quads per sample
+constexpr int kSamplesPerBlock = 8;
+constexpr int kVmThreads = kQuads * kSamplesPerBlock;
+
+struct GradGrid { float* plane[3]; float* line[3]; };
+
+cublasHandle_t blas_handle() {
+  static cublasHandle_t h = nullptr;
+  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+  return h;
+}
+
+// Row-major C[M,N] (+)= op(A) op(B).  !ta: A stored [M][K] (lda); ta: A stored [K][M].  !tb: B stored [K][N]; tb: B stored [N][K].
+struct Gemm {
+  cublasHandle_t h;
+  cublasComputeType_t ct;
+  int operator()(bool ta, bool tb, int64_t M, int N, int64_t K, const float* A, int lda, const float* B, int ldb, float beta,
+                 float* C, int ldc) const {
+    const float alpha = 1.0f;
+    const cublasStatus_t s = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, (int)M, (int)K, &alpha,
+                                          B, CUDA_R_32F, ldb, A, CUDA_R_32F, lda, &beta, C, CUDA_R_32F, ldc, ct, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasGemmEx failed (%d) M=%lld N=%d K=%lld", (int)s, (long long)M, N, (long long)K); return EDN_E_CUDA; }
+    return 0;
+  }
+};
+
+// ---- sample geometry ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sample_point(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t idx, int S,
+                                             float p[3]) {
+  const float* row = rb + (idx / S) * 11;
+  const float z = __ldg(z_vals + idx);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(__ldg(row + i), __fmul_rn(__ldg(row + 3 + i), z));   // as the forward kernels
+}
+
+// taps of VM component `comp` (plane over axes matMode[comp], line over vecMode[comp]) with the tap-weight derivatives
+struct CompTaps {
+  Taps2 pt; Taps1 lt;
+  float dwx[4], dwy[4], dl[2];   // d w_k / d ix, d w_k / d iy (plane), d u_k / d iy (line); zero for out-of-range taps
+  int ax, ay, av;                // point axes feeding plane x (W), plane y (H), line
+  float sx, sy, sv;              // d ix / d n = (W - 1) / 2, ...
+};
+
+__device__ __forceinline__ void comp_taps(const GridDev& g, const float n[3], int comp, CompTaps& t, bool want_grad) {
+  t.ax = (comp == 2) ? 1 : 0;
+  t.ay = (comp == 0) ? 1 : 2;
+  t.av = 2 - comp;
+  const int H = g.ph[comp], W = g.pw[comp], L = g.ll[comp];
+  plane_taps(n[t.ax], n[t.ay], H, W, t.pt);
+  line_taps(n[t.av], L, t.lt);
+  if (!want_grad) return;
+  {
+    const float ix = unnormalize(n[t.ax], W), iy = unnormalize(n[t.ay], H);
+    const float x0 = floorf(ix), y0 = floorf(iy), x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+    const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
+    const bool vx0 = (x0 >= 0.0f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.0f) && (x1 <= (float)(W - 1));
+    const bool vy0 = (y0 >= 0.0f) && (y0 <= (float)(H - 1)), vy1 = (y1 >= 0.0f) && (y1 <= (float)(H - 1));
+    t.dwx[0] = (vx0 && vy0) ? -wy0 : 0.f; t.dwy[0] = (vx0 && vy0) ? -wx0 : 0.f;
+    t.dwx[1] = (vx1 && vy0) ? wy0 : 0.f;  t.dwy[1] = (vx1 && vy0) ? -wx1 : 0.f;
+    t.dwx[2] = (vx0 && vy1) ? -wy1 : 0.f; t.dwy[2] = (vx0 && vy1) ? wx0 : 0.f;
+    t.dwx[3] = (vx1 && vy1) ? wy1 : 0.f;  t.dwy[3] = (vx1 && vy1) ? wx1 : 0.f;
+  }
+  {
+    const float iy = unnormalize(n[t.av], L);
+    const float y0 = floorf(iy), y1 = y0 + 1.0f;
+    t.dl[0] = ((y0 >= 0.0f) && (y0 <= (float)(L - 1))) ? -1.f : 0.f;
+    t.dl[1] = ((y1 >= 0.0f) && (y1 <= (float)(L - 1))) ? 1.f : 0.f;
+  }
+  t.sx = 0.5f * (float)(W - 1); t.sy = 0.5f * (float)(H - 1); t.sv = 0.5f * (float)(L - 1);
+}
+
+__device__ __forceinline__ void quad_of(int q, int& comp, int& c, int& C) {
+  if (q < 16) { comp = 0; c = q * 4; C = 64; }
+  else if (q < 20) { comp = 1; c = (q - 16) * 4; C = 16; }
+  else { comp = 2; c = (q - 20) * 4; C = 16; }
+}
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 scale4(const float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ void fma4(float4& acc, const float4 v, float s) {
+  acc.x = fmaf(v.x, s, acc.x); acc.y = fmaf(v.y, s, acc.y); acc.z = fmaf(v.z, s, acc.z); acc.w = fmaf(v.w, s, acc.w);
+}
+
+// P[m][96] = plane (.) line products (voxnerf.py:132-149); 24 threads per sample, one channel quad each.
+template <typename T>
+__global__ void __launch_bounds__(kVmThreads) vm_products_kernel(const GridDev g, const float* __restrict__ rb,
+                                                                  const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
+                                                                  float* __restrict__ P) {
+  const int64_t t = (int64_t)blockIdx.x * kVmThreads + threadIdx.x;
+  const int64_t m = t / kQuads;
+  const int q = (int)(t % kQuads);
+  if (m >= Mc) return;
+  float p[3], n[3];
+  sample_point(rb, z_vals, m0 + m, S, p);
+  normalize_pt(g, p, n);
+  int comp, c, C;
+  quad_of(q, comp, c, C);
+  CompTaps tp;
+  comp_taps(g, n, comp, tp, false);
+  const float4 v = gather4<T>(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), C, c, tp.pt, tp.lt);
+  *reinterpret_cast<float4*>(P + m * kAppComp + q * 4) = v;
+}
+
+// Backward of the products: scatter-add into the channel-last gradient planes / lines and accumulate d pts.
+template <typename T>
+__global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g, const GradGrid gg, const float* __restrict__ rb,
+                                                                 const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
+                                                                 const float* __restrict__ dP, float* __restrict__ dpts) {
+  __shared__ float dn_s[kSamplesPerBlock][3];
+  if (threadIdx.x < kSamplesPerBlock * 3) (&dn_s[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * kVmThreads + threadIdx.x;
+  const int64_t m = t / kQuads;
+  const int q = (int)(t % kQuads);
+  const int ls = threadIdx.x / kQuads;
+  if (m < Mc) {
+    float p[3], n[3];
+    sample_point(rb, z_vals, m0 + m, S, p);
+    normalize_pt(g, p, n);
+    int comp, c, C;
+    quad_of(q, comp, c, C);
+    CompTaps tp;
+    comp_taps(g, n, comp, tp, true);
+    const T* plane = reinterpret_cast<const T*>(g.plane[comp]);
+    const T* line = reinterpret_cast<const T*>(g.line[comp]);
+    float4 v[4], l[2];
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f), ln = pl;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = load4<T>(plane + (size_t)tp.pt.off[k] * C + c); fma4(pl, v[k], tp.pt.w[k]); }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { l[k] = load4<T>(line + (size_t)tp.lt.off[k] * C + c); fma4(ln, l[k], tp.lt.w[k]); }
+    const float4 dp = *reinterpret_cast<const float4*>(dP + m * kAppComp + q * 4);
+    const float4 dpl = mul4(dp, ln), dln = mul4(dp, pl);
+    float gx = 0.f, gy = 0.f, gv = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tp.pt.w[k] != 0.f) atomicAdd(reinterpret_cast<float4*>(gg.plane[comp] + (size_t)tp.pt.off[k] * C + c), scale4(dpl, tp.pt.w[k]));
+      const float dv = dot4(dpl, v[k]);
+      gx = fmaf(tp.dwx[k], dv, gx);
+      gy = fmaf(tp.dwy[k], dv, gy);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (tp.lt.w[k] != 0.f) atomicAdd(reinterpret_cast<float4*>(gg.line[comp] + (size_t)tp.lt.off[k] * C + c), scale4(dln, tp.lt.w[k]));
+      gv = fmaf(tp.dl[k], dot4(dln, l[k]), gv);
+    }
+    atomicAdd(&dn_s[ls][tp.ax], gx * tp.sx);
+    atomicAdd(&dn_s[ls][tp.ay], gy * tp.sy);
+    atomicAdd(&dn_s[ls][tp.av], gv * tp.sv);
+  }
+  __syncthreads();
+  if (threadIdx.x < kSamplesPerBlock * 3) {
+    const int s = threadIdx.x / 3, i = threadIdx.x % 3;
+    const int64_t mm = (int64_t)blockIdx.x * kSamplesPerBlock + s;
+    if (mm < Mc) dpts[mm * 4 + i] += dn_s[s][i] * g.inv[i];     // n = (p - amin) * inv - 1
+  }
+}
+
+// Positional encodings (embedding.py:88-98): X0[:, nf : ldX) = [PE(pts) (63) | 0], SG[:, 1+geo : ldS) = [PE(viewdir) (27) | 0].
+__device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
+  if (j < 3) return x[j];
+  if (j >= n_pe) return 0.f;
+  const int k = (j - 3) / 6, rem = (j - 3) % 6, axis = rem % 3;
+  const float a = x[axis] * (float)(1 << k);
+  return rem < 3 ? sinf(a) : cosf(a);
+}
+
+__global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
+                          float* __restrict__ X0, int ldX, int nf, float* __restrict__ SG, int ldS, int geo) {
+  const int wp = ldX - nf, wd = ldS - 1 - geo, J = wp + wd;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / J;
+  const int j = (int)(t % J);
+  if (m >= Mc) return;
+  if (j < wp) {
+    float p[3];
+    sample_point(rb, z_vals, m0 + m, S, p);
+    X0[m * ldX + nf + j] = pe_value(p, j, kPePts);
+  } else {
+    const float* row = rb + ((m0 + m) / S) * 11 + 8;
+    const float vd[3] = {__ldg(row), __ldg(row + 1), __ldg(row + 2)};
+    SG[m * ldS + 1 + geo + (j - wp)] = pe_value(vd, j - wp, kPeDir);
+  }
+}
+
+// d pts from the PE(pts) columns of dX0: writes (=) dpts[m][0..2].
+__global__ void pe_bwd_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
+                              const float* __restrict__ dX0, int ldX, int nf, float* __restrict__ dpts) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / 3;
+  const int i = (int)(t % 3);
+  if (m >= Mc) return;
+  float p[3];
+  sample_point(rb, z_vals, m0 + m, S, p);
+  const float* gr = dX0 + m * ldX + nf;
+  float acc = gr[i];
+#pragma unroll
+  for (int k = 0; k < kPeFreqPts; ++k) {
+    const float fr = (float)(1 << k);
+    float sn, cs;
+    sincosf(p[i] * fr, &sn, &cs);
+    acc += fr * (cs * gr[3 + 6 * k + i] - sn * gr[6 + 6 * k + i]);
+  }
+  dpts[m * 4 + i] = acc;
+}
+
+// Y[m][0..n) = relu(Y + bias)
+__global__ void relu_bias_kernel(float* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
+  const int nq = n >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / nq;
+  const int j = (int)(t % nq) * 4;
+  if (m >= M) return;
+  float4 v = *reinterpret_cast<float4*>(Y + m * ld + j);
+  if (bias) { v.x += __ldg(bias + j); v.y += __ldg(bias + j + 1); v.z += __ldg(bias + j + 2); v.w += __ldg(bias + j + 3); }
+  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  *reinterpret_cast<float4*>(Y + m * ld + j) = v;
+}
+
+// D[m][j] = H[m][j] > 0 ? D[m][j] : 0   (ReLU backward; H is the post-activation)
+__global__ void relu_mask_kernel(float* __restrict__ D, const float* __restrict__ H, int ld, int n, int64_t M) {
+  const int nq = n >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / nq;
+  const int j = (int)(t % nq) * 4;
+  if (m >= M) return;
+  float4 d = *reinterpret_cast<float4*>(D + m * ld + j);
+  const float4 h = *reinterpret_cast<const float4*>(H + m * ld + j);
+  d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
+  *reinterpret_cast<float4*>(D + m * ld + j) = d;
+}
+
+// dH3[m][j] = H3[m][j] > 0 ? sum_c dRGB[m][c] * W2[c][j] : 0     (color_net.2 is [3][hid]: a K = 3 contraction)
+__global__ void head_bwd_kernel(const float* __restrict__ dRGB, const float* __restrict__ W2, const float* __restrict__ H3, int hid,
+                                int64_t M, float* __restrict__ dH3) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / hid;
+  const int j = (int)(t % hid);
+  if (m >= M) return;
+  const float4 g = *reinterpret_cast<const float4*>(dRGB + m * 4);
+  const float v = g.x * __ldg(W2 + j) + g.y * __ldg(W2 + hid + j) + g.z * __ldg(W2 + 2 * hid + j);
+  dH3[m * hid + j] = H3[m * hid + j] > 0.f ? v : 0.f;
+}
+
+// out[j] += sum_m D[m][j]  (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ D, int ld, int n, int64_t M, float* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= n) return;
+  const int64_t r0 = (int64_t)blockIdx.x * 512, r1 = min(r0 + 512, M);
+  float acc = 0.f;
+  for (int64_t m = r0; m < r1; ++m) acc += D[m * ld + j];
+  atomicAdd(out + j, acc);
+}
+
+// dSG[m][1 + j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
+__global__ void add_feat_grad_kernel(float* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ d_feat) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / geo;
+  const int j = (int)(t % geo);
+  if (m >= M) return;
+  dSG[m * ldS + 1 + j] += d_feat[m * geo + j];
+}
+
+// Compositing backward (voxnerf.py:153-201), one thread per ray of the chunk.
+//   w_i = alpha_i T_i, T_i = prod_{j<i} (1 - alpha_j);  g_i = dL/dw_i = d_rgb . c_i + d_depth z_i + d_acc + d_weights_i
+//   dL/dalpha_i = T_i (g_i - S_i),  S_i = sum_{k>i} g_k alpha_k prod_{i<j<k} (1 - alpha_j) = g_{i+1} alpha_{i+1} + (1 - alpha_{i+1}) S_{i+1}
+// (no division by 1 - alpha_i: exact when a sample saturates, like torch's cumprod backward).
+__global__ void composite_bwd_kernel(const float* __restrict__ SG, int ldS, const float* __restrict__ RGB, const float* __restrict__ b2,
+                                     const float* __restrict__ rb, const float* __restrict__ z_vals, const float* __restrict__ noise,
+                                     int64_t r0, int64_t Rc, int S, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
+                                     const float* __restrict__ d_acc, const float* __restrict__ d_weights, float* __restrict__ al,
+                                     float* __restrict__ tr, float* __restrict__ dRGB, float* __restrict__ dSG, float* __restrict__ d_rb) {
+  const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rl >= Rc) return;
+  const int64_t r = r0 + rl;
+  const float* z = z_vals + r * S;
+  const float* nz = noise ? noise + r * (S - 1) : nullptr;
+  const float* row = rb + r * 11;
+  const float d[3] = {row[3], row[4], row[5]};
+  const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  const int64_t mb = rl * S;
+  float T = 1.0f;
+  for (int s = 0; s < S; ++s) {
+    const float a = alpha_of_sample(SG[(mb + s) * ldS], z[s], s + 1 < S ? z[s + 1] : 0.f, nz && s + 1 < S ? nz[s] : 0.f, dn, false, 0.f,
+                                    s == S - 1);
+    al[mb + s] = a; tr[mb + s] = T;
+    T = T * (1.0f - a);
+  }
+  const float gr[3] = {d_rgb ? d_rgb[r * 3] : 0.f, d_rgb ? d_rgb[r * 3 + 1] : 0.f, d_rgb ? d_rgb[r * 3 + 2] : 0.f};
+  const float gd = d_depth ? d_depth[r] : 0.f, ga = d_acc ? d_acc[r] : 0.f;
+  const float bb[3] = {b2 ? b2[0] : 0.f, b2 ? b2[1] : 0.f, b2 ? b2[2] : 0.f};
+  float Ssum = 0.f, ddn = 0.f;
+  for (int s = S - 1; s >= 0; --s) {
+    const int64_t m = mb + s;
+    const float a = al[m], Ti = tr[m], w = a * Ti;
+    const float4 x = *reinterpret_cast<const float4*>(RGB + m * 4);
+    const float c[3] = {sigmoidf_(x.x + bb[0]), sigmoidf_(x.y + bb[1]), sigmoidf_(x.z + bb[2])};
+    const float gw = gr[0] * c[0] + gr[1] * c[1] + gr[2] * c[2] + gd * z[s] + ga + (d_weights ? d_weights[r * S + s] : 0.f);
+    *reinterpret_cast<float4*>(dRGB + m * 4) = make_float4(w * gr[0] * c[0] * (1.f - c[0]), w * gr[1] * c[1] * (1.f - c[1]),
+                                                           w * gr[2] * c[2] * (1.f - c[2]), 0.f);
+    float dsig = 0.f;
+    if (s < S - 1) {
+      const float da = Ti * (gw - Ssum);
+      const float dz = z[s + 1] - z[s];
+      const float dist = __fmul_rn(dz, dn);
+      const float sraw = SG[m * ldS] + (nz ? nz[s] : 0.f);
+      const float sg = fmaxf(sraw, 0.f), one_m = 1.0f - a;
+      dsig = sraw > 0.f ? da * dist * one_m : 0.f;
+      ddn = fmaf(da * sg * one_m, dz, ddn);
+    }
+    dSG[m * ldS] = dsig;
+    Ssum = gw * a + (1.0f - a) * Ssum;
+  }
+  if (dn > 0.f) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d_rb[r * 11 + 3 + i] += ddn * d[i] / dn;     // dists = dz * ||rays_d||  (voxnerf.py:160)
+  }
+}
+
+// d ray_batch from the per-sample d pts (pts = o + d z) and the PE(viewdir) columns of dSG; one warp per ray.
+__global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* __restrict__ dSG, int ldS, int geo,
+                                  const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t r0, int64_t Rc, int S,
+                                  float* __restrict__ d_rb) {
+  const int64_t rl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (rl >= Rc) return;
+  const int64_t r = r0 + rl;
+  float acc[6 + kPeDir];
+#pragma unroll
+  for (int j = 0; j < 6 + kPeDir; ++j) acc[j] = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const int64_t m = rl * S + s;
+    const float z = z_vals[r * S + s];
+    const float4 g = *reinterpret_cast<const float4*>(dpts + m * 4);
+    acc[0] += g.x; acc[1] += g.y; acc[2] += g.z;
+    acc[3] = fmaf(z, g.x, acc[3]); acc[4] = fmaf(z, g.y, acc[4]); acc[5] = fmaf(z, g.z, acc[5]);
+    const float* gv = dSG + m * ldS + 1 + geo;
+#pragma unroll
+    for (int j = 0; j < kPeDir; ++j) acc[6 + j] += gv[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 6 + kPeDir; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane == 0) {
+    float* out = d_rb + r * 11;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] += acc[i];
+    const float* vd = rb + r * 11 + 8;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float g = acc[6 + i];
+#pragma unroll
+      for (int k = 0; k < kPeFreqDir; ++k) {
+        const float fr = (float)(1 << k);
+        float sn, cs;
+        sincosf(vd[i] * fr, &sn, &cs);
+        g += fr * (cs * acc[6 + 3 + 6 * k + i] - sn * acc[6 + 6 + 6 * k + i]);
+      }
+      out[8 + i] += g;
+    }
+  }
+}
+
+struct Dims {
+  int ng, nf, hid, geo, ldX, ldS, kin, cin;
+};
+inline Dims make_dims(int n_grids, int hidden, int geo) {
+  Dims d;
+  d.ng = n_grids; d.nf = 32 * n_grids; d.hid = hidden; d.geo = geo;
+  d.kin = d.nf + kPePts;                 // 95 | 127
+  d.cin = geo + kPeDir;                  // 42 | 155
+  d.ldX = (d.kin + 3) & ~3;              // 96 | 128
+  d.ldS = (1 + d.cin + 3) & ~3;          // 44 | 156
+  return d;
+}
+inline int64_t floats_per_sample(const Dims& d) {
+  return (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + 4 /*RGB*/ + 4 /*dRGB*/ +
+         d.hid * 2 /*D1 D2*/ + d.ldS /*dSG*/ + d.ldX /*dX0*/ + kAppComp /*dP*/ + 4 /*dpts*/ + 2 /*alpha, T*/;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+}  // namespace edn
+
+extern "C" int64_t edn_field_bwd_workspace_bytes(int32_t n_grids, int32_t hidden, int32_t geo_feat, int64_t chunk_rays,
+                                                 int32_t n_samples) {
+  using namespace edn;
+  if (n_grids < 1 || n_grids > 2 || hidden <= 0 || geo_feat <= 0 || chunk_rays <= 0 || n_samples <= 0) return -1;
+  return floats_per_sample(make_dims(n_grids, hidden, geo_feat)) * chunk_rays * n_samples * (int64_t)sizeof(float);
+}
+
+extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid* grid1, const edn_field_weights* w,
+                                    const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays,
+                                    int32_t n_samples, int32_t precision, const float* d_rgb, const float* d_depth,
+                                    const float* d_acc, const float* d_weights, const float* d_feat,
+                                    const edn_field_weights* grad_w, const edn_vm_grid_grad* grad_grid0,
+                                    const edn_vm_grid_grad* grad_grid1, float* d_ray_batch, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(grid0 && w && grad_w && grad_grid0 && ray_batch && z_vals && d_ray_batch && workspace, "edn_render_field_bwd: null pointer");
+  EDN_REQUIRE(n_samples >= 2, "edn_render_field_bwd: n_samples must be >= 2");
+  const int ng = w->n_grids;
+  EDN_REQUIRE(ng == 1 || ng == 2, "edn_render_field_bwd: n_grids must be 1 or 2");
+  EDN_REQUIRE(ng == 1 || (grid1 && grad_grid1), "edn_render_field_bwd: n_grids = 2 needs grid1 and grad_grid1");
+  EDN_REQUIRE(w->hidden % 4 == 0 && w->hidden > 0 && w->hidden <= 256 && w->geo_feat > 0, "edn_render_field_bwd: unsupported MLP dims");
+  EDN_REQUIRE(w->sigma0 && w->sigma1 && w->color0 && w->color1 && w->color2 && w->basis[0] && (ng == 1 || w->basis[1]),
+              "edn_render_field_bwd: null weight");
+  EDN_REQUIRE(grad_w->sigma0 && grad_w->sigma1 && grad_w->color0 && grad_w->color1 && grad_w->color2 && grad_w->basis[0] &&
+                  (ng == 1 || grad_w->basis[1]), "edn_render_field_bwd: null weight gradient");
+  EDN_REQUIRE(!w->color0_b == !grad_w->color0_b && !w->color1_b == !grad_w->color1_b && !w->color2_b == !grad_w->color2_b,
+              "edn_render_field_bwd: bias / bias-gradient mismatch");
+  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_render_field_bwd: bad precision");
+  if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
+  const edn_vm_grid* grids[2] = {grid0, grid1};
+  const edn_vm_grid_grad* ggr[2] = {grad_grid0, grad_grid1};
+  GridDev gd[2];
+  GradGrid gg[2];
+  for (int g = 0; g < ng; ++g) {
+    int rc = make_grid_dev(grids[g], &gd[g]);
+    if (rc) return rc;
+    EDN_REQUIRE(grids[g]->dtype == EDN_F32 || grids[g]->dtype == EDN_BF16, "edn_render_field_bwd: bad grid dtype");
+    for (int i = 0; i < 3; ++i) {
+      EDN_REQUIRE(ggr[g]->plane[i] && ggr[g]->line[i], "edn_render_field_bwd: null grid gradient");
+      gg[g].plane[i] = ggr[g]->plane[i];
+      gg[g].line[i] = ggr[g]->line[i];
+    }
+  }
+  const Dims D = make_dims(ng, w->hidden, w->geo_feat);
+  const int S = n_samples, hid = D.hid, geo = D.geo;
+  const int64_t per_ray = floats_per_sample(D) * S * (int64_t)sizeof(float);
+  int64_t chunk = workspace_bytes / per_ray;
+  EDN_REQUIRE(chunk >= 1, "edn_render_field_bwd: workspace too small (%lld bytes, one ray needs %lld)", (long long)workspace_bytes,
+              (long long)per_ray);
+  chunk = chunk < n_rays ? chunk : n_rays;
+  if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;         // keep GEMM row counts well inside int range
+
+  cublasHandle_t h = blas_handle();
+  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
+  const Gemm gemm{h, precision == EDN_F32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32};
+
+  // workspace carve-up (sized for `chunk` rays)
+  const int64_t Mmax = chunk * S;
+  float* base = reinterpret_cast<float*>(workspace);
+  auto take = [&](int64_t per) { float* p = base; base += per * Mmax; return p; };
+  float* P[2] = {take(kAppComp), ng == 2 ? take(kAppComp) : nullptr};
+  float* X0 = take(D.ldX);
+  float* H1 = take(hid);
+  float* H2 = take(hid);
+  float* H3 = take(hid);
+  float* SG = take(D.ldS);
+  float* RGB = take(4);
+  float* dRGB = take(4);
+  float* D1 = take(hid);
+  float* D2 = take(hid);
+  float* dSG = take(D.ldS);
+  float* dX0 = take(D.ldX);
+  float* dP = take(kAppComp);
+  float* dpts = take(4);
+  float* al = take(1);
+  float* tr = take(1);
+
+#define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
+    const int64_t Rc = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
+    const int64_t M = Rc * S, m0 = r0 * S;
+    // ---- recompute the forward activations -------------------------------------------------------------------------
+    for (int g = 0; g < ng; ++g) {
+      if (grids[g]->dtype == EDN_F32) vm_products_kernel<float><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
+      else vm_products_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
+      EDN_RC(gemm(false, true, M, kAppDim, kAppComp, P[g], kAppComp, w->basis[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
+    }
+    {
+      const int J = (D.ldX - D.nf) + (D.ldS - 1 - geo);
+      pe_kernel<<<blocks_for(M * J, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo);
+    }
+    EDN_RC(gemm(false, true, M, hid, D.kin, X0, D.ldX, w->sigma0, D.kin, 0.f, H1, hid));
+    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
+    EDN_RC(gemm(false, true, M, 1 + geo, hid, H1, hid, w->sigma1, hid, 0.f, SG, D.ldS));
+    EDN_RC(gemm(false, true, M, hid, D.cin, SG + 1, D.ldS, w->color0, D.cin, 0.f, H2, hid));
+    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
+    EDN_RC(gemm(false, true, M, hid, hid, H2, hid, w->color1, hid, 0.f, H3, hid));
+    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
+    EDN_RC(gemm(false, true, M, 3, hid, H3, hid, w->color2, hid, 0.f, RGB, 4));
+    // ---- compositing backward ------------------------------------------------------------------------------------------
+    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(SG, D.ldS, RGB, w->color2_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
+                                                           d_acc, d_weights, al, tr, dRGB, dSG, d_ray_batch);
+    // ---- color_net backward ----------------------------------------------------------------------------------------------
+    EDN_RC(gemm(true, false, 3, hid, M, dRGB, 4, H3, hid, 1.f, grad_w->color2, hid));
+    if (grad_w->color2_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, grad_w->color2_b);
+    head_bwd_kernel<<<blocks_for(M * hid, 256), 256, 0, st>>>(dRGB, w->color2, H3, hid, M, D1);                 // D1 = dH3
+    EDN_RC(gemm(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
+    if (grad_w->color1_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
+    EDN_RC(gemm(false, false, M, hid, hid, D1, hid, w->color1, hid, 0.f, D2, hid));                               // D2 = dH2
+    relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
+    EDN_RC(gemm(true, false, hid, D.cin, M, D2, hid, SG + 1, D.ldS, 1.f, grad_w->color0, D.cin));
+    if (grad_w->color0_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
+    EDN_RC(gemm(false, false, M, D.cin, hid, D2, hid, w->color0, D.cin, 0.f, dSG + 1, D.ldS));                    // [d geo | d PE(dir)]
+    if (d_feat) add_feat_grad_kernel<<<blocks_for(M * geo, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, d_feat + m0 * geo);
+    // ---- sigma_net backward ------------------------------------------------------------------------------------------------
+    EDN_RC(gemm(true, false, 1 + geo, hid, M, dSG, D.ldS, H1, hid, 1.f, grad_w->sigma1, hid));
+    EDN_RC(gemm(false, false, M, hid, 1 + geo, dSG, D.ldS, w->sigma1, hid, 0.f, D1, hid));                        // D1 = dH1
+    relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
+    EDN_RC(gemm(true, false, hid, D.kin, M, D1, hid, X0, D.ldX, 1.f, grad_w->sigma0, D.kin));
+    EDN_RC(gemm(false, false, M, D.kin, hid, D1, hid, w->sigma0, D.kin, 0.f, dX0, D.ldX));
+    // ---- inputs: PE(pts), basis_mat, VM grids ----------------------------------------------------------------------------------
+    pe_bwd_kernel<<<blocks_for(M * 3, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, dX0, D.ldX, D.nf, dpts);
+    for (int g = 0; g < ng; ++g) {
+      EDN_RC(gemm(true, false, kAppDim, kAppComp, M, dX0 + 32 * g, D.ldX, P[g], kAppComp, 1.f, grad_w->basis[g], kAppComp));
+      EDN_RC(gemm(false, false, M, kAppComp, kAppDim, dX0 + 32 * g, D.ldX, w->basis[g], kAppComp, 0.f, dP, kAppComp));
+      if (grids[g]->dtype == EDN_F32) vm_scatter_kernel<float><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
+      else vm_scatter_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
+    }
+    ray_reduce_kernel<<<blocks_for(Rc * 32, 256), 256, 0, st>>>(dpts, dSG, D.ldS, geo, ray_batch, z_vals, r0, Rc, S, d_ray_batch);
+    EDN_CUDA_OK(cudaGetLastError());
+  }
+#undef EDN_RC
+  return EDN_OK;
+}

@@ -169,6 +169,13 @@ class RenderEngine(SamplerHost):
         self.aabb_min, self.aabb_max = [float(x) for x in aabb_min], [float(x) for x in aabb_max]
         self.repack(params)
 
+    def workspace(self, nbytes):
+        """Cached scratch buffer (grown on demand) for the backward pass's recomputed activations."""
+        ws = getattr(self, "_workspace", None)
+        if ws is None or ws.numel() < nbytes:
+            self._workspace = ws = torch.empty((int(nbytes),), dtype=torch.uint8, device=self.device)
+        return ws
+
     def _launch(self, name, fn):
         if self.profile is None:
             return fn()
@@ -182,6 +189,8 @@ class RenderEngine(SamplerHost):
     def repack(self, params):
         """(Re)build the render-layout copies; call after the parameters changed (optimizer step / checkpoint load)."""
         P = {k: (v if v.is_cuda else v.to(self.device)) for k, v in params.items() if isinstance(v, torch.Tensor)}
+        # reference-layout fp32 views of the two fields' parameters: what the backward pass reads (backward.py)
+        self.params = {k: v.detach().float().contiguous() for k, v in P.items() if k.startswith(("mlp_coarse.", "mlp_fine."))}
         grid_dtype = self.prec_code
         self.coarse = PackedField(P, "mlp_coarse.", self.aabb_min, self.aabb_max, True, grid_dtype)
         if self.prec_code == EDN_BF16:

@@ -134,6 +134,52 @@ int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_
                         int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* weights,
                         float* rgb, float* depth, float* acc, float* feat, void* stream);
 
+/* ---- backward of the render path (the reference relies on torch autograd: loss.backward() at run_nerf.py:594) -------- */
+
+/* One PDRF field's weights -- or their gradients -- in the reference's own nn.Linear layout ([out][in], fp32), i.e. the
+ * state_dict tensors as they are: basis[g] = basis_mat.weight [32][96] of grid g feeding the field (coarse field: its own
+ * grid; fine field: the coarse grid, then the fine grid, renderer.py:194-195), sigma0 [hidden][32*n_grids+63],
+ * sigma1 [1+geo_feat][hidden], color0 [hidden][geo_feat+27], color1 [hidden][hidden], color2 [3][hidden], biases or NULL. */
+typedef struct edn_field_weights {
+  float* basis[2];
+  float* sigma0;
+  float* sigma1;
+  float* color0;
+  float* color1;
+  float* color2;
+  float* color0_b;
+  float* color1_b;
+  float* color2_b;
+  int32_t hidden;
+  int32_t geo_feat;
+  int32_t n_grids;
+} edn_field_weights;
+
+/* Gradient planes / lines of one VM grid in RENDER LAYOUT (channel-last fp32, same dims as the edn_vm_grid). */
+typedef struct edn_vm_grid_grad {
+  float* plane[3];
+  float* line[3];
+} edn_vm_grid_grad;
+
+/* Backward of one field's render pass: VoxelNeRFBase.sample + forward + raw2outputs (voxnerf.py:132-259) evaluated at
+ * pts = o + d * z_vals (z_vals are constants: the coarse depths carry no gradient and z_samples is detached,
+ * renderer.py:203).  Coarse field: grid1 = NULL, z_vals = the coarse depths; fine field: grid0 / grid1 = coarse / fine grid,
+ * z_vals = merged depths.  Upstream gradients d_rgb [R][3], d_depth [R], d_acc [R], d_weights [R][S], d_feat [R][S][geo]
+ * (each may be NULL = zero).  Everything below is ACCUMULATED into (+=): grad_w (same layout as w), grad_grid*, and
+ * d_ray_batch [R][11] (columns o, d, viewdirs).  precision: EDN_F32 = fp32 GEMMs (parity), EDN_BF16 = TF32 tensor-core GEMMs.
+ * The activations are recomputed chunk by chunk into `workspace`; edn_field_bwd_workspace_bytes gives the size for a chunk
+ * of `chunk_rays` rays (any workspace holding >= 1 ray works; larger chunks run faster). */
+int64_t edn_field_bwd_workspace_bytes(int32_t n_grids, int32_t hidden, int32_t geo_feat, int64_t chunk_rays, int32_t n_samples);
+int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid* grid1, const edn_field_weights* w,
+                         const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays, int32_t n_samples,
+                         int32_t precision, const float* d_rgb, const float* d_depth, const float* d_acc,
+                         const float* d_weights, const float* d_feat, const edn_field_weights* grad_w,
+                         const edn_vm_grid_grad* grad_grid0, const edn_vm_grid_grad* grad_grid1, float* d_ray_batch,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Channel-last gradient plane [H][W][C] -> += into the reference layout [1,C,H,W] (inverse of edn_pack_vm_plane). */
+int edn_unpack_vm_plane_grad(const float* src_hwc, float* dst_chw, int32_t C, int32_t H, int32_t W, int32_t accumulate, void* stream);
+
 /* ---- mode = nerf ("run_network") -------------------------------------------------------------------------------------- */
 
 /* Vanilla NeRF field weights (networks/nerf.py:23-44), TRANSPOSED [in][out] fp32:

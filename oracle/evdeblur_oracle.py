@@ -326,6 +326,7 @@ def render_rays(P, cfg, ray_batch, n_samples, n_importance=0, perturb=0., lindis
         z_mid = .5 * (z[..., 1:] + z[..., :-1])
         z_s, inds = sample_pdf(z_mid, w0[..., 1:-1], n_importance, rand.get("u") if perturb > 0 else None,
                                norm=cfg.get("pdf_norm", "fp64"))
+        z_s = z_s.detach()                                                           # renderer.py:203
         z_all, order = merge_samples(z, z_s)
         pts1 = o[:, None, :] + d[:, None, :] * z_s[..., None]
         ft1 = torch.cat([vm_sample(P, "mlp_coarse.", pts1, amin, amax), vm_sample(P, "mlp_fine.", pts1, amin, amax)], -1)
