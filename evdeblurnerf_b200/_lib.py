@@ -46,6 +46,16 @@ class RbkParams(C.Structure):
                                                              ("rv_window", C.c_float)]
 
 
+class RbkGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("img_embed", "r_branch_w", "r_branch_b", "v_branch_w", "v_branch_b", "w_branch_w",
+                                           "w_branch_b", "r_linear_w", "r_linear_b", "v_linear_w", "v_linear_b", "w_linear_w",
+                                           "w_linear_b")]
+
+
+class CrfGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3")]
+
+
 class CrfParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3")] + [
         ("extra_features", C.c_int32), ("gamma", C.c_float)]
@@ -90,6 +100,16 @@ SIGNATURES = {
                                        _I32, _P, _P, _P, _P, _P, C.POINTER(FieldWeights), C.POINTER(VmGridGrad),
                                        C.POINTER(VmGridGrad), _P, _P, _I64, _P]),
     "edn_unpack_vm_plane_grad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "edn_rbk_bwd_workspace_floats": (C.c_int64, [_I64, _I32]),
+    "edn_rbk_warp_ndc_bwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, C.POINTER(RbkGrads), _P, _P]),
+    "edn_weighted_sum_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
+    "edn_crf_bwd": (C.c_int, [C.POINTER(CrfParams), _P, _P, _I32, _I32, _I64, _P, _P, C.POINTER(CrfGrads), _P]),
+    "edn_egm_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _F, _P, _P, _P, _P]),
+    "edn_img2mse_bwd": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "edn_tv_loss_app_bwd": (C.c_int, [C.POINTER(C.c_void_p * 3), C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int32 * 3),
+                                      C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _P,
+                                      C.POINTER(C.c_void_p * 3), C.POINTER(C.c_void_p * 3), _P]),
+    "edn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),

@@ -1,0 +1,235 @@
+"""torch.autograd bridges: the reference trains by `loss.backward()` through its PyTorch graph (run_nerf.py:594); here each
+fused forward entry point is paired with its hand-written backward (field_bwd.cu, ray_bwd.cu, loss_bwd.cu) in a
+`torch.autograd.Function`, so outputs of the host mirrors participate in autograd exactly like the reference's and
+parameter `.grad`s come out under the reference's own names / shapes (SURVEY.md 8(b) "Ownership / memory").
+
+Forward arithmetic is identical to the no-grad path (same kernels); nothing per-sample is saved -- the render backward
+recomputes activations chunk by chunk (see field_bwd.cu).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CrfGrads, RbkGrads, check, ptr, stream_ptr
+from .backward import RenderGradients, render_rays_backward
+
+_RBK_NAMES = ("view_embed_module.img_embed", "r_branch.0.weight", "r_branch.0.bias", "v_branch.0.weight", "v_branch.0.bias",
+              "w_branch.0.weight", "w_branch.0.bias", "r_linear.weight", "r_linear.bias", "v_linear.weight", "v_linear.bias",
+              "w_linear.weight", "w_linear.bias")
+_RBK_FIELDS = ("img_embed", "r_branch_w", "r_branch_b", "v_branch_w", "v_branch_b", "w_branch_w", "w_branch_b", "r_linear_w",
+               "r_linear_b", "v_linear_w", "v_linear_b", "w_linear_w", "w_linear_b")
+
+
+def _c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+class WeightedSumFn(torch.autograd.Function):
+    """rbk_weighted_sum for one tensor (blurmodel.py:112-127): x [N*E, ...], ccw [N,E] -> [N, ...]."""
+
+    @staticmethod
+    def forward(ctx, x, ccw):
+        N, E = ccw.shape
+        xf, wf = _c(x), _c(ccw)
+        Cn = max(1, xf.numel() // max(1, N * E))
+        out = torch.empty((N,) + tuple(xf.shape[1:]), dtype=torch.float32, device=xf.device)
+        check(_lib.load().edn_weighted_sum(ptr(xf), ptr(wf), ptr(out), N, E, Cn, stream_ptr()), "edn_weighted_sum")
+        ctx.save_for_backward(xf, wf)
+        ctx.dims = (N, E, Cn)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        xf, wf = ctx.saved_tensors
+        N, E, Cn = ctx.dims
+        d_x = torch.empty_like(xf) if ctx.needs_input_grad[0] else None
+        d_w = torch.empty_like(wf) if ctx.needs_input_grad[1] else None
+        if N > 0:
+            check(_lib.load().edn_weighted_sum_bwd(ptr(xf), ptr(wf), ptr(_c(d_out)), N, E, Cn, ptr(d_x), ptr(d_w), stream_ptr()),
+                  "edn_weighted_sum_bwd")
+        return d_x, d_w
+
+
+class Img2MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        xf, yf = _c(x), _c(y)
+        out = torch.empty((1,), dtype=torch.float32, device=xf.device)
+        check(_lib.load().edn_img2mse(ptr(xf), ptr(yf), xf.numel(), ptr(out), stream_ptr()), "edn_img2mse")
+        ctx.save_for_backward(xf, yf)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        xf, yf = ctx.saved_tensors
+        d_x = torch.empty_like(xf)
+        check(_lib.load().edn_img2mse_bwd(ptr(xf), ptr(yf), xf.numel(), ptr(_c(d_loss).reshape(1)), ptr(d_x), stream_ptr()),
+              "edn_img2mse_bwd")
+        return d_x, None
+
+
+class EgmLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ls, le, b, mask, cw, log_eps):
+        M, Cn = ls.shape
+        out = torch.empty((1,), dtype=torch.float32, device=ls.device)
+        check(_lib.load().edn_egm_loss_fwd(ptr(ls), ptr(le), ptr(b), ptr(mask), ptr(cw), Cn, M, float(log_eps), ptr(out), stream_ptr()),
+              "edn_egm_loss_fwd")
+        ctx.save_for_backward(ls, le, b)
+        ctx.aux = (mask, cw, float(log_eps))
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        ls, le, b = ctx.saved_tensors
+        mask, cw, eps = ctx.aux
+        M, Cn = ls.shape
+        d_ls, d_le = torch.empty_like(ls), torch.empty_like(le)
+        check(_lib.load().edn_egm_loss_bwd(ptr(ls), ptr(le), ptr(b), ptr(mask), ptr(cw), Cn, M, eps, ptr(_c(d_loss).reshape(1)),
+                                           ptr(d_ls), ptr(d_le), stream_ptr()), "edn_egm_loss_bwd")
+        return d_ls, d_le, None, None, None, None
+
+
+class CrfFn(torch.autograd.Function):
+    """CRF.forward / encode_rgb / encode_luma (tonemapping.py:59-139).  `weights`: the 8 CRF tensors w0, b0, ..., w3, b3 (may
+    be empty when the mapping has no learnt part)."""
+
+    @staticmethod
+    def forward(ctx, x, feat, per_channel, flags, cp, *weights):
+        M = x.shape[0]
+        luma = bool(flags & _lib.CRF_LUMA)
+        out = torch.empty((M, 1 if luma else 3), dtype=torch.float32, device=x.device)
+        check(_lib.load().edn_crf_fwd(C.byref(cp), ptr(x), ptr(feat), per_channel, flags, M, ptr(out), stream_ptr()), "edn_crf_fwd")
+        ctx.save_for_backward(x, *([feat] if feat is not None else []))
+        ctx.aux = (feat is not None, per_channel, flags, cp, [tuple(w.shape) for w in weights])
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        has_feat, per_channel, flags, cp, shapes = ctx.aux
+        x = ctx.saved_tensors[0]
+        feat = ctx.saved_tensors[1] if has_feat else None
+        M = x.shape[0]
+        d_x = torch.empty_like(x)
+        gw = [torch.zeros(s, dtype=torch.float32, device=x.device) for s in shapes]
+        learn = bool(flags & _lib.CRF_LEARN) and not (flags & _lib.CRF_SKIP_LEARN)
+        g = None
+        if learn and len(gw) == 8:
+            g = CrfGrads()
+            for slot, t in zip(("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3"), gw):
+                setattr(g, slot, t.data_ptr())
+        check(_lib.load().edn_crf_bwd(C.byref(cp), ptr(x), ptr(feat), per_channel, flags, M, ptr(_c(d_out)), ptr(d_x),
+                                      C.byref(g) if g is not None else None, stream_ptr()), "edn_crf_bwd")
+        return (d_x, None, None, None, None) + tuple(gw)
+
+
+class TvLossFn(torch.autograd.Function):
+    """VoxelNeRFBase.TV_loss_app (voxnerf.py:126-130) over 3 planes + 3 lines in the reference layout."""
+
+    @staticmethod
+    def _arrays(planes, lines):
+        pp = (C.c_void_p * 3)(*[t.data_ptr() for t in planes])
+        lp = (C.c_void_p * 3)(*[t.data_ptr() for t in lines])
+        ph = (C.c_int32 * 3)(*[t.shape[2] for t in planes])
+        pw = (C.c_int32 * 3)(*[t.shape[3] for t in planes])
+        ll = (C.c_int32 * 3)(*[t.shape[2] for t in lines])
+        nc = (C.c_int32 * 3)(*[t.shape[1] for t in planes])
+        return pp, lp, ph, pw, ll, nc
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        ts = [_c(t) for t in tensors]
+        planes, lines = ts[:3], ts[3:]
+        pp, lp, ph, pw, ll, nc = TvLossFn._arrays(planes, lines)
+        dev = planes[0].device
+        ws = torch.empty((12,), dtype=torch.float64, device=dev)
+        out = torch.empty((1,), dtype=torch.float32, device=dev)
+        check(_lib.load().edn_tv_loss_app(C.byref(pp), C.byref(lp), C.byref(ph), C.byref(pw), C.byref(ll), C.byref(nc), ptr(ws),
+                                          ptr(out), stream_ptr()), "edn_tv_loss_app")
+        ctx.save_for_backward(*ts)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        ts = list(ctx.saved_tensors)
+        planes, lines = ts[:3], ts[3:]
+        pp, lp, ph, pw, ll, nc = TvLossFn._arrays(planes, lines)
+        grads = [torch.zeros_like(t) for t in ts]
+        gp = (C.c_void_p * 3)(*[t.data_ptr() for t in grads[:3]])
+        gl = (C.c_void_p * 3)(*[t.data_ptr() for t in grads[3:]])
+        check(_lib.load().edn_tv_loss_app_bwd(C.byref(pp), C.byref(lp), C.byref(ph), C.byref(pw), C.byref(ll), C.byref(nc),
+                                              ptr(_c(d_loss).reshape(1)), C.byref(gp), C.byref(gl), stream_ptr()),
+              "edn_tv_loss_app_bwd")
+        return tuple(grads)
+
+
+class RenderSubRaysFn(torch.autograd.Function):
+    """Blur-kernel warp + render() prologue + c2f render_rays of the N*E sub-rays (renderer.py:303-309 -> 129-264) as ONE
+    autograd node.  Inputs: the parameter tensors (for graph connectivity; the kernels read the engine's packed copies).
+    Outputs: rgb_map, depth_map, acc_map, rgb0, depth0, acc0 [N*E, ...] and the blur weights [N,E]; everything else the
+    forward produced (z_vals, weights, img_embed ...) is returned through `owner.last_render` without gradient."""
+
+    @staticmethod
+    def forward(ctx, owner, kn, H, W, focal, rays, images_idx, near, far, ndc, kwargs, names, *params):
+        eng = owner.engine
+        kw = dict(kwargs)
+        kw["retraw"] = True
+        if kn is not None:
+            k = kn.warp(H, W, focal, rays, images_idx, near, far, ndc, want_new_rays=False)
+            rb, weight = k["ray_batch"], k["weight"]
+        else:
+            from .renderer import build_ray_batch
+            rb, weight, k = build_ray_batch(H, W, focal, rays, near, far, ndc), None, {}
+        R, dev = rb.shape[0], rb.device
+        Nc, Ni = int(kw["N_samples"]), int(kw.get("N_importance", 0))
+        # draw the density noise here so that backward sees the very same tensors (voxnerf.py:175)
+        rand = dict(kw.pop("rand", None) or {})
+        std = float(kw.get("raw_noise_std", 0.))
+        if std > 0.:
+            eng._calls += 1
+            if "noise0" not in rand:
+                rand["noise0"] = eng._random((R, Nc - 1), 1, normal=True, scale=std)
+            if Ni > 0 and "noise1" not in rand:
+                rand["noise1"] = eng._random((R, Nc + Ni - 1), 3, normal=True, scale=std)
+        out = owner.render_rays(rb, rand=rand, **kw)
+        owner.last_render = dict(out, ray_batch=rb, img_embed=k.get("img_embed"), weight=weight)
+        ctx.owner, ctx.kn, ctx.names = owner, kn, names
+        ctx.geom = (H, W, focal, ndc)
+        ctx.two_stage = Ni > 0
+        ctx.saved = {"ray_batch": rb, "z_vals0": out["z_vals0"] if Ni > 0 else out["z_vals"], "z_vals": out["z_vals"] if Ni > 0 else None,
+                     "noise0": rand.get("noise0"), "noise1": rand.get("noise1")}
+        ctx.rays = _c(rays)
+        ctx.idx = images_idx.reshape(-1).to(torch.int64).contiguous() if images_idx is not None else None
+        zero3, zero1 = torch.zeros((R, 3), device=dev), torch.zeros((R,), device=dev)
+        res = (out["rgb_map"], out["depth_map"], out["acc_map"], out.get("rgb0", zero3), out.get("depth0", zero1), out.get("acc0", zero1),
+               weight if weight is not None else torch.zeros((0,), device=dev))
+        return res
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_acc, d_rgb0, d_depth0, d_acc0, d_weight):
+        owner, kn = ctx.owner, ctx.kn
+        eng = owner.engine
+        lib = _lib.load()
+        d_out = {"rgb_map": d_rgb, "depth_map": d_depth, "acc_map": d_acc}
+        if ctx.two_stage:
+            d_out.update(rgb0=d_rgb0, depth0=d_depth0, acc0=d_acc0)
+        grads, d_rb = render_rays_backward(eng, ctx.saved, d_out, grads=RenderGradients(eng), chunk_rays=owner.backward_chunk_rays)
+        named = grads.finish()
+        if kn is not None:
+            H, W, focal, ndc = ctx.geom
+            N = ctx.rays.shape[0]
+            g = RbkGrads()
+            for nm, field in zip(_RBK_NAMES, _RBK_FIELDS):
+                t = torch.zeros_like(kn.tensors[nm])
+                named[kn.prefix + nm] = t
+                setattr(g, field, t.data_ptr())
+            ws = torch.empty((int(lib.edn_rbk_bwd_workspace_floats(N, kn.num_motion)),), dtype=torch.float32, device=d_rb.device)
+            check(lib.edn_rbk_warp_ndc_bwd(C.byref(kn.p), ptr(ctx.rays), ptr(ctx.idx), N, int(H), int(W), float(focal), 1 if ndc else 0,
+                                           ptr(d_rb), ptr(_c(d_weight)) if d_weight is not None and d_weight.numel() else None,
+                                           C.byref(g), ptr(ws), stream_ptr()), "edn_rbk_warp_ndc_bwd")
+        out = []
+        for nm in ctx.names:
+            gr = named.get(nm)
+            out.append(gr)
+        return (None,) * 12 + tuple(out)

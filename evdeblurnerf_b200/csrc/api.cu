@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cublas_v2.h>
+
 #include "common.cuh"
 
 namespace edn {
@@ -19,6 +21,12 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("CUDA error %s (%d) at %s", cudaGetErrorString(e), (int)e, what);
   return EDN_E_CUDA;
+}
+
+cublasHandle_t blas_handle() {
+  static cublasHandle_t h = nullptr;
+  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+  return h;
 }
 
 int num_sms() {

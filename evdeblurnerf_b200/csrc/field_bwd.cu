@@ -13,9 +13,7 @@
 //   P_g [96]   plane (.) line products of grid g            X0 [ldX] = [ft_0 (32) | ft_1 (32) | PE(pts) (63) | 0]
 //   H1  [hid]  relu(sigma_net.0)                            SG [ldS] = [sigma | geo_feat | PE(viewdir) (27) | 0]
 //   H2, H3 [hid] relu(color_net.0/1)                        RGB [4]  = color_net.2 pre-activation
-#include <cublas_v2.h>
-
-#include "common.cuh"
+#include "bwd_common.cuh"
 
 namespace edn {
 namespace {
@@ -25,26 +23,6 @@ constexpr int kSamplesPerBlock = 8;
 constexpr int kVmThreads = kQuads * kSamplesPerBlock;
 
 struct GradGrid { float* plane[3]; float* line[3]; };
-
-cublasHandle_t blas_handle() {
-  static cublasHandle_t h = nullptr;
-  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
-  return h;
-}
-
-// Row-major C[M,N] (+)= op(A) op(B).  !ta: A stored [M][K] (lda); ta: A stored [K][M].  !tb: B stored [K][N]; tb: B stored [N][K].
-struct Gemm {
-  cublasHandle_t h;
-  cublasComputeType_t ct;
-  int operator()(bool ta, bool tb, int64_t M, int N, int64_t K, const float* A, int lda, const float* B, int ldb, float beta,
-                 float* C, int ldc) const {
-    const float alpha = 1.0f;
-    const cublasStatus_t s = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, (int)M, (int)K, &alpha,
-                                          B, CUDA_R_32F, ldb, A, CUDA_R_32F, lda, &beta, C, CUDA_R_32F, ldc, ct, CUBLAS_GEMM_DEFAULT);
-    if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasGemmEx failed (%d) M=%lld N=%d K=%lld", (int)s, (long long)M, N, (long long)K); return EDN_E_CUDA; }
-    return 0;
-  }
-};
 
 // ---- sample geometry ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sample_point(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t idx, int S,
@@ -227,32 +205,6 @@ __global__ void pe_bwd_kernel(const float* __restrict__ rb, const float* __restr
   dpts[m * 4 + i] = acc;
 }
 
-// Y[m][0..n) = relu(Y + bias)
-__global__ void relu_bias_kernel(float* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
-  const int nq = n >> 2;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = t / nq;
-  const int j = (int)(t % nq) * 4;
-  if (m >= M) return;
-  float4 v = *reinterpret_cast<float4*>(Y + m * ld + j);
-  if (bias) { v.x += __ldg(bias + j); v.y += __ldg(bias + j + 1); v.z += __ldg(bias + j + 2); v.w += __ldg(bias + j + 3); }
-  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  *reinterpret_cast<float4*>(Y + m * ld + j) = v;
-}
-
-// D[m][j] = H[m][j] > 0 ? D[m][j] : 0   (ReLU backward; H is the post-activation)
-__global__ void relu_mask_kernel(float* __restrict__ D, const float* __restrict__ H, int ld, int n, int64_t M) {
-  const int nq = n >> 2;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = t / nq;
-  const int j = (int)(t % nq) * 4;
-  if (m >= M) return;
-  float4 d = *reinterpret_cast<float4*>(D + m * ld + j);
-  const float4 h = *reinterpret_cast<const float4*>(H + m * ld + j);
-  d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
-  *reinterpret_cast<float4*>(D + m * ld + j) = d;
-}
-
 // dH3[m][j] = H3[m][j] > 0 ? sum_c dRGB[m][c] * W2[c][j] : 0     (color_net.2 is [3][hid]: a K = 3 contraction)
 __global__ void head_bwd_kernel(const float* __restrict__ dRGB, const float* __restrict__ W2, const float* __restrict__ H3, int hid,
                                 int64_t M, float* __restrict__ dH3) {
@@ -263,16 +215,6 @@ __global__ void head_bwd_kernel(const float* __restrict__ dRGB, const float* __r
   const float4 g = *reinterpret_cast<const float4*>(dRGB + m * 4);
   const float v = g.x * __ldg(W2 + j) + g.y * __ldg(W2 + hid + j) + g.z * __ldg(W2 + 2 * hid + j);
   dH3[m * hid + j] = H3[m * hid + j] > 0.f ? v : 0.f;
-}
-
-// out[j] += sum_m D[m][j]  (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ D, int ld, int n, int64_t M, float* __restrict__ out) {
-  const int j = threadIdx.x;
-  if (j >= n) return;
-  const int64_t r0 = (int64_t)blockIdx.x * 512, r1 = min(r0 + 512, M);
-  float acc = 0.f;
-  for (int64_t m = r0; m < r1; ++m) acc += D[m * ld + j];
-  atomicAdd(out + j, acc);
 }
 
 // dSG[m][1 + j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
@@ -402,8 +344,6 @@ inline int64_t floats_per_sample(const Dims& d) {
   return (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + 4 /*RGB*/ + 4 /*dRGB*/ +
          d.hid * 2 /*D1 D2*/ + d.ldS /*dSG*/ + d.ldX /*dX0*/ + kAppComp /*dP*/ + 4 /*dpts*/ + 2 /*alpha, T*/;
 }
-
-inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
 }  // namespace edn

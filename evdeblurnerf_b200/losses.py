@@ -40,6 +40,11 @@ class TonemappingTransform:
                     setattr(cp, "w" + slot, w.data_ptr())
                     setattr(cp, "b" + slot, b.data_ptr())
             self.cp[which] = cp
+        self.params = params
+
+    def _weights(self, which):
+        pre = f"tonemapping_{which}.linear."
+        return [self.params[pre + f"{idx}.{kind}"] for idx in (0, 2, 4, 6) for kind in ("weight", "bias")]
 
     def _run(self, which, x, feat, skip_learn, luma):
         mt = self.map_type[which]
@@ -56,6 +61,12 @@ class TonemappingTransform:
         if feat is not None and self.extra[which] > 0 and mt == "learn":
             f = _f32c(feat)
             per_channel = 1 if f.ndim == 3 else 0
+        ws = self._weights(which) if mt == "learn" else []
+        if torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in ws)):
+            from .autograd import CrfFn
+            xin = x.to(torch.float32).reshape(-1, 3).contiguous()       # keeps the graph (no detach)
+            out = CrfFn.apply(xin, f, per_channel, flags, self.cp[which], *ws)
+            return out.reshape(*shape[:-1], 1 if luma else 3)
         out = torch.empty((M, 1 if luma else 3), dtype=torch.float32, device=xf.device)
         check(_lib.load().edn_crf_fwd(C.byref(self.cp[which]), ptr(xf), ptr(f), per_channel, flags, M, ptr(out), stream_ptr()),
               "edn_crf_fwd")
@@ -96,6 +107,10 @@ def egm_loss(luma_start, luma_end, bii, color_mask=None, color_weight=None, log_
             cw = torch.as_tensor(color_weight, dtype=torch.float32, device=ls.device).contiguous()
     elif Cn != 1:
         raise RuntimeError("egm_loss: 3-channel luma needs a color_mask")
+    if torch.is_grad_enabled() and (luma_start.requires_grad or luma_end.requires_grad):
+        from .autograd import EgmLossFn
+        return EgmLossFn.apply(luma_start.to(torch.float32).reshape(M, -1).contiguous(),
+                               luma_end.to(torch.float32).reshape(M, -1).contiguous(), b, mask, cw, float(log_eps))
     out = torch.empty((1,), dtype=torch.float32, device=ls.device)
     check(_lib.load().edn_egm_loss_fwd(ptr(ls), ptr(le), ptr(b), ptr(mask), ptr(cw), Cn, M, float(log_eps), ptr(out), stream_ptr()),
           "edn_egm_loss_fwd")
@@ -106,6 +121,9 @@ def img2mse(x, y):
     """utils/metrics.py:7."""
     xf, yf = _f32c(x), _f32c(y)
     assert xf.shape == yf.shape
+    if torch.is_grad_enabled() and x.requires_grad:
+        from .autograd import Img2MseFn
+        return Img2MseFn.apply(x.to(torch.float32).contiguous(), yf)
     out = torch.empty((1,), dtype=torch.float32, device=xf.device)
     check(_lib.load().edn_img2mse(ptr(xf), ptr(yf), xf.numel(), ptr(out), stream_ptr()), "edn_img2mse")
     return out[0]
@@ -113,6 +131,10 @@ def img2mse(x, y):
 
 def tv_loss_app(params, prefix):
     """VoxelNeRFBase.TV_loss_app (voxnerf.py:126-130) on the reference-layout parameters `prefix + app_plane.i / app_line.i`."""
+    raw = [params[prefix + f"app_plane.{i}"] for i in range(3)] + [params[prefix + f"app_line.{i}"] for i in range(3)]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in raw):
+        from .autograd import TvLossFn
+        return TvLossFn.apply(*raw)
     planes = [_f32c(params[prefix + f"app_plane.{i}"]) for i in range(3)]
     lines = [_f32c(params[prefix + f"app_line.{i}"]) for i in range(3)]
     dev = planes[0].device

@@ -21,6 +21,7 @@ class RigidBlurringModel:
     def __init__(self, params, num_motion, rv_window=0.1, prefix="kernelsnet."):
         self.num_motion, self.rv_window, self.prefix = int(num_motion), float(rv_window), prefix
         self.keep = []
+        self.tensors = {}       # name (without prefix) -> fp32 view of the parameter (shares storage when already fp32)
         p = RbkParams()
 
         def g(name):
@@ -28,6 +29,7 @@ class RigidBlurringModel:
             if not t.is_cuda:
                 raise RuntimeError("RigidBlurringModel parameters must be CUDA tensors")
             self.keep.append(t)
+            self.tensors[name] = t
             return t
 
         emb = g("view_embed_module.img_embed")
@@ -137,6 +139,9 @@ class AdaptiveWeightProposal:
 
 def weighted_sum(x, ccw):
     """x [N*E, ...] , ccw [N,E] -> [N, ...]."""
+    if torch.is_grad_enabled() and (x.requires_grad or ccw.requires_grad):
+        from .autograd import WeightedSumFn
+        return WeightedSumFn.apply(x, ccw)
     N, E = ccw.shape
     xf = x.detach().to(torch.float32).contiguous()
     Cn = max(1, xf.numel() // max(1, N * E))
@@ -180,6 +185,39 @@ class NeRFAll:
         if self.use_awp and self.mode != "c2f":
             raise NotImplementedError("kernel_use_awp with mode = nerf (256-channel depth_feature) is not built")
         self.training = True
+        self.backward_chunk_rays = 2048     # rays per recompute chunk of the backward pass (workspace ~ 8.6 KB x samples)
+        self.last_render = None
+        self._grad_names = sorted(k for k in self.params if k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.")))
+        self._packed_version = self._param_version()
+
+    # ---- autograd plumbing (the reference trains through torch autograd, run_nerf.py:594) --------------------------------
+    def _param_version(self):
+        return sum(int(v._version) for v in self.params.values())
+
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(self.params[k].requires_grad for k in self._grad_names)
+
+    def repack(self):
+        """Refresh the render-layout copies after the parameters changed (optimizer.step(), load_state_dict)."""
+        self.engine.repack(self.params)
+        self._packed_version = self._param_version()
+
+    def _maybe_repack(self):
+        # in-place updates (optimizer steps) bump the tensors' version counters
+        if self.mode == "c2f" and self._param_version() != self._packed_version:
+            self.repack()
+
+    def _render_sub_rays(self, H, W, K, rays, images_idx, near, far, ndc, kwargs, blur=True):
+        """Differentiable warp + render of the sub-rays -> (rgb, depth, acc, rgb0, depth0, acc0, weight1), see autograd.py."""
+        from .autograd import RenderSubRaysFn
+        if self.mode != "c2f":
+            raise NotImplementedError("backward of mode = nerf is not built (DESIGN.md section 8)")
+        if self.use_awp:
+            raise NotImplementedError("backward through the AWP branch is not built (DESIGN.md section 8)")
+        names = self._grad_names
+        return RenderSubRaysFn.apply(self, self.kernelsnet if blur else None, H, W, float(K[0][0]), rays, images_idx, near, far, ndc,
+                                     kwargs, names,
+                                     *[self.params[n] for n in names])
 
     def train(self, mode=True):
         self.training = bool(mode)
@@ -223,6 +261,10 @@ class NeRFAll:
         ndc, near, far = kwargs.pop("ndc", True), kwargs.pop("near", 0.), kwargs.pop("far", 1.)
         kwargs.pop("use_viewdirs", None)
         other_loss, other_tensors = {}, {}
+        self._maybe_repack()
+        if self._wants_grad():
+            return self._forward_with_grad(H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far,
+                                           kwargs)
         if self.kernelsnet is not None and not force_baseline:
             k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, rays_info["images_idx"], near, far, ndc, want_new_rays=False)
             weight1 = k["weight"]
@@ -257,9 +299,37 @@ class NeRFAll:
 
     __call__ = forward
 
+    def _forward_with_grad(self, H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far, kwargs):
+        """Training branch of forward() (renderer.py:277-378) with outputs attached to the autograd graph."""
+        other_loss, other_tensors = {}, {}
+        blur = self.kernelsnet is not None and not force_baseline
+        rgb, depth, acc, rgb0, depth0, acc0, weight1 = self._render_sub_rays(
+            H, W, K, rays, rays_info["images_idx"] if blur else None, near, far, ndc, kwargs, blur=blur)
+        if blur:
+            N, E = weight1.shape
+            rgb_b = weighted_sum(rgb, weight1)
+            rgb1 = weighted_sum(rgb0, weight1) if N_importance > 0 else None
+            if return_pts0_rgb:
+                other_tensors["stage1_rgb_pts0"] = rgb.reshape(N, E, 3)[:, 0]
+                if N_importance > 0:
+                    other_tensors["stage1_rgb1_pts0"] = rgb0.reshape(N, E, 3)[:, 0]
+        else:
+            rgb_b, rgb1 = rgb, (rgb0 if N_importance > 0 else None)
+            other_tensors["stage1_rgb_pts0"] = rgb
+            if N_importance > 0:
+                other_tensors["stage1_rgb1_pts0"] = rgb0
+        other_loss["TV"] = self.tv_loss(N_importance > 0)
+        return rgb_b, rgb1, other_loss, other_tensors
+
     def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):
         """The render part of the training forward (renderer.py:303-343 without the loss terms): blur-kernel warp ->
         NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum.  Returns (rgb [N,3], rgb0 [N,3] | None)."""
+        self._maybe_repack()
+        if self._wants_grad():
+            rgb, _, _, rgb0, _, _, weight1 = self._render_sub_rays(H, W, K, rays, images_idx, near, far, ndc, kwargs)
+            if self.kernelsnet is None:
+                return rgb, (rgb0 if kwargs.get("N_importance", 0) > 0 else None)
+            return weighted_sum(rgb, weight1), (weighted_sum(rgb0, weight1) if kwargs.get("N_importance", 0) > 0 else None)
         if self.kernelsnet is None:           # kernel_type = none: one exposure per ray, no blending
             out = self.render_rays(build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc), **kwargs)
             return out["rgb_map"], out.get("rgb0")
@@ -273,6 +343,7 @@ class NeRFAll:
         """renderer.py:361-365: (TV_loss_app(coarse) [+ TV_loss_app(fine)]) * 5 (mode = c2f only)."""
         if self.mode != "c2f":
             return None
+        self._maybe_repack()
         tv = tv_loss_app(self.params, "mlp_coarse.")
         if with_fine:
             tv = tv + tv_loss_app(self.params, "mlp_fine.")

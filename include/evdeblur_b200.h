@@ -239,6 +239,31 @@ int edn_rbk_warp_ndc_fwd(const edn_rbk_params* p, const float* rays, const int64
 int edn_build_ray_batch(const float* rays, int64_t n_rays, int32_t H, int32_t W, float focal, float near, float far,
                         int32_t ndc, float* ray_batch, void* stream);
 
+/* Gradients of the DP-NeRF kernel-net parameters, same names / layouts as edn_rbk_params (r / v entries may be NULL when
+ * num_motion == 0). */
+typedef struct edn_rbk_grads {
+  float* img_embed;
+  float* r_branch_w; float* r_branch_b;
+  float* v_branch_w; float* v_branch_b;
+  float* w_branch_w; float* w_branch_b;
+  float* r_linear_w; float* r_linear_b;
+  float* v_linear_w; float* v_linear_b;
+  float* w_linear_w; float* w_linear_b;
+} edn_rbk_grads;
+
+/* Backward of edn_rbk_warp_ndc_fwd (dpnerf/blurmodel.py:129-173, utils/rigid_warping.py:18-154, renderer.py:423-446,
+ * utils/rays.py:104-145): d_ray_batch [N*E][11] (what edn_render_field_bwd accumulated; NULL only if num_motion == 0),
+ * d_weight [N][E] or NULL -> ACCUMULATES the kernel-net parameter gradients into `grads`.
+ * workspace: edn_rbk_bwd_workspace_floats(n_rays, num_motion) floats. */
+int64_t edn_rbk_bwd_workspace_floats(int64_t n_rays, int32_t num_motion);
+int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, const int64_t* images_idx, int64_t n_rays, int32_t H,
+                         int32_t W, float focal, int32_t ndc, const float* d_ray_batch, const float* d_weight,
+                         const edn_rbk_grads* grads, float* workspace, void* stream);
+
+/* Backward of edn_weighted_sum: d_out [N][C] -> d_x [N*E][C] (or NULL), d_w [N][E] (or NULL); both overwritten. */
+int edn_weighted_sum_bwd(const float* x, const float* w, const float* d_out, int64_t n, int32_t n_exposure, int64_t channels,
+                         float* d_x, float* d_w, void* stream);
+
 /* ---- adaptive weight proposal -------------------------------------------------------------------------------------------- */
 
 /* AdaptiveWeightProposal weights (networks/dpnerf/awp.py:37-47, mam.py:13-65), fp32:
@@ -289,19 +314,51 @@ typedef struct edn_crf_params {
 int edn_crf_fwd(const edn_crf_params* p, const float* x, const float* feat, int32_t feat_per_channel, int32_t flags,
                 int64_t m, float* out, void* stream);
 
+/* Gradients of the CRF MLP, same layout as edn_crf_params. */
+typedef struct edn_crf_grads {
+  float* w0; float* b0;
+  float* w1; float* b1;
+  float* w2; float* b2;
+  float* w3; float* b3;
+} edn_crf_grads;
+
+/* Backward of edn_crf_fwd: d_out [M][3] (or [M][1] with EDN_CRF_LUMA) -> d_x [M][3] (overwritten, may be NULL); the CRF
+ * parameter gradients are ACCUMULATED into `grads` (may be NULL: no parameter gradients). */
+int edn_crf_bwd(const edn_crf_params* p, const float* x, const float* feat, int32_t feat_per_channel, int32_t flags, int64_t m,
+                const float* d_out, float* d_x, const edn_crf_grads* grads, void* stream);
+
 /* egm_loss (utils/events.py:260-284): luma_* [M][channels], bii [M], color_mask [M][3] uint8 one-hot or NULL,
  * color_weight [3] or NULL -> out [1]. */
 int edn_egm_loss_fwd(const float* luma_start, const float* luma_end, const float* bii, const uint8_t* color_mask,
                      const float* color_weight, int32_t channels, int64_t m, float log_eps, float* out, void* stream);
 
+/* Backward of edn_egm_loss_fwd: d_loss [1] (device) -> d_luma_start / d_luma_end [M][channels] (overwritten). */
+int edn_egm_loss_bwd(const float* luma_start, const float* luma_end, const float* bii, const uint8_t* color_mask,
+                     const float* color_weight, int32_t channels, int64_t m, float log_eps, const float* d_loss,
+                     float* d_luma_start, float* d_luma_end, void* stream);
+
 /* img2mse (utils/metrics.py:7): mean((x - y)^2) over n elements -> out [1]. */
 int edn_img2mse(const float* x, const float* y, int64_t n, float* out, void* stream);
+
+/* Backward of edn_img2mse: d_loss [1] (device) -> d_x [n] (overwritten). */
+int edn_img2mse_bwd(const float* x, const float* y, int64_t n, const float* d_loss, float* d_x, void* stream);
 
 /* VoxelNeRFBase.TV_loss_app (voxnerf.py:126-130, 306-324) on the reference-layout ([1,C,H,W] fp32) planes / lines of one
  * field.  workspace: 12 doubles.  out [1] = sum_i 1e-2 TV(plane_i) + 1e-3 TV(line_i). */
 int edn_tv_loss_app(const float* const planes_chw[3], const float* const lines_chw[3], const int32_t plane_h[3],
                     const int32_t plane_w[3], const int32_t line_len[3], const int32_t n_comp[3], double* workspace,
                     float* out, void* stream);
+
+/* Backward of edn_tv_loss_app: d_loss [1] (device); the gradients are ACCUMULATED into grad_*_chw (reference layout). */
+int edn_tv_loss_app_bwd(const float* const planes_chw[3], const float* const lines_chw[3], const int32_t plane_h[3],
+                        const int32_t plane_w[3], const int32_t line_len[3], const int32_t n_comp[3], const float* d_loss,
+                        float* const grad_planes_chw[3], float* const grad_lines_chw[3], void* stream);
+
+/* Fused Adam sweep over one flat fp32 buffer (torch.optim.Adam semantics as constructed at run_nerf.py:272-274; weight_decay
+ * is the L2 term of the color_net group, run_nerf.py:244-250).  step >= 1 is the update count used for bias correction.
+ * All four buffers 16-byte aligned. */
+int edn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 /* EDI prior for one frame (utils/edi.py:7-95, data/loader_events.py:99-131): events ev_x / ev_y / ev_p (p > 0 = positive),
  * n_seg (even) sub-interval index ranges [seg_start[j], seg_end[j]) (device int64), blurry [H][W][C].
