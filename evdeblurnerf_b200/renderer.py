@@ -257,6 +257,7 @@ class NeRFAll:
         assert rays is not None, "Please specify rays when in the training mode"
         force_baseline = kwargs.pop("force_naive", True)
         return_pts0_rgb = kwargs.pop("return_pts0_rgb", False)
+        want_tv = kwargs.pop("want_tv", True)     # not in the reference: lets a caller skip the TV term it would discard
         N_importance = kwargs.get("N_importance", 0)
         ndc, near, far = kwargs.pop("ndc", True), kwargs.pop("near", 0.), kwargs.pop("far", 1.)
         kwargs.pop("use_viewdirs", None)
@@ -264,7 +265,7 @@ class NeRFAll:
         self._maybe_repack()
         if self._wants_grad():
             return self._forward_with_grad(H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far,
-                                           kwargs)
+                                           kwargs, want_tv)
         if self.kernelsnet is not None and not force_baseline:
             k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, rays_info["images_idx"], near, far, ndc, want_new_rays=False)
             weight1 = k["weight"]
@@ -282,7 +283,7 @@ class NeRFAll:
             if N_importance > 0:
                 rgb1_pts = extras["rgb0"].reshape(N, E, 3)
                 rgb1 = weighted_sum(extras["rgb0"], weight1)
-            if self.mode == "c2f":
+            if self.mode == "c2f" and want_tv:
                 other_loss["TV"] = self.tv_loss(N_importance > 0)
             if return_pts0_rgb:
                 other_tensors["stage1_rgb_pts0"] = rgb_pts[:, 0]
@@ -293,13 +294,14 @@ class NeRFAll:
         other_tensors["stage1_rgb_pts0"] = rgb
         if N_importance > 0:
             other_tensors["stage1_rgb1_pts0"] = extras["rgb0"]
-        if self.mode == "c2f":
+        if self.mode == "c2f" and want_tv:
             other_loss["TV"] = self.tv_loss(N_importance > 0)
         return rgb, extras.get("rgb0"), other_loss, other_tensors
 
     __call__ = forward
 
-    def _forward_with_grad(self, H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far, kwargs):
+    def _forward_with_grad(self, H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far, kwargs,
+                           want_tv=True):
         """Training branch of forward() (renderer.py:277-378) with outputs attached to the autograd graph."""
         other_loss, other_tensors = {}, {}
         blur = self.kernelsnet is not None and not force_baseline
@@ -318,7 +320,8 @@ class NeRFAll:
             other_tensors["stage1_rgb_pts0"] = rgb
             if N_importance > 0:
                 other_tensors["stage1_rgb1_pts0"] = rgb0
-        other_loss["TV"] = self.tv_loss(N_importance > 0)
+        if want_tv:
+            other_loss["TV"] = self.tv_loss(N_importance > 0)
         return rgb_b, rgb1, other_loss, other_tensors
 
     def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):

@@ -1,0 +1,146 @@
+"""The reference's training iteration (run_nerf.py:423-613), mode = c2f + RBK, re-laid-out for one process per GPU.
+
+* Every trainable tensor (the two PDRF fields, the DP-NeRF kernel net, the CRF) is a VIEW into one flat fp32 buffer, under
+  its reference state_dict name and shape (checkpoints round-trip); `.grad`s are views into a second flat buffer.  The
+  gradient exchange across ranks is therefore ONE all-reduce (NCCL over NVLink) and the optimizer ONE fused
+  Adam launch per parameter group (edn_adam_step) -- torch.optim.Adam semantics, betas (0.9, 0.999), optional L2 weight
+  decay on `color_net.N.weight` (run_nerf.py:243-274), learning-rate warm-up + exponential decay (run_nerf.py:604-613).
+* Rays shard across ranks (each rank renders its own slice of the batch); losses are means over rays, so gradients are
+  averaged (all-reduce sum / world size).
+* Loss mixing follows run_nerf.py:448-504, 539-594: photometric MSE on CRF-encoded fine + coarse colours, TV regulariser,
+  optional event generation-model loss on start/end event rays rendered through the force_naive branch.
+"""
+import re
+
+import torch
+
+from . import _lib
+from ._lib import check, stream_ptr
+from .losses import TonemappingTransform, egm_loss, img2mse
+from .renderer import NeRFAll
+
+_WD_RE = re.compile(r"\.color_net\.[0-9]+\.weight$")     # run_nerf.py:246
+
+
+def lr_at(step, lrate, decay_k, warmup_iters=0, warmup_factor=1.0):
+    """run_nerf.py:604-613: the learning rate in force AFTER `step` updates (global_step)."""
+    if warmup_iters > 0 and step < warmup_iters:
+        return lrate * ((1 - warmup_factor) * step / warmup_iters + warmup_factor)
+    return lrate * (0.1 ** (step / (decay_k * 1000)))
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient / Adam-moment buffers with named views; group 0 = weight-decayed tensors."""
+
+    def __init__(self, tensors, device, weight_decay_re=_WD_RE):
+        names = sorted(tensors)
+        wd = [n for n in names if weight_decay_re.search(n)]
+        rest = [n for n in names if n not in wd]
+        self.order = wd + rest
+        self.offset, off = {}, 0
+        for n in self.order:
+            self.offset[n] = off
+            off += (tensors[n].numel() + 3) // 4 * 4          # 16-byte aligned views
+            if n == (wd[-1] if wd else None):
+                self.split = off
+        if not wd:
+            self.split = 0
+        self.numel = off
+        self.param = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.param)
+        self.exp_avg = torch.zeros_like(self.param)
+        self.exp_avg_sq = torch.zeros_like(self.param)
+        self.views = {}
+        for n in self.order:
+            t = tensors[n]
+            v = self.param[self.offset[n]: self.offset[n] + t.numel()].view(t.shape)
+            v.copy_(t.detach().to(device=device, dtype=torch.float32))
+            v.requires_grad_(True)
+            v.grad = self.grad[self.offset[n]: self.offset[n] + t.numel()].view(t.shape)
+            self.views[n] = v
+
+    def all_reduce_mean(self, group=None):
+        """The one gradient exchange of a step: sum over ranks of the flat gradient buffer, divided by the world size."""
+        if torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+            torch.distributed.all_reduce(self.grad, group=group)
+            self.grad.div_(torch.distributed.get_world_size(group))
+
+    def adam(self, lr, step, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        lib = _lib.load()
+        for lo, hi, wd in ((0, self.split, weight_decay), (self.split, self.numel, 0.0)):
+            if hi > lo:
+                check(lib.edn_adam_step(self.param[lo:].data_ptr(), self.grad[lo:].data_ptr(), self.exp_avg[lo:].data_ptr(),
+                                        self.exp_avg_sq[lo:].data_ptr(), hi - lo, float(lr), betas[0], betas[1], eps, float(wd),
+                                        int(step), stream_ptr()), "edn_adam_step")
+
+
+class Trainer:
+    def __init__(self, state, crf_state, aabb_min, aabb_max, kernel_ptnum=5, precision="bf16", lrate=5e-4, lrate_decay=250,
+                 lrate_warmup_iters=0, lrate_warmup_factor=1.0, colornet_weightdecay=0.0, tv_loss_weight=1e-2,
+                 event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("evdeblurnerf_b200.Trainer needs a CUDA device (no CPU fallback)")
+        dev = torch.device(device if device is not None else "cuda")
+        trainable = {k: v for k, v in state.items() if isinstance(v, torch.Tensor) and v.is_floating_point()
+                     and k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet."))}
+        crf_train = {"crf." + k: v for k, v in (crf_state or {}).items() if isinstance(v, torch.Tensor) and v.is_floating_point()}
+        self.flat = FlatParams({**trainable, **crf_train}, dev)
+        P = {k: self.flat.views[k] for k in trainable}
+        Pc = {k[4:]: self.flat.views[k] for k in crf_train}
+        self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision).train()
+        self.crf = TonemappingTransform(Pc, **(crf_kwargs or dict(map_type_rgb="gamma", map_type_event="learn" if Pc else "gamma",
+                                                                  extra_features_event=2)))
+        self.hp = dict(lrate=lrate, decay=lrate_decay, warm_it=lrate_warmup_iters, warm_f=lrate_warmup_factor,
+                       wd=colornet_weightdecay, tv_w=tv_loss_weight, ev_w=event_loss_weight)
+        self.render_kwargs = dict(render_kwargs or dict(N_samples=64, N_importance=64, perturb=1., raw_noise_std=1.))
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
+        self.rank = torch.distributed.get_rank(process_group) if torch.distributed.is_initialized() else 0
+        self.nerf.engine.seed(seed * 1000003 + self.rank)      # per-rank draw streams (SURVEY 8(e) caveat 2)
+        self.global_step = 0
+
+    # run_nerf.py:438-504 (+ 539-557 when event rays are given)
+    def loss(self, batch, H, W, K):
+        out = {}
+        rgb, rgb0, extra_loss, _ = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
+                                             **self.render_kwargs)
+        target = batch["rgbsf"].reshape(-1, 3)
+        img_loss = img2mse(self.crf(rgb, mode="encode_rgb"), target)
+        out["img_loss"] = img_loss.detach()
+        if rgb0 is not None:
+            img_loss = img_loss + img2mse(self.crf(rgb0, mode="encode_rgb"), target)
+        loss = img_loss
+        if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
+            loss = loss + extra_loss["TV"] * self.hp["tv_w"]
+        if self.hp["ev_w"] > 0 and "ev_rays_start" in batch:
+            feat = batch.get("ev_extra_feat")
+            lum = []
+            for key in ("ev_rays_start", "ev_rays_end"):
+                c, c0, _, _ = self.nerf(H, W, K, rays=batch[key], rays_info=None, retraw=True, force_naive=True, want_tv=False,
+                                        **self.render_kwargs)   # TV of these calls is never used (run_nerf.py:500-501)
+                lum.append((self.crf(c, mode="encode_luma", ev_extra_feat=feat), self.crf(c0, mode="encode_luma", ev_extra_feat=feat)))
+            ev = egm_loss(lum[0][0], lum[1][0], batch["bii"]) + egm_loss(lum[0][1], lum[1][1], batch["bii"])   # stage1 + stage0
+            out["event_loss"] = ev.detach()
+            loss = loss + ev * self.hp["ev_w"]
+        out["loss"] = loss
+        return out
+
+    def step(self, batch, H, W, K):
+        """One optimisation step on this rank's shard of the batch -> dict of detached loss terms."""
+        hp = self.hp
+        self.flat.grad.zero_()
+        out = self.loss(batch, H, W, K)
+        out["loss"].backward()
+        self.flat.all_reduce_mean(self.group)
+        self.global_step += 1
+        # iteration g of the reference runs with the rate it set at the end of iteration g - 1 from global_step = g - 1
+        lr = lr_at(max(self.global_step - 2, 0), hp["lrate"], hp["decay"], hp["warm_it"], hp["warm_f"])
+        self.flat.adam(lr, self.global_step, weight_decay=hp["wd"])
+        self.nerf.repack()
+        out["loss"] = out["loss"].detach()
+        out["lr"] = lr
+        return out
+
+    def state_dict(self):
+        """Reference-format tensors (run_nerf.py:628-634 saves network / optimizer state dicts)."""
+        return {k: v.detach().clone() for k, v in self.flat.views.items()}

@@ -41,3 +41,40 @@ def test_shard_bounds_cover_exactly_once():
 def test_sharded_render_world2_gloo():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 4097), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from evdeblurnerf_b200.trainer import FlatParams
+    g = torch.Generator().manual_seed(0)
+    tensors = {"mlp_fine.color_net.1.weight": torch.randn(5, 7, generator=g), "mlp_fine.sigma_net.0.weight": torch.randn(3, 3, generator=g),
+               "mlp_coarse.app_plane.0": torch.randn(1, 2, 3, 5, generator=g), "kernelsnet.r_linear.bias": torch.randn(6, generator=g)}
+    flat = FlatParams(tensors, "cpu")
+    for k, v in flat.views.items():
+        assert torch.equal(v.detach(), tensors[k]) and v.grad.data_ptr() >= flat.grad.data_ptr()
+        assert v.data_ptr() % 16 == 0 or (v.data_ptr() - flat.param.data_ptr()) % 16 == 0
+    # rank-dependent "loss": autograd accumulates straight into the flat gradient buffer through the views
+    loss = sum(((rank + 1) * (i + 1)) * (v ** 2).sum() for i, v in enumerate(flat.views[k] for k in sorted(flat.views)))
+    loss.backward()
+    flat.all_reduce_mean()
+    mean_scale = sum(r + 1 for r in range(world)) / world
+    for i, k in enumerate(sorted(flat.views)):
+        assert torch.allclose(flat.views[k].grad, 2 * mean_scale * (i + 1) * tensors[k], rtol=1e-6, atol=1e-6), k
+    # weight-decayed tensors (color_net.N.weight, run_nerf.py:246) form the leading segment
+    assert flat.order[0] == "mlp_fine.color_net.1.weight" and flat.split == 36
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_all_reduce_world2_gloo():
+    port = _free_port()
+    mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_lr_schedule_matches_reference_formula():
+    from evdeblurnerf_b200.trainer import lr_at
+    # run_nerf.py:604-613 with lrate 5e-4, lrate_decay 250, warm-up 2000 its from factor 0.1
+    assert abs(lr_at(0, 5e-4, 250, 2000, 0.1) - 5e-5) < 1e-12
+    assert abs(lr_at(1000, 5e-4, 250, 2000, 0.1) - 5e-4 * 0.55) < 1e-12
+    assert abs(lr_at(250000, 5e-4, 250, 2000, 0.1) - 5e-5) < 1e-12
+    assert abs(lr_at(0, 5e-4, 250) - 5e-4) < 1e-12

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Config 4 (BASELINE.json): full training step -- forward, losses, backward, gradient all-reduce, fused Adam -- on the
+headline batch (4096 primary rays x 5 exposures x 64+64 samples, full-size grids).  Prints one JSON line per precision.
+
+    python tools/bench_train_step.py [--steps K] [--warmup W] [--precision bf16 fp32]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_train_step.py   (weak scaling, NCCL all-reduce)
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", nargs="+", default=["bf16", "fp32"])
+    ap.add_argument("--rays", type=int, default=bench.N_RAYS)
+    ap.add_argument("--chunk-rays", type=int, default=2048)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    from evdeblurnerf_b200.parallel import max_over_ranks
+    from evdeblurnerf_b200.trainer import Trainer
+    dev = torch.device("cuda", local)
+    for precision in args.precision:
+        P = bench.make_params(dev, seed=0)
+        tr = Trainer(P, None, *bench.AABB, kernel_ptnum=bench.N_EXPOSURE, precision=precision, tv_loss_weight=1e-2, device=dev,
+                     render_kwargs=dict(N_samples=bench.NC, N_importance=bench.NI, perturb=1., raw_noise_std=1.))
+        del P
+        tr.nerf.backward_chunk_rays = args.chunk_rays
+        batches = []
+        for s in range(args.steps + args.warmup):
+            rays, idx = bench.make_rays(args.rays, seed=1000 * rank + s)
+            g = torch.Generator().manual_seed(s)
+            batches.append({"rays": rays.to(dev), "images_idx": idx.to(dev), "rgbsf": torch.rand(args.rays, 3, generator=g).to(dev)})
+        for s in range(args.warmup):
+            tr.step(batches[s], bench.H, bench.W, bench.KMAT)
+        tr.nerf.engine.profile = {}
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.steps):
+            out = tr.step(batches[args.warmup + s], bench.H, bench.W, bench.KMAT)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+        kern = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in tr.nerf.engine.profile.items()}
+        if rank == 0:
+            print(json.dumps({"metric": "training rays/s (fwd + loss + bwd + all-reduce + Adam)", "value": world * args.rays / (ms * 1e-3),
+                              "unit": "rays/s", "n_gpus": world, "ms_per_step": ms, "precision": precision,
+                              "kernels_ms": kern, "loss": float(out["loss"]),
+                              "config": {"workload": f"{args.rays} rays x {bench.N_EXPOSURE} exposures x {bench.NC}+{bench.NI} samples, "
+                                                     "full-size VM grids, TV + MSE losses, Adam over 36.8M parameters",
+                                         "backward_chunk_rays": args.chunk_rays}}), flush=True)
+        del tr
+        torch.cuda.empty_cache()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
