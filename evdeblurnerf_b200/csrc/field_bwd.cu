@@ -11,7 +11,10 @@
 //
 // Buffers per sample m of a chunk (fp32, row-major):
 //   P_g [96]   plane (.) line products of grid g            X0 [ldX] = [ft_0 (32) | ft_1 (32) | PE(pts) (63) | 0]
-//   H1  [hid]  relu(sigma_net.0)                            SG [ldS] = [sigma | geo_feat | PE(viewdir) (27) | 0]
+//   H1  [hid]  relu(sigma_net.0)                            SG [ldS] = [geo_feat | sigma | PE(viewdir) (27) | 0]
+// Every GEMM operand is 16-byte aligned with K, N multiples of 4 (cuBLAS then picks its sm_100 tensor-op kernels instead of
+// the align1 fallbacks): the MLP weights are re-laid-out once per call into zero-padded / row-permuted copies (sigma_net.1:
+// geo rows first, sigma row last; color_net.0: a zero column under sigma) and their gradients are folded back at the end.
 //   H2, H3 [hid] relu(color_net.0/1)                        RGB [4]  = color_net.2 pre-activation
 #include "bwd_common.cuh"
 
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
   }
 }
 
-// Positional encodings (embedding.py:88-98): X0[:, nf : ldX) = [PE(pts) (63) | 0], SG[:, 1+geo : ldS) = [PE(viewdir) (27) | 0].
+// Positional encodings (embedding.py:88-98): X0[:, nf : ldX) = [PE(pts) (63) | 0] (dirs = 0), SG[:, geo+1 : ldS) = [PE(viewdir) (27) | 0]
+// (dirs = 1; launched after the sigma_net.1 GEMM, whose padded output columns overlap the first PE(viewdir) columns).
 __device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
   if (j < 3) return x[j];
   if (j >= n_pe) return 0.f;
@@ -167,21 +171,46 @@ __device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
 }
 
 __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                          float* __restrict__ X0, int ldX, int nf, float* __restrict__ SG, int ldS, int geo) {
-  const int wp = ldX - nf, wd = ldS - 1 - geo, J = wp + wd;
+                          float* __restrict__ X0, int ldX, int nf, float* __restrict__ SG, int ldS, int geo, int dirs) {
+  const int J = dirs ? ldS - 1 - geo : ldX - nf;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / J;
   const int j = (int)(t % J);
   if (m >= Mc) return;
-  if (j < wp) {
+  if (!dirs) {
     float p[3];
     sample_point(rb, z_vals, m0 + m, S, p);
     X0[m * ldX + nf + j] = pe_value(p, j, kPePts);
   } else {
     const float* row = rb + ((m0 + m) / S) * 11 + 8;
     const float vd[3] = {__ldg(row), __ldg(row + 1), __ldg(row + 2)};
-    SG[m * ldS + 1 + geo + (j - wp)] = pe_value(vd, j - wp, kPeDir);
+    SG[m * ldS + geo + 1 + j] = pe_value(vd, j, kPeDir);
   }
+}
+
+// Weight re-layout between the reference nn.Linear tensors and the aligned copies the GEMMs read (to_padded = 1), and the
+// fold-back of their gradients (to_padded = 0: ref += padded).  One thread per padded element.
+//   mode 0: zero-pad columns            ref [rows][cols_r]      -> pad [rows][cols_p]
+//   mode 1: sigma_net.1                 ref [1+geo][cols]       -> pad [rows_p][cols]: rows 0..geo-1 = ref rows 1..geo, row geo = ref row 0
+//   mode 2: color_net.0                 ref [rows][geo+27]      -> pad [rows][cols_p]: col geo (under sigma) = 0, PE(dir) cols shifted by one
+//   mode 3: zero-pad rows               ref [rows_r][cols]      -> pad [rows_p][cols]
+__global__ void relayout_kernel(float* __restrict__ pad, float* __restrict__ ref, int mode, int rows_p, int cols_p, int rows_r, int cols_r,
+                                int geo, int to_padded) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows_p * cols_p) return;
+  const int r = t / cols_p, c = t % cols_p;
+  int rr = r, cc = c;
+  if (mode == 1) rr = r < geo ? r + 1 : (r == geo ? 0 : -1);
+  if (mode == 2) cc = c < geo ? c : (c == geo ? -1 : c - 1);
+  const bool valid = rr >= 0 && rr < rows_r && cc >= 0 && cc < cols_r;
+  if (to_padded) pad[t] = valid ? ref[rr * cols_r + cc] : 0.f;
+  else if (valid) ref[rr * cols_r + cc] += pad[t];
+}
+
+// dSG[m][geo] = dsig[m]
+__global__ void set_sigma_grad_kernel(float* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ dsig) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) dSG[m * ldS + geo] = dsig[m];
 }
 
 // d pts from the PE(pts) columns of dX0: writes (=) dpts[m][0..2].
@@ -217,24 +246,24 @@ __global__ void head_bwd_kernel(const float* __restrict__ dRGB, const float* __r
   dH3[m * hid + j] = H3[m * hid + j] > 0.f ? v : 0.f;
 }
 
-// dSG[m][1 + j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
+// dSG[m][j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
 __global__ void add_feat_grad_kernel(float* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ d_feat) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / geo;
   const int j = (int)(t % geo);
   if (m >= M) return;
-  dSG[m * ldS + 1 + j] += d_feat[m * geo + j];
+  dSG[m * ldS + j] += d_feat[m * geo + j];
 }
 
 // Compositing backward (voxnerf.py:153-201), one thread per ray of the chunk.
 //   w_i = alpha_i T_i, T_i = prod_{j<i} (1 - alpha_j);  g_i = dL/dw_i = d_rgb . c_i + d_depth z_i + d_acc + d_weights_i
 //   dL/dalpha_i = T_i (g_i - S_i),  S_i = sum_{k>i} g_k alpha_k prod_{i<j<k} (1 - alpha_j) = g_{i+1} alpha_{i+1} + (1 - alpha_{i+1}) S_{i+1}
 // (no division by 1 - alpha_i: exact when a sample saturates, like torch's cumprod backward).
-__global__ void composite_bwd_kernel(const float* __restrict__ SG, int ldS, const float* __restrict__ RGB, const float* __restrict__ b2,
+__global__ void composite_bwd_kernel(const float* __restrict__ SG /* + geo: the sigma column */, int ldS, const float* __restrict__ RGB, const float* __restrict__ b2,
                                      const float* __restrict__ rb, const float* __restrict__ z_vals, const float* __restrict__ noise,
                                      int64_t r0, int64_t Rc, int S, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
                                      const float* __restrict__ d_acc, const float* __restrict__ d_weights, float* __restrict__ al,
-                                     float* __restrict__ tr, float* __restrict__ dRGB, float* __restrict__ dSG, float* __restrict__ d_rb) {
+                                     float* __restrict__ tr, float* __restrict__ dRGB, float* __restrict__ dsig_out, float* __restrict__ d_rb) {
   const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (rl >= Rc) return;
   const int64_t r = r0 + rl;
@@ -273,7 +302,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ SG, int ldS, cons
       dsig = sraw > 0.f ? da * dist * one_m : 0.f;
       ddn = fmaf(da * sg * one_m, dz, ddn);
     }
-    dSG[m * ldS] = dsig;
+    dsig_out[m] = dsig;
     Ssum = gw * a + (1.0f - a) * Ssum;
   }
   if (dn > 0.f) {
@@ -299,7 +328,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* _
     const float4 g = *reinterpret_cast<const float4*>(dpts + m * 4);
     acc[0] += g.x; acc[1] += g.y; acc[2] += g.z;
     acc[3] = fmaf(z, g.x, acc[3]); acc[4] = fmaf(z, g.y, acc[4]); acc[5] = fmaf(z, g.z, acc[5]);
-    const float* gv = dSG + m * ldS + 1 + geo;
+    const float* gv = dSG + m * ldS + geo + 1;
 #pragma unroll
     for (int j = 0; j < kPeDir; ++j) acc[6 + j] += gv[j];
   }
@@ -329,7 +358,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* _
 }
 
 struct Dims {
-  int ng, nf, hid, geo, ldX, ldS, kin, cin;
+  int ng, nf, hid, geo, ldX, ldS, kin, cin, sgn;
 };
 inline Dims make_dims(int n_grids, int hidden, int geo) {
   Dims d;
@@ -338,11 +367,15 @@ inline Dims make_dims(int n_grids, int hidden, int geo) {
   d.cin = geo + kPeDir;                  // 42 | 155
   d.ldX = (d.kin + 3) & ~3;              // 96 | 128
   d.ldS = (1 + d.cin + 3) & ~3;          // 44 | 156
+  d.sgn = (1 + geo + 3) & ~3;            // 16 | 132: padded output width of sigma_net.1
   return d;
 }
 inline int64_t floats_per_sample(const Dims& d) {
   return (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + 4 /*RGB*/ + 4 /*dRGB*/ +
-         d.hid * 2 /*D1 D2*/ + d.ldS /*dSG*/ + d.ldX /*dX0*/ + kAppComp /*dP*/ + 4 /*dpts*/ + 2 /*alpha, T*/;
+         d.hid * 2 /*D1 D2*/ + d.ldS /*dSG*/ + d.ldX /*dX0*/ + kAppComp /*dP*/ + 4 /*dpts*/ + 3 /*alpha, T, d sigma*/;
+}
+inline int64_t weight_scratch_floats(const Dims& d) {     // padded weights + their gradients
+  return 2 * ((int64_t)d.hid * d.ldX + (int64_t)d.sgn * d.hid + (int64_t)d.hid * d.ldS + 4 * (int64_t)d.hid);
 }
 
 }  // namespace
@@ -352,7 +385,8 @@ extern "C" int64_t edn_field_bwd_workspace_bytes(int32_t n_grids, int32_t hidden
                                                  int32_t n_samples) {
   using namespace edn;
   if (n_grids < 1 || n_grids > 2 || hidden <= 0 || geo_feat <= 0 || chunk_rays <= 0 || n_samples <= 0) return -1;
-  return floats_per_sample(make_dims(n_grids, hidden, geo_feat)) * chunk_rays * n_samples * (int64_t)sizeof(float);
+  const Dims d = make_dims(n_grids, hidden, geo_feat);
+  return (floats_per_sample(d) * chunk_rays * n_samples + weight_scratch_floats(d)) * (int64_t)sizeof(float);
 }
 
 extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid* grid1, const edn_field_weights* w,
@@ -394,7 +428,8 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   const Dims D = make_dims(ng, w->hidden, w->geo_feat);
   const int S = n_samples, hid = D.hid, geo = D.geo;
   const int64_t per_ray = floats_per_sample(D) * S * (int64_t)sizeof(float);
-  int64_t chunk = workspace_bytes / per_ray;
+  const int64_t wfloats = weight_scratch_floats(D);
+  int64_t chunk = (workspace_bytes - wfloats * (int64_t)sizeof(float)) / per_ray;
   EDN_REQUIRE(chunk >= 1, "edn_render_field_bwd: workspace too small (%lld bytes, one ray needs %lld)", (long long)workspace_bytes,
               (long long)per_ray);
   chunk = chunk < n_rays ? chunk : n_rays;
@@ -409,6 +444,26 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   // workspace carve-up (sized for `chunk` rays)
   const int64_t Mmax = chunk * S;
   float* base = reinterpret_cast<float*>(workspace);
+  // aligned weight copies and their gradient accumulators
+  const int nW[4] = {hid * D.ldX, D.sgn * hid, hid * D.ldS, 4 * hid};
+  float* Wp[4];
+  float* gWp[4];
+  for (int i = 0; i < 4; ++i) { Wp[i] = base; base += nW[i]; }
+  for (int i = 0; i < 4; ++i) { gWp[i] = base; base += nW[i]; }
+  EDN_CUDA_OK(cudaMemsetAsync(gWp[0], 0, sizeof(float) * (size_t)(nW[0] + nW[1] + nW[2] + nW[3]), st));
+  auto relayout = [&](int i, float* ref, bool to_padded) {
+    float* pad = to_padded ? Wp[i] : gWp[i];
+    switch (i) {
+      case 0: relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(pad, ref, 0, hid, D.ldX, hid, D.kin, geo, to_padded); break;
+      case 1: relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(pad, ref, 1, D.sgn, hid, 1 + geo, hid, geo, to_padded); break;
+      case 2: relayout_kernel<<<blocks_for(nW[2], 256), 256, 0, st>>>(pad, ref, 2, hid, D.ldS, hid, D.cin, geo, to_padded); break;
+      default: relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(pad, ref, 3, 4, hid, 3, hid, geo, to_padded); break;
+    }
+  };
+  relayout(0, w->sigma0, true);
+  relayout(1, w->sigma1, true);
+  relayout(2, w->color0, true);
+  relayout(3, w->color2, true);
   auto take = [&](int64_t per) { float* p = base; base += per * Mmax; return p; };
   float* P[2] = {take(kAppComp), ng == 2 ? take(kAppComp) : nullptr};
   float* X0 = take(D.ldX);
@@ -426,6 +481,7 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   float* dpts = take(4);
   float* al = take(1);
   float* tr = take(1);
+  float* dsig = take(1);
 
 #define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
   for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
@@ -437,39 +493,38 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
       else vm_products_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
       EDN_RC(gemm(false, true, M, kAppDim, kAppComp, P[g], kAppComp, w->basis[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
     }
-    {
-      const int J = (D.ldX - D.nf) + (D.ldS - 1 - geo);
-      pe_kernel<<<blocks_for(M * J, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo);
-    }
-    EDN_RC(gemm(false, true, M, hid, D.kin, X0, D.ldX, w->sigma0, D.kin, 0.f, H1, hid));
+    pe_kernel<<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo, 0);
+    EDN_RC(gemm(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
     relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
-    EDN_RC(gemm(false, true, M, 1 + geo, hid, H1, hid, w->sigma1, hid, 0.f, SG, D.ldS));
-    EDN_RC(gemm(false, true, M, hid, D.cin, SG + 1, D.ldS, w->color0, D.cin, 0.f, H2, hid));
+    EDN_RC(gemm(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
+    pe_kernel<<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo, 1);
+    EDN_RC(gemm(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
     relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
     EDN_RC(gemm(false, true, M, hid, hid, H2, hid, w->color1, hid, 0.f, H3, hid));
     relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
-    EDN_RC(gemm(false, true, M, 3, hid, H3, hid, w->color2, hid, 0.f, RGB, 4));
+    EDN_RC(gemm(false, true, M, 4, hid, H3, hid, Wp[3], hid, 0.f, RGB, 4));
     // ---- compositing backward ------------------------------------------------------------------------------------------
-    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(SG, D.ldS, RGB, w->color2_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
-                                                           d_acc, d_weights, al, tr, dRGB, dSG, d_ray_batch);
+    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(SG + geo, D.ldS, RGB, w->color2_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
+                                                           d_acc, d_weights, al, tr, dRGB, dsig, d_ray_batch);
     // ---- color_net backward ----------------------------------------------------------------------------------------------
-    EDN_RC(gemm(true, false, 3, hid, M, dRGB, 4, H3, hid, 1.f, grad_w->color2, hid));
+    EDN_RC(gemm(true, false, 4, hid, M, dRGB, 4, H3, hid, 1.f, gWp[3], hid));
     if (grad_w->color2_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, grad_w->color2_b);
     head_bwd_kernel<<<blocks_for(M * hid, 256), 256, 0, st>>>(dRGB, w->color2, H3, hid, M, D1);                 // D1 = dH3
     EDN_RC(gemm(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
     if (grad_w->color1_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
     EDN_RC(gemm(false, false, M, hid, hid, D1, hid, w->color1, hid, 0.f, D2, hid));                               // D2 = dH2
     relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
-    EDN_RC(gemm(true, false, hid, D.cin, M, D2, hid, SG + 1, D.ldS, 1.f, grad_w->color0, D.cin));
+    EDN_RC(gemm(true, false, hid, D.ldS, M, D2, hid, SG, D.ldS, 1.f, gWp[2], D.ldS));
     if (grad_w->color0_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
-    EDN_RC(gemm(false, false, M, D.cin, hid, D2, hid, w->color0, D.cin, 0.f, dSG + 1, D.ldS));                    // [d geo | d PE(dir)]
+    EDN_RC(gemm(false, false, M, D.ldS, hid, D2, hid, Wp[2], D.ldS, 0.f, dSG, D.ldS));                            // [d geo | 0 | d PE(dir)]
+    set_sigma_grad_kernel<<<blocks_for(M, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, dsig);
     if (d_feat) add_feat_grad_kernel<<<blocks_for(M * geo, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, d_feat + m0 * geo);
     // ---- sigma_net backward ------------------------------------------------------------------------------------------------
-    EDN_RC(gemm(true, false, 1 + geo, hid, M, dSG, D.ldS, H1, hid, 1.f, grad_w->sigma1, hid));
-    EDN_RC(gemm(false, false, M, hid, 1 + geo, dSG, D.ldS, w->sigma1, hid, 0.f, D1, hid));                        // D1 = dH1
+    EDN_RC(gemm(true, false, D.sgn, hid, M, dSG, D.ldS, H1, hid, 1.f, gWp[1], hid));     // pad rows collect d PE(dir): dropped at fold-back
+    EDN_RC(gemm(false, false, M, hid, D.sgn, dSG, D.ldS, Wp[1], hid, 0.f, D1, hid));                              // D1 = dH1 (pad rows of W are 0)
     relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
-    EDN_RC(gemm(true, false, hid, D.kin, M, D1, hid, X0, D.ldX, 1.f, grad_w->sigma0, D.kin));
-    EDN_RC(gemm(false, false, M, D.kin, hid, D1, hid, w->sigma0, D.kin, 0.f, dX0, D.ldX));
+    EDN_RC(gemm(true, false, hid, D.ldX, M, D1, hid, X0, D.ldX, 1.f, gWp[0], D.ldX));
+    EDN_RC(gemm(false, false, M, D.ldX, hid, D1, hid, Wp[0], D.ldX, 0.f, dX0, D.ldX));
     // ---- inputs: PE(pts), basis_mat, VM grids ----------------------------------------------------------------------------------
     pe_bwd_kernel<<<blocks_for(M * 3, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, dX0, D.ldX, D.nf, dpts);
     for (int g = 0; g < ng; ++g) {
@@ -482,5 +537,10 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
     EDN_CUDA_OK(cudaGetLastError());
   }
 #undef EDN_RC
+  relayout(0, grad_w->sigma0, false);
+  relayout(1, grad_w->sigma1, false);
+  relayout(2, grad_w->color0, false);
+  relayout(3, grad_w->color2, false);
+  EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

@@ -185,7 +185,7 @@ class NeRFAll:
         if self.use_awp and self.mode != "c2f":
             raise NotImplementedError("kernel_use_awp with mode = nerf (256-channel depth_feature) is not built")
         self.training = True
-        self.backward_chunk_rays = 2048     # rays per recompute chunk of the backward pass (workspace ~ 8.6 KB x samples)
+        self.backward_chunk_rays = 8192     # rays per recompute chunk of the backward pass (workspace ~ 8.6 KB x samples)
         self.last_render = None
         self._grad_names = sorted(k for k in self.params if k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.")))
         self._packed_version = self._param_version()

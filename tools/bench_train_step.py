@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", nargs="+", default=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=bench.N_RAYS)
-    ap.add_argument("--chunk-rays", type=int, default=2048)
+    ap.add_argument("--chunk-rays", type=int, default=20480)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
