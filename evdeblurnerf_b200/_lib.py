@@ -113,8 +113,8 @@ SIGNATURES = {
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
-    "edn_awp_workspace_floats": (C.c_int64, [_I64, _I32, _I32]),
-    "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "edn_awp_workspace_floats": (C.c_int64, [_I64, _I32, _I32, _I32]),
+    "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P]),
     "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
     "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
     "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),

@@ -8,7 +8,11 @@
 //                                        conv attention, convd -> pre-BatchNorm y.
 //   awp_bn_stats_kernel / awp_out_kernel: train-mode BatchNorm1d batch statistics over (rays, exposures), residual +
 //                                        leaky ReLU, average pool over exposures, sigmoid(w_linear), normalise.
-#include "common.cuh"
+// precision = EDN_BF16 replaces awp_sample_kernel (fp32 SIMT, the parity path) by the per-sample MLP as four tall TF32 GEMMs
+// over all N*E*S samples (cuBLAS; plain [M,128|64] x [64] contractions) + awp_integrate_kernel (integration, attention logits,
+// "inter" pooling) -- 15 ms -> ~3 ms on the headline batch -- and keeps the layer activations for the backward pass.
+#include "awp_layout.cuh"
+#include "bwd_common.cuh"
 
 namespace edn {
 namespace {
@@ -183,6 +187,63 @@ __global__ void __launch_bounds__(kT, 1) awp_sample_kernel(const AwpArgs a) {
     }
     if (tid < 64) a.gint[sr * 64 + tid] = sm[L::gint + tid];
     __syncthreads();
+  }
+}
+
+// Feature integration + attention logits + "inter" pooling of one sub-ray from its materialised h_local [S][64] and
+// xl [S][32] (GEMM path); same arithmetic and summation order as awp_sample_kernel.  128 threads.
+__global__ void __launch_bounds__(128) awp_integrate_kernel(const AwpArgs a, const float* __restrict__ h_all) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, S = a.S;
+  float* Hs = sm;                 // [S][65]
+  float* Al = Hs + S * 65;        // [S][65]
+  float* Q = Al + S * 65;         // [S][65]
+  float* xls = Q + S * 65;        // [S][33]
+  float* atts = xls + S * 33;     // [S]
+  const int64_t sr = blockIdx.x;
+  const float* h = h_all + sr * S * 64;
+  const float* xl = a.xl + sr * S * 32;
+  for (int i = tid; i < S * 64; i += 128) Hs[(i >> 6) * 65 + (i & 63)] = h[i];
+  for (int i = tid; i < S * 32; i += 128) xls[(i >> 5) * 33 + (i & 31)] = xl[i];
+  __syncthreads();
+  const float* rd = a.rays_d + sr * a.rays_d_stride;
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])), __fmul_rn(rd[2], rd[2])));
+  for (int s = tid; s < S; s += 128) {
+    const bool has = s < S - 1;
+    const float dist = has ? __fmul_rn(a.z_vals[sr * S + s + 1] - a.z_vals[sr * S + s], dnorm) : 0.f;
+    float p = 1.0f;
+    for (int c = 0; c < 64; ++c) {
+      const float al = has ? 1.0f - expf(-__fmul_rn(Hs[s * 65 + c], dist)) : 0.f;
+      Al[s * 65 + c] = al;
+      p *= (1.0f - al);
+      Q[s * 65 + c] = p;
+    }
+    float t = 0.f;
+    for (int c = 0; c < 32; ++c) t = fmaf(__ldg(a.p.line_conv_att + c), xls[s * 33 + c], t);
+    atts[s] = t;
+    a.att[sr * S + s] = t;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float g = 0.f, prev = 1.0f;
+    for (int s = 0; s < S; ++s) {
+      g = fmaf(Al[s * 65 + tid] * prev, Hs[s * 65 + tid], g);
+      prev = Q[s * 65 + tid];
+    }
+    a.gint[sr * 64 + tid] = g;
+  } else if (tid < 96) {
+    const int lane = tid - 64;
+    float mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmaxf(mx, atts[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int s = lane; s < S; s += 32) sum += expf(atts[s] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc = fmaf(xls[s * 33 + lane], expf(atts[s] - mx) / sum, acc);
+    a.inter[sr * 32 + lane] = acc;
   }
 }
 
@@ -377,14 +438,13 @@ __global__ void awp_out_kernel(const AwpArgs a, float bn_eps) {
 }  // namespace
 }  // namespace edn
 
-extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples) {
-  const int64_t NE = n_rays * n_exposure;
-  return NE * 64 + NE * 32 + NE * n_samples * 32 + NE * n_samples + 2 * NE * 32 + 2 * 64 /* stats as doubles */;
+extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, int32_t precision) {
+  return edn::awp_ws_floats(n_rays, n_exposure, n_samples, precision == EDN_BF16);
 }
 
 extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                            int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                           float bn_eps, float* workspace, float* ccw, void* stream) {
+                           float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream) {
   using namespace edn;
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && workspace && ccw, "edn_awp_fwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS,
@@ -399,18 +459,39 @@ extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, 
   AwpArgs a{};
   a.p = *p; a.depth_feature = depth_feature; a.z_vals = z_vals; a.rays_d = rays_d; a.rays_d_stride = rays_d_stride;
   a.view_feature = view_feature; a.N = n_rays; a.E = n_exposure; a.S = n_samples; a.ccw = ccw;
-  float* w = workspace;
-  a.gint = w; w += NE * 64;
-  a.inter = w; w += NE * 32;
-  a.xl = w; w += NE * n_samples * 32;
-  a.att = w; w += NE * n_samples;
-  a.x = w; w += NE * 32;
-  a.y = w; w += NE * 32;
-  a.stats = reinterpret_cast<double*>(w + (((uintptr_t)w & 7) ? 1 : 0));
-  const size_t smem1 = AwpSmem::total * sizeof(float);
-  EDN_CUDA_OK(cudaFuncSetAttribute(awp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  const int64_t g1 = NE < (int64_t)num_sms() ? NE : (int64_t)num_sms();
-  awp_sample_kernel<<<(unsigned)g1, kT, smem1, st>>>(a);
+  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_awp_fwd: bad precision");
+  const bool gemm_path = precision == EDN_BF16;
+  const AwpWs ws = awp_ws_carve(workspace, n_rays, n_exposure, n_samples, gemm_path);
+  a.gint = ws.gint; a.inter = ws.inter; a.xl = ws.xl; a.att = ws.att; a.x = ws.x; a.y = ws.y; a.stats = ws.stats;
+  if (!gemm_path) {
+    const size_t smem1 = AwpSmem::total * sizeof(float);
+    EDN_CUDA_OK(cudaFuncSetAttribute(awp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    const int64_t g1 = NE < (int64_t)num_sms() ? NE : (int64_t)num_sms();
+    awp_sample_kernel<<<(unsigned)g1, kT, smem1, st>>>(a);
+  } else {
+    EDN_REQUIRE((reinterpret_cast<uintptr_t>(depth_feature) & 15) == 0, "edn_awp_fwd: depth_feature must be 16-byte aligned");
+    cublasHandle_t h = blas_handle();
+    if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+    if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
+    const Gemm gemm{h, CUBLAS_COMPUTE_32F_FAST_TF32};
+    const int64_t M = NE * n_samples;
+    EDN_REQUIRE(M < (int64_t)1 << 31, "edn_awp_fwd: too many samples for one GEMM");
+    const float* X = depth_feature;
+    int K = 128;
+    for (int l = 0; l < 4; ++l) {
+      int rc = gemm(false, false, M, 64, K, X, K, p->sample_t[l], 64, 0.f, ws.act[l], 64);
+      if (rc) return rc;
+      relu_bias_kernel<<<blocks_for(M * 16, 256), 256, 0, st>>>(ws.act[l], 64, 64, M, p->sample_b[l]);
+      X = ws.act[l];
+      K = 64;
+    }
+    int rc = gemm(false, false, M, 32, 64, ws.act[3], 64, p->mam_linear_t, 32, 0.f, ws.xl, 32);
+    if (rc) return rc;
+    add_bias_kernel<<<blocks_for(M * 32, 256), 256, 0, st>>>(ws.xl, 32, M, p->mam_linear_b);
+    const size_t smem_i = sizeof(float) * (size_t)(n_samples * (3 * 65 + 33 + 1));
+    EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+    awp_integrate_kernel<<<(unsigned)NE, 128, smem_i, st>>>(a, ws.act[3]);
+  }
   const size_t smem2 = sizeof(RaySmem);
   EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   awp_ray_kernel<<<(unsigned)n_rays, 128, smem2, st>>>(a);

@@ -39,6 +39,13 @@ __global__ void relu_bias_kernel(float* __restrict__ Y, int ld, int n, int64_t M
   *reinterpret_cast<float4*>(Y + m * ld + j) = v;
 }
 
+// Y[m][0..n) += bias   (Y contiguous, row length n)
+__global__ void add_bias_kernel(float* __restrict__ Y, int n, int64_t M, const float* __restrict__ bias) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * n) return;
+  Y[t] += bias[t % n];
+}
+
 // D[m][j] = H[m][j] > 0 ? D[m][j] : 0   (ReLU backward; H is the post-activation)
 __global__ void relu_mask_kernel(float* __restrict__ D, const float* __restrict__ H, int ld, int n, int64_t M) {
   const int nq = n >> 2;

@@ -191,11 +191,6 @@ __global__ void scatter_embed_kernel(const float* __restrict__ d_emb, const int6
   if (t >= N * kW) return;
   atomicAdd(d_table + idx[t / kW] * kW + (t % kW), d_emb[t]);
 }
-__global__ void add_bias_kernel(float* __restrict__ Y, int n, int64_t M, const float* __restrict__ bias) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M * n) return;
-  Y[t] += bias[t % n];
-}
 
 // rbk_weighted_sum backward: out[n][c] = sum_e w[n][e] x[n*E+e][c]
 __global__ void weighted_sum_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ d_out,

@@ -86,8 +86,9 @@ class AdaptiveWeightProposal:
 
     ccw_fine_scale = 0.05     # awp.py:22
 
-    def __init__(self, params, num_motion, prefix="awpnet.", bn_eps=1e-5):
+    def __init__(self, params, num_motion, prefix="awpnet.", bn_eps=1e-5, precision=_lib.EDN_F32):
         self.E, self.bn_eps, self.keep = int(num_motion) + 1, float(bn_eps), []
+        self.precision = int(precision)     # EDN_F32: fused fp32 kernels (parity); EDN_BF16: TF32 GEMM chain for the sample MLP
         p = AwpParams()
 
         def g(name, transpose=False, shape=None):
@@ -130,10 +131,10 @@ class AdaptiveWeightProposal:
             rd = rd.contiguous()
         vf = view_feature.detach().float().contiguous()
         lib = _lib.load()
-        ws = torch.empty((int(lib.edn_awp_workspace_floats(N, E, S)),), dtype=torch.float32, device=df.device)
+        ws = torch.empty((int(lib.edn_awp_workspace_floats(N, E, S, self.precision)),), dtype=torch.float32, device=df.device)
         ccw = torch.empty((N, E), dtype=torch.float32, device=df.device)
-        check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps, ptr(ws),
-                              ptr(ccw), stream_ptr()), "edn_awp_fwd")
+        check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps,
+                              self.precision, ptr(ws), ptr(ccw), stream_ptr()), "edn_awp_fwd")
         return ccw
 
 
@@ -181,7 +182,8 @@ class NeRFAll:
         if "kernelsnet.r_linear.weight" in self.params:
             self.kernelsnet = RigidBlurringModel(self.params, kernel_ptnum - 1)
         self.kernel_type, self.use_awp = "RBK", bool(use_awp)
-        self.awpnet = AdaptiveWeightProposal(self.params, kernel_ptnum - 1) if self.use_awp else None
+        self.awpnet = (AdaptiveWeightProposal(self.params, kernel_ptnum - 1,
+                                              precision=_lib.EDN_BF16 if precision == "bf16" else _lib.EDN_F32) if self.use_awp else None)
         if self.use_awp and self.mode != "c2f":
             raise NotImplementedError("kernel_use_awp with mode = nerf (256-channel depth_feature) is not built")
         self.training = True

@@ -283,11 +283,13 @@ typedef struct edn_awp_params {
 
 /* AdaptiveWeightProposal.forward (awp.py:79-117) in train mode (BatchNorm1d uses batch statistics, mam.py:24-27):
  * depth_feature [N*E][S][128], z_vals [N*E][S], rays_d rows of 3 floats with row stride rays_d_stride (e.g. ray_batch + 3,
- * stride 11), view_feature [N][32] -> ccw [N][E].  workspace: edn_awp_workspace_floats() floats. */
-int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
+ * stride 11), view_feature [N][32] -> ccw [N][E].  workspace: edn_awp_workspace_floats() floats.
+ * precision: EDN_F32 = fused fp32 SIMT kernels (parity path); EDN_BF16 = the per-sample MLP as tall TF32 GEMMs (the layer
+ * activations stay in the workspace for edn_awp_bwd). */
+int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, int32_t precision);
 int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                 int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                float bn_eps, float* workspace, float* ccw, void* stream);
+                float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream);
 
 /* ---- loss path ------------------------------------------------------------------------------------------------------ */
 

@@ -160,6 +160,11 @@ def test_awp_forward_against_oracle(cuda_params):
     ccw = awp(ref["depth_feature"].cuda(), ref["z_vals"].cuda(), rb.cuda()[:, 3:6], g["img_embed"].cuda())
     assert_close(ccw, ccw_ref, "ccw", rtol=1e-4, atol=1e-6)
     assert_close(ccw.sum(-1), torch.ones(48), "rows sum to 1", rtol=1e-5)
+    # bf16-mode path: the per-sample MLP as TF32 tensor-core GEMMs (10-bit mantissa operands): 2e-3 relative
+    from evdeblurnerf_b200 import _lib
+    awp_tc = AdaptiveWeightProposal(Pg, 4, precision=_lib.EDN_BF16)
+    ccw_tc = awp_tc(ref["depth_feature"].cuda(), ref["z_vals"].cuda(), rb.cuda()[:, 3:6], g["img_embed"].cuda())
+    assert_close(ccw_tc, ccw_ref, "ccw (TF32 GEMM path)", rtol=2e-3, atol=1e-5)
 
 
 def test_forward_train_with_awp_golden(cuda_params):
