@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import CrfGrads, RbkGrads, check, ptr, stream_ptr
+from ._lib import AwpGrads, CrfGrads, RbkGrads, check, ptr, stream_ptr
 from .backward import RenderGradients, render_rays_backward
 
 _RBK_NAMES = ("view_embed_module.img_embed", "r_branch.0.weight", "r_branch.0.bias", "v_branch.0.weight", "v_branch.0.bias",
@@ -202,19 +202,28 @@ class RenderSubRaysFn(torch.autograd.Function):
         ctx.rays = _c(rays)
         ctx.idx = images_idx.reshape(-1).to(torch.int64).contiguous() if images_idx is not None else None
         zero3, zero1 = torch.zeros((R, 3), device=dev), torch.zeros((R,), device=dev)
+        empty = torch.zeros((0,), device=dev)
+        ctx.has_feat = "depth_feature" in out
         res = (out["rgb_map"], out["depth_map"], out["acc_map"], out.get("rgb0", zero3), out.get("depth0", zero1), out.get("acc0", zero1),
-               weight if weight is not None else torch.zeros((0,), device=dev))
+               weight if weight is not None else empty, out.get("depth_feature", empty), rb.clone(),
+               k["img_embed"] if k.get("img_embed") is not None else empty)
         return res
 
     @staticmethod
-    def backward(ctx, d_rgb, d_depth, d_acc, d_rgb0, d_depth0, d_acc0, d_weight):
+    def backward(ctx, d_rgb, d_depth, d_acc, d_rgb0, d_depth0, d_acc0, d_weight, d_feat, d_rb_out, d_img_embed):
         owner, kn = ctx.owner, ctx.kn
         eng = owner.engine
         lib = _lib.load()
         d_out = {"rgb_map": d_rgb, "depth_map": d_depth, "acc_map": d_acc}
         if ctx.two_stage:
             d_out.update(rgb0=d_rgb0, depth0=d_depth0, acc0=d_acc0)
+        if ctx.has_feat and d_feat is not None and d_feat.numel():
+            d_out["depth_feature"] = d_feat
         grads, d_rb = render_rays_backward(eng, ctx.saved, d_out, grads=RenderGradients(eng), chunk_rays=owner.backward_chunk_rays)
+        if d_rb_out is not None and d_rb_out.numel():
+            d_rb += d_rb_out                                   # direct uses of the ray batch (AWP reads rays_d)
+        if d_img_embed is not None and not d_img_embed.numel():
+            d_img_embed = None
         named = grads.finish()
         if kn is not None:
             H, W, focal, ndc = ctx.geom
@@ -227,9 +236,66 @@ class RenderSubRaysFn(torch.autograd.Function):
             ws = torch.empty((int(lib.edn_rbk_bwd_workspace_floats(N, kn.num_motion)),), dtype=torch.float32, device=d_rb.device)
             check(lib.edn_rbk_warp_ndc_bwd(C.byref(kn.p), ptr(ctx.rays), ptr(ctx.idx), N, int(H), int(W), float(focal), 1 if ndc else 0,
                                            ptr(d_rb), ptr(_c(d_weight)) if d_weight is not None and d_weight.numel() else None,
+                                           ptr(_c(d_img_embed)) if d_img_embed is not None else None,
                                            C.byref(g), ptr(ws), stream_ptr()), "edn_rbk_warp_ndc_bwd")
         out = []
         for nm in ctx.names:
             gr = named.get(nm)
             out.append(gr)
         return (None,) * 12 + tuple(out)
+
+
+_AWP_FIELDS = (   # (struct field, index | None, state_dict name, transposed)
+    [("sample_t", l, f"sample_feature_embed_layer.{l}.weight", True) for l in range(4)] +
+    [("sample_b", l, f"sample_feature_embed_layer.{l}.bias", False) for l in range(4)] +
+    [("motion_w", l, f"motion_feature_embed_layer.{l}.weight", False) for l in range(2)] +
+    [("motion_b", l, f"motion_feature_embed_layer.{l}.bias", False) for l in range(2)] +
+    [("mam_linear_t", None, "MAM.linear.weight", True), ("mam_linear_b", None, "MAM.linear.bias", False),
+     ("line_conv_att", None, "MAM.Corr.line_conv_att.weight", False), ("conva", None, "MAM.Corr.conva.weight", False),
+     ("convb", None, "MAM.Corr.convb.weight", False), ("convc", None, "MAM.Corr.convc.weight", False),
+     ("convn", None, "MAM.Corr.convn.weight", False), ("convl", None, "MAM.Corr.convl.weight", False),
+     ("convd_w", None, "MAM.Corr.convd.0.weight", False), ("bn_weight", None, "MAM.Corr.convd.1.weight", False),
+     ("bn_bias", None, "MAM.Corr.convd.1.bias", False), ("w_linear_w", None, "w_linear.weight", False),
+     ("w_linear_b", None, "w_linear.bias", False)])
+AWP_PARAM_NAMES = tuple(f[2] for f in _AWP_FIELDS)
+
+
+class AwpFn(torch.autograd.Function):
+    """AdaptiveWeightProposal.forward (awp.py:79-117) with its hand-written backward (awp_bwd.cu).
+    Inputs: depth_feature [N*E,S,128], z_vals [N*E,S] (no gradient), rays_d [N*E,3], view_feature [N,32], then the AWP
+    parameter tensors in AWP_PARAM_NAMES order (graph connectivity; the kernels read the module's packed copies)."""
+
+    @staticmethod
+    def forward(ctx, awp, depth_feature, z_vals, rays_d, view_feature, *params):
+        df, z, rd, vf = _c(depth_feature), _c(z_vals), _c(rays_d), _c(view_feature)
+        ctx.awp = awp
+        ctx.save_for_backward(df, z, rd, vf)
+        ctx.shapes = [tuple(t.shape) for t in params]
+        return awp.run(df, z, rd, vf)
+
+    @staticmethod
+    def backward(ctx, d_ccw):
+        awp = ctx.awp
+        df, z, rd, vf = ctx.saved_tensors
+        lib = _lib.load()
+        NE, S, _ = df.shape
+        E = awp.E
+        N = NE // E
+        dev = df.device
+        g = AwpGrads()
+        bufs = []
+        for (field, idx, _, transposed), shp in zip(_AWP_FIELDS, ctx.shapes):
+            t = torch.zeros(shp[::-1] if transposed else shp, dtype=torch.float32, device=dev)
+            bufs.append(t)
+            if idx is None:
+                setattr(g, field, t.data_ptr())
+            else:
+                getattr(g, field)[idx] = t.data_ptr()
+        d_df = torch.empty_like(df)
+        d_rd = torch.zeros_like(rd)
+        d_vf = torch.empty_like(vf)
+        ws = torch.empty((int(lib.edn_awp_bwd_workspace_floats(N, E, S)),), dtype=torch.float32, device=dev)
+        check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, awp.precision, ptr(_c(d_ccw)),
+                              C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf), ptr(ws), stream_ptr()), "edn_awp_bwd")
+        outs = [(b.t().contiguous() if f[3] else b) for f, b in zip(_AWP_FIELDS, bufs)]
+        return (None, d_df, None, d_rd, d_vf) + tuple(outs)

@@ -442,10 +442,10 @@ extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, 
   return edn::awp_ws_floats(n_rays, n_exposure, n_samples, precision == EDN_BF16);
 }
 
-extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
-                           int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                           float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream) {
-  using namespace edn;
+namespace edn {
+int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
+                const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
+                bool tf32, float* workspace, float* ccw, void* stream) {
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && workspace && ccw, "edn_awp_fwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS,
               "edn_awp_fwd: need 1 <= E <= %d and 2 <= S <= %d", kMaxE, kMaxS);
@@ -459,8 +459,6 @@ extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, 
   AwpArgs a{};
   a.p = *p; a.depth_feature = depth_feature; a.z_vals = z_vals; a.rays_d = rays_d; a.rays_d_stride = rays_d_stride;
   a.view_feature = view_feature; a.N = n_rays; a.E = n_exposure; a.S = n_samples; a.ccw = ccw;
-  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_awp_fwd: bad precision");
-  const bool gemm_path = precision == EDN_BF16;
   const AwpWs ws = awp_ws_carve(workspace, n_rays, n_exposure, n_samples, gemm_path);
   a.gint = ws.gint; a.inter = ws.inter; a.xl = ws.xl; a.att = ws.att; a.x = ws.x; a.y = ws.y; a.stats = ws.stats;
   if (!gemm_path) {
@@ -473,7 +471,7 @@ extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, 
     cublasHandle_t h = blas_handle();
     if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
     if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
-    const Gemm gemm{h, CUBLAS_COMPUTE_32F_FAST_TF32};
+    const Gemm gemm{h, tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F};
     const int64_t M = NE * n_samples;
     EDN_REQUIRE(M < (int64_t)1 << 31, "edn_awp_fwd: too many samples for one GEMM");
     const float* X = depth_feature;
@@ -499,4 +497,14 @@ extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, 
   awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
+}
+}  // namespace edn
+
+extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
+                           int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
+                           float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_awp_fwd: bad precision");
+  return awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, n_rays, n_exposure, n_samples, bn_eps,
+                     precision == EDN_BF16, true, workspace, ccw, stream);
 }

@@ -2,6 +2,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/evdeblur_b200.h"
+
 namespace edn {
 
 struct AwpWs {
@@ -35,5 +37,10 @@ inline AwpWs awp_ws_carve(float* w, int64_t N, int E, int S, bool gemm) {
   if (gemm) for (int l = 0; l < 4; ++l) { a.act[l] = w; w += NE * S * 64; }
   return a;
 }
+
+// awp.cu: the forward into `workspace` (gemm_path = materialised per-sample MLP, needed by the backward; tf32 = tensor-core GEMMs)
+int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
+                const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
+                bool tf32, float* workspace, float* ccw, void* stream);
 
 }  // namespace edn

@@ -219,7 +219,7 @@ extern "C" int64_t edn_rbk_bwd_workspace_floats(int64_t n_rays, int32_t num_moti
 
 extern "C" int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, const int64_t* images_idx, int64_t n_rays, int32_t H,
                                     int32_t W, float focal, int32_t ndc, const float* d_ray_batch, const float* d_weight,
-                                    const edn_rbk_grads* g, float* workspace, void* stream) {
+                                    const float* d_img_embed, const edn_rbk_grads* g, float* workspace, void* stream) {
   using namespace edn;
   EDN_REQUIRE(p && rays && images_idx && g && workspace, "edn_rbk_warp_ndc_bwd: null pointer");
   const int M = p->num_motion, E = M + 1;
@@ -265,6 +265,10 @@ extern "C" int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, 
                                                                d_out[0], d_out[1]);
   rbk_weight_bwd_kernel<<<blocks_for(N, 128), 128, 0, st>>>(out[2], d_weight, N, E, d_out[2]);
   bool first = true;
+  if (d_img_embed) {       // gradient of the view latents handed to AWP (awp.py:88-94)
+    EDN_CUDA_OK(cudaMemcpyAsync(d_emb, d_img_embed, sizeof(float) * (size_t)N * kW, cudaMemcpyDeviceToDevice, st));
+    first = false;
+  }
   for (int t = (M > 0 ? 0 : 2); t < 3; ++t) {
     EDN_RC(gemm(true, false, on[t], kW, N, d_out[t], on[t], Hb[t], kW, 1.f, glw[t], kW));
     colsum_kernel<<<blocks_for(N, 512), 64, 0, st>>>(d_out[t], on[t], on[t], N, glb[t]);

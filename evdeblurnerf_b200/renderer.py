@@ -88,6 +88,7 @@ class AdaptiveWeightProposal:
 
     def __init__(self, params, num_motion, prefix="awpnet.", bn_eps=1e-5, precision=_lib.EDN_F32):
         self.E, self.bn_eps, self.keep = int(num_motion) + 1, float(bn_eps), []
+        self.params, self.prefix = params, prefix
         self.precision = int(precision)     # EDN_F32: fused fp32 kernels (parity); EDN_BF16: TF32 GEMM chain for the sample MLP
         p = AwpParams()
 
@@ -120,6 +121,14 @@ class AdaptiveWeightProposal:
 
     def __call__(self, depth_feature, z_vals, rays_d, view_feature):
         """awp.py:79: depth_feature [N*E,S,128], z_vals [N*E,S], rays_d [N*E,3] (may be a strided view), view_feature [N,32]."""
+        from .autograd import AWP_PARAM_NAMES, AwpFn
+        ps = [self.params[self.prefix + n] for n in AWP_PARAM_NAMES]
+        if torch.is_grad_enabled() and (depth_feature.requires_grad or rays_d.requires_grad or view_feature.requires_grad
+                                        or any(t.requires_grad for t in ps)):
+            return AwpFn.apply(self, depth_feature, z_vals, rays_d, view_feature, *ps)
+        return self.run(depth_feature, z_vals, rays_d, view_feature)
+
+    def run(self, depth_feature, z_vals, rays_d, view_feature):
         df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
         NE, S, Fd = df.shape
         if Fd != 128:
@@ -189,7 +198,8 @@ class NeRFAll:
         self.training = True
         self.backward_chunk_rays = 8192     # rays per recompute chunk of the backward pass (workspace ~ 8.6 KB x samples)
         self.last_render = None
-        self._grad_names = sorted(k for k in self.params if k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.")))
+        self._grad_names = sorted(k for k in self.params if k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet."))
+                                  and self.params[k].is_floating_point())
         self._packed_version = self._param_version()
 
     # ---- autograd plumbing (the reference trains through torch autograd, run_nerf.py:594) --------------------------------
@@ -197,11 +207,13 @@ class NeRFAll:
         return sum(int(v._version) for v in self.params.values())
 
     def _wants_grad(self):
-        return torch.is_grad_enabled() and any(self.params[k].requires_grad for k in self._grad_names)
+        return torch.is_grad_enabled() and any(v.requires_grad for v in self.params.values())
 
     def repack(self):
         """Refresh the render-layout copies after the parameters changed (optimizer.step(), load_state_dict)."""
         self.engine.repack(self.params)
+        if self.use_awp:
+            self.awpnet = AdaptiveWeightProposal(self.params, self.awpnet.E - 1, precision=self.awpnet.precision)
         self._packed_version = self._param_version()
 
     def _maybe_repack(self):
@@ -214,8 +226,6 @@ class NeRFAll:
         from .autograd import RenderSubRaysFn
         if self.mode != "c2f":
             raise NotImplementedError("backward of mode = nerf is not built (DESIGN.md section 8)")
-        if self.use_awp:
-            raise NotImplementedError("backward through the AWP branch is not built (DESIGN.md section 8)")
         names = self._grad_names
         return RenderSubRaysFn.apply(self, self.kernelsnet if blur else None, H, W, float(K[0][0]), rays, images_idx, near, far, ndc,
                                      kwargs, names,
@@ -307,10 +317,16 @@ class NeRFAll:
         """Training branch of forward() (renderer.py:277-378) with outputs attached to the autograd graph."""
         other_loss, other_tensors = {}, {}
         blur = self.kernelsnet is not None and not force_baseline
-        rgb, depth, acc, rgb0, depth0, acc0, weight1 = self._render_sub_rays(
+        rgb, depth, acc, rgb0, depth0, acc0, weight1, feat, rb, img_embed = self._render_sub_rays(
             H, W, K, rays, rays_info["images_idx"] if blur else None, near, far, ndc, kwargs, blur=blur)
         if blur:
             N, E = weight1.shape
+            if self.use_awp:     # renderer.py:310-330
+                ccw = self.awpnet(feat, self.last_render["z_vals"], rb[:, 3:6], img_embed)
+                ccw = normalize_ccw(ccw, self.awpnet.ccw_fine_scale)
+                other_tensors["rgb_awp"] = weighted_sum(rgb, ccw)
+                other_tensors["ccw_fine"] = ccw
+                other_tensors["stage1_img_embed"] = img_embed
             rgb_b = weighted_sum(rgb, weight1)
             rgb1 = weighted_sum(rgb0, weight1) if N_importance > 0 else None
             if return_pts0_rgb:
@@ -331,7 +347,7 @@ class NeRFAll:
         NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum.  Returns (rgb [N,3], rgb0 [N,3] | None)."""
         self._maybe_repack()
         if self._wants_grad():
-            rgb, _, _, rgb0, _, _, weight1 = self._render_sub_rays(H, W, K, rays, images_idx, near, far, ndc, kwargs)
+            rgb, _, _, rgb0, _, _, weight1 = self._render_sub_rays(H, W, K, rays, images_idx, near, far, ndc, kwargs)[:7]
             if self.kernelsnet is None:
                 return rgb, (rgb0 if kwargs.get("N_importance", 0) > 0 else None)
             return weighted_sum(rgb, weight1), (weighted_sum(rgb0, weight1) if kwargs.get("N_importance", 0) > 0 else None)

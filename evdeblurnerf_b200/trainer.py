@@ -77,17 +77,19 @@ class FlatParams:
 class Trainer:
     def __init__(self, state, crf_state, aabb_min, aabb_max, kernel_ptnum=5, precision="bf16", lrate=5e-4, lrate_decay=250,
                  lrate_warmup_iters=0, lrate_warmup_factor=1.0, colornet_weightdecay=0.0, tv_loss_weight=1e-2,
-                 event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0):
+                 event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0,
+                 use_awp=False, awp_fine_loss_weight=None):
         if not torch.cuda.is_available():
             raise RuntimeError("evdeblurnerf_b200.Trainer needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if device is not None else "cuda")
         trainable = {k: v for k, v in state.items() if isinstance(v, torch.Tensor) and v.is_floating_point()
-                     and k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet."))}
+                     and k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.") + (("awpnet.",) if use_awp else ()))}
         crf_train = {"crf." + k: v for k, v in (crf_state or {}).items() if isinstance(v, torch.Tensor) and v.is_floating_point()}
         self.flat = FlatParams({**trainable, **crf_train}, dev)
         P = {k: self.flat.views[k] for k in trainable}
         Pc = {k[4:]: self.flat.views[k] for k in crf_train}
-        self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision).train()
+        self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision, use_awp=use_awp).train()
+        self.awp_fine_loss_weight = awp_fine_loss_weight
         self.crf = TonemappingTransform(Pc, **(crf_kwargs or dict(map_type_rgb="gamma", map_type_event="learn" if Pc else "gamma",
                                                                   extra_features_event=2)))
         self.hp = dict(lrate=lrate, decay=lrate_decay, warm_it=lrate_warmup_iters, warm_f=lrate_warmup_factor,
@@ -102,14 +104,19 @@ class Trainer:
     # run_nerf.py:438-504 (+ 539-557 when event rays are given)
     def loss(self, batch, H, W, K):
         out = {}
-        rgb, rgb0, extra_loss, _ = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
-                                             **self.render_kwargs)
+        rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
+                                                        **self.render_kwargs)
         target = batch["rgbsf"].reshape(-1, 3)
         img_loss = img2mse(self.crf(rgb, mode="encode_rgb"), target)
         out["img_loss"] = img_loss.detach()
         if rgb0 is not None:
             img_loss = img_loss + img2mse(self.crf(rgb0, mode="encode_rgb"), target)
         loss = img_loss
+        if extra_tensor.get("rgb_awp") is not None:          # run_nerf.py:464-475
+            fine = img2mse(self.crf(extra_tensor["rgb_awp"], mode="encode_rgb"), target)
+            out["img_fine_loss"] = fine.detach()
+            flw = self.awp_fine_loss_weight                   # kernel_awp_use_coarse_to_fine_opt: annealed mix, else plain sum
+            loss = loss + fine if flw is None else loss * (1 - flw) + fine * flw
         if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
             loss = loss + extra_loss["TV"] * self.hp["tv_w"]
         if self.hp["ev_w"] > 0 and "ev_rays_start" in batch:

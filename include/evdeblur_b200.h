@@ -253,12 +253,13 @@ typedef struct edn_rbk_grads {
 
 /* Backward of edn_rbk_warp_ndc_fwd (dpnerf/blurmodel.py:129-173, utils/rigid_warping.py:18-154, renderer.py:423-446,
  * utils/rays.py:104-145): d_ray_batch [N*E][11] (what edn_render_field_bwd accumulated; NULL only if num_motion == 0),
- * d_weight [N][E] or NULL -> ACCUMULATES the kernel-net parameter gradients into `grads`.
+ * d_weight [N][E] or NULL, d_img_embed [N][32] or NULL (gradient of the returned view latents, used by AWP)
+ * -> ACCUMULATES the kernel-net parameter gradients into `grads`.
  * workspace: edn_rbk_bwd_workspace_floats(n_rays, num_motion) floats. */
 int64_t edn_rbk_bwd_workspace_floats(int64_t n_rays, int32_t num_motion);
 int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, const int64_t* images_idx, int64_t n_rays, int32_t H,
                          int32_t W, float focal, int32_t ndc, const float* d_ray_batch, const float* d_weight,
-                         const edn_rbk_grads* grads, float* workspace, void* stream);
+                         const float* d_img_embed, const edn_rbk_grads* grads, float* workspace, void* stream);
 
 /* Backward of edn_weighted_sum: d_out [N][C] -> d_x [N*E][C] (or NULL), d_w [N][E] (or NULL); both overwritten. */
 int edn_weighted_sum_bwd(const float* x, const float* w, const float* d_out, int64_t n, int32_t n_exposure, int64_t channels,
@@ -290,6 +291,28 @@ int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_s
 int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                 int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
                 float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream);
+
+/* Gradients of the AWP parameters, same field layout as edn_awp_params (sample_t / mam_linear_t TRANSPOSED like the weights). */
+typedef struct edn_awp_grads {
+  float* sample_t[4]; float* sample_b[4];
+  float* motion_w[2]; float* motion_b[2];
+  float* mam_linear_t; float* mam_linear_b;
+  float* line_conv_att;
+  float* conva; float* convb; float* convc; float* convn; float* convl;
+  float* convd_w; float* bn_weight; float* bn_bias;
+  float* w_linear_w; float* w_linear_b;
+} edn_awp_grads;
+
+/* Backward of edn_awp_fwd (awp.py:79-117, 49-77; mam.py:13-84; train-mode BatchNorm): d_ccw [N][E] ->
+ *   grads (ACCUMULATED), d_depth_feature [N*E][S][128] (overwritten; feed it to edn_render_field_bwd's d_feat),
+ *   d_rays_d rows of 3 floats with row stride d_rays_d_stride (ACCUMULATED; may be NULL), d_view_feature [N][32] (overwritten;
+ *   may be NULL).  The forward is recomputed into the workspace (edn_awp_bwd_workspace_floats floats).
+ *   precision: EDN_F32 = fp32 GEMMs, EDN_BF16 = TF32 tensor-core GEMMs. */
+int64_t edn_awp_bwd_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
+int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
+                int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
+                float bn_eps, int32_t precision, const float* d_ccw, const edn_awp_grads* grads, float* d_depth_feature,
+                float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace, void* stream);
 
 /* ---- loss path ------------------------------------------------------------------------------------------------------ */
 
