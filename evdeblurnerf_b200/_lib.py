@@ -107,8 +107,8 @@ SIGNATURES = {
     "edn_rbk_bwd_workspace_floats": (C.c_int64, [_I64, _I32]),
     "edn_rbk_warp_ndc_bwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, C.POINTER(RbkGrads), _P, _P]),
     "edn_awp_bwd_workspace_floats": (C.c_int64, [_I64, _I32, _I32]),
-    "edn_awp_bwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _I32, _P, C.POINTER(AwpGrads), _P, _P,
-                              _I32, _P, _P, _P]),
+    "edn_awp_bwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _I32, _I32, _P, C.POINTER(AwpGrads), _P,
+                              _P, _I32, _P, _P, _P]),
     "edn_weighted_sum_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "edn_crf_bwd": (C.c_int, [C.POINTER(CrfParams), _P, _P, _I32, _I32, _I64, _P, _P, C.POINTER(CrfGrads), _P]),
     "edn_egm_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _F, _P, _P, _P, _P]),

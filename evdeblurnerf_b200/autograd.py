@@ -271,7 +271,11 @@ class AwpFn(torch.autograd.Function):
         ctx.awp = awp
         ctx.save_for_backward(df, z, rd, vf)
         ctx.shapes = [tuple(t.shape) for t in params]
-        return awp.run(df, z, rd, vf)
+        # run the forward straight into a backward-sized workspace: in bf16 mode it keeps the layer activations, so the
+        # backward does not recompute them
+        NE, S, _ = df.shape
+        ctx.ws = torch.empty((int(_lib.load().edn_awp_bwd_workspace_floats(NE // awp.E, awp.E, S)),), dtype=torch.float32, device=df.device)
+        return awp.run(df, z, rd, vf, workspace=ctx.ws)
 
     @staticmethod
     def backward(ctx, d_ccw):
@@ -294,8 +298,9 @@ class AwpFn(torch.autograd.Function):
         d_df = torch.empty_like(df)
         d_rd = torch.zeros_like(rd)
         d_vf = torch.empty_like(vf)
-        ws = torch.empty((int(lib.edn_awp_bwd_workspace_floats(N, E, S)),), dtype=torch.float32, device=dev)
-        check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, awp.precision, ptr(_c(d_ccw)),
-                              C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf), ptr(ws), stream_ptr()), "edn_awp_bwd")
+        ws, ctx.ws = ctx.ws, None
+        check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, awp.precision,
+                              1 if awp.precision == _lib.EDN_BF16 else 0, ptr(_c(d_ccw)), C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf),
+                              ptr(ws), stream_ptr()), "edn_awp_bwd")
         outs = [(b.t().contiguous() if f[3] else b) for f, b in zip(_AWP_FIELDS, bufs)]
         return (None, d_df, None, d_rd, d_vf) + tuple(outs)

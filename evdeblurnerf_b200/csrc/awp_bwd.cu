@@ -531,8 +531,9 @@ extern "C" int64_t edn_awp_bwd_workspace_floats(int64_t n_rays, int32_t n_exposu
 
 extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                            int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                           float bn_eps, int32_t precision, const float* d_ccw, const edn_awp_grads* grads, float* d_depth_feature,
-                           float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace, void* stream) {
+                           float bn_eps, int32_t precision, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
+                           float* d_depth_feature, float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace,
+                           void* stream) {
   using namespace edn;
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && d_ccw && grads && d_depth_feature && workspace, "edn_awp_bwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS, "edn_awp_bwd: need 1 <= E <= %d and 2 <= S <= %d", kMaxE, kMaxS);
@@ -551,8 +552,10 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   base += (4 - ((uintptr_t)base / 4) % 4) % 4;
   auto take = [&](int64_t n) { float* q = base; base += (n + 3) / 4 * 4; return q; };
   float* ccw_tmp = take(NE);
-  int rc = awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, N, E, S, bn_eps, true, tf32, workspace, ccw_tmp, stream);
-  if (rc) return rc;
+  if (!forward_in_workspace) {
+    int rc = awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, N, E, S, bn_eps, true, tf32, workspace, ccw_tmp, stream);
+    if (rc) return rc;
+  }
   BwdArgs a{};
   a.p = *p; a.g = *grads; a.ws = awp_ws_carve(workspace, N, E, S, true);
   a.z_vals = z_vals; a.rays_d = rays_d; a.rays_d_stride = rays_d_stride; a.view_feature = view_feature;

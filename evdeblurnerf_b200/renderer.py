@@ -128,7 +128,7 @@ class AdaptiveWeightProposal:
             return AwpFn.apply(self, depth_feature, z_vals, rays_d, view_feature, *ps)
         return self.run(depth_feature, z_vals, rays_d, view_feature)
 
-    def run(self, depth_feature, z_vals, rays_d, view_feature):
+    def run(self, depth_feature, z_vals, rays_d, view_feature, workspace=None):
         df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
         NE, S, Fd = df.shape
         if Fd != 128:
@@ -140,7 +140,8 @@ class AdaptiveWeightProposal:
             rd = rd.contiguous()
         vf = view_feature.detach().float().contiguous()
         lib = _lib.load()
-        ws = torch.empty((int(lib.edn_awp_workspace_floats(N, E, S, self.precision)),), dtype=torch.float32, device=df.device)
+        ws = workspace if workspace is not None else torch.empty((int(lib.edn_awp_workspace_floats(N, E, S, self.precision)),),
+                                                                 dtype=torch.float32, device=df.device)
         ccw = torch.empty((N, E), dtype=torch.float32, device=df.device)
         check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps,
                               self.precision, ptr(ws), ptr(ccw), stream_ptr()), "edn_awp_fwd")

@@ -306,13 +306,16 @@ typedef struct edn_awp_grads {
 /* Backward of edn_awp_fwd (awp.py:79-117, 49-77; mam.py:13-84; train-mode BatchNorm): d_ccw [N][E] ->
  *   grads (ACCUMULATED), d_depth_feature [N*E][S][128] (overwritten; feed it to edn_render_field_bwd's d_feat),
  *   d_rays_d rows of 3 floats with row stride d_rays_d_stride (ACCUMULATED; may be NULL), d_view_feature [N][32] (overwritten;
- *   may be NULL).  The forward is recomputed into the workspace (edn_awp_bwd_workspace_floats floats).
+ *   may be NULL).  The forward is recomputed into the workspace (edn_awp_bwd_workspace_floats floats) unless
+ *   forward_in_workspace != 0: then `workspace` is the buffer edn_awp_fwd(precision = EDN_BF16) just filled for the same inputs
+ *   (allocated with the backward's size).
  *   precision: EDN_F32 = fp32 GEMMs, EDN_BF16 = TF32 tensor-core GEMMs. */
 int64_t edn_awp_bwd_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
 int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                 int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                float bn_eps, int32_t precision, const float* d_ccw, const edn_awp_grads* grads, float* d_depth_feature,
-                float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace, void* stream);
+                float bn_eps, int32_t precision, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
+                float* d_depth_feature, float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace,
+                void* stream);
 
 /* ---- loss path ------------------------------------------------------------------------------------------------------ */
 

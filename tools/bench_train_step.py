@@ -12,6 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import torch  # noqa: E402
 
@@ -25,6 +26,7 @@ def main():
     ap.add_argument("--precision", nargs="+", default=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=bench.N_RAYS)
     ap.add_argument("--chunk-rays", type=int, default=20480)
+    ap.add_argument("--awp", action="store_true", help="train with the AWP branch (kernel_use_awp, as in the shipped configs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -37,7 +39,11 @@ def main():
     dev = torch.device("cuda", local)
     for precision in args.precision:
         P = bench.make_params(dev, seed=0)
+        if args.awp:
+            from bench_awp_forward import awp_params
+            P.update(awp_params(dev, bench.N_EXPOSURE))
         tr = Trainer(P, None, *bench.AABB, kernel_ptnum=bench.N_EXPOSURE, precision=precision, tv_loss_weight=1e-2, device=dev,
+                     use_awp=args.awp,
                      render_kwargs=dict(N_samples=bench.NC, N_importance=bench.NI, perturb=1., raw_noise_std=1.))
         del P
         tr.nerf.backward_chunk_rays = args.chunk_rays
@@ -62,7 +68,7 @@ def main():
         kern = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in tr.nerf.engine.profile.items()}
         if rank == 0:
             print(json.dumps({"metric": "training rays/s (fwd + loss + bwd + all-reduce + Adam)", "value": world * args.rays / (ms * 1e-3),
-                              "unit": "rays/s", "n_gpus": world, "ms_per_step": ms, "precision": precision,
+                              "unit": "rays/s", "n_gpus": world, "ms_per_step": ms, "precision": precision, "awp": bool(args.awp),
                               "kernels_ms": kern, "loss": float(out["loss"]),
                               "config": {"workload": f"{args.rays} rays x {bench.N_EXPOSURE} exposures x {bench.NC}+{bench.NI} samples, "
                                                      "full-size VM grids, TV + MSE losses, Adam over 36.8M parameters",
