@@ -317,3 +317,25 @@ def test_trainer_with_awp_reduces_loss():
     assert float(hist[-1]["img_fine_loss"]) < 0.7 * float(hist[0]["img_fine_loss"])
     moved = [k for k, v in before.items() if float((tr.flat.views[k].detach() - v).abs().max()) > 0]
     assert len(moved) >= 25, moved
+
+
+def test_trainer_with_event_loss_trains_crf_and_fields():
+    """Config 3 shape of the iteration: blurred-ray photometric loss + event generation-model loss on start / end event rays
+    rendered through the force_naive branch + learnable CRF (run_nerf.py:534-591)."""
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if v.is_floating_point() and not k.startswith("awpnet.")}
+    batch = _tiny_batch(32, 34)
+    M = 24
+    gen = torch.Generator().manual_seed(9)
+    ev0, _ = synthetic_rays(M, seed=35)
+    ev1, _ = synthetic_rays(M, seed=36)      # unrelated pixels, a constant brightness increment: a fittable toy target
+    batch.update(ev_rays_start=ev0.cuda(), ev_rays_end=ev1.cuda(), bii=torch.full((M,), 0.4).cuda(),
+                 ev_extra_feat=torch.rand(M, 2, generator=gen).cuda())
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", lrate=2e-3, tv_loss_weight=0.01, event_loss_weight=0.5,
+                 render_kwargs=dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.))
+    crf0 = {k: v.detach().clone() for k, v in tr.flat.views.items() if k.startswith("crf.")}
+    hist = [tr.step(batch, H, W, KMAT) for _ in range(40)]
+    assert float(hist[-1]["event_loss"]) < 0.8 * float(hist[0]["event_loss"]), (hist[0]["event_loss"], hist[-1]["event_loss"])
+    assert float(hist[-1]["loss"]) < float(hist[0]["loss"])
+    assert all(float((tr.flat.views[k].detach() - v).abs().max()) > 0 for k, v in crf0.items()), "CRF parameters must receive gradients"

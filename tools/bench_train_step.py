@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--precision", nargs="+", default=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=bench.N_RAYS)
     ap.add_argument("--chunk-rays", type=int, default=20480)
+    ap.add_argument("--events", type=int, default=0, help="config 3: add M start/end event-ray pairs + EGM loss + learnable CRF")
     ap.add_argument("--awp", action="store_true", help="train with the AWP branch (kernel_use_awp, as in the shipped configs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -42,7 +43,14 @@ def main():
         if args.awp:
             from bench_awp_forward import awp_params
             P.update(awp_params(dev, bench.N_EXPOSURE))
-        tr = Trainer(P, None, *bench.AABB, kernel_ptnum=bench.N_EXPOSURE, precision=precision, tv_loss_weight=1e-2, device=dev,
+        crf_state = None
+        if args.events:
+            g = torch.Generator().manual_seed(5)
+            crf_state = {}
+            for idx, (o, i) in ((0, (16, 3)), (2, (16, 16)), (4, (16, 16)), (6, (1, 16))):
+                crf_state[f"tonemapping_event.linear.{idx}.weight"] = (torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5
+                crf_state[f"tonemapping_event.linear.{idx}.bias"] = (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5
+        tr = Trainer(P, crf_state, *bench.AABB, event_loss_weight=1.0 if args.events else 0.0, kernel_ptnum=bench.N_EXPOSURE, precision=precision, tv_loss_weight=1e-2, device=dev,
                      use_awp=args.awp,
                      render_kwargs=dict(N_samples=bench.NC, N_importance=bench.NI, perturb=1., raw_noise_std=1.))
         del P
@@ -51,7 +59,14 @@ def main():
         for s in range(args.steps + args.warmup):
             rays, idx = bench.make_rays(args.rays, seed=1000 * rank + s)
             g = torch.Generator().manual_seed(s)
-            batches.append({"rays": rays.to(dev), "images_idx": idx.to(dev), "rgbsf": torch.rand(args.rays, 3, generator=g).to(dev)})
+            b = {"rays": rays.to(dev), "images_idx": idx.to(dev), "rgbsf": torch.rand(args.rays, 3, generator=g).to(dev)}
+            if args.events:
+                ev0, _ = bench.make_rays(args.events, seed=77000 + s)
+                ev1 = ev0.clone()
+                ev1[:, :, 0] += 0.005 * torch.randn(args.events, 3, generator=g)
+                b.update(ev_rays_start=ev0.to(dev), ev_rays_end=ev1.to(dev), ev_extra_feat=torch.rand(args.events, 2, generator=g).to(dev),
+                         bii=(0.25 * torch.randint(-2, 3, (args.events,), generator=g).float()).to(dev))
+            batches.append(b)
         for s in range(args.warmup):
             tr.step(batches[s], bench.H, bench.W, bench.KMAT)
         tr.nerf.engine.profile = {}
@@ -68,7 +83,7 @@ def main():
         kern = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in tr.nerf.engine.profile.items()}
         if rank == 0:
             print(json.dumps({"metric": "training rays/s (fwd + loss + bwd + all-reduce + Adam)", "value": world * args.rays / (ms * 1e-3),
-                              "unit": "rays/s", "n_gpus": world, "ms_per_step": ms, "precision": precision, "awp": bool(args.awp),
+                              "unit": "rays/s", "n_gpus": world, "ms_per_step": ms, "precision": precision, "awp": bool(args.awp), "event_rays": args.events,
                               "kernels_ms": kern, "loss": float(out["loss"]),
                               "config": {"workload": f"{args.rays} rays x {bench.N_EXPOSURE} exposures x {bench.NC}+{bench.NI} samples, "
                                                      "full-size VM grids, TV + MSE losses, Adam over 36.8M parameters",
