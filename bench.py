@@ -95,14 +95,50 @@ def make_rays(n, seed):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in a thread every ~2 ms (the region is tens of
+    milliseconds; `nvidia-smi -lms` starts too slowly for that), `nvidia-smi` polling as the fallback."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.sm, self.mx, self.reasons = gpu_index, [], None, set()
+        self.stop_flag, self.thread, self.proc, self.rows = threading.Event(), None, None, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -116,6 +152,17 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._sample_nvml()          # at least one sample taken while the last timed kernels are still in flight
+            except Exception:
+                pass
+            self.stop_flag.set()
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is not None:
             self.proc.terminate()
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
@@ -127,7 +174,7 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_reference_step(P_cpu, rays_cpu, idx_cpu, threads):
