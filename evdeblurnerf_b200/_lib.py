@@ -66,6 +66,11 @@ class NerfMlp(C.Structure):
         "alpha_w", "alpha_b", "feature_t", "feature_b", "views_t", "views_b", "rgb_t", "rgb_b")]
 
 
+class NerfWeights(C.Structure):
+    _fields_ = [("pts_w", C.c_void_p * 8), ("pts_b", C.c_void_p * 8)] + [(n, C.c_void_p) for n in (
+        "alpha_w", "alpha_b", "feature_w", "feature_b", "views_w", "views_b", "rgb_w", "rgb_b")]
+
+
 class AwpParams(C.Structure):
     _fields_ = [("sample_t", C.c_void_p * 4), ("sample_b", C.c_void_p * 4), ("motion_w", C.c_void_p * 2),
                 ("motion_b", C.c_void_p * 2)] + [(n, C.c_void_p) for n in (
@@ -117,6 +122,9 @@ SIGNATURES = {
                                       C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _P,
                                       C.POINTER(C.c_void_p * 3), C.POINTER(C.c_void_p * 3), _P]),
     "edn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),
+    "edn_nerf_bwd_workspace_bytes": (C.c_int64, [_I64, _I32]),
+    "edn_nerf_field_bwd": (C.c_int, [C.POINTER(NerfWeights), _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32,
+                                     C.POINTER(NerfWeights), _P, _P, _I64, _P]),
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),

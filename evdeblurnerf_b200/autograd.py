@@ -12,7 +12,6 @@ import torch
 
 from . import _lib
 from ._lib import AwpGrads, CrfGrads, RbkGrads, check, ptr, stream_ptr
-from .backward import RenderGradients, render_rays_backward
 
 _RBK_NAMES = ("view_embed_module.img_embed", "r_branch.0.weight", "r_branch.0.bias", "v_branch.0.weight", "v_branch.0.bias",
               "w_branch.0.weight", "w_branch.0.bias", "r_linear.weight", "r_linear.bias", "v_linear.weight", "v_linear.bias",
@@ -197,6 +196,7 @@ class RenderSubRaysFn(torch.autograd.Function):
         ctx.owner, ctx.kn, ctx.names = owner, kn, names
         ctx.geom = (H, W, focal, ndc)
         ctx.two_stage = Ni > 0
+        ctx.white_bkgd = bool(kw.get("white_bkgd", False))
         ctx.saved = {"ray_batch": rb, "z_vals0": out["z_vals0"] if Ni > 0 else out["z_vals"], "z_vals": out["z_vals"] if Ni > 0 else None,
                      "noise0": rand.get("noise0"), "noise1": rand.get("noise1")}
         ctx.rays = _c(rays)
@@ -219,12 +219,11 @@ class RenderSubRaysFn(torch.autograd.Function):
             d_out.update(rgb0=d_rgb0, depth0=d_depth0, acc0=d_acc0)
         if ctx.has_feat and d_feat is not None and d_feat.numel():
             d_out["depth_feature"] = d_feat
-        grads, d_rb = render_rays_backward(eng, ctx.saved, d_out, grads=RenderGradients(eng), chunk_rays=owner.backward_chunk_rays)
+        named, d_rb = eng.backward(ctx.saved, d_out, chunk_rays=owner.backward_chunk_rays, white_bkgd=ctx.white_bkgd)
         if d_rb_out is not None and d_rb_out.numel():
             d_rb += d_rb_out                                   # direct uses of the ray batch (AWP reads rays_d)
         if d_img_embed is not None and not d_img_embed.numel():
             d_img_embed = None
-        named = grads.finish()
         if kn is not None:
             H, W, focal, ndc = ctx.geom
             N = ctx.rays.shape[0]

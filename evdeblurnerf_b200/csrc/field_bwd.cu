@@ -171,8 +171,8 @@ __device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
 }
 
 __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                          float* __restrict__ X0, int ldX, int nf, float* __restrict__ SG, int ldS, int geo, int dirs) {
-  const int J = dirs ? ldS - 1 - geo : ldX - nf;
+                          float* __restrict__ X0, int ldX, int nf, int wp, float* __restrict__ SG, int ldS, int geo, int dirs) {
+  const int J = dirs ? ldS - 1 - geo : wp;      // wp: columns written after the features ([PE(pts) (63) | zero padding])
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / J;
   const int j = (int)(t % J);
@@ -493,11 +493,11 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
       else vm_products_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
       EDN_RC(gemm(false, true, M, kAppDim, kAppComp, P[g], kAppComp, w->basis[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
     }
-    pe_kernel<<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo, 0);
+    pe_kernel<<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
     EDN_RC(gemm(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
     relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
     EDN_RC(gemm(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
-    pe_kernel<<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, SG, D.ldS, geo, 1);
+    pe_kernel<<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
     EDN_RC(gemm(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
     relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
     EDN_RC(gemm(false, true, M, hid, hid, H2, hid, w->color1, hid, 0.f, H3, hid));
@@ -541,6 +541,190 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   relayout(1, grad_w->sigma1, false);
   relayout(2, grad_w->color0, false);
   relayout(3, grad_w->color2, false);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
+
+
+// =====================================================================================================================
+// mode = nerf: backward of NeRF.mlpforward + NeRF.raw2outputs (networks/nerf.py:46-72, 131-162, 74-129) at pts = o + d * z_vals.
+// Same recipe: recompute the 8 x 256 MLP (skip concat after layer 4), alpha / feature heads, view branch and rgb head of a
+// chunk of rays as aligned row-major matrices, then walk back.  Per-sample buffers:
+//   XH [320] = [PE(pts) (63) | 0 | h_4 (256)]  (the skip input of layer 5 in place)      H_l [256], l = 0..3, 5..7
+//   AF [284] = [feature (256) | sigma | PE(viewdir) (27)]   (feature_linear and alpha_linear as ONE GEMM; views_linears reads it
+//   through a zero column under sigma)                       HV [128]   RGB [4]
+// =====================================================================================================================
+namespace edn {
+namespace {
+
+constexpr int kNW = 256, kNXH = 320, kNAF = 284, kNAFn = 260, kNHV = 128;
+
+inline int64_t nerf_floats_per_sample() {
+  return kNXH * 2 /*XH, dXH*/ + kNW * 7 /*H0-3, H5-7*/ + kNAF * 2 /*AF, dAF*/ + kNHV * 2 /*HV, dHV*/ + 8 /*RGB, dRGB*/ + kNW * 2 /*D1, D2*/ + 4 /*dpts*/ + 3;
+}
+inline int64_t nerf_weight_scratch_floats() {   // padded weights + gradients: W0p [256][64], W5p [256][320], Waf [260][256], Wvp [128][284], Wrp [4][128], baf [260] (x2)
+  return 2 * ((int64_t)kNW * 64 + (int64_t)kNW * kNXH + (int64_t)kNAFn * kNW + (int64_t)kNHV * kNAF + 4 * kNHV + kNAFn);
+}
+
+__global__ void add_bias_ld_kernel(float* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / n;
+  const int j = (int)(t % n);
+  if (m < M) Y[m * ld + j] += bias[j];
+}
+__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] += src[t];
+}
+}  // namespace
+}  // namespace edn
+
+extern "C" int64_t edn_nerf_bwd_workspace_bytes(int64_t chunk_rays, int32_t n_samples) {
+  using namespace edn;
+  if (chunk_rays <= 0 || n_samples <= 0) return -1;
+  return (nerf_floats_per_sample() * chunk_rays * n_samples + nerf_weight_scratch_floats()) * (int64_t)sizeof(float);
+}
+
+extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_batch, const float* z_vals, const float* noise,
+                                  int64_t n_rays, int32_t n_samples, int32_t flags, int32_t precision, const float* d_rgb,
+                                  const float* d_depth, const float* d_acc, const float* d_weights, const float* d_feat,
+                                  int32_t feature_after_linear, const edn_nerf_weights* g, float* d_ray_batch, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(w && g && ray_batch && z_vals && d_ray_batch && workspace, "edn_nerf_field_bwd: null pointer");
+  EDN_REQUIRE(n_samples >= 2, "edn_nerf_field_bwd: n_samples must be >= 2");
+  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_nerf_field_bwd: bad precision");
+  for (int l = 0; l < 8; ++l) EDN_REQUIRE(w->pts_w[l] && w->pts_b[l] && g->pts_w[l] && g->pts_b[l], "edn_nerf_field_bwd: null pts_linears.%d", l);
+  EDN_REQUIRE(w->alpha_w && w->alpha_b && w->feature_w && w->feature_b && w->views_w && w->views_b && w->rgb_w && g->alpha_w && g->alpha_b &&
+              g->feature_w && g->feature_b && g->views_w && g->views_b && g->rgb_w && (!w->rgb_b == !g->rgb_b), "edn_nerf_field_bwd: null weight");
+  if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
+  const int S = n_samples;
+  const int64_t per_ray = nerf_floats_per_sample() * S * (int64_t)sizeof(float);
+  int64_t chunk = (workspace_bytes - nerf_weight_scratch_floats() * (int64_t)sizeof(float)) / per_ray;
+  EDN_REQUIRE(chunk >= 1, "edn_nerf_field_bwd: workspace too small (%lld bytes, one ray needs %lld)", (long long)workspace_bytes, (long long)per_ray);
+  chunk = chunk < n_rays ? chunk : n_rays;
+  if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;
+  cublasHandle_t h = blas_handle();
+  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
+  const Gemm gemm{h, precision == EDN_F32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32};
+
+  float* base = reinterpret_cast<float*>(workspace);
+  const int nW[6] = {kNW * 64, kNW * kNXH, kNAFn * kNW, kNHV * kNAF, 4 * kNHV, kNAFn};
+  float* Wp[6];
+  float* gWp[6];
+  for (int i = 0; i < 6; ++i) { Wp[i] = base; base += nW[i]; }
+  for (int i = 0; i < 6; ++i) { gWp[i] = base; base += nW[i]; }
+  int tot_w = 0;
+  for (int i = 0; i < 6; ++i) tot_w += nW[i];
+  EDN_CUDA_OK(cudaMemsetAsync(gWp[0], 0, sizeof(float) * (size_t)tot_w, st));
+  // aligned copies: pts_linears.0 [256][63] -> [256][64]; pts_linears.5 [256][319] -> [256][320] (zero column after the PE part);
+  // [feature_linear; alpha_linear; 0] -> [260][256]; views_linears.0 [128][283] -> [128][284] (zero column under sigma); rgb [3][128] -> [4][128]
+  relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(Wp[0], w->pts_w[0], 0, kNW, 64, kNW, 63, 0, 1);
+  relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(Wp[1], w->pts_w[5], 2, kNW, kNXH, kNW, 319, 63, 1);
+  EDN_CUDA_OK(cudaMemsetAsync(Wp[2], 0, sizeof(float) * (size_t)nW[2], st));
+  EDN_CUDA_OK(cudaMemcpyAsync(Wp[2], w->feature_w, sizeof(float) * kNW * kNW, cudaMemcpyDeviceToDevice, st));
+  EDN_CUDA_OK(cudaMemcpyAsync(Wp[2] + kNW * kNW, w->alpha_w, sizeof(float) * kNW, cudaMemcpyDeviceToDevice, st));
+  relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(Wp[3], w->views_w, 2, kNHV, kNAF, kNHV, 283, 256, 1);
+  relayout_kernel<<<blocks_for(nW[4], 256), 256, 0, st>>>(Wp[4], w->rgb_w, 3, 4, kNHV, 3, kNHV, 0, 1);
+  EDN_CUDA_OK(cudaMemsetAsync(Wp[5], 0, sizeof(float) * kNAFn, st));
+  EDN_CUDA_OK(cudaMemcpyAsync(Wp[5], w->feature_b, sizeof(float) * kNW, cudaMemcpyDeviceToDevice, st));
+  EDN_CUDA_OK(cudaMemcpyAsync(Wp[5] + kNW, w->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  const int64_t Mmax = chunk * S;
+  auto take = [&](int64_t per) { float* p = base; base += per * Mmax; return p; };
+  float* XH = take(kNXH);
+  float* H[8];
+  for (int l = 0; l < 8; ++l) H[l] = (l == 4) ? XH + 64 : take(kNW);
+  const int ldH[8] = {kNW, kNW, kNW, kNW, kNXH, kNW, kNW, kNW};
+  float* AF = take(kNAF);
+  float* HV = take(kNHV);
+  float* RGB = take(4);
+  float* dRGB = take(4);
+  float* dHV = take(kNHV);
+  float* dAF = take(kNAF);
+  float* dXH = take(kNXH);
+  float* D1 = take(kNW);
+  float* D2 = take(kNW);
+  float* dpts = take(4);
+  float* al = take(1);
+  float* tr = take(1);
+  float* dsig = take(1);
+  // per-layer weights as used by the GEMMs: (pointer, K, ld)
+  const float* Wl[8]; int Kl[8];
+  for (int l = 0; l < 8; ++l) { Wl[l] = w->pts_w[l]; Kl[l] = kNW; }
+  Wl[0] = Wp[0]; Kl[0] = 64; Wl[5] = Wp[1]; Kl[5] = kNXH;
+  float* gWl[8];
+  for (int l = 0; l < 8; ++l) gWl[l] = g->pts_w[l];
+  gWl[0] = gWp[0]; gWl[5] = gWp[1];
+
+#define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
+    const int64_t Rc = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
+    const int64_t M = Rc * S, m0 = r0 * S;
+    // ---- forward recompute ----------------------------------------------------------------------------------------------
+    pe_kernel<<<blocks_for(M * 64, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 64, AF, kNAF, 256, 0);
+    for (int l = 0; l < 8; ++l) {
+      const float* X = (l == 0 || l == 5) ? XH : H[l - 1];
+      const int ldx = (l == 0 || l == 5) ? kNXH : ldH[l - 1];
+      EDN_RC(gemm(false, true, M, kNW, Kl[l], X, ldx, Wl[l], Kl[l], 0.f, H[l], ldH[l]));
+      relu_bias_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(H[l], ldH[l], kNW, M, w->pts_b[l]);
+    }
+    EDN_RC(gemm(false, true, M, kNAFn, kNW, H[7], kNW, Wp[2], kNW, 0.f, AF, kNAF));
+    add_bias_ld_kernel<<<blocks_for(M * 257, 256), 256, 0, st>>>(AF, kNAF, 257, M, Wp[5]);
+    pe_kernel<<<blocks_for(M * 27, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 0, AF, kNAF, 256, 1);
+    EDN_RC(gemm(false, true, M, kNHV, kNAF, AF, kNAF, Wp[3], kNAF, 0.f, HV, kNHV));
+    relu_bias_kernel<<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(HV, kNHV, kNHV, M, w->views_b);
+    EDN_RC(gemm(false, true, M, 4, kNHV, HV, kNHV, Wp[4], kNHV, 0.f, RGB, 4));
+    // ---- compositing backward (nerf.py:74-129: sigma = channel 3, rgb = sigmoid) ------------------------------------------------
+    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(AF + 256, kNAF, RGB, w->rgb_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
+                                                           d_acc, d_weights, al, tr, dRGB, dsig, d_ray_batch);
+    // ---- heads ------------------------------------------------------------------------------------------------------------
+    EDN_RC(gemm(true, false, 4, kNHV, M, dRGB, 4, HV, kNHV, 1.f, gWp[4], kNHV));
+    if (g->rgb_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, g->rgb_b);
+    head_bwd_kernel<<<blocks_for(M * kNHV, 256), 256, 0, st>>>(dRGB, w->rgb_w, HV, kNHV, M, dHV);
+    EDN_RC(gemm(true, false, kNHV, kNAF, M, dHV, kNHV, AF, kNAF, 1.f, gWp[3], kNAF));
+    colsum_kernel<<<blocks_for(M, 512), 128, 0, st>>>(dHV, kNHV, kNHV, M, g->views_b);
+    EDN_RC(gemm(false, false, M, kNAF, kNHV, dHV, kNHV, Wp[3], kNAF, 0.f, dAF, kNAF));
+    set_sigma_grad_kernel<<<blocks_for(M, 256), 256, 0, st>>>(dAF, kNAF, 256, M, dsig);
+    if (d_feat && feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * kNW, 256), 256, 0, st>>>(dAF, kNAF, kNW, M, d_feat + m0 * kNW);
+    EDN_RC(gemm(true, false, kNAFn, kNW, M, dAF, kNAF, H[7], kNW, 1.f, gWp[2], kNW));
+    colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(dAF, kNAF, kNW, M, g->feature_b);
+    colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dAF + kNW, kNAF, 1, M, g->alpha_b);
+    EDN_RC(gemm(false, false, M, kNW, kNAFn, dAF, kNAF, Wp[2], kNW, 0.f, D1, kNW));
+    if (d_feat && !feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * kNW, 256), 256, 0, st>>>(D1, kNW, kNW, M, d_feat + m0 * kNW);
+    // ---- the 8 x 256 trunk, layers 7..0 (D = gradient at the layer's post-activation) -------------------------------------------------
+    float* D = D1;
+    int ldD = kNW;
+    for (int l = 7; l >= 0; --l) {
+      relu_mask_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(D, H[l], ldD, kNW, M);      // ldD == ldH[l] (320 only for l = 4)
+      const float* X = (l == 0 || l == 5) ? XH : H[l - 1];
+      const int ldx = (l == 0 || l == 5) ? kNXH : ldH[l - 1];
+      EDN_RC(gemm(true, false, kNW, Kl[l], M, D, ldD, X, ldx, 1.f, gWl[l], Kl[l]));
+      colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D, ldD, kNW, M, g->pts_b[l]);
+      if (l == 5) {          // d [x | h_4] in one GEMM; continue with the h_4 part in place
+        EDN_RC(gemm(false, false, M, kNXH, kNW, D, ldD, Wl[5], kNXH, 0.f, dXH, kNXH));
+        D = dXH + 64; ldD = kNXH;
+      } else if (l == 0) {   // += the first layer's share of d x (the skip connection's share is already there)
+        EDN_RC(gemm(false, false, M, 64, kNW, D, ldD, Wl[0], 64, 1.f, dXH, kNXH));
+      } else {
+        float* out = (D == D1) ? D2 : D1;     // l == 4 comes from dXH + 64 -> D1
+        EDN_RC(gemm(false, false, M, kNW, kNW, D, ldD, Wl[l], kNW, 0.f, out, kNW));
+        D = out; ldD = kNW;
+      }
+    }
+    pe_bwd_kernel<<<blocks_for(M * 3, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, dXH, kNXH, 0, dpts);
+    ray_reduce_kernel<<<blocks_for(Rc * 32, 256), 256, 0, st>>>(dpts, dAF, kNAF, 256, ray_batch, z_vals, r0, Rc, S, d_ray_batch);
+    EDN_CUDA_OK(cudaGetLastError());
+  }
+#undef EDN_RC
+  relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(gWp[0], g->pts_w[0], 0, kNW, 64, kNW, 63, 0, 0);
+  relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(gWp[1], g->pts_w[5], 2, kNW, kNXH, kNW, 319, 63, 0);
+  add_vec_kernel<<<blocks_for(kNW * kNW, 256), 256, 0, st>>>(g->feature_w, gWp[2], kNW * kNW);
+  add_vec_kernel<<<blocks_for(kNW, 256), 256, 0, st>>>(g->alpha_w, gWp[2] + kNW * kNW, kNW);
+  relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(gWp[3], g->views_w, 2, kNHV, kNAF, kNHV, 283, 256, 0);
+  relayout_kernel<<<blocks_for(nW[4], 256), 256, 0, st>>>(gWp[4], g->rgb_w, 3, 4, kNHV, 3, kNHV, 0, 0);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

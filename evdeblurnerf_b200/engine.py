@@ -176,6 +176,12 @@ class RenderEngine(SamplerHost):
             self._workspace = ws = torch.empty((int(nbytes),), dtype=torch.uint8, device=self.device)
         return ws
 
+    def backward(self, saved, d_out, chunk_rays=8192, white_bkgd=False):
+        """Backward of render_rays -> ({state_dict name: gradient in the reference layout}, d_ray_batch [R, 11])."""
+        from .backward import RenderGradients, render_rays_backward
+        grads, d_rb = render_rays_backward(self, saved, d_out, grads=RenderGradients(self), chunk_rays=chunk_rays)
+        return grads.finish(), d_rb
+
     def _launch(self, name, fn):
         if self.profile is None:
             return fn()
@@ -351,6 +357,7 @@ class RenderEngine(SamplerHost):
 SamplerHost._launch = RenderEngine._launch
 SamplerHost._linspace = RenderEngine._linspace
 SamplerHost.sample_pdf_merge = RenderEngine.sample_pdf_merge
+SamplerHost.workspace = RenderEngine.workspace
 
 
 class NerfRenderEngine(SamplerHost):
@@ -362,10 +369,32 @@ class NerfRenderEngine(SamplerHost):
             raise RuntimeError("evdeblurnerf_b200.NerfRenderEngine needs a CUDA device (no CPU fallback)")
         _lib.load()
         self._init_host(device)
+        self.rmnearplane, self.use_awp = rmnearplane, use_awp
+        self.prec_code = EDN_F32
+        self.repack(params)
+
+    def repack(self, params):
+        from .nerf_mode import NeRF
         P = {k: (v if v.is_cuda else v.to(self.device)) for k, v in params.items() if isinstance(v, torch.Tensor)}
-        ef = "before_linear" if use_awp else "after_linear"       # renderer.py:88-99
-        self.mlp_coarse = NeRF(P, "mlp_coarse.", ef, rmnearplane)
-        self.mlp_fine = NeRF(P, "mlp_fine.", ef, rmnearplane) if "mlp_fine.pts_linears.0.weight" in P else None
+        ef = "before_linear" if self.use_awp else "after_linear"       # renderer.py:88-99
+        self.mlp_coarse = NeRF(P, "mlp_coarse.", ef, self.rmnearplane)
+        self.mlp_fine = NeRF(P, "mlp_fine.", ef, self.rmnearplane) if "mlp_fine.pts_linears.0.weight" in P else None
+
+    def backward(self, saved, d_out, chunk_rays=4096, white_bkgd=False):
+        """Backward of render_rays (mode = nerf) -> ({state_dict name: gradient}, d_ray_batch [R, 11])."""
+        rb = saved["ray_batch"].float().contiguous()
+        d_rb = torch.zeros_like(rb)
+        named = {}
+        two_stage = saved.get("z_vals") is not None and self.mlp_fine is not None
+        if two_stage:
+            named.update(self.mlp_fine.backward(self, rb, saved["z_vals"], saved.get("noise1"), d_out.get("rgb_map"), d_out.get("depth_map"),
+                                                d_out.get("acc_map"), d_rb, white_bkgd, d_out.get("depth_feature"), chunk_rays))
+            named.update(self.mlp_coarse.backward(self, rb, saved["z_vals0"], saved.get("noise0"), d_out.get("rgb0"), d_out.get("depth0"),
+                                                  d_out.get("acc0"), d_rb, white_bkgd, None, chunk_rays))
+        else:
+            named.update(self.mlp_coarse.backward(self, rb, saved["z_vals0"], saved.get("noise0"), d_out.get("rgb_map"), d_out.get("depth_map"),
+                                                  d_out.get("acc_map"), d_rb, white_bkgd, d_out.get("depth_feature"), chunk_rays))
+        return named, d_rb
 
     def render_rays(self, ray_batch, N_samples, **kw):
         from .nerf_mode import render_rays_nerf

@@ -6,7 +6,24 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import FLAG_LINDISP, FLAG_TRAIN, FLAG_WHITE_BKGD, NerfMlp, check, ptr, stream_ptr
+from ._lib import FLAG_LINDISP, FLAG_TRAIN, FLAG_WHITE_BKGD, NerfMlp, NerfWeights, check, ptr, stream_ptr
+
+_NERF_TENSORS = ([(f"pts_linears.{i}.weight", "pts_w", i) for i in range(8)] + [(f"pts_linears.{i}.bias", "pts_b", i) for i in range(8)] +
+                 [("alpha_linear.weight", "alpha_w", None), ("alpha_linear.bias", "alpha_b", None),
+                  ("feature_linear.weight", "feature_w", None), ("feature_linear.bias", "feature_b", None),
+                  ("views_linears.0.weight", "views_w", None), ("views_linears.0.bias", "views_b", None),
+                  ("rgb_linear.weight", "rgb_w", None), ("rgb_linear.bias", "rgb_b", None)])
+
+
+def _nerf_struct(T, prefix):
+    w = NerfWeights()
+    for name, field, idx in _NERF_TENSORS:
+        t = T.get(prefix + name)
+        if idx is None:
+            setattr(w, field, ptr(t))
+        else:
+            getattr(w, field)[idx] = ptr(t)
+    return w
 
 
 class NeRF:
@@ -15,6 +32,9 @@ class NeRF:
     def __init__(self, params, prefix, extract_feature="before_linear", render_rmnearplane=0):
         self.extract_feature, self.rmnearplane = extract_feature, float(render_rmnearplane)
         self.keep = []
+        self.prefix = prefix
+        # reference-layout fp32 views: what the backward pass reads (edn_nerf_field_bwd)
+        self.params = {k: v.detach().float().contiguous() for k, v in params.items() if k.startswith(prefix)}
         m = NerfMlp()
 
         def g(name):
@@ -56,6 +76,26 @@ class NeRF:
         check(_lib.load().edn_nerf_mlp_fwd(C.byref(self.m), ptr(rb), ptr(z), R, S, 1 if self.extract_feature == "after_linear" else 0,
                                            ptr(raw), ptr(feat), stream_ptr()), "edn_nerf_mlp_fwd")
         return raw, feat
+
+    def backward(self, engine, ray_batch, z_vals, noise, d_rgb, d_depth, d_acc, d_ray_batch, white_bkgd=False, d_feat=None,
+                 chunk_rays=4096, precision=_lib.EDN_F32):
+        """Backward of mlpforward_at + raw2outputs -> {state_dict name: gradient}; d_ray_batch is accumulated in place."""
+        lib = _lib.load()
+        R, S = z_vals.shape
+        grads = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        if R == 0:
+            return grads
+        if white_bkgd and d_rgb is not None:      # rgb_map += 1 - acc_map (nerf.py:126-127)
+            d_acc = (d_acc if d_acc is not None else 0) - d_rgb.sum(-1)
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        keep = [f(t) for t in (ray_batch, z_vals, noise, d_rgb, d_depth, d_acc, d_feat)]
+        w, g = _nerf_struct(self.params, self.prefix), _nerf_struct(grads, self.prefix)
+        nbytes = int(lib.edn_nerf_bwd_workspace_bytes(min(R, int(chunk_rays)), S))
+        ws = engine.workspace(nbytes)
+        check(lib.edn_nerf_field_bwd(C.byref(w), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), R, S, 0, int(precision), ptr(keep[3]), ptr(keep[4]),
+                                     ptr(keep[5]), None, ptr(keep[6]), 1 if self.extract_feature == "after_linear" else 0, C.byref(g),
+                                     ptr(d_ray_batch), ptr(ws), nbytes, stream_ptr()), "edn_nerf_field_bwd")
+        return grads
 
     def raw2outputs(self, raw, z_vals, ray_batch, noise=None, white_bkgd=False, is_train=True):
         """NeRF.raw2outputs (nerf.py:74) -> (rgb_map, depth_map, acc_map, weights)."""

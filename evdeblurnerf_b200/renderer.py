@@ -219,14 +219,12 @@ class NeRFAll:
 
     def _maybe_repack(self):
         # in-place updates (optimizer steps) bump the tensors' version counters
-        if self.mode == "c2f" and self._param_version() != self._packed_version:
+        if self._param_version() != self._packed_version:
             self.repack()
 
     def _render_sub_rays(self, H, W, K, rays, images_idx, near, far, ndc, kwargs, blur=True):
         """Differentiable warp + render of the sub-rays -> (rgb, depth, acc, rgb0, depth0, acc0, weight1), see autograd.py."""
         from .autograd import RenderSubRaysFn
-        if self.mode != "c2f":
-            raise NotImplementedError("backward of mode = nerf is not built (DESIGN.md section 8)")
         names = self._grad_names
         return RenderSubRaysFn.apply(self, self.kernelsnet if blur else None, H, W, float(K[0][0]), rays, images_idx, near, far, ndc,
                                      kwargs, names,

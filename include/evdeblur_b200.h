@@ -205,6 +205,29 @@ int edn_nerf_raw2outputs(const float* raw, const float* z_vals, const float* ray
                          int32_t n_samples, int32_t flags, float rmnearplane, float* weights, float* rgb, float* depth,
                          float* acc, void* stream);
 
+/* Vanilla NeRF field weights -- or their gradients -- in the reference's nn.Linear layout ([out][in] fp32, the state_dict tensors as
+ * they are): pts_w[0] [256][63], pts_w[1..4,6,7] [256][256], pts_w[5] [256][319], alpha_w [1][256], feature_w [256][256],
+ * views_w [128][283], rgb_w [3][128]; rgb_b may be NULL. */
+typedef struct edn_nerf_weights {
+  float* pts_w[8];
+  float* pts_b[8];
+  float* alpha_w; float* alpha_b;
+  float* feature_w; float* feature_b;
+  float* views_w; float* views_b;
+  float* rgb_w; float* rgb_b;
+} edn_nerf_weights;
+
+/* Backward of edn_nerf_mlp_fwd + edn_nerf_raw2outputs (nerf.py:46-72, 131-162, 74-129; autograd at run_nerf.py:594) at
+ * pts = o + d * z_vals.  Upstream gradients d_rgb [R][3], d_depth [R], d_acc [R], d_weights [R][S], d_feat [R][S][256]
+ * (each may be NULL; for EDN_FLAG_WHITE_BKGD pass d_acc - sum_c d_rgb_c as d_acc, nerf.py:126-127); feature_after_linear
+ * selects which tensor d_feat refers to (feature_linear output, or the trunk output h).  grad_w and d_ray_batch [R][11] are
+ * ACCUMULATED.  precision: EDN_F32 = fp32 GEMMs, EDN_BF16 = TF32 tensor-core GEMMs. */
+int64_t edn_nerf_bwd_workspace_bytes(int64_t chunk_rays, int32_t n_samples);
+int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays,
+                       int32_t n_samples, int32_t flags, int32_t precision, const float* d_rgb, const float* d_depth,
+                       const float* d_acc, const float* d_weights, const float* d_feat, int32_t feature_after_linear,
+                       const edn_nerf_weights* grad_w, float* d_ray_batch, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Coarse sample placement alone (renderer.py:163-178), bit-exact: z_vals [R][n_samples]. */
 int edn_place_samples(const float* ray_batch, const float* t_vals, const float* t_rand, int64_t n_rays, int32_t n_samples,
                       int32_t flags, float* z_vals, void* stream);

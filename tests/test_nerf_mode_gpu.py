@@ -83,3 +83,60 @@ def test_nerfall_facade_nerf_mode(case5):
     assert nerf.mode == "nerf"
     out = nerf.render_rays(g["ray_batch"].cuda(), 64, retraw=True, N_importance=64)
     assert_close(out["rgb_map"], g["rgb_map"], "facade rgb_map", rtol=1e-4, atol=5e-4)
+
+
+def _grad_close(a, b, name, tol=2e-4):
+    scale = float(torch.as_tensor(b).abs().max())
+    assert scale > 0, f"{name}: oracle gradient is identically zero"
+    assert_close(a, b, name, rtol=tol, atol=tol * scale)
+
+
+@pytest.mark.parametrize("before_linear,white_bkgd", [(True, False), (False, True)])
+def test_nerf_field_backward_matches_autograd(case5, before_linear, white_bkgd):
+    """edn_nerf_field_bwd against torch autograd on the oracle: all 24 tensors of the field, d ray_batch; upstream gradients on
+    rgb / depth / acc and on the extracted feature (both extract_feature modes), white background on / off; 2e-4 of max."""
+    from evdeblurnerf_b200 import NerfRenderEngine
+    from evdeblurnerf_b200.nerf_mode import NeRF
+    g, Pn = case5
+    gen = torch.Generator().manual_seed(12)
+    Pn = dict(Pn)
+    Pn["mlp_fine.rgb_linear.bias"] = 0.1 * torch.randn(3, generator=gen)
+    R, S = 20, 45
+    rb = g["ray_batch"][:R]
+    z = torch.sort(torch.rand(R, S, generator=gen), -1)[0]
+    noise = 0.3 * torch.randn(R, S - 1, generator=gen)
+    cot = {"rgb": torch.randn(R, 3, generator=gen), "depth": torch.randn(R, generator=gen), "acc": torch.randn(R, generator=gen),
+           "feat": 0.05 * torch.randn(R, S, 256, generator=gen)}
+    Po = {k: v.clone().requires_grad_(True) for k, v in Pn.items()}
+    rbo = rb.clone().requires_grad_(True)
+    o, d, vd = rbo[:, :3], rbo[:, 3:6], rbo[:, -3:]
+    raw, feat = oc.nerf_mlpforward(Po, "mlp_fine.", o[:, None] + d[:, None] * z[..., None], vd, before_linear=before_linear)
+    rgb, _, acc, _, depth = oc.nerf_raw2outputs(raw, z, d, noise, white_bkgd=white_bkgd)
+    ((rgb * cot["rgb"]).sum() + (depth * cot["depth"]).sum() + (acc * cot["acc"]).sum() + (feat * cot["feat"]).sum()).backward()
+
+    eng = NerfRenderEngine({k.replace("mlp_fine.", "mlp_coarse."): v.cuda() for k, v in Pn.items()}, use_awp=before_linear)
+    net = NeRF({k: v.cuda() for k, v in Pn.items()}, "mlp_fine.", "before_linear" if before_linear else "after_linear")
+    d_rb = torch.zeros(R, 11).cuda()
+    grads = net.backward(eng, rb.cuda(), z.cuda(), noise.cuda(), cot["rgb"].cuda(), cot["depth"].cuda(), cot["acc"].cuda(), d_rb,
+                         white_bkgd=white_bkgd, d_feat=cot["feat"].cuda(), chunk_rays=7)
+    for k in Po:
+        _grad_close(grads[k], Po[k].grad, k)
+    _grad_close(d_rb[:, :6], rbo.grad[:, :6], "d ray_batch[o, d]")
+    _grad_close(d_rb[:, 8:], rbo.grad[:, 8:], "d ray_batch[viewdirs]")
+
+
+def test_nerfall_nerf_mode_loss_backward(case5):
+    """loss.backward() through the facade in mode = nerf (coarse + fine fields): gradients reach every tensor of both fields."""
+    from evdeblurnerf_b200 import NeRFAll, img2mse
+    g, Pn = case5
+    Pg = {k: v.clone().cuda().requires_grad_(True) for k, v in Pn.items()}
+    Pg.update({k.replace("mlp_fine.", "mlp_coarse."): v.detach().clone().requires_grad_(True) for k, v in list(Pg.items())})
+    nerf = NeRFAll(Pg, *AABB).train()
+    R = 16
+    rays = torch.stack([g["ray_batch"][:R, :3], g["ray_batch"][:R, 3:6]], -1).cuda()
+    rgb, rgb0, _, _ = nerf(400, 400, [[400.0, 0, 200.0], [0, 400.0, 200.0], [0, 0, 1.0]], rays=rays, rays_info=None, force_naive=True,
+                           ndc=False, N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    (img2mse(rgb, target) + img2mse(rgb0, target)).backward()
+    for k, v in Pg.items():
+        assert v.grad is not None and float(v.grad.abs().max()) > 0, k
