@@ -78,6 +78,10 @@ class AwpParams(C.Structure):
                     "bn_weight", "bn_bias", "w_linear_w", "w_linear_b")]
 
 
+class AwpOptions(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("keep_activations", C.c_int32), ("phase", C.c_int32), ("bn_rows_total", C.c_int64)]
+
+
 class AwpGrads(AwpParams):
     pass
 
@@ -112,7 +116,7 @@ SIGNATURES = {
     "edn_rbk_bwd_workspace_floats": (C.c_int64, [_I64, _I32]),
     "edn_rbk_warp_ndc_bwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, C.POINTER(RbkGrads), _P, _P]),
     "edn_awp_bwd_workspace_floats": (C.c_int64, [_I64, _I32, _I32]),
-    "edn_awp_bwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _I32, _I32, _P, C.POINTER(AwpGrads), _P,
+    "edn_awp_bwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, C.POINTER(AwpOptions), _I32, _P, C.POINTER(AwpGrads), _P,
                               _P, _I32, _P, _P, _P]),
     "edn_weighted_sum_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "edn_crf_bwd": (C.c_int, [C.POINTER(CrfParams), _P, _P, _I32, _I32, _I64, _P, _P, C.POINTER(CrfGrads), _P]),
@@ -128,8 +132,10 @@ SIGNATURES = {
     "edn_nerf_mlp_fwd": (C.c_int, [C.POINTER(NerfMlp), _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "edn_nerf_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "edn_place_samples": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
-    "edn_awp_workspace_floats": (C.c_int64, [_I64, _I32, _I32, _I32]),
-    "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P]),
+    "edn_awp_workspace_floats": (C.c_int64, [_I64, _I32, _I32, C.POINTER(AwpOptions)]),
+    "edn_awp_stats_offset_floats": (C.c_int64, [_I64, _I32, _I32]),
+    "edn_awp_bwd_sums_offset_floats": (C.c_int64, [_I64, _I32, _I32]),
+    "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, C.POINTER(AwpOptions), _P, _P, _P]),
     "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
     "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
     "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),

@@ -259,6 +259,23 @@ _AWP_FIELDS = (   # (struct field, index | None, state_dict name, transposed)
 AWP_PARAM_NAMES = tuple(f[2] for f in _AWP_FIELDS)
 
 
+def awp_grad_buffers(shapes, device):
+    """Zeroed gradient buffers in the layout edn_awp_bwd writes (transposed where the packed weights are) + their struct."""
+    g, bufs = AwpGrads(), []
+    for (field, idx, _, transposed), shp in zip(_AWP_FIELDS, shapes):
+        t = torch.zeros(tuple(shp)[::-1] if transposed else tuple(shp), dtype=torch.float32, device=device)
+        bufs.append(t)
+        if idx is None:
+            setattr(g, field, t.data_ptr())
+        else:
+            getattr(g, field)[idx] = t.data_ptr()
+    return g, bufs
+
+
+def awp_grads_to_reference(bufs):
+    return [(b.t().contiguous() if f[3] else b) for f, b in zip(_AWP_FIELDS, bufs)]
+
+
 class AwpFn(torch.autograd.Function):
     """AdaptiveWeightProposal.forward (awp.py:79-117) with its hand-written backward (awp_bwd.cu).
     Inputs: depth_feature [N*E,S,128], z_vals [N*E,S] (no gradient), rays_d [N*E,3], view_feature [N,32], then the AWP
@@ -274,7 +291,7 @@ class AwpFn(torch.autograd.Function):
         # backward does not recompute them
         NE, S, _ = df.shape
         ctx.ws = torch.empty((int(_lib.load().edn_awp_bwd_workspace_floats(NE // awp.E, awp.E, S)),), dtype=torch.float32, device=df.device)
-        return awp.run(df, z, rd, vf, workspace=ctx.ws)
+        return awp.run(df, z, rd, vf, workspace=ctx.ws, keep_activations=True)
 
     @staticmethod
     def backward(ctx, d_ccw):
@@ -285,21 +302,17 @@ class AwpFn(torch.autograd.Function):
         E = awp.E
         N = NE // E
         dev = df.device
-        g = AwpGrads()
-        bufs = []
-        for (field, idx, _, transposed), shp in zip(_AWP_FIELDS, ctx.shapes):
-            t = torch.zeros(shp[::-1] if transposed else shp, dtype=torch.float32, device=dev)
-            bufs.append(t)
-            if idx is None:
-                setattr(g, field, t.data_ptr())
-            else:
-                getattr(g, field)[idx] = t.data_ptr()
+        g, bufs = awp_grad_buffers(ctx.shapes, dev)
         d_df = torch.empty_like(df)
         d_rd = torch.zeros_like(rd)
         d_vf = torch.empty_like(vf)
         ws, ctx.ws = ctx.ws, None
-        check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, awp.precision,
-                              1 if awp.precision == _lib.EDN_BF16 else 0, ptr(_c(d_ccw)), C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf),
-                              ptr(ws), stream_ptr()), "edn_awp_bwd")
-        outs = [(b.t().contiguous() if f[3] else b) for f, b in zip(_AWP_FIELDS, bufs)]
-        return (None, d_df, None, d_rd, d_vf) + tuple(outs)
+        world = awp._world()
+        phases = [awp.options(True)] if world == 1 else [awp.options(True, 1), awp.options(True, 2, NE * world)]
+        dcc = _c(d_ccw)
+        for o in phases:      # the forward's workspace still holds the activations and the (all-reduced) batch sums
+            check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, C.byref(o), 1, ptr(dcc),
+                                  C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf), ptr(ws), stream_ptr()), "edn_awp_bwd")
+            if o.phase == 1:
+                awp._all_reduce_block(ws, int(lib.edn_awp_bwd_sums_offset_floats(N, E, S)))
+        return (None, d_df, None, d_rd, d_vf) + tuple(awp_grads_to_reference(bufs))

@@ -57,6 +57,7 @@ struct AwpArgs {
   float* y;      // [N][E][32]
   double* stats; // [32][2] sum, sum of squares
   float* ccw;    // [N][E]
+  double bn_rows;  // rows behind the batch sums (N * E, over all ranks when the sums were all-reduced)
 };
 
 // Y[r][cg*16..] = relu(bias + X[r][0..K) . Wt[K][64]); 256 threads: row = tid/4, 16 columns per thread
@@ -411,7 +412,7 @@ __global__ void awp_out_kernel(const AwpArgs a, float bn_eps) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.N) return;
   const int E = a.E;
-  const double rows = (double)(a.N * E);
+  const double rows = a.bn_rows;
   float pooled[32];
   for (int c = 0; c < 32; ++c) {
     const double mean = a.stats[2 * c] / rows;
@@ -438,14 +439,15 @@ __global__ void awp_out_kernel(const AwpArgs a, float bn_eps) {
 }  // namespace
 }  // namespace edn
 
-extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, int32_t precision) {
-  return edn::awp_ws_floats(n_rays, n_exposure, n_samples, precision == EDN_BF16);
+extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, const edn_awp_options* opt) {
+  return edn::awp_ws_floats(n_rays, n_exposure, n_samples, opt && (opt->precision == EDN_BF16 || opt->keep_activations));
 }
 
 namespace edn {
 int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
                 const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
-                bool tf32, float* workspace, float* ccw, void* stream) {
+                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream) {
+  EDN_REQUIRE(phase >= 0 && phase <= 2, "edn_awp_fwd: phase must be 0, 1 or 2");
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && workspace && ccw, "edn_awp_fwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS,
               "edn_awp_fwd: need 1 <= E <= %d and 2 <= S <= %d", kMaxE, kMaxS);
@@ -461,6 +463,12 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
   a.view_feature = view_feature; a.N = n_rays; a.E = n_exposure; a.S = n_samples; a.ccw = ccw;
   const AwpWs ws = awp_ws_carve(workspace, n_rays, n_exposure, n_samples, gemm_path);
   a.gint = ws.gint; a.inter = ws.inter; a.xl = ws.xl; a.att = ws.att; a.x = ws.x; a.y = ws.y; a.stats = ws.stats;
+  a.bn_rows = (double)(bn_rows_total > 0 ? bn_rows_total : NE);
+  if (phase == 2) {      // finish from the (all-reduced) batch sums already in the workspace
+    awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
+    EDN_CUDA_OK(cudaGetLastError());
+    return EDN_OK;
+  }
   if (!gemm_path) {
     const size_t smem1 = AwpSmem::total * sizeof(float);
     EDN_CUDA_OK(cudaFuncSetAttribute(awp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
@@ -494,7 +502,7 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
   EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   awp_ray_kernel<<<(unsigned)n_rays, 128, smem2, st>>>(a);
   awp_bn_stats_kernel<<<1, 256, 0, st>>>(a.y, NE, a.stats);
-  awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
+  if (phase == 0) awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }
@@ -502,9 +510,16 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
 
 extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                            int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                           float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream) {
+                           float bn_eps, const edn_awp_options* opt, float* workspace, float* ccw, void* stream) {
   using namespace edn;
-  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_awp_fwd: bad precision");
+  EDN_REQUIRE(opt && (opt->precision == EDN_F32 || opt->precision == EDN_BF16), "edn_awp_fwd: bad options");
   return awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, n_rays, n_exposure, n_samples, bn_eps,
-                     precision == EDN_BF16, true, workspace, ccw, stream);
+                     opt->precision == EDN_BF16 || opt->keep_activations, opt->precision == EDN_BF16, opt->phase, opt->bn_rows_total,
+                     workspace, ccw, stream);
+}
+
+extern "C" int64_t edn_awp_stats_offset_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples) {
+  float* zero = nullptr;
+  const edn::AwpWs ws = edn::awp_ws_carve(zero, n_rays, n_exposure, n_samples, false);
+  return reinterpret_cast<float*>(ws.stats) - zero;
 }

@@ -26,6 +26,7 @@ struct BwdArgs {
   int64_t N;
   int E, S;
   float bn_eps;
+  double bn_rows;       // rows behind the BatchNorm batch sums (N * E over all ranks)
   const float* d_ccw;   // [N][E]
   float* d_yn;          // [N][E][32]  gradient at the BatchNorm output
   float* d_x;           // [N][E][32]  gradient at the motion features (residual path, then + attention path)
@@ -42,7 +43,7 @@ struct BwdArgs {
 __global__ void __launch_bounds__(128) awp_out_bwd_kernel(const BwdArgs a) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int E = a.E, lane = threadIdx.x & 31;
-  const double rows = (double)(a.N * E);
+  const double rows = a.bn_rows;
   float s1[32], s2[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   RayBwdSmem& s = *reinterpret_cast<RayBwdSmem*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S, warp = tid >> 5, lane = tid & 31;
   const int64_t n = blockIdx.x;
-  const double rows = (double)(a.N * E);
+  const double rows = a.bn_rows;
   // ---- load / recompute the forward intermediates --------------------------------------------------------------------
   for (int i = tid; i < E * 32; i += 128) {
     const int e = i >> 5, c = i & 31;
@@ -525,19 +526,27 @@ extern "C" int64_t edn_awp_bwd_workspace_floats(int64_t n_rays, int32_t n_exposu
   using namespace edn;
   if (n_rays < 0 || n_exposure < 1 || n_samples < 2) return -1;
   const int64_t NE = n_rays * n_exposure, M = NE * n_samples;
-  return awp_ws_floats(n_rays, n_exposure, n_samples, true) + 16 + 2 * NE * 32 /* d_yn, d_x */ + 2 * 64 + 4 /* bn sums (doubles) */ +
+  return awp_ws_floats(n_rays, n_exposure, n_samples, true) + 16 + NE + 2 * NE * 32 /* ccw, d_yn, d_x */ + 2 * 64 + 4 /* bn sums (doubles) */ +
          M * 32 /* d_xl */ + 2 * M * 64 /* d_h, chain ping-pong */ + 2 * NE * 112 /* IN, dIN */ + 2 * NE * 32 /* H0, dH */ + 32 * 112 * 2 /* padded W0 + grad */;
+}
+
+extern "C" int64_t edn_awp_bwd_sums_offset_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples) {
+  float* zero = nullptr;
+  const edn::AwpBwdHead h = edn::awp_bwd_head(zero, n_rays, n_exposure, n_samples);
+  return reinterpret_cast<float*>(h.bn_sums) - zero;
 }
 
 extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                            int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                           float bn_eps, int32_t precision, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
+                           float bn_eps, const edn_awp_options* opt, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
                            float* d_depth_feature, float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace,
                            void* stream) {
   using namespace edn;
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && d_ccw && grads && d_depth_feature && workspace, "edn_awp_bwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS, "edn_awp_bwd: need 1 <= E <= %d and 2 <= S <= %d", kMaxE, kMaxS);
-  EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_awp_bwd: bad precision");
+  EDN_REQUIRE(opt && (opt->precision == EDN_F32 || opt->precision == EDN_BF16) && opt->phase >= 0 && opt->phase <= 2, "edn_awp_bwd: bad options");
+  EDN_REQUIRE(opt->phase == 0 || forward_in_workspace, "edn_awp_bwd: phased (synchronised BatchNorm) backward needs the forward's workspace");
+  const int precision = opt->precision, phase = opt->phase;
   for (int l = 0; l < 4; ++l) EDN_REQUIRE(grads->sample_t[l] && grads->sample_b[l], "edn_awp_bwd: null gradient buffer");
   EDN_REQUIRE(grads->motion_w[0] && grads->motion_b[0] && grads->motion_w[1] && grads->motion_b[1] && grads->mam_linear_t && grads->mam_linear_b &&
               grads->line_conv_att && grads->conva && grads->convb && grads->convc && grads->convn && grads->convl && grads->convd_w &&
@@ -547,24 +556,22 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   const int64_t N = n_rays, NE = n_rays * n_exposure, M = NE * n_samples;
   const int E = n_exposure, S = n_samples;
   const bool tf32 = precision == EDN_BF16;
-  // forward into the workspace (ccw itself is not needed: scratch)
-  float* base = workspace + awp_ws_floats(N, E, S, true);
-  base += (4 - ((uintptr_t)base / 4) % 4) % 4;
+  const AwpBwdHead head = awp_bwd_head(workspace, N, E, S);
+  float* base = head.next;
   auto take = [&](int64_t n) { float* q = base; base += (n + 3) / 4 * 4; return q; };
-  float* ccw_tmp = take(NE);
-  if (!forward_in_workspace) {
-    int rc = awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, N, E, S, bn_eps, true, tf32, workspace, ccw_tmp, stream);
+  if (!forward_in_workspace) {      // recompute the forward (ccw itself is not needed: scratch)
+    int rc = awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, N, E, S, bn_eps, true, tf32, 0, 0, workspace, head.ccw_tmp, stream);
     if (rc) return rc;
   }
   BwdArgs a{};
   a.p = *p; a.g = *grads; a.ws = awp_ws_carve(workspace, N, E, S, true);
   a.z_vals = z_vals; a.rays_d = rays_d; a.rays_d_stride = rays_d_stride; a.view_feature = view_feature;
   a.N = N; a.E = E; a.S = S; a.bn_eps = bn_eps; a.d_ccw = d_ccw;
+  a.bn_rows = (double)(opt->bn_rows_total > 0 ? opt->bn_rows_total : NE);
   a.d_rays_d = d_rays_d; a.d_rays_d_stride = d_rays_d_stride; a.d_view_feature = d_view_feature;
-  a.d_yn = take(NE * 32);
-  a.d_x = take(NE * 32);
-  a.bn_sums = reinterpret_cast<double*>(take(2 * 64 + 2));
-  if ((uintptr_t)a.bn_sums & 7) a.bn_sums = reinterpret_cast<double*>(reinterpret_cast<float*>(a.bn_sums) + 1);
+  a.d_yn = head.d_yn;
+  a.d_x = head.d_x;
+  a.bn_sums = head.bn_sums;
   a.d_xl = take(M * 32);
   a.d_h = take(M * 64);
   float* Dn = take(M * 64);
@@ -574,16 +581,21 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   float* dH = take(NE * 32);
   float* W0p = take(32 * 112);
   float* gW0p = take(32 * 112);
-  EDN_CUDA_OK(cudaMemsetAsync(a.bn_sums, 0, 64 * sizeof(double), st));
 
   cublasHandle_t h = blas_handle();
   if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F};
 #define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
-  // 1. output head + BatchNorm sums, 2. per-ray attention backward
-  awp_out_bwd_kernel<<<blocks_for(N, 128), 128, 0, st>>>(a);
-  awp_bn_param_grad_kernel<<<1, 32, 0, st>>>(a);
+  // 1. output head + BatchNorm sums (d gamma / d beta take the LOCAL sums; the per-ray backward below the all-reduced ones)
+  if (phase != 2) {
+    EDN_CUDA_OK(cudaMemsetAsync(a.bn_sums, 0, 64 * sizeof(double), st));
+    awp_out_bwd_kernel<<<blocks_for(N, 128), 128, 0, st>>>(a);
+    awp_bn_param_grad_kernel<<<1, 32, 0, st>>>(a);
+    EDN_CUDA_OK(cudaGetLastError());
+    if (phase == 1) return EDN_OK;
+  }
+  // 2. per-ray attention backward
   EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RayBwdSmem)));
   awp_ray_bwd_kernel<<<(unsigned)N, 128, sizeof(RayBwdSmem), st>>>(a);
   // 3. motion MLP (awp.py:104-108) over the N*E sub-rays: x = relu(W1 relu(W0 IN + b0) + b1)

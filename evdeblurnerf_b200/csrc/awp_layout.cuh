@@ -38,9 +38,26 @@ inline AwpWs awp_ws_carve(float* w, int64_t N, int E, int S, bool gemm) {
   return a;
 }
 
-// awp.cu: the forward into `workspace` (gemm_path = materialised per-sample MLP, needed by the backward; tf32 = tensor-core GEMMs)
+// awp.cu: the forward into `workspace` (gemm_path = materialised per-sample MLP, needed by the backward; tf32 = tensor-core
+// GEMMs; phase / bn_rows as in edn_awp_options)
 int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
                 const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
-                bool tf32, float* workspace, float* ccw, void* stream);
+                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream);
+
+// Backward scratch that precedes the large buffers (awp_bwd.cu): ccw_tmp [NE], d_yn [NE][32], d_x [NE][32], bn_sums [64] doubles.
+struct AwpBwdHead { float* ccw_tmp; float* d_yn; float* d_x; double* bn_sums; float* next; };
+inline AwpBwdHead awp_bwd_head(float* workspace, int64_t N, int E, int S) {
+  const int64_t NE = N * E;
+  float* base = workspace + awp_ws_floats(N, E, S, true);
+  base += (4 - ((uintptr_t)base / 4) % 4) % 4;
+  auto take = [&](int64_t n) { float* q = base; base += (n + 3) / 4 * 4; return q; };
+  AwpBwdHead h{};
+  h.ccw_tmp = take(NE);
+  h.d_yn = take(NE * 32);
+  h.d_x = take(NE * 32);
+  h.bn_sums = reinterpret_cast<double*>(take(2 * 64));
+  h.next = base;
+  return h;
+}
 
 }  // namespace edn

@@ -128,7 +128,25 @@ class AdaptiveWeightProposal:
             return AwpFn.apply(self, depth_feature, z_vals, rays_d, view_feature, *ps)
         return self.run(depth_feature, z_vals, rays_d, view_feature)
 
-    def run(self, depth_feature, z_vals, rays_d, view_feature, workspace=None):
+    # ---- synchronised BatchNorm: with torch.distributed initialised and world_size > 1 the batch sums of
+    #      CorrelationModule's BatchNorm1d are all-reduced between two phases of the pass, so N ranks x N/world rays reproduce
+    #      the single-GPU statistics (equal shard sizes assumed) --------------------------------------------------------------
+    sync_bn = True
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if (self.sync_bn and dist.is_available() and dist.is_initialized()) else 1
+
+    def options(self, keep_activations=False, phase=0, bn_rows_total=0):
+        return _lib.AwpOptions(self.precision, 1 if keep_activations else 0, int(phase), int(bn_rows_total))
+
+    @staticmethod
+    def _all_reduce_block(ws, offset_floats):
+        import torch.distributed as dist
+        block = ws[offset_floats: offset_floats + 128].view(torch.float64)
+        dist.all_reduce(block)
+
+    def run(self, depth_feature, z_vals, rays_d, view_feature, workspace=None, keep_activations=False):
         df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
         NE, S, Fd = df.shape
         if Fd != 128:
@@ -140,11 +158,17 @@ class AdaptiveWeightProposal:
             rd = rd.contiguous()
         vf = view_feature.detach().float().contiguous()
         lib = _lib.load()
-        ws = workspace if workspace is not None else torch.empty((int(lib.edn_awp_workspace_floats(N, E, S, self.precision)),),
+        opt = self.options(keep_activations)
+        ws = workspace if workspace is not None else torch.empty((int(lib.edn_awp_workspace_floats(N, E, S, C.byref(opt))),),
                                                                  dtype=torch.float32, device=df.device)
         ccw = torch.empty((N, E), dtype=torch.float32, device=df.device)
-        check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps,
-                              self.precision, ptr(ws), ptr(ccw), stream_ptr()), "edn_awp_fwd")
+        world = self._world()
+        phases = [self.options(keep_activations)] if world == 1 else [self.options(keep_activations, 1), self.options(keep_activations, 2, NE * world)]
+        for o in phases:
+            check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps,
+                                  C.byref(o), ptr(ws), ptr(ccw), stream_ptr()), "edn_awp_fwd")
+            if o.phase == 1:
+                self._all_reduce_block(ws, int(lib.edn_awp_stats_offset_floats(N, E, S)))
         return ccw
 
 

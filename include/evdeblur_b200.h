@@ -308,12 +308,23 @@ typedef struct edn_awp_params {
 /* AdaptiveWeightProposal.forward (awp.py:79-117) in train mode (BatchNorm1d uses batch statistics, mam.py:24-27):
  * depth_feature [N*E][S][128], z_vals [N*E][S], rays_d rows of 3 floats with row stride rays_d_stride (e.g. ray_batch + 3,
  * stride 11), view_feature [N][32] -> ccw [N][E].  workspace: edn_awp_workspace_floats() floats.
- * precision: EDN_F32 = fused fp32 SIMT kernels (parity path); EDN_BF16 = the per-sample MLP as tall TF32 GEMMs (the layer
- * activations stay in the workspace for edn_awp_bwd). */
-int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, int32_t precision);
+ * Options: see edn_awp_options below. */
+typedef struct edn_awp_options {
+  int32_t precision;         /* EDN_F32 = fused fp32 SIMT kernels (parity path); EDN_BF16 = per-sample MLP as tall TF32 GEMMs */
+  int32_t keep_activations;  /* forward: run the per-sample MLP as GEMMs (fp32 ones under EDN_F32) and keep the layer activations
+                                in the workspace, so that edn_awp_bwd(forward_in_workspace = 1) does not recompute them */
+  int32_t phase;             /* synchronised BatchNorm across ranks: 0 = whole pass with this call's batch sums;
+                                1 = stop after the local batch sums (64 doubles at edn_awp_stats_offset_floats /
+                                edn_awp_bwd_sums_offset_floats inside the workspace; the caller all-reduces them in place);
+                                2 = finish from the sums in the workspace */
+  int64_t bn_rows_total;     /* rows behind the batch sums = N * E summed over all ranks; 0 = this call's N * E */
+} edn_awp_options;
+
+int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, const edn_awp_options* opt);
+int64_t edn_awp_stats_offset_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
 int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                 int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                float bn_eps, int32_t precision, float* workspace, float* ccw, void* stream);
+                float bn_eps, const edn_awp_options* opt, float* workspace, float* ccw, void* stream);
 
 /* Gradients of the AWP parameters, same field layout as edn_awp_params (sample_t / mam_linear_t TRANSPOSED like the weights). */
 typedef struct edn_awp_grads {
@@ -330,13 +341,14 @@ typedef struct edn_awp_grads {
  *   grads (ACCUMULATED), d_depth_feature [N*E][S][128] (overwritten; feed it to edn_render_field_bwd's d_feat),
  *   d_rays_d rows of 3 floats with row stride d_rays_d_stride (ACCUMULATED; may be NULL), d_view_feature [N][32] (overwritten;
  *   may be NULL).  The forward is recomputed into the workspace (edn_awp_bwd_workspace_floats floats) unless
- *   forward_in_workspace != 0: then `workspace` is the buffer edn_awp_fwd(precision = EDN_BF16) just filled for the same inputs
- *   (allocated with the backward's size).
- *   precision: EDN_F32 = fp32 GEMMs, EDN_BF16 = TF32 tensor-core GEMMs. */
+ *   forward_in_workspace != 0: then `workspace` is the buffer edn_awp_fwd(keep_activations or EDN_BF16) just filled for the same
+ *   inputs (allocated with the backward's size).  opt->precision: EDN_F32 = fp32 GEMMs, EDN_BF16 = TF32 tensor-core GEMMs;
+ *   opt->phase 1 / 2 split the pass around the all-reduce of the BatchNorm gradient sums (needs forward_in_workspace). */
 int64_t edn_awp_bwd_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
+int64_t edn_awp_bwd_sums_offset_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples);
 int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d,
                 int32_t rays_d_stride, const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples,
-                float bn_eps, int32_t precision, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
+                float bn_eps, const edn_awp_options* opt, int32_t forward_in_workspace, const float* d_ccw, const edn_awp_grads* grads,
                 float* d_depth_feature, float* d_rays_d, int32_t d_rays_d_stride, float* d_view_feature, float* workspace,
                 void* stream);
 

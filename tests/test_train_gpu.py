@@ -339,3 +339,79 @@ def test_trainer_with_event_loss_trains_crf_and_fields():
     assert float(hist[-1]["event_loss"]) < 0.8 * float(hist[0]["event_loss"]), (hist[0]["event_loss"], hist[-1]["event_loss"])
     assert float(hist[-1]["loss"]) < float(hist[0]["loss"])
     assert all(float((tr.flat.views[k].detach() - v).abs().max()) > 0 for k, v in crf0.items()), "CRF parameters must receive gradients"
+
+
+def test_awp_sync_batchnorm_two_shards_equal_full_batch():
+    """SURVEY 8(e) caveat 1: AWP's BatchNorm uses batch statistics over ALL rays.  Two half shards whose batch sums are summed
+    between the two phases of the pass (what `all_reduce` does across ranks) must reproduce the full-batch ccw and gradients."""
+    import ctypes as C
+    from evdeblurnerf_b200 import _lib
+    from evdeblurnerf_b200.autograd import AWP_PARAM_NAMES, awp_grad_buffers, awp_grads_to_reference
+    from evdeblurnerf_b200.renderer import AdaptiveWeightProposal
+    lib = _lib.load()
+    P, _ = small_params()
+    Pa = {k: v.cuda() for k, v in P.items() if k.startswith("awpnet.")}
+    N, E, S = 16, 5, 48
+    gen = torch.Generator().manual_seed(77)
+    df = (torch.randn(N * E, S, 128, generator=gen).abs() * 0.5).cuda()
+    z = torch.sort(torch.rand(N * E, S, generator=gen), -1)[0].cuda()
+    rd = torch.randn(N * E, 3, generator=gen).cuda()
+    vf = torch.randn(N, 32, generator=gen).cuda()
+    cot = torch.randn(N, E, generator=gen).cuda()
+    awp = AdaptiveWeightProposal(Pa, E - 1)
+    shapes = [tuple(Pa["awpnet." + n].shape) for n in AWP_PARAM_NAMES]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd(lo, hi, opt, ws=None):
+        n = hi - lo
+        if ws is None:
+            ws = torch.empty((int(lib.edn_awp_bwd_workspace_floats(n, E, S)),), device="cuda")
+        ccw = torch.empty((n, E), device="cuda")
+        _lib.check(lib.edn_awp_fwd(C.byref(awp.p), df[lo * E:hi * E].data_ptr(), z[lo * E:hi * E].data_ptr(), rd[lo * E:hi * E].data_ptr(), 3,
+                                   vf[lo:hi].data_ptr(), n, E, S, awp.bn_eps, C.byref(opt), ws.data_ptr(), ccw.data_ptr(), st), "fwd")
+        return ws, ccw
+
+    def bwd(lo, hi, opt, ws, g, outs):
+        n = hi - lo
+        d_df, d_rd, d_vf = outs
+        _lib.check(lib.edn_awp_bwd(C.byref(awp.p), df[lo * E:hi * E].data_ptr(), z[lo * E:hi * E].data_ptr(), rd[lo * E:hi * E].data_ptr(), 3,
+                                   vf[lo:hi].data_ptr(), n, E, S, awp.bn_eps, C.byref(opt), 1, cot[lo:hi].contiguous().data_ptr(), C.byref(g),
+                                   d_df[lo * E:hi * E].data_ptr(), d_rd[lo * E:hi * E].data_ptr(), 3, d_vf[lo:hi].data_ptr(), ws.data_ptr(), st), "bwd")
+
+    def block(ws, off):
+        return ws[off: off + 128].view(torch.float64)
+
+    new_outs = lambda: (torch.zeros_like(df), torch.zeros_like(rd), torch.zeros_like(vf))
+    # full batch, single phase
+    ws_full, ccw_full = fwd(0, N, awp.options(True, 0))
+    g_full, bufs_full = awp_grad_buffers(shapes, "cuda")
+    outs_full = new_outs()
+    bwd(0, N, awp.options(True, 0), ws_full, g_full, outs_full)
+    # two shards, batch sums exchanged between the phases
+    h = N // 2
+    shards = [(0, h), (h, N)]
+    off_f, off_b = int(lib.edn_awp_stats_offset_floats(h, E, S)), int(lib.edn_awp_bwd_sums_offset_floats(h, E, S))
+    wss = [fwd(lo, hi, awp.options(True, 1))[0] for lo, hi in shards]
+    tot = block(wss[0], off_f) + block(wss[1], off_f)
+    for w in wss:
+        block(w, off_f).copy_(tot)
+    ccw = torch.cat([fwd(lo, hi, awp.options(True, 2, N * E), w)[1] for (lo, hi), w in zip(shards, wss)])
+    assert_close(ccw, ccw_full, "ccw (2 shards, summed batch sums)", rtol=2e-5, atol=1e-7)
+    g2, bufs2 = awp_grad_buffers(shapes, "cuda")
+    outs2 = new_outs()
+    for (lo, hi), w in zip(shards, wss):
+        bwd(lo, hi, awp.options(True, 1, N * E), w, g2, outs2)
+    tot = block(wss[0], off_b) + block(wss[1], off_b)
+    for w in wss:
+        block(w, off_b).copy_(tot)
+    for (lo, hi), w in zip(shards, wss):
+        bwd(lo, hi, awp.options(True, 2, N * E), w, g2, outs2)
+    for name, a, b in zip(("d depth_feature", "d rays_d", "d view_feature"), outs2, outs_full):
+        grad_close(a, b, name, tol=2e-5)
+    for name, a, b in zip(AWP_PARAM_NAMES, awp_grads_to_reference(bufs2), awp_grads_to_reference(bufs_full)):
+        if name.endswith("MAM.linear.bias"):
+            continue
+        grad_close(a, b, name, tol=1e-3)     # ~1e-6-sized gradients from cancelling sums, accumulated by unordered atomics
+    # without the exchange the shards normalise over their own rays: different numbers (the caveat is real)
+    alone = torch.cat([fwd(lo, hi, awp.options(True, 0))[1] for lo, hi in shards])
+    assert float((alone - ccw_full).abs().max()) > 1e-4
