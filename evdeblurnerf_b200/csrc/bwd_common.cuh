@@ -10,6 +10,31 @@ namespace edn {
 cublasHandle_t blas_handle();   // api.cu: process-wide cuBLAS handle (NULL if cublasCreate failed)
 
 // Row-major C[M,N] (+)= op(A) op(B).  !ta: A stored [M][K] (lda); ta: A stored [K][M].  !tb: B stored [K][N]; tb: B stored [N][K].
+template <typename T> struct CuType;
+template <> struct CuType<float> { static constexpr cudaDataType_t v = CUDA_R_32F; };
+template <> struct CuType<__nv_bfloat16> { static constexpr cudaDataType_t v = CUDA_R_16BF; };
+
+// element <-> float conversions and 4-wide vector access for the activation storage type of the backward pass
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float4 ldv4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldv4(const __nv_bfloat16* p) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ void stv4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stv4(__nv_bfloat16* p, const float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<const unsigned*>(&a);
+  r.y = *reinterpret_cast<const unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
 struct Gemm {
   cublasHandle_t h;
   cublasComputeType_t ct;
@@ -21,22 +46,33 @@ struct Gemm {
     if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasGemmEx failed (%d) M=%lld N=%d K=%lld", (int)s, (long long)M, N, (long long)K); return EDN_E_CUDA; }
     return 0;
   }
+  // typed variant: A and B share a storage type (fp32 -> this->ct, bf16 -> fp32 accumulation), C may be wider (fp32 weight gradients)
+  template <typename TA, typename TC>
+  int run(bool ta, bool tb, int64_t M, int N, int64_t K, const TA* A, int lda, const TA* B, int ldb, float beta, TC* C, int ldc) const {
+    const float alpha = 1.0f;
+    const cublasComputeType_t c = (CuType<TA>::v == CUDA_R_32F) ? ct : CUBLAS_COMPUTE_32F;
+    const cublasStatus_t s = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, (int)M, (int)K, &alpha,
+                                          B, CuType<TA>::v, ldb, A, CuType<TA>::v, lda, &beta, C, CuType<TC>::v, ldc, c, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasGemmEx failed (%d) M=%lld N=%d K=%lld", (int)s, (long long)M, N, (long long)K); return EDN_E_CUDA; }
+    return 0;
+  }
 };
 
 
 namespace {
 
 // Y[m][0..n) = relu(Y + bias)
-__global__ void relu_bias_kernel(float* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
+template <typename AT>
+__global__ void relu_bias_kernel(AT* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
   const int nq = n >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / nq;
   const int j = (int)(t % nq) * 4;
   if (m >= M) return;
-  float4 v = *reinterpret_cast<float4*>(Y + m * ld + j);
+  float4 v = ldv4(Y + m * ld + j);
   if (bias) { v.x += __ldg(bias + j); v.y += __ldg(bias + j + 1); v.z += __ldg(bias + j + 2); v.w += __ldg(bias + j + 3); }
   v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  *reinterpret_cast<float4*>(Y + m * ld + j) = v;
+  stv4(Y + m * ld + j, v);
 }
 
 // Y[m][0..n) += bias   (Y contiguous, row length n)
@@ -47,25 +83,27 @@ __global__ void add_bias_kernel(float* __restrict__ Y, int n, int64_t M, const f
 }
 
 // D[m][j] = H[m][j] > 0 ? D[m][j] : 0   (ReLU backward; H is the post-activation)
-__global__ void relu_mask_kernel(float* __restrict__ D, const float* __restrict__ H, int ld, int n, int64_t M) {
+template <typename AT>
+__global__ void relu_mask_kernel(AT* __restrict__ D, const AT* __restrict__ H, int ld, int n, int64_t M) {
   const int nq = n >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / nq;
   const int j = (int)(t % nq) * 4;
   if (m >= M) return;
-  float4 d = *reinterpret_cast<float4*>(D + m * ld + j);
-  const float4 h = *reinterpret_cast<const float4*>(H + m * ld + j);
+  float4 d = ldv4(D + m * ld + j);
+  const float4 h = ldv4(H + m * ld + j);
   d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
-  *reinterpret_cast<float4*>(D + m * ld + j) = d;
+  stv4(D + m * ld + j, d);
 }
 
 // out[j] += sum_m D[m][j]  (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ D, int ld, int n, int64_t M, float* __restrict__ out) {
+template <typename AT>
+__global__ void colsum_kernel(const AT* __restrict__ D, int ld, int n, int64_t M, float* __restrict__ out) {
   const int j = threadIdx.x;
   if (j >= n) return;
   const int64_t r0 = (int64_t)blockIdx.x * 512, r1 = min(r0 + 512, M);
   float acc = 0.f;
-  for (int64_t m = r0; m < r1; ++m) acc += D[m * ld + j];
+  for (int64_t m = r0; m < r1; ++m) acc += to_f(D[m * ld + j]);
   atomicAdd(out + j, acc);
 }
 

@@ -86,10 +86,10 @@ __device__ __forceinline__ void fma4(float4& acc, const float4 v, float s) {
 }
 
 // P[m][96] = plane (.) line products (voxnerf.py:132-149); 24 threads per sample, one channel quad each.
-template <typename T>
+template <typename T, typename AT>
 __global__ void __launch_bounds__(kVmThreads) vm_products_kernel(const GridDev g, const float* __restrict__ rb,
                                                                   const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                                                                  float* __restrict__ P) {
+                                                                  AT* __restrict__ P) {
   const int64_t t = (int64_t)blockIdx.x * kVmThreads + threadIdx.x;
   const int64_t m = t / kQuads;
   const int q = (int)(t % kQuads);
@@ -102,14 +102,14 @@ __global__ void __launch_bounds__(kVmThreads) vm_products_kernel(const GridDev g
   CompTaps tp;
   comp_taps(g, n, comp, tp, false);
   const float4 v = gather4<T>(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), C, c, tp.pt, tp.lt);
-  *reinterpret_cast<float4*>(P + m * kAppComp + q * 4) = v;
+  stv4(P + m * kAppComp + q * 4, v);
 }
 
 // Backward of the products: scatter-add into the channel-last gradient planes / lines and accumulate d pts.
-template <typename T>
+template <typename T, typename AT>
 __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g, const GradGrid gg, const float* __restrict__ rb,
                                                                  const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                                                                 const float* __restrict__ dP, float* __restrict__ dpts) {
+                                                                 const AT* __restrict__ dP, float* __restrict__ dpts) {
   __shared__ float dn_s[kSamplesPerBlock][3];
   if (threadIdx.x < kSamplesPerBlock * 3) (&dn_s[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
     for (int k = 0; k < 4; ++k) { v[k] = load4<T>(plane + (size_t)tp.pt.off[k] * C + c); fma4(pl, v[k], tp.pt.w[k]); }
 #pragma unroll
     for (int k = 0; k < 2; ++k) { l[k] = load4<T>(line + (size_t)tp.lt.off[k] * C + c); fma4(ln, l[k], tp.lt.w[k]); }
-    const float4 dp = *reinterpret_cast<const float4*>(dP + m * kAppComp + q * 4);
+    const float4 dp = ldv4(dP + m * kAppComp + q * 4);
     const float4 dpl = mul4(dp, ln), dln = mul4(dp, pl);
     float gx = 0.f, gy = 0.f, gv = 0.f;
 #pragma unroll
@@ -170,8 +170,9 @@ __device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
   return rem < 3 ? sinf(a) : cosf(a);
 }
 
+template <typename AT>
 __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                          float* __restrict__ X0, int ldX, int nf, int wp, float* __restrict__ SG, int ldS, int geo, int dirs) {
+                          AT* __restrict__ X0, int ldX, int nf, int wp, AT* __restrict__ SG, int ldS, int geo, int dirs) {
   const int J = dirs ? ldS - 1 - geo : wp;      // wp: columns written after the features ([PE(pts) (63) | zero padding])
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / J;
@@ -180,11 +181,11 @@ __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict_
   if (!dirs) {
     float p[3];
     sample_point(rb, z_vals, m0 + m, S, p);
-    X0[m * ldX + nf + j] = pe_value(p, j, kPePts);
+    X0[m * ldX + nf + j] = from_f<AT>(pe_value(p, j, kPePts));
   } else {
     const float* row = rb + ((m0 + m) / S) * 11 + 8;
     const float vd[3] = {__ldg(row), __ldg(row + 1), __ldg(row + 2)};
-    SG[m * ldS + geo + 1 + j] = pe_value(vd, j, kPeDir);
+    SG[m * ldS + geo + 1 + j] = from_f<AT>(pe_value(vd, j, kPeDir));
   }
 }
 
@@ -194,76 +195,106 @@ __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict_
 //   mode 1: sigma_net.1                 ref [1+geo][cols]       -> pad [rows_p][cols]: rows 0..geo-1 = ref rows 1..geo, row geo = ref row 0
 //   mode 2: color_net.0                 ref [rows][geo+27]      -> pad [rows][cols_p]: col geo (under sigma) = 0, PE(dir) cols shifted by one
 //   mode 3: zero-pad rows               ref [rows_r][cols]      -> pad [rows_p][cols]
-__global__ void relayout_kernel(float* __restrict__ pad, float* __restrict__ ref, int mode, int rows_p, int cols_p, int rows_r, int cols_r,
-                                int geo, int to_padded) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rows_p * cols_p) return;
+__device__ __forceinline__ bool relayout_map(int t, int mode, int cols_p, int rows_r, int cols_r, int geo, int& src) {
   const int r = t / cols_p, c = t % cols_p;
   int rr = r, cc = c;
   if (mode == 1) rr = r < geo ? r + 1 : (r == geo ? 0 : -1);
   if (mode == 2) cc = c < geo ? c : (c == geo ? -1 : c - 1);
-  const bool valid = rr >= 0 && rr < rows_r && cc >= 0 && cc < cols_r;
-  if (to_padded) pad[t] = valid ? ref[rr * cols_r + cc] : 0.f;
-  else if (valid) ref[rr * cols_r + cc] += pad[t];
+  src = rr * cols_r + cc;
+  return rr >= 0 && rr < rows_r && cc >= 0 && cc < cols_r;
+}
+template <typename AT>
+__global__ void relayout_to_padded_kernel(AT* __restrict__ pad, const float* __restrict__ ref, int mode, int rows_p, int cols_p, int rows_r,
+                                          int cols_r, int geo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows_p * cols_p) return;
+  int src;
+  const bool valid = relayout_map(t, mode, cols_p, rows_r, cols_r, geo, src);
+  pad[t] = from_f<AT>(valid ? ref[src] : 0.f);
+}
+__global__ void relayout_fold_kernel(const float* __restrict__ pad, float* __restrict__ ref, int mode, int rows_p, int cols_p, int rows_r,
+                                     int cols_r, int geo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows_p * cols_p) return;
+  int src;
+  if (relayout_map(t, mode, cols_p, rows_r, cols_r, geo, src)) ref[src] += pad[t];
+}
+// dst[m][0..n) = src[m][0..n)  (fp32 -> storage type, different leading dimensions)
+template <typename AT>
+__global__ void convert_cols_kernel(AT* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int n, int64_t M) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / n;
+  const int j = (int)(t % n);
+  if (m < M) dst[m * ldd + j] = from_f<AT>(src[m * lds + j]);
+}
+template <typename AT>
+__global__ void convert_kernel(AT* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = from_f<AT>(src[t]);
 }
 
 // dSG[m][geo] = dsig[m]
-__global__ void set_sigma_grad_kernel(float* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ dsig) {
+template <typename AT>
+__global__ void set_sigma_grad_kernel(AT* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ dsig) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < M) dSG[m * ldS + geo] = dsig[m];
+  if (m < M) dSG[m * ldS + geo] = from_f<AT>(dsig[m]);
 }
 
 // d pts from the PE(pts) columns of dX0: writes (=) dpts[m][0..2].
+template <typename AT>
 __global__ void pe_bwd_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                              const float* __restrict__ dX0, int ldX, int nf, float* __restrict__ dpts) {
+                              const AT* __restrict__ dX0, int ldX, int nf, float* __restrict__ dpts) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / 3;
   const int i = (int)(t % 3);
   if (m >= Mc) return;
   float p[3];
   sample_point(rb, z_vals, m0 + m, S, p);
-  const float* gr = dX0 + m * ldX + nf;
-  float acc = gr[i];
+  const AT* gr = dX0 + m * ldX + nf;
+  float acc = to_f(gr[i]);
 #pragma unroll
   for (int k = 0; k < kPeFreqPts; ++k) {
     const float fr = (float)(1 << k);
     float sn, cs;
     sincosf(p[i] * fr, &sn, &cs);
-    acc += fr * (cs * gr[3 + 6 * k + i] - sn * gr[6 + 6 * k + i]);
+    acc += fr * (cs * to_f(gr[3 + 6 * k + i]) - sn * to_f(gr[6 + 6 * k + i]));
   }
   dpts[m * 4 + i] = acc;
 }
 
 // dH3[m][j] = H3[m][j] > 0 ? sum_c dRGB[m][c] * W2[c][j] : 0     (color_net.2 is [3][hid]: a K = 3 contraction)
-__global__ void head_bwd_kernel(const float* __restrict__ dRGB, const float* __restrict__ W2, const float* __restrict__ H3, int hid,
-                                int64_t M, float* __restrict__ dH3) {
+template <typename AT>
+__global__ void head_bwd_kernel(const AT* __restrict__ dRGB, int nr, const float* __restrict__ W2, const AT* __restrict__ H3, int hid,
+                                int64_t M, AT* __restrict__ dH3) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / hid;
   const int j = (int)(t % hid);
   if (m >= M) return;
-  const float4 g = *reinterpret_cast<const float4*>(dRGB + m * 4);
+  const float4 g = ldv4(dRGB + m * nr);
   const float v = g.x * __ldg(W2 + j) + g.y * __ldg(W2 + hid + j) + g.z * __ldg(W2 + 2 * hid + j);
-  dH3[m * hid + j] = H3[m * hid + j] > 0.f ? v : 0.f;
+  dH3[m * hid + j] = from_f<AT>(to_f(H3[m * hid + j]) > 0.f ? v : 0.f);
 }
 
 // dSG[m][j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
-__global__ void add_feat_grad_kernel(float* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ d_feat) {
+template <typename AT>
+__global__ void add_feat_grad_kernel(AT* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ d_feat) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / geo;
   const int j = (int)(t % geo);
   if (m >= M) return;
-  dSG[m * ldS + j] += d_feat[m * geo + j];
+  dSG[m * ldS + j] = from_f<AT>(to_f(dSG[m * ldS + j]) + d_feat[m * geo + j]);
 }
 
 // Compositing backward (voxnerf.py:153-201), one thread per ray of the chunk.
 //   w_i = alpha_i T_i, T_i = prod_{j<i} (1 - alpha_j);  g_i = dL/dw_i = d_rgb . c_i + d_depth z_i + d_acc + d_weights_i
 //   dL/dalpha_i = T_i (g_i - S_i),  S_i = sum_{k>i} g_k alpha_k prod_{i<j<k} (1 - alpha_j) = g_{i+1} alpha_{i+1} + (1 - alpha_{i+1}) S_{i+1}
 // (no division by 1 - alpha_i: exact when a sample saturates, like torch's cumprod backward).
-__global__ void composite_bwd_kernel(const float* __restrict__ SG /* + geo: the sigma column */, int ldS, const float* __restrict__ RGB, const float* __restrict__ b2,
+template <typename AT>
+__global__ void composite_bwd_kernel(const AT* __restrict__ SG /* + geo: the sigma column */, int ldS, const float* __restrict__ RGB, int nr, const float* __restrict__ b2,
                                      const float* __restrict__ rb, const float* __restrict__ z_vals, const float* __restrict__ noise,
                                      int64_t r0, int64_t Rc, int S, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
                                      const float* __restrict__ d_acc, const float* __restrict__ d_weights, float* __restrict__ al,
-                                     float* __restrict__ tr, float* __restrict__ dRGB, float* __restrict__ dsig_out, float* __restrict__ d_rb) {
+                                     float* __restrict__ tr, AT* __restrict__ dRGB, float* __restrict__ dsig_out, float* __restrict__ d_rb) {
   const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (rl >= Rc) return;
   const int64_t r = r0 + rl;
@@ -275,7 +306,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ SG /* + geo: the 
   const int64_t mb = rl * S;
   float T = 1.0f;
   for (int s = 0; s < S; ++s) {
-    const float a = alpha_of_sample(SG[(mb + s) * ldS], z[s], s + 1 < S ? z[s + 1] : 0.f, nz && s + 1 < S ? nz[s] : 0.f, dn, false, 0.f,
+    const float a = alpha_of_sample(to_f(SG[(mb + s) * ldS]), z[s], s + 1 < S ? z[s + 1] : 0.f, nz && s + 1 < S ? nz[s] : 0.f, dn, false, 0.f,
                                     s == S - 1);
     al[mb + s] = a; tr[mb + s] = T;
     T = T * (1.0f - a);
@@ -287,17 +318,17 @@ __global__ void composite_bwd_kernel(const float* __restrict__ SG /* + geo: the 
   for (int s = S - 1; s >= 0; --s) {
     const int64_t m = mb + s;
     const float a = al[m], Ti = tr[m], w = a * Ti;
-    const float4 x = *reinterpret_cast<const float4*>(RGB + m * 4);
+    const float4 x = *reinterpret_cast<const float4*>(RGB + m * nr);
     const float c[3] = {sigmoidf_(x.x + bb[0]), sigmoidf_(x.y + bb[1]), sigmoidf_(x.z + bb[2])};
     const float gw = gr[0] * c[0] + gr[1] * c[1] + gr[2] * c[2] + gd * z[s] + ga + (d_weights ? d_weights[r * S + s] : 0.f);
-    *reinterpret_cast<float4*>(dRGB + m * 4) = make_float4(w * gr[0] * c[0] * (1.f - c[0]), w * gr[1] * c[1] * (1.f - c[1]),
-                                                           w * gr[2] * c[2] * (1.f - c[2]), 0.f);
+    stv4(dRGB + m * nr, make_float4(w * gr[0] * c[0] * (1.f - c[0]), w * gr[1] * c[1] * (1.f - c[1]), w * gr[2] * c[2] * (1.f - c[2]), 0.f));
+    if (nr > 4) stv4(dRGB + m * nr + 4, make_float4(0.f, 0.f, 0.f, 0.f));
     float dsig = 0.f;
     if (s < S - 1) {
       const float da = Ti * (gw - Ssum);
       const float dz = z[s + 1] - z[s];
       const float dist = __fmul_rn(dz, dn);
-      const float sraw = SG[m * ldS] + (nz ? nz[s] : 0.f);
+      const float sraw = to_f(SG[m * ldS]) + (nz ? nz[s] : 0.f);
       const float sg = fmaxf(sraw, 0.f), one_m = 1.0f - a;
       dsig = sraw > 0.f ? da * dist * one_m : 0.f;
       ddn = fmaf(da * sg * one_m, dz, ddn);
@@ -312,7 +343,8 @@ __global__ void composite_bwd_kernel(const float* __restrict__ SG /* + geo: the 
 }
 
 // d ray_batch from the per-sample d pts (pts = o + d z) and the PE(viewdir) columns of dSG; one warp per ray.
-__global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* __restrict__ dSG, int ldS, int geo,
+template <typename AT>
+__global__ void ray_reduce_kernel(const float* __restrict__ dpts, const AT* __restrict__ dSG, int ldS, int geo,
                                   const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t r0, int64_t Rc, int S,
                                   float* __restrict__ d_rb) {
   const int64_t rl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -328,9 +360,9 @@ __global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* _
     const float4 g = *reinterpret_cast<const float4*>(dpts + m * 4);
     acc[0] += g.x; acc[1] += g.y; acc[2] += g.z;
     acc[3] = fmaf(z, g.x, acc[3]); acc[4] = fmaf(z, g.y, acc[4]); acc[5] = fmaf(z, g.z, acc[5]);
-    const float* gv = dSG + m * ldS + geo + 1;
+    const AT* gv = dSG + m * ldS + geo + 1;
 #pragma unroll
-    for (int j = 0; j < kPeDir; ++j) acc[6 + j] += gv[j];
+    for (int j = 0; j < kPeDir; ++j) acc[6 + j] += to_f(gv[j]);
   }
 #pragma unroll
   for (int j = 0; j < 6 + kPeDir; ++j) {
@@ -358,24 +390,173 @@ __global__ void ray_reduce_kernel(const float* __restrict__ dpts, const float* _
 }
 
 struct Dims {
-  int ng, nf, hid, geo, ldX, ldS, kin, cin, sgn;
+  int ng, nf, hid, geo, ldX, ldS, kin, cin, sgn, nr, esz;
 };
-inline Dims make_dims(int n_grids, int hidden, int geo) {
+// al = elements per 16 bytes of the activation storage type (4: fp32, 8: bf16); every leading dimension is a multiple of it
+inline Dims make_dims(int n_grids, int hidden, int geo, int al) {
   Dims d;
   d.ng = n_grids; d.nf = 32 * n_grids; d.hid = hidden; d.geo = geo;
-  d.kin = d.nf + kPePts;                 // 95 | 127
-  d.cin = geo + kPeDir;                  // 42 | 155
-  d.ldX = (d.kin + 3) & ~3;              // 96 | 128
-  d.ldS = (1 + d.cin + 3) & ~3;          // 44 | 156
-  d.sgn = (1 + geo + 3) & ~3;            // 16 | 132: padded output width of sigma_net.1
+  d.kin = d.nf + kPePts;                          // 95 | 127
+  d.cin = geo + kPeDir;                           // 42 | 155
+  d.ldX = (d.kin + al - 1) / al * al;             // 96 | 128
+  d.ldS = (1 + d.cin + al - 1) / al * al;         // fp32: 44 | 156, bf16: 48 | 160
+  d.sgn = (1 + geo + al - 1) / al * al;           // padded output width of sigma_net.1: 16 | 132 (fp32), 16 | 136 (bf16)
+  d.nr = al;                                      // padded width of the rgb head
+  d.esz = 16 / al;
   return d;
 }
-inline int64_t floats_per_sample(const Dims& d) {
-  return (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + 4 /*RGB*/ + 4 /*dRGB*/ +
-         d.hid * 2 /*D1 D2*/ + d.ldS /*dSG*/ + d.ldX /*dX0*/ + kAppComp /*dP*/ + 4 /*dpts*/ + 3 /*alpha, T, d sigma*/;
+inline int64_t bytes_per_sample(const Dims& d) {
+  const int64_t act = (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + d.nr /*dRGB*/ + d.hid * 2 /*D1 D2*/ +
+                      d.ldS /*dSG*/ + d.nf /*dXf*/ + kAppComp /*dP*/;
+  return act * d.esz + (int64_t)sizeof(float) * (d.ldX /*dX0*/ + d.nr /*RGB*/ + 4 /*dpts*/ + 3 /*alpha, T, d sigma*/);
 }
-inline int64_t weight_scratch_floats(const Dims& d) {     // padded weights + their gradients
-  return 2 * ((int64_t)d.hid * d.ldX + (int64_t)d.sgn * d.hid + (int64_t)d.hid * d.ldS + 4 * (int64_t)d.hid);
+inline int64_t weight_scratch_bytes(const Dims& d) {     // aligned weight copies (storage type) + fp32 gradients of the re-laid-out ones
+  const int64_t relaid = (int64_t)d.hid * d.ldX + (int64_t)d.sgn * d.hid + (int64_t)d.hid * d.ldS + (int64_t)d.nr * d.hid;
+  const int64_t plain = (int64_t)d.hid * d.hid + (int64_t)d.ng * kAppDim * kAppComp;
+  return (relaid + plain) * d.esz + relaid * (int64_t)sizeof(float) + 256;
+}
+
+struct FieldBwdCall {
+  const edn_vm_grid* grids[2];
+  GridDev gd[2];
+  GradGrid gg[2];
+  const edn_field_weights* w;
+  const edn_field_weights* grad_w;
+  const float* ray_batch; const float* z_vals; const float* noise;
+  int64_t n_rays; int S;
+  const float* d_rgb; const float* d_depth; const float* d_acc; const float* d_weights; const float* d_feat;
+  float* d_ray_batch;
+  void* workspace; int64_t workspace_bytes;
+  cudaStream_t st;
+  cublasComputeType_t ct;
+};
+
+template <typename AT>
+int field_bwd_run(const FieldBwdCall& c) {
+  constexpr int al = 16 / (int)sizeof(AT);
+  const edn_field_weights* w = c.w;
+  const edn_field_weights* grad_w = c.grad_w;
+  const int ng = w->n_grids;
+  const Dims D = make_dims(ng, w->hidden, w->geo_feat, al);
+  const int S = c.S, hid = D.hid, geo = D.geo;
+  cudaStream_t st = c.st;
+  const float* ray_batch = c.ray_batch; const float* z_vals = c.z_vals;
+  const int64_t n_rays = c.n_rays;
+  const int64_t per_ray = bytes_per_sample(D) * S;
+  int64_t chunk = (c.workspace_bytes - weight_scratch_bytes(D)) / per_ray;
+  EDN_REQUIRE(chunk >= 1, "edn_render_field_bwd: workspace too small (%lld bytes, one ray needs %lld)", (long long)c.workspace_bytes,
+              (long long)(per_ray + weight_scratch_bytes(D)));
+  chunk = chunk < n_rays ? chunk : n_rays;
+  if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;         // keep GEMM row counts well inside int range
+
+  cublasHandle_t h = blas_handle();
+  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
+  const Gemm gemm{h, c.ct};
+
+  char* base = reinterpret_cast<char*>(c.workspace);
+  auto carve = [&](int64_t bytes) { char* p = base; base += (bytes + 15) / 16 * 16; return p; };
+  // aligned weight copies in the storage type; fp32 gradient accumulators for the re-laid-out ones
+  const int nW[4] = {hid * D.ldX, D.sgn * hid, hid * D.ldS, D.nr * hid};
+  AT* Wp[4];
+  float* gWp[4];
+  for (int i = 0; i < 4; ++i) Wp[i] = reinterpret_cast<AT*>(carve((int64_t)nW[i] * sizeof(AT)));
+  AT* Wc1 = reinterpret_cast<AT*>(carve((int64_t)hid * hid * sizeof(AT)));
+  AT* Wb[2] = {nullptr, nullptr};
+  for (int g = 0; g < ng; ++g) Wb[g] = reinterpret_cast<AT*>(carve((int64_t)kAppDim * kAppComp * sizeof(AT)));
+  gWp[0] = reinterpret_cast<float*>(carve((int64_t)(nW[0] + nW[1] + nW[2] + nW[3]) * sizeof(float)));
+  for (int i = 1; i < 4; ++i) gWp[i] = gWp[i - 1] + nW[i - 1];
+  EDN_CUDA_OK(cudaMemsetAsync(gWp[0], 0, sizeof(float) * (size_t)(nW[0] + nW[1] + nW[2] + nW[3]), st));
+  relayout_to_padded_kernel<AT><<<blocks_for(nW[0], 256), 256, 0, st>>>(Wp[0], w->sigma0, 0, hid, D.ldX, hid, D.kin, geo);
+  relayout_to_padded_kernel<AT><<<blocks_for(nW[1], 256), 256, 0, st>>>(Wp[1], w->sigma1, 1, D.sgn, hid, 1 + geo, hid, geo);
+  relayout_to_padded_kernel<AT><<<blocks_for(nW[2], 256), 256, 0, st>>>(Wp[2], w->color0, 2, hid, D.ldS, hid, D.cin, geo);
+  relayout_to_padded_kernel<AT><<<blocks_for(nW[3], 256), 256, 0, st>>>(Wp[3], w->color2, 3, D.nr, hid, 3, hid, geo);
+  convert_kernel<AT><<<blocks_for(hid * hid, 256), 256, 0, st>>>(Wc1, w->color1, hid * hid);
+  for (int g = 0; g < ng; ++g) convert_kernel<AT><<<blocks_for(kAppDim * kAppComp, 256), 256, 0, st>>>(Wb[g], w->basis[g], kAppDim * kAppComp);
+
+  const int64_t Mmax = chunk * S;
+  auto take = [&](int64_t per) { return reinterpret_cast<AT*>(carve(per * Mmax * (int64_t)sizeof(AT))); };
+  auto takef = [&](int64_t per) { return reinterpret_cast<float*>(carve(per * Mmax * (int64_t)sizeof(float))); };
+  AT* P[2] = {take(kAppComp), ng == 2 ? take(kAppComp) : nullptr};
+  AT* X0 = take(D.ldX);
+  AT* H1 = take(hid);
+  AT* H2 = take(hid);
+  AT* H3 = take(hid);
+  AT* SG = take(D.ldS);
+  AT* dRGB = take(D.nr);
+  AT* D1 = take(hid);
+  AT* D2 = take(hid);
+  AT* dSG = take(D.ldS);
+  AT* dXf = take(D.nf);            // feature columns of dX0 in the storage type (GEMM operand of the basis_mat backward)
+  AT* dP = take(kAppComp);
+  float* dX0 = takef(D.ldX);       // fp32: its PE columns are multiplied by up to 2^9 in the PE backward
+  float* RGB = takef(D.nr);
+  float* dpts = takef(4);
+  float* al_ = takef(1);
+  float* tr = takef(1);
+  float* dsig = takef(1);
+
+#define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
+    const int64_t Rc = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
+    const int64_t M = Rc * S, m0 = r0 * S;
+    // ---- recompute the forward activations -------------------------------------------------------------------------
+    for (int g = 0; g < ng; ++g) {
+      if (c.grids[g]->dtype == EDN_F32) vm_products_kernel<float, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], ray_batch, z_vals, m0, M, S, P[g]);
+      else vm_products_kernel<__nv_bfloat16, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], ray_batch, z_vals, m0, M, S, P[g]);
+      EDN_RC(gemm.run(false, true, M, kAppDim, kAppComp, P[g], kAppComp, Wb[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
+    }
+    pe_kernel<AT><<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
+    EDN_RC(gemm.run(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
+    EDN_RC(gemm.run(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
+    pe_kernel<AT><<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
+    EDN_RC(gemm.run(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
+    EDN_RC(gemm.run(false, true, M, hid, hid, H2, hid, Wc1, hid, 0.f, H3, hid));
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
+    EDN_RC(gemm.run(false, true, M, D.nr, hid, H3, hid, Wp[3], hid, 0.f, RGB, D.nr));
+    // ---- compositing backward ------------------------------------------------------------------------------------------
+    composite_bwd_kernel<AT><<<blocks_for(Rc, 64), 64, 0, st>>>(SG + geo, D.ldS, RGB, D.nr, w->color2_b, ray_batch, z_vals, c.noise, r0, Rc, S, c.d_rgb,
+                                                               c.d_depth, c.d_acc, c.d_weights, al_, tr, dRGB, dsig, c.d_ray_batch);
+    // ---- color_net backward ----------------------------------------------------------------------------------------------
+    EDN_RC(gemm.run(true, false, D.nr, hid, M, dRGB, D.nr, H3, hid, 1.f, gWp[3], hid));
+    if (grad_w->color2_b) colsum_kernel<AT><<<blocks_for(M, 512), 32, 0, st>>>(dRGB, D.nr, 3, M, grad_w->color2_b);
+    head_bwd_kernel<AT><<<blocks_for(M * hid, 256), 256, 0, st>>>(dRGB, D.nr, w->color2, H3, hid, M, D1);               // D1 = dH3
+    EDN_RC(gemm.run(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
+    if (grad_w->color1_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
+    EDN_RC(gemm.run(false, false, M, hid, hid, D1, hid, Wc1, hid, 0.f, D2, hid));                                       // D2 = dH2
+    relu_mask_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
+    EDN_RC(gemm.run(true, false, hid, D.ldS, M, D2, hid, SG, D.ldS, 1.f, gWp[2], D.ldS));
+    if (grad_w->color0_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
+    EDN_RC(gemm.run(false, false, M, D.ldS, hid, D2, hid, Wp[2], D.ldS, 0.f, dSG, D.ldS));                              // [d geo | 0 | d PE(dir)]
+    set_sigma_grad_kernel<AT><<<blocks_for(M, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, dsig);
+    if (c.d_feat) add_feat_grad_kernel<AT><<<blocks_for(M * geo, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, c.d_feat + m0 * geo);
+    // ---- sigma_net backward ------------------------------------------------------------------------------------------------
+    EDN_RC(gemm.run(true, false, D.sgn, hid, M, dSG, D.ldS, H1, hid, 1.f, gWp[1], hid));      // pad rows collect d PE(dir): dropped at fold-back
+    EDN_RC(gemm.run(false, false, M, hid, D.sgn, dSG, D.ldS, Wp[1], hid, 0.f, D1, hid));                                // D1 = dH1 (pad rows of W are 0)
+    relu_mask_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
+    EDN_RC(gemm.run(true, false, hid, D.ldX, M, D1, hid, X0, D.ldX, 1.f, gWp[0], D.ldX));
+    EDN_RC(gemm.run(false, false, M, D.ldX, hid, D1, hid, Wp[0], D.ldX, 0.f, dX0, D.ldX));
+    // ---- inputs: PE(pts), basis_mat, VM grids ----------------------------------------------------------------------------------
+    pe_bwd_kernel<float><<<blocks_for(M * 3, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, dX0, D.ldX, D.nf, dpts);
+    convert_cols_kernel<AT><<<blocks_for(M * D.nf, 256), 256, 0, st>>>(dXf, D.nf, dX0, D.ldX, D.nf, M);
+    for (int g = 0; g < ng; ++g) {
+      EDN_RC(gemm.run(true, false, kAppDim, kAppComp, M, dXf + 32 * g, D.nf, P[g], kAppComp, 1.f, grad_w->basis[g], kAppComp));
+      EDN_RC(gemm.run(false, false, M, kAppComp, kAppDim, dXf + 32 * g, D.nf, Wb[g], kAppComp, 0.f, dP, kAppComp));
+      if (c.grids[g]->dtype == EDN_F32) vm_scatter_kernel<float, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
+      else vm_scatter_kernel<__nv_bfloat16, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
+    }
+    ray_reduce_kernel<AT><<<blocks_for(Rc * 32, 256), 256, 0, st>>>(dpts, dSG, D.ldS, geo, ray_batch, z_vals, r0, Rc, S, c.d_ray_batch);
+    EDN_CUDA_OK(cudaGetLastError());
+  }
+#undef EDN_RC
+  relayout_fold_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(gWp[0], grad_w->sigma0, 0, hid, D.ldX, hid, D.kin, geo);
+  relayout_fold_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(gWp[1], grad_w->sigma1, 1, D.sgn, hid, 1 + geo, hid, geo);
+  relayout_fold_kernel<<<blocks_for(nW[2], 256), 256, 0, st>>>(gWp[2], grad_w->color0, 2, hid, D.ldS, hid, D.cin, geo);
+  relayout_fold_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(gWp[3], grad_w->color2, 3, D.nr, hid, 3, hid, geo);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
 }
 
 }  // namespace
@@ -385,8 +566,8 @@ extern "C" int64_t edn_field_bwd_workspace_bytes(int32_t n_grids, int32_t hidden
                                                  int32_t n_samples) {
   using namespace edn;
   if (n_grids < 1 || n_grids > 2 || hidden <= 0 || geo_feat <= 0 || chunk_rays <= 0 || n_samples <= 0) return -1;
-  const Dims d = make_dims(n_grids, hidden, geo_feat);
-  return (floats_per_sample(d) * chunk_rays * n_samples + weight_scratch_floats(d)) * (int64_t)sizeof(float);
+  const Dims d = make_dims(n_grids, hidden, geo_feat, 4);       // fp32 storage: the larger of the two layouts
+  return bytes_per_sample(d) * chunk_rays * n_samples + weight_scratch_bytes(d);
 }
 
 extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid* grid1, const edn_field_weights* w,
@@ -402,7 +583,7 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   const int ng = w->n_grids;
   EDN_REQUIRE(ng == 1 || ng == 2, "edn_render_field_bwd: n_grids must be 1 or 2");
   EDN_REQUIRE(ng == 1 || (grid1 && grad_grid1), "edn_render_field_bwd: n_grids = 2 needs grid1 and grad_grid1");
-  EDN_REQUIRE(w->hidden % 4 == 0 && w->hidden > 0 && w->hidden <= 256 && w->geo_feat > 0, "edn_render_field_bwd: unsupported MLP dims");
+  EDN_REQUIRE(w->hidden % 8 == 0 && w->hidden > 0 && w->hidden <= 256 && w->geo_feat > 0, "edn_render_field_bwd: unsupported MLP dims");
   EDN_REQUIRE(w->sigma0 && w->sigma1 && w->color0 && w->color1 && w->color2 && w->basis[0] && (ng == 1 || w->basis[1]),
               "edn_render_field_bwd: null weight");
   EDN_REQUIRE(grad_w->sigma0 && grad_w->sigma1 && grad_w->color0 && grad_w->color1 && grad_w->color2 && grad_w->basis[0] &&
@@ -411,140 +592,27 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
               "edn_render_field_bwd: bias / bias-gradient mismatch");
   EDN_REQUIRE(precision == EDN_F32 || precision == EDN_BF16, "edn_render_field_bwd: bad precision");
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
-  const edn_vm_grid* grids[2] = {grid0, grid1};
+  FieldBwdCall c{};
+  c.grids[0] = grid0; c.grids[1] = grid1;
   const edn_vm_grid_grad* ggr[2] = {grad_grid0, grad_grid1};
-  GridDev gd[2];
-  GradGrid gg[2];
   for (int g = 0; g < ng; ++g) {
-    int rc = make_grid_dev(grids[g], &gd[g]);
+    int rc = make_grid_dev(c.grids[g], &c.gd[g]);
     if (rc) return rc;
-    EDN_REQUIRE(grids[g]->dtype == EDN_F32 || grids[g]->dtype == EDN_BF16, "edn_render_field_bwd: bad grid dtype");
+    EDN_REQUIRE(c.grids[g]->dtype == EDN_F32 || c.grids[g]->dtype == EDN_BF16, "edn_render_field_bwd: bad grid dtype");
     for (int i = 0; i < 3; ++i) {
       EDN_REQUIRE(ggr[g]->plane[i] && ggr[g]->line[i], "edn_render_field_bwd: null grid gradient");
-      gg[g].plane[i] = ggr[g]->plane[i];
-      gg[g].line[i] = ggr[g]->line[i];
+      c.gg[g].plane[i] = ggr[g]->plane[i];
+      c.gg[g].line[i] = ggr[g]->line[i];
     }
   }
-  const Dims D = make_dims(ng, w->hidden, w->geo_feat);
-  const int S = n_samples, hid = D.hid, geo = D.geo;
-  const int64_t per_ray = floats_per_sample(D) * S * (int64_t)sizeof(float);
-  const int64_t wfloats = weight_scratch_floats(D);
-  int64_t chunk = (workspace_bytes - wfloats * (int64_t)sizeof(float)) / per_ray;
-  EDN_REQUIRE(chunk >= 1, "edn_render_field_bwd: workspace too small (%lld bytes, one ray needs %lld)", (long long)workspace_bytes,
-              (long long)per_ray);
-  chunk = chunk < n_rays ? chunk : n_rays;
-  if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;         // keep GEMM row counts well inside int range
-
-  cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
-  const Gemm gemm{h, precision == EDN_F32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32};
-
-  // workspace carve-up (sized for `chunk` rays)
-  const int64_t Mmax = chunk * S;
-  float* base = reinterpret_cast<float*>(workspace);
-  // aligned weight copies and their gradient accumulators
-  const int nW[4] = {hid * D.ldX, D.sgn * hid, hid * D.ldS, 4 * hid};
-  float* Wp[4];
-  float* gWp[4];
-  for (int i = 0; i < 4; ++i) { Wp[i] = base; base += nW[i]; }
-  for (int i = 0; i < 4; ++i) { gWp[i] = base; base += nW[i]; }
-  EDN_CUDA_OK(cudaMemsetAsync(gWp[0], 0, sizeof(float) * (size_t)(nW[0] + nW[1] + nW[2] + nW[3]), st));
-  auto relayout = [&](int i, float* ref, bool to_padded) {
-    float* pad = to_padded ? Wp[i] : gWp[i];
-    switch (i) {
-      case 0: relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(pad, ref, 0, hid, D.ldX, hid, D.kin, geo, to_padded); break;
-      case 1: relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(pad, ref, 1, D.sgn, hid, 1 + geo, hid, geo, to_padded); break;
-      case 2: relayout_kernel<<<blocks_for(nW[2], 256), 256, 0, st>>>(pad, ref, 2, hid, D.ldS, hid, D.cin, geo, to_padded); break;
-      default: relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(pad, ref, 3, 4, hid, 3, hid, geo, to_padded); break;
-    }
-  };
-  relayout(0, w->sigma0, true);
-  relayout(1, w->sigma1, true);
-  relayout(2, w->color0, true);
-  relayout(3, w->color2, true);
-  auto take = [&](int64_t per) { float* p = base; base += per * Mmax; return p; };
-  float* P[2] = {take(kAppComp), ng == 2 ? take(kAppComp) : nullptr};
-  float* X0 = take(D.ldX);
-  float* H1 = take(hid);
-  float* H2 = take(hid);
-  float* H3 = take(hid);
-  float* SG = take(D.ldS);
-  float* RGB = take(4);
-  float* dRGB = take(4);
-  float* D1 = take(hid);
-  float* D2 = take(hid);
-  float* dSG = take(D.ldS);
-  float* dX0 = take(D.ldX);
-  float* dP = take(kAppComp);
-  float* dpts = take(4);
-  float* al = take(1);
-  float* tr = take(1);
-  float* dsig = take(1);
-
-#define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
-  for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
-    const int64_t Rc = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
-    const int64_t M = Rc * S, m0 = r0 * S;
-    // ---- recompute the forward activations -------------------------------------------------------------------------
-    for (int g = 0; g < ng; ++g) {
-      if (grids[g]->dtype == EDN_F32) vm_products_kernel<float><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
-      else vm_products_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], ray_batch, z_vals, m0, M, S, P[g]);
-      EDN_RC(gemm(false, true, M, kAppDim, kAppComp, P[g], kAppComp, w->basis[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
-    }
-    pe_kernel<<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
-    EDN_RC(gemm(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
-    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
-    EDN_RC(gemm(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
-    pe_kernel<<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
-    EDN_RC(gemm(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
-    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
-    EDN_RC(gemm(false, true, M, hid, hid, H2, hid, w->color1, hid, 0.f, H3, hid));
-    relu_bias_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
-    EDN_RC(gemm(false, true, M, 4, hid, H3, hid, Wp[3], hid, 0.f, RGB, 4));
-    // ---- compositing backward ------------------------------------------------------------------------------------------
-    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(SG + geo, D.ldS, RGB, w->color2_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
-                                                           d_acc, d_weights, al, tr, dRGB, dsig, d_ray_batch);
-    // ---- color_net backward ----------------------------------------------------------------------------------------------
-    EDN_RC(gemm(true, false, 4, hid, M, dRGB, 4, H3, hid, 1.f, gWp[3], hid));
-    if (grad_w->color2_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, grad_w->color2_b);
-    head_bwd_kernel<<<blocks_for(M * hid, 256), 256, 0, st>>>(dRGB, w->color2, H3, hid, M, D1);                 // D1 = dH3
-    EDN_RC(gemm(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
-    if (grad_w->color1_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
-    EDN_RC(gemm(false, false, M, hid, hid, D1, hid, w->color1, hid, 0.f, D2, hid));                               // D2 = dH2
-    relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
-    EDN_RC(gemm(true, false, hid, D.ldS, M, D2, hid, SG, D.ldS, 1.f, gWp[2], D.ldS));
-    if (grad_w->color0_b) colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
-    EDN_RC(gemm(false, false, M, D.ldS, hid, D2, hid, Wp[2], D.ldS, 0.f, dSG, D.ldS));                            // [d geo | 0 | d PE(dir)]
-    set_sigma_grad_kernel<<<blocks_for(M, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, dsig);
-    if (d_feat) add_feat_grad_kernel<<<blocks_for(M * geo, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, d_feat + m0 * geo);
-    // ---- sigma_net backward ------------------------------------------------------------------------------------------------
-    EDN_RC(gemm(true, false, D.sgn, hid, M, dSG, D.ldS, H1, hid, 1.f, gWp[1], hid));     // pad rows collect d PE(dir): dropped at fold-back
-    EDN_RC(gemm(false, false, M, hid, D.sgn, dSG, D.ldS, Wp[1], hid, 0.f, D1, hid));                              // D1 = dH1 (pad rows of W are 0)
-    relu_mask_kernel<<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
-    EDN_RC(gemm(true, false, hid, D.ldX, M, D1, hid, X0, D.ldX, 1.f, gWp[0], D.ldX));
-    EDN_RC(gemm(false, false, M, D.ldX, hid, D1, hid, Wp[0], D.ldX, 0.f, dX0, D.ldX));
-    // ---- inputs: PE(pts), basis_mat, VM grids ----------------------------------------------------------------------------------
-    pe_bwd_kernel<<<blocks_for(M * 3, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, dX0, D.ldX, D.nf, dpts);
-    for (int g = 0; g < ng; ++g) {
-      EDN_RC(gemm(true, false, kAppDim, kAppComp, M, dX0 + 32 * g, D.ldX, P[g], kAppComp, 1.f, grad_w->basis[g], kAppComp));
-      EDN_RC(gemm(false, false, M, kAppComp, kAppDim, dX0 + 32 * g, D.ldX, w->basis[g], kAppComp, 0.f, dP, kAppComp));
-      if (grids[g]->dtype == EDN_F32) vm_scatter_kernel<float><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
-      else vm_scatter_kernel<__nv_bfloat16><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(gd[g], gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
-    }
-    ray_reduce_kernel<<<blocks_for(Rc * 32, 256), 256, 0, st>>>(dpts, dSG, D.ldS, geo, ray_batch, z_vals, r0, Rc, S, d_ray_batch);
-    EDN_CUDA_OK(cudaGetLastError());
-  }
-#undef EDN_RC
-  relayout(0, grad_w->sigma0, false);
-  relayout(1, grad_w->sigma1, false);
-  relayout(2, grad_w->color0, false);
-  relayout(3, grad_w->color2, false);
-  EDN_CUDA_OK(cudaGetLastError());
-  return EDN_OK;
+  c.w = w; c.grad_w = grad_w; c.ray_batch = ray_batch; c.z_vals = z_vals; c.noise = noise; c.n_rays = n_rays; c.S = n_samples;
+  c.d_rgb = d_rgb; c.d_depth = d_depth; c.d_acc = d_acc; c.d_weights = d_weights; c.d_feat = d_feat; c.d_ray_batch = d_ray_batch;
+  c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.st = reinterpret_cast<cudaStream_t>(stream);
+  // EDN_F32: fp32 activations, exact fp32 GEMMs (parity).  EDN_BF16: bf16 activations and GEMM operands, fp32 accumulation and fp32
+  // weight gradients (the usual mixed-precision recipe: half the activation traffic, bf16 tensor-core GEMMs).
+  c.ct = CUBLAS_COMPUTE_32F;
+  return precision == EDN_F32 ? field_bwd_run<float>(c) : field_bwd_run<__nv_bfloat16>(c);
 }
-
 
 // =====================================================================================================================
 // mode = nerf: backward of NeRF.mlpforward + NeRF.raw2outputs (networks/nerf.py:46-72, 131-162, 74-129) at pts = o + d * z_vals.
@@ -621,13 +689,13 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
   EDN_CUDA_OK(cudaMemsetAsync(gWp[0], 0, sizeof(float) * (size_t)tot_w, st));
   // aligned copies: pts_linears.0 [256][63] -> [256][64]; pts_linears.5 [256][319] -> [256][320] (zero column after the PE part);
   // [feature_linear; alpha_linear; 0] -> [260][256]; views_linears.0 [128][283] -> [128][284] (zero column under sigma); rgb [3][128] -> [4][128]
-  relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(Wp[0], w->pts_w[0], 0, kNW, 64, kNW, 63, 0, 1);
-  relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(Wp[1], w->pts_w[5], 2, kNW, kNXH, kNW, 319, 63, 1);
+  relayout_to_padded_kernel<float><<<blocks_for(nW[0], 256), 256, 0, st>>>(Wp[0], w->pts_w[0], 0, kNW, 64, kNW, 63, 0);
+  relayout_to_padded_kernel<float><<<blocks_for(nW[1], 256), 256, 0, st>>>(Wp[1], w->pts_w[5], 2, kNW, kNXH, kNW, 319, 63);
   EDN_CUDA_OK(cudaMemsetAsync(Wp[2], 0, sizeof(float) * (size_t)nW[2], st));
   EDN_CUDA_OK(cudaMemcpyAsync(Wp[2], w->feature_w, sizeof(float) * kNW * kNW, cudaMemcpyDeviceToDevice, st));
   EDN_CUDA_OK(cudaMemcpyAsync(Wp[2] + kNW * kNW, w->alpha_w, sizeof(float) * kNW, cudaMemcpyDeviceToDevice, st));
-  relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(Wp[3], w->views_w, 2, kNHV, kNAF, kNHV, 283, 256, 1);
-  relayout_kernel<<<blocks_for(nW[4], 256), 256, 0, st>>>(Wp[4], w->rgb_w, 3, 4, kNHV, 3, kNHV, 0, 1);
+  relayout_to_padded_kernel<float><<<blocks_for(nW[3], 256), 256, 0, st>>>(Wp[3], w->views_w, 2, kNHV, kNAF, kNHV, 283, 256);
+  relayout_to_padded_kernel<float><<<blocks_for(nW[4], 256), 256, 0, st>>>(Wp[4], w->rgb_w, 3, 4, kNHV, 3, kNHV, 0);
   EDN_CUDA_OK(cudaMemsetAsync(Wp[5], 0, sizeof(float) * kNAFn, st));
   EDN_CUDA_OK(cudaMemcpyAsync(Wp[5], w->feature_b, sizeof(float) * kNW, cudaMemcpyDeviceToDevice, st));
   EDN_CUDA_OK(cudaMemcpyAsync(Wp[5] + kNW, w->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -678,12 +746,12 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     relu_bias_kernel<<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(HV, kNHV, kNHV, M, w->views_b);
     EDN_RC(gemm(false, true, M, 4, kNHV, HV, kNHV, Wp[4], kNHV, 0.f, RGB, 4));
     // ---- compositing backward (nerf.py:74-129: sigma = channel 3, rgb = sigmoid) ------------------------------------------------
-    composite_bwd_kernel<<<blocks_for(Rc, 64), 64, 0, st>>>(AF + 256, kNAF, RGB, w->rgb_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
+    composite_bwd_kernel<float><<<blocks_for(Rc, 64), 64, 0, st>>>(AF + 256, kNAF, RGB, 4, w->rgb_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
                                                            d_acc, d_weights, al, tr, dRGB, dsig, d_ray_batch);
     // ---- heads ------------------------------------------------------------------------------------------------------------
     EDN_RC(gemm(true, false, 4, kNHV, M, dRGB, 4, HV, kNHV, 1.f, gWp[4], kNHV));
     if (g->rgb_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, g->rgb_b);
-    head_bwd_kernel<<<blocks_for(M * kNHV, 256), 256, 0, st>>>(dRGB, w->rgb_w, HV, kNHV, M, dHV);
+    head_bwd_kernel<float><<<blocks_for(M * kNHV, 256), 256, 0, st>>>(dRGB, 4, w->rgb_w, HV, kNHV, M, dHV);
     EDN_RC(gemm(true, false, kNHV, kNAF, M, dHV, kNHV, AF, kNAF, 1.f, gWp[3], kNAF));
     colsum_kernel<<<blocks_for(M, 512), 128, 0, st>>>(dHV, kNHV, kNHV, M, g->views_b);
     EDN_RC(gemm(false, false, M, kNAF, kNHV, dHV, kNHV, Wp[3], kNAF, 0.f, dAF, kNAF));
@@ -719,12 +787,12 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     EDN_CUDA_OK(cudaGetLastError());
   }
 #undef EDN_RC
-  relayout_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(gWp[0], g->pts_w[0], 0, kNW, 64, kNW, 63, 0, 0);
-  relayout_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(gWp[1], g->pts_w[5], 2, kNW, kNXH, kNW, 319, 63, 0);
+  relayout_fold_kernel<<<blocks_for(nW[0], 256), 256, 0, st>>>(gWp[0], g->pts_w[0], 0, kNW, 64, kNW, 63, 0);
+  relayout_fold_kernel<<<blocks_for(nW[1], 256), 256, 0, st>>>(gWp[1], g->pts_w[5], 2, kNW, kNXH, kNW, 319, 63);
   add_vec_kernel<<<blocks_for(kNW * kNW, 256), 256, 0, st>>>(g->feature_w, gWp[2], kNW * kNW);
   add_vec_kernel<<<blocks_for(kNW, 256), 256, 0, st>>>(g->alpha_w, gWp[2] + kNW * kNW, kNW);
-  relayout_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(gWp[3], g->views_w, 2, kNHV, kNAF, kNHV, 283, 256, 0);
-  relayout_kernel<<<blocks_for(nW[4], 256), 256, 0, st>>>(gWp[4], g->rgb_w, 3, 4, kNHV, 3, kNHV, 0, 0);
+  relayout_fold_kernel<<<blocks_for(nW[3], 256), 256, 0, st>>>(gWp[3], g->views_w, 2, kNHV, kNAF, kNHV, 283, 256);
+  relayout_fold_kernel<<<blocks_for(nW[4], 256), 256, 0, st>>>(gWp[4], g->rgb_w, 3, 4, kNHV, 3, kNHV, 0);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

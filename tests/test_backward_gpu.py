@@ -116,3 +116,30 @@ def test_backward_accumulates_and_chunking_is_invisible():
     c = acc.finish()
     for k in ("mlp_fine.sigma_net.0.weight", "mlp_coarse.app_plane.0", "mlp_fine.basis_mat.weight"):
         grad_close(c[k], 2 * b[k], "accumulate " + k, tol=2e-5)
+
+
+def test_bf16_mode_gradients_are_close_to_the_fp32_oracle():
+    """bf16 mode: bf16 VM planes, bf16 activation storage and GEMM operands in the backward (fp32 accumulation, fp32 weight
+    gradients).  Not a parity mode: every gradient tensor must point the same way as the fp32 oracle's (cosine > 0.995) with a
+    relative L2 error under 10 %."""
+    from evdeblurnerf_b200 import RenderEngine
+    from evdeblurnerf_b200.backward import render_rays_backward
+    R, Nc, Ni = 64, 32, 32
+    P, rb = setup(9, R, bias=True)
+    cot = cotangents(9, R)
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="bf16")
+    out = eng.render_rays(rb.cuda(), Nc, retraw=True, N_importance=Ni)
+    ref, ref_rb = oracle_grads(P, rb, Nc, out["z_vals"].cpu(), cot)
+    saved = {"ray_batch": rb.cuda(), "z_vals0": out["z_vals0"], "z_vals": out["z_vals"]}
+    grads, d_rb = render_rays_backward(eng, saved, {k: v.cuda() for k, v in cot.items()}, chunk_rays=40)
+    got = grads.finish()
+    worst = {}
+    keep = [0, 1, 2, 3, 4, 5, 8, 9, 10]          # near / far are constants of the render path (no gradient by design)
+    for k, g in list(ref.items()) + [("d_ray_batch", ref_rb[:, keep])]:
+        a = (d_rb[:, keep] if k == "d_ray_batch" else got[k]).detach().cpu().double().flatten()
+        b = g.double().flatten()
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        rel = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        worst[k] = (cos, rel)
+    bad = {k: v for k, v in worst.items() if v[0] < 0.995 or v[1] > 0.10}
+    assert not bad, bad
