@@ -143,3 +143,36 @@ def test_bf16_mode_gradients_are_close_to_the_fp32_oracle():
         worst[k] = (cos, rel)
     bad = {k: v for k, v in worst.items() if v[0] < 0.995 or v[1] > 0.10}
     assert not bad, bad
+
+
+def test_backward_error_paths_and_empty_batch():
+    """Error behaviour mirrors the reference's exceptions: a too small workspace or a missing gradient buffer raises with
+    the library's message; an empty ray batch is a no-op."""
+    import ctypes as C
+    from evdeblurnerf_b200 import RenderEngine, _lib
+    from evdeblurnerf_b200.backward import RenderGradients, _field_struct, render_rays_backward
+    P, rb = setup(11, 8)
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32")
+    out = eng.render_rays(rb.cuda(), 32, retraw=True, N_importance=32)
+    saved = {"ray_batch": rb.cuda(), "z_vals0": out["z_vals0"], "z_vals": out["z_vals"]}
+    # empty batch
+    empty = {"ray_batch": rb.cuda()[:0], "z_vals0": out["z_vals0"][:0], "z_vals": out["z_vals"][:0]}
+    grads, d_rb = render_rays_backward(eng, empty, {})
+    assert d_rb.shape == (0, 11) and all(float(v.abs().max()) == 0.0 for v in grads.finish().values())
+    # workspace too small
+    lib = _lib.load()
+    g = RenderGradients(eng)
+    w = _field_struct(eng.params, "mlp_fine.", ["mlp_coarse.", "mlp_fine."])
+    gw = _field_struct(g.w, "mlp_fine.", ["mlp_coarse.", "mlp_fine."])
+    d_rbuf = torch.zeros(8, 11).cuda()
+    ws = torch.empty(1024, dtype=torch.uint8).cuda()
+    args = lambda gw_, ws_, n_: (C.byref(eng.coarse.grid), C.byref(eng.fine.grid), C.byref(w), saved["ray_batch"].data_ptr(),
+                                 saved["z_vals"].data_ptr(), None, 8, 64, 0, None, None, None, None, None, C.byref(gw_),
+                                 C.byref(g.grid_struct["mlp_coarse."]), C.byref(g.grid_struct["mlp_fine."]), d_rbuf.data_ptr(), ws_.data_ptr(), n_,
+                                 torch.cuda.current_stream().cuda_stream)
+    with pytest.raises(RuntimeError, match="workspace too small"):
+        _lib.check(lib.edn_render_field_bwd(*args(gw, ws, 1024)), "edn_render_field_bwd")
+    gw.sigma0 = None
+    big = torch.empty(int(lib.edn_field_bwd_workspace_bytes(2, 256, 128, 8, 64)), dtype=torch.uint8).cuda()
+    with pytest.raises(RuntimeError, match="null weight gradient"):
+        _lib.check(lib.edn_render_field_bwd(*args(gw, big, big.numel())), "edn_render_field_bwd")
