@@ -35,6 +35,31 @@ __device__ __forceinline__ void stv4(__nv_bfloat16* p, const float4 v) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// 16-byte vectors of the storage type: kVec<T> elements
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int n = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int n = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 struct Gemm {
   cublasHandle_t h;
   cublasComputeType_t ct;
@@ -61,18 +86,20 @@ struct Gemm {
 
 namespace {
 
-// Y[m][0..n) = relu(Y + bias)
+// Y[m][0..n) = relu(Y + bias); one 16-byte vector per thread (n and ld multiples of the vector width)
 template <typename AT>
 __global__ void relu_bias_kernel(AT* __restrict__ Y, int ld, int n, int64_t M, const float* __restrict__ bias) {
-  const int nq = n >> 2;
+  constexpr int V = Vec16<AT>::n;
+  const int nq = n / V;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / nq;
-  const int j = (int)(t % nq) * 4;
+  const int j = (int)(t % nq) * V;
   if (m >= M) return;
-  float4 v = ldv4(Y + m * ld + j);
-  if (bias) { v.x += __ldg(bias + j); v.y += __ldg(bias + j + 1); v.z += __ldg(bias + j + 2); v.w += __ldg(bias + j + 3); }
-  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  stv4(Y + m * ld + j, v);
+  Vec16<AT> x;
+  x.load(Y + m * ld + j);
+#pragma unroll
+  for (int i = 0; i < V; ++i) x.v[i] = fmaxf(x.v[i] + (bias ? __ldg(bias + j + i) : 0.f), 0.f);
+  x.store(Y + m * ld + j);
 }
 
 // Y[m][0..n) += bias   (Y contiguous, row length n)
@@ -85,15 +112,18 @@ __global__ void add_bias_kernel(float* __restrict__ Y, int n, int64_t M, const f
 // D[m][j] = H[m][j] > 0 ? D[m][j] : 0   (ReLU backward; H is the post-activation)
 template <typename AT>
 __global__ void relu_mask_kernel(AT* __restrict__ D, const AT* __restrict__ H, int ld, int n, int64_t M) {
-  const int nq = n >> 2;
+  constexpr int V = Vec16<AT>::n;
+  const int nq = n / V;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = t / nq;
-  const int j = (int)(t % nq) * 4;
+  const int j = (int)(t % nq) * V;
   if (m >= M) return;
-  float4 d = ldv4(D + m * ld + j);
-  const float4 h = ldv4(H + m * ld + j);
-  d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
-  stv4(D + m * ld + j, d);
+  Vec16<AT> d, h;
+  d.load(D + m * ld + j);
+  h.load(H + m * ld + j);
+#pragma unroll
+  for (int i = 0; i < V; ++i) d.v[i] = h.v[i] > 0.f ? d.v[i] : 0.f;
+  d.store(D + m * ld + j);
 }
 
 // out[j] += sum_m D[m][j]  (bias gradients)

@@ -162,30 +162,37 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
 
 // Positional encodings (embedding.py:88-98): X0[:, nf : ldX) = [PE(pts) (63) | 0] (dirs = 0), SG[:, geo+1 : ldS) = [PE(viewdir) (27) | 0]
 // (dirs = 1; launched after the sigma_net.1 GEMM, whose padded output columns overlap the first PE(viewdir) columns).
-__device__ __forceinline__ float pe_value(const float x[3], int j, int n_pe) {
-  if (j < 3) return x[j];
-  if (j >= n_pe) return 0.f;
-  const int k = (j - 3) / 6, rem = (j - 3) % 6, axis = rem % 3;
-  const float a = x[axis] * (float)(1 << k);
-  return rem < 3 ? sinf(a) : cosf(a);
-}
-
+// One thread per (sample, group): group 0 writes the 3 identity columns (and the zero padding behind the encoding), group
+// 1 + k the sin / cos triplets of frequency 2^k (one sincosf per axis).
 template <typename AT>
 __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
                           AT* __restrict__ X0, int ldX, int nf, int wp, AT* __restrict__ SG, int ldS, int geo, int dirs) {
-  const int J = dirs ? ldS - 1 - geo : wp;      // wp: columns written after the features ([PE(pts) (63) | zero padding])
+  const int L = dirs ? kPeFreqDir : kPeFreqPts, n_pe = 3 + 6 * L;
+  const int width = dirs ? ldS - 1 - geo : wp;        // columns to fill: [PE | zero padding]
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = t / J;
-  const int j = (int)(t % J);
+  const int64_t m = t / (L + 1);
+  const int gq = (int)(t % (L + 1));
   if (m >= Mc) return;
-  if (!dirs) {
-    float p[3];
-    sample_point(rb, z_vals, m0 + m, S, p);
-    X0[m * ldX + nf + j] = from_f<AT>(pe_value(p, j, kPePts));
-  } else {
+  float x[3];
+  if (!dirs) sample_point(rb, z_vals, m0 + m, S, x);
+  else {
     const float* row = rb + ((m0 + m) / S) * 11 + 8;
-    const float vd[3] = {__ldg(row), __ldg(row + 1), __ldg(row + 2)};
-    SG[m * ldS + geo + 1 + j] = from_f<AT>(pe_value(vd, j, kPeDir));
+    x[0] = __ldg(row); x[1] = __ldg(row + 1); x[2] = __ldg(row + 2);
+  }
+  AT* out = dirs ? SG + m * ldS + geo + 1 : X0 + m * ldX + nf;
+  if (gq == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = from_f<AT>(x[i]);
+    for (int j = n_pe; j < width; ++j) out[j] = from_f<AT>(0.f);
+  } else {
+    const float fr = (float)(1 << (gq - 1));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float sn, cs;
+      sincosf(x[i] * fr, &sn, &cs);
+      out[3 + 6 * (gq - 1) + i] = from_f<AT>(sn);
+      out[6 + 6 * (gq - 1) + i] = from_f<AT>(cs);
+    }
   }
 }
 
@@ -262,17 +269,24 @@ __global__ void pe_bwd_kernel(const float* __restrict__ rb, const float* __restr
   dpts[m * 4 + i] = acc;
 }
 
-// dH3[m][j] = H3[m][j] > 0 ? sum_c dRGB[m][c] * W2[c][j] : 0     (color_net.2 is [3][hid]: a K = 3 contraction)
+// dH3[m][j] = H3[m][j] > 0 ? sum_c dRGB[m][c] * W2[c][j] : 0     (color_net.2 is [3][hid]: a K = 3 contraction); one 16-byte
+// vector of H3 / dH3 per thread
 template <typename AT>
 __global__ void head_bwd_kernel(const AT* __restrict__ dRGB, int nr, const float* __restrict__ W2, const AT* __restrict__ H3, int hid,
                                 int64_t M, AT* __restrict__ dH3) {
+  constexpr int V = Vec16<AT>::n;
+  const int nq = hid / V;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = t / hid;
-  const int j = (int)(t % hid);
+  const int64_t m = t / nq;
+  const int j = (int)(t % nq) * V;
   if (m >= M) return;
   const float4 g = ldv4(dRGB + m * nr);
-  const float v = g.x * __ldg(W2 + j) + g.y * __ldg(W2 + hid + j) + g.z * __ldg(W2 + 2 * hid + j);
-  dH3[m * hid + j] = from_f<AT>(to_f(H3[m * hid + j]) > 0.f ? v : 0.f);
+  Vec16<AT> h;
+  h.load(H3 + m * hid + j);
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    h.v[i] = h.v[i] > 0.f ? g.x * __ldg(W2 + j + i) + g.y * __ldg(W2 + hid + j + i) + g.z * __ldg(W2 + 2 * hid + j + i) : 0.f;
+  h.store(dH3 + m * hid + j);
 }
 
 // dSG[m][j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
@@ -506,15 +520,15 @@ int field_bwd_run(const FieldBwdCall& c) {
       else vm_products_kernel<__nv_bfloat16, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], ray_batch, z_vals, m0, M, S, P[g]);
       EDN_RC(gemm.run(false, true, M, kAppDim, kAppComp, P[g], kAppComp, Wb[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
     }
-    pe_kernel<AT><<<blocks_for(M * (D.ldX - D.nf), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
+    pe_kernel<AT><<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
     EDN_RC(gemm.run(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
     EDN_RC(gemm.run(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
-    pe_kernel<AT><<<blocks_for(M * (D.ldS - 1 - geo), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
+    pe_kernel<AT><<<blocks_for(M * (kPeFreqDir + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
     EDN_RC(gemm.run(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
     EDN_RC(gemm.run(false, true, M, hid, hid, H2, hid, Wc1, hid, 0.f, H3, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
+    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
     EDN_RC(gemm.run(false, true, M, D.nr, hid, H3, hid, Wp[3], hid, 0.f, RGB, D.nr));
     // ---- compositing backward ------------------------------------------------------------------------------------------
     composite_bwd_kernel<AT><<<blocks_for(Rc, 64), 64, 0, st>>>(SG + geo, D.ldS, RGB, D.nr, w->color2_b, ray_batch, z_vals, c.noise, r0, Rc, S, c.d_rgb,
@@ -522,11 +536,11 @@ int field_bwd_run(const FieldBwdCall& c) {
     // ---- color_net backward ----------------------------------------------------------------------------------------------
     EDN_RC(gemm.run(true, false, D.nr, hid, M, dRGB, D.nr, H3, hid, 1.f, gWp[3], hid));
     if (grad_w->color2_b) colsum_kernel<AT><<<blocks_for(M, 512), 32, 0, st>>>(dRGB, D.nr, 3, M, grad_w->color2_b);
-    head_bwd_kernel<AT><<<blocks_for(M * hid, 256), 256, 0, st>>>(dRGB, D.nr, w->color2, H3, hid, M, D1);               // D1 = dH3
+    head_bwd_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(dRGB, D.nr, w->color2, H3, hid, M, D1);               // D1 = dH3
     EDN_RC(gemm.run(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
     if (grad_w->color1_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
     EDN_RC(gemm.run(false, false, M, hid, hid, D1, hid, Wc1, hid, 0.f, D2, hid));                                       // D2 = dH2
-    relu_mask_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
+    relu_mask_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(D2, H2, hid, hid, M);
     EDN_RC(gemm.run(true, false, hid, D.ldS, M, D2, hid, SG, D.ldS, 1.f, gWp[2], D.ldS));
     if (grad_w->color0_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
     EDN_RC(gemm.run(false, false, M, D.ldS, hid, D2, hid, Wp[2], D.ldS, 0.f, dSG, D.ldS));                              // [d geo | 0 | d PE(dir)]
@@ -535,7 +549,7 @@ int field_bwd_run(const FieldBwdCall& c) {
     // ---- sigma_net backward ------------------------------------------------------------------------------------------------
     EDN_RC(gemm.run(true, false, D.sgn, hid, M, dSG, D.ldS, H1, hid, 1.f, gWp[1], hid));      // pad rows collect d PE(dir): dropped at fold-back
     EDN_RC(gemm.run(false, false, M, hid, D.sgn, dSG, D.ldS, Wp[1], hid, 0.f, D1, hid));                                // D1 = dH1 (pad rows of W are 0)
-    relu_mask_kernel<AT><<<blocks_for(M * (hid / 4), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
+    relu_mask_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(D1, H1, hid, hid, M);
     EDN_RC(gemm.run(true, false, hid, D.ldX, M, D1, hid, X0, D.ldX, 1.f, gWp[0], D.ldX));
     EDN_RC(gemm.run(false, false, M, D.ldX, hid, D1, hid, Wp[0], D.ldX, 0.f, dX0, D.ldX));
     // ---- inputs: PE(pts), basis_mat, VM grids ----------------------------------------------------------------------------------
@@ -732,7 +746,7 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     const int64_t Rc = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
     const int64_t M = Rc * S, m0 = r0 * S;
     // ---- forward recompute ----------------------------------------------------------------------------------------------
-    pe_kernel<<<blocks_for(M * 64, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 64, AF, kNAF, 256, 0);
+    pe_kernel<<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 64, AF, kNAF, 256, 0);
     for (int l = 0; l < 8; ++l) {
       const float* X = (l == 0 || l == 5) ? XH : H[l - 1];
       const int ldx = (l == 0 || l == 5) ? kNXH : ldH[l - 1];
@@ -741,7 +755,7 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     }
     EDN_RC(gemm(false, true, M, kNAFn, kNW, H[7], kNW, Wp[2], kNW, 0.f, AF, kNAF));
     add_bias_ld_kernel<<<blocks_for(M * 257, 256), 256, 0, st>>>(AF, kNAF, 257, M, Wp[5]);
-    pe_kernel<<<blocks_for(M * 27, 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 0, AF, kNAF, 256, 1);
+    pe_kernel<<<blocks_for(M * (kPeFreqDir + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 0, AF, kNAF, 256, 1);
     EDN_RC(gemm(false, true, M, kNHV, kNAF, AF, kNAF, Wp[3], kNAF, 0.f, HV, kNHV));
     relu_bias_kernel<<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(HV, kNHV, kNHV, M, w->views_b);
     EDN_RC(gemm(false, true, M, 4, kNHV, HV, kNHV, Wp[4], kNHV, 0.f, RGB, 4));
@@ -751,7 +765,7 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     // ---- heads ------------------------------------------------------------------------------------------------------------
     EDN_RC(gemm(true, false, 4, kNHV, M, dRGB, 4, HV, kNHV, 1.f, gWp[4], kNHV));
     if (g->rgb_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, g->rgb_b);
-    head_bwd_kernel<float><<<blocks_for(M * kNHV, 256), 256, 0, st>>>(dRGB, 4, w->rgb_w, HV, kNHV, M, dHV);
+    head_bwd_kernel<float><<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(dRGB, 4, w->rgb_w, HV, kNHV, M, dHV);
     EDN_RC(gemm(true, false, kNHV, kNAF, M, dHV, kNHV, AF, kNAF, 1.f, gWp[3], kNAF));
     colsum_kernel<<<blocks_for(M, 512), 128, 0, st>>>(dHV, kNHV, kNHV, M, g->views_b);
     EDN_RC(gemm(false, false, M, kNAF, kNHV, dHV, kNHV, Wp[3], kNAF, 0.f, dAF, kNAF));
