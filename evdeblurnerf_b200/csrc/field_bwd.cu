@@ -110,13 +110,11 @@ template <typename T, typename AT>
 __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g, const GradGrid gg, const float* __restrict__ rb,
                                                                  const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
                                                                  const AT* __restrict__ dP, float* __restrict__ dpts) {
-  __shared__ float dn_s[kSamplesPerBlock][3];
-  if (threadIdx.x < kSamplesPerBlock * 3) (&dn_s[0][0])[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float part[kVmThreads][3];      // per-thread coordinate-gradient contributions (no shared-memory atomics: fp32 ones are CAS loops)
+  part[threadIdx.x][0] = 0.f; part[threadIdx.x][1] = 0.f; part[threadIdx.x][2] = 0.f;
   const int64_t t = (int64_t)blockIdx.x * kVmThreads + threadIdx.x;
   const int64_t m = t / kQuads;
   const int q = (int)(t % kQuads);
-  const int ls = threadIdx.x / kQuads;
   if (m < Mc) {
     float p[3], n[3];
     sample_point(rb, z_vals, m0 + m, S, p);
@@ -148,15 +146,18 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
       if (tp.lt.w[k] != 0.f) atomicAdd(reinterpret_cast<float4*>(gg.line[comp] + (size_t)tp.lt.off[k] * C + c), scale4(dln, tp.lt.w[k]));
       gv = fmaf(tp.dl[k], dot4(dln, l[k]), gv);
     }
-    atomicAdd(&dn_s[ls][tp.ax], gx * tp.sx);
-    atomicAdd(&dn_s[ls][tp.ay], gy * tp.sy);
-    atomicAdd(&dn_s[ls][tp.av], gv * tp.sv);
+    part[threadIdx.x][tp.ax] = gx * tp.sx;      // (ax, ay, av) is a permutation of the three point axes
+    part[threadIdx.x][tp.ay] = gy * tp.sy;
+    part[threadIdx.x][tp.av] = gv * tp.sv;
   }
   __syncthreads();
   if (threadIdx.x < kSamplesPerBlock * 3) {
     const int s = threadIdx.x / 3, i = threadIdx.x % 3;
     const int64_t mm = (int64_t)blockIdx.x * kSamplesPerBlock + s;
-    if (mm < Mc) dpts[mm * 4 + i] += dn_s[s][i] * g.inv[i];     // n = (p - amin) * inv - 1
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) acc += part[s * kQuads + q][i];
+    if (mm < Mc) dpts[mm * 4 + i] += acc * g.inv[i];            // n = (p - amin) * inv - 1
   }
 }
 
