@@ -248,6 +248,117 @@ __global__ void __launch_bounds__(128) awp_integrate_kernel(const AwpArgs a, con
   }
 }
 
+// Same computation for S <= 128 with FOUR threads per sample (16 channels each, 512 threads): the channel cumprod is a local
+// prefix product + a 3-step shuffle across the row's four lanes, the sums over samples are warp-shuffle + shared-memory
+// reductions.  (The products are associated differently from the sequential kernels: last-bit differences.)
+__global__ void __launch_bounds__(512) awp_integrate4_kernel(const AwpArgs a, const float* __restrict__ h_all) {
+  __shared__ float Qs[128][64];
+  __shared__ float atts[128];
+  __shared__ float red[16][64];
+  __shared__ float redm[16], reds[16];
+  const int tid = threadIdx.x, S = a.S, r = tid >> 2, q = tid & 3, c0 = q * 16, warp = tid >> 5, lane = tid & 31;
+  const int64_t sr = blockIdx.x;
+  const bool valid = r < S, has = r < S - 1;
+  const float* rd = a.rays_d + sr * a.rays_d_stride;
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])), __fmul_rn(rd[2], rd[2])));
+  float h[16], al[16], Q[16], xl[8];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(h_all + (sr * S + r) * 64 + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i += 4) {
+    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.xl + (sr * S + r) * 32 + q * 8 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xl[i] = v.x; xl[i + 1] = v.y; xl[i + 2] = v.z; xl[i + 3] = v.w;
+  }
+  const float dist = has ? __fmul_rn(a.z_vals[sr * S + r + 1] - a.z_vals[sr * S + r], dnorm) : 0.f;
+  float p = 1.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    al[i] = has ? 1.0f - expf(-__fmul_rn(h[i], dist)) : 0.f;
+    p *= (1.0f - al[i]);
+    Q[i] = p;
+  }
+  {   // exclusive product over the lower quarters of the row
+    const float t1 = __shfl_up_sync(0xffffffffu, p, 1), t2 = __shfl_up_sync(0xffffffffu, p, 2), t3 = __shfl_up_sync(0xffffffffu, p, 3);
+    const float e = (q >= 1 ? t1 : 1.0f) * (q >= 2 ? t2 : 1.0f) * (q >= 3 ? t3 : 1.0f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Q[i] *= e;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&Qs[r][c0 + i]) = make_float4(Q[i], Q[i + 1], Q[i + 2], Q[i + 3]);
+  {   // attention logit of the row
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t = fmaf(__ldg(a.p.line_conv_att + q * 8 + i), xl[i], t);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (q == 0) { atts[r] = valid ? t : -INFINITY; if (valid) a.att[sr * S + r] = t; }
+  }
+  __syncthreads();
+  // integrate: g[c] = sum_s al[s][c] Q[s-1][c] h[s][c]
+  float g[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float qp = r > 0 ? Qs[r - 1][c0 + i] : 1.0f;
+    g[i] = valid ? al[i] * qp * h[i] : 0.f;
+  }
+  // softmax over the samples
+  float mx = atts[min(r, 127)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) redm[warp] = mx;
+  __syncthreads();
+  mx = redm[0];
+#pragma unroll
+  for (int w = 1; w < 16; ++w) mx = fmaxf(mx, redm[w]);
+  const float ex = valid ? expf(atts[r] - mx) : 0.f;
+  float sm = (q == 0) ? ex : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  if (lane == 0) reds[warp] = sm;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) tot += reds[w];
+  const float pr = ex / tot;
+  float xi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xi[i] = xl[i] * pr;
+  // sums over the rows of the warp (lanes with the same quarter), then over the 16 warps
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xi[i] += __shfl_xor_sync(0xffffffffu, xi[i], o);
+  }
+  if (lane < 4) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[warp][c0 + i] = g[i];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t += red[w][tid];
+    a.gint[sr * 64 + tid] = t;
+  }
+  __syncthreads();
+  if (lane < 4) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][q * 8 + i] = xi[i];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t += red[w][tid];
+    a.inter[sr * 32 + tid] = t;
+  }
+}
+
 // ---- per primary ray ---------------------------------------------------------------------------------------------------
 struct RaySmem {
   float view[48];                 // img_embed (32) | PE(viewdir, L = 2) (15)
@@ -494,9 +605,13 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
     int rc = gemm(false, false, M, 32, 64, ws.act[3], 64, p->mam_linear_t, 32, 0.f, ws.xl, 32);
     if (rc) return rc;
     add_bias_kernel<<<blocks_for(M * 32, 256), 256, 0, st>>>(ws.xl, 32, M, p->mam_linear_b);
-    const size_t smem_i = sizeof(float) * (size_t)(n_samples * (3 * 65 + 33 + 1));
-    EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
-    awp_integrate_kernel<<<(unsigned)NE, 128, smem_i, st>>>(a, ws.act[3]);
+    if (n_samples <= 128) {
+      awp_integrate4_kernel<<<(unsigned)NE, 512, 0, st>>>(a, ws.act[3]);
+    } else {
+      const size_t smem_i = sizeof(float) * (size_t)(n_samples * (3 * 65 + 33 + 1));
+      EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+      awp_integrate_kernel<<<(unsigned)NE, 128, smem_i, st>>>(a, ws.act[3]);
+    }
   }
   const size_t smem2 = sizeof(RaySmem);
   EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

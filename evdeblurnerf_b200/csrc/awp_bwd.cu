@@ -109,22 +109,23 @@ __global__ void awp_bn_param_grad_kernel(const BwdArgs a) {
 }
 
 // ---- phase 2: per primary ray, attention backward ---------------------------------------------------------------------------
+template <int EMAX, int SMAX>
 struct RayBwdSmem {
-  float x[kMaxE][32], dy[kMaxE][32], cf[kMaxE][32], dcf[kMaxE][32];
-  float inter[kMaxE][32], dinter[kMaxE][32];
-  float inter_a[16][kMaxE], dinter_a[16][kMaxE];
-  float xlog[kMaxE][16], dxlog[kMaxE][16];
-  float inter_n[kMaxE][16], dinter_n[kMaxE][16];
-  float x_inter[kMaxE][kMaxE], dlg_inter[kMaxE][kMaxE];
-  float att[kMaxE][kMaxS];        // logits, later d att
-  float pE[kMaxE][kMaxS];         // softmax over exposures
-  float pS[kMaxE][kMaxS];         // softmax over samples
-  float intra[32][kMaxS];         // later d intra
-  float intra_b[16][kMaxS], dintra_b[16][kMaxS];
-  float x_intra[kMaxE][kMaxS];    // later d logits
-  float intra_l[kMaxS][16], dintra_l[kMaxS][16];
+  float x[EMAX][32], dy[EMAX][32], cf[EMAX][32], dcf[EMAX][32];
+  float inter[EMAX][32], dinter[EMAX][32];
+  float inter_a[16][EMAX], dinter_a[16][EMAX];
+  float xlog[EMAX][16], dxlog[EMAX][16];
+  float inter_n[EMAX][16], dinter_n[EMAX][16];
+  float x_inter[EMAX][EMAX], dlg_inter[EMAX][EMAX];
+  float att[EMAX][SMAX];        // logits, later d att
+  float pE[EMAX][SMAX];         // softmax over exposures
+  float pS[EMAX][SMAX];         // softmax over samples
+  float intra[32][SMAX];        // later d intra
+  float intra_b[16][SMAX], dintra_b[16][SMAX];
+  float x_intra[EMAX][SMAX];    // later d logits
+  float intra_l[SMAX][16], dintra_l[SMAX][16];
   float g_convd[32 * 32], g_conva[16 * 32], g_convb[16 * 32], g_convc[16 * 32], g_convn[16 * 16], g_convl[16 * 16], g_latt[32];
-  float red[kMaxE];
+  float red[EMAX];
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -138,9 +139,12 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// EMAX / SMAX bound the exposure / sample counts of this instantiation (shared memory: 88 KB for E <= 8, S <= 128 -> two CTAs per
+// SM; 200 KB for the largest one)
+template <int EMAX, int SMAX>
 __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float smraw[];
-  RayBwdSmem& s = *reinterpret_cast<RayBwdSmem*>(smraw);
+  RayBwdSmem<EMAX, SMAX>& s = *reinterpret_cast<RayBwdSmem<EMAX, SMAX>*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S, warp = tid >> 5, lane = tid & 31;
   const int64_t n = blockIdx.x;
   const double rows = a.bn_rows;
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   __syncthreads();
   // softmax over exposures (per sample) and "intra"
   for (int sp = tid; sp < S; sp += 128) {
-    float mx = -INFINITY, pe[kMaxE], sum = 0.f;
+    float mx = -INFINITY, pe[EMAX], sum = 0.f;
     for (int e = 0; e < E; ++e) { pe[e] = s.att[e][sp]; mx = fmaxf(mx, pe[e]); }
     for (int e = 0; e < E; ++e) { pe[e] = expf(pe[e] - mx); sum += pe[e]; }
     for (int e = 0; e < E; ++e) s.pE[e][sp] = pe[e] / sum;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   }
   if (tid < E) {
     const int e = tid;
-    float lg[kMaxE], mx = -INFINITY, sum = 0.f;
+    float lg[EMAX], mx = -INFINITY, sum = 0.f;
     for (int e2 = 0; e2 < E; ++e2) {
       float t = 0.f;
       for (int k = 0; k < 16; ++k) t = fmaf(s.xlog[e][k], s.inter_a[k][e2], t);
@@ -513,6 +517,100 @@ __global__ void __launch_bounds__(128) awp_integrate_bwd_kernel(const BwdArgs a,
   }
 }
 
+// S <= 128: four threads per sample (16 channels each); the suffix recursion over the channels runs locally and is stitched
+// across the row's four lanes with three dependent shuffles.
+__global__ void __launch_bounds__(512) awp_integrate4_bwd_kernel(const BwdArgs a, const float* __restrict__ h_all, const float* __restrict__ dIN) {
+  extern __shared__ __align__(16) float sm4[];
+  float (*Qs)[64] = reinterpret_cast<float (*)[64]>(sm4);                 // [128][64]
+  float (*AH)[64] = reinterpret_cast<float (*)[64]>(sm4 + 128 * 64);      // [129][64]: al * h of each row (row s needs row s + 1); row 128 = 0
+  float* G = sm4 + 128 * 64 + 129 * 64;                                   // [64]
+  float* red = G + 64;                                                    // [16]
+  const int tid = threadIdx.x, S = a.S, r = tid >> 2, q = tid & 3, c0 = q * 16, warp = tid >> 5, lane = tid & 31;
+  const int64_t sr = blockIdx.x;
+  const bool valid = r < S, has = r < S - 1;
+  if (tid < 64) { G[tid] = dIN[sr * 112 + tid]; AH[128][tid] = 0.f; }
+  const float* rd = a.rays_d + sr * a.rays_d_stride;
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])), __fmul_rn(rd[2], rd[2])));
+  float h[16], al[16], Q[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(h_all + (sr * S + r) * 64 + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w;
+  }
+  const float dz = has ? a.z_vals[sr * S + r + 1] - a.z_vals[sr * S + r] : 0.f;
+  const float dist = __fmul_rn(dz, dnorm);
+  float p = 1.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    al[i] = has ? 1.0f - expf(-__fmul_rn(h[i], dist)) : 0.f;
+    p *= (1.0f - al[i]);
+    Q[i] = p;
+  }
+  float e;
+  {
+    const float t1 = __shfl_up_sync(0xffffffffu, p, 1), t2 = __shfl_up_sync(0xffffffffu, p, 2), t3 = __shfl_up_sync(0xffffffffu, p, 3);
+    e = (q >= 1 ? t1 : 1.0f) * (q >= 2 ? t2 : 1.0f) * (q >= 3 ? t3 : 1.0f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Q[i] *= e;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    *reinterpret_cast<float4*>(&Qs[r][c0 + i]) = make_float4(Q[i], Q[i + 1], Q[i + 2], Q[i + 3]);
+    *reinterpret_cast<float4*>(&AH[r][c0 + i]) = make_float4(al[i] * h[i], al[i + 1] * h[i + 1], al[i + 2] * h[i + 2], al[i + 3] * h[i + 3]);
+  }
+  __syncthreads();
+  // dQ[c] = G[c] al[s+1][c] h[s+1][c];  T_c = dQ_c + q_{c+1} T_{c+1}  (T beyond the last channel = 0)
+  float dQ[16], T[16], Mc[16];      // T with zero inflow; Mc = d T_c / d inflow
+  const float qn = __shfl_down_sync(0xffffffffu, 1.0f - al[0], 1);     // q of the next quarter's first channel
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dQ[i] = has ? G[c0 + i] * AH[r + 1][c0 + i] : 0.f;
+  {
+    float t = 0.f, m = (q < 3) ? qn : 0.f;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+      t = dQ[i] + (i < 15 ? (1.0f - al[i + 1]) * t : 0.f);
+      T[i] = t;
+      Mc[i] = m;
+      m *= (1.0f - al[i]);
+    }
+  }
+  // stitch: inflow of quarter q = T at the first channel of quarter q + 1
+  float first = T[0];                       // quarter 3: exact already
+  float inflow = 0.f;
+#pragma unroll
+  for (int step = 2; step >= 0; --step) {
+    const float nb = __shfl_down_sync(0xffffffffu, first, 1);
+    if (q == step) { inflow = nb; first = T[0] + Mc[0] * nb; }
+  }
+  float ddist = 0.f;
+  float out[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float Tc = T[i] + Mc[i] * inflow;
+    const float pex = i > 0 ? Q[i - 1] : e;
+    const float qp = r > 0 ? Qs[r - 1][c0 + i] : 1.0f;
+    const float qv = 1.0f - al[i];
+    const float dal = G[c0 + i] * qp * h[i] - pex * Tc;
+    out[i] = G[c0 + i] * al[i] * qp + dal * dist * qv;
+    ddist = fmaf(dal * h[i], qv, ddist);
+  }
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      *reinterpret_cast<float4*>(a.d_h + (sr * S + r) * 64 + c0 + i) = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
+  }
+  float ddn = valid ? ddist * dz : 0.f;
+  ddn = warp_sum(ddn);
+  if (lane == 0) red[warp] = ddn;
+  __syncthreads();
+  if (tid == 0 && a.d_rays_d && dnorm > 0.f) {
+    float t = 0.f;
+    for (int w = 0; w < 16; ++w) t += red[w];
+    float* o = a.d_rays_d + sr * a.d_rays_d_stride;
+    for (int i = 0; i < 3; ++i) o[i] += t * rd[i] / dnorm;
+  }
+}
+
 __global__ void fold_w0_kernel(const float* __restrict__ src, float* __restrict__ dst) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 32 * 111) return;
@@ -596,8 +694,18 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
     if (phase == 1) return EDN_OK;
   }
   // 2. per-ray attention backward
-  EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RayBwdSmem)));
-  awp_ray_bwd_kernel<<<(unsigned)N, 128, sizeof(RayBwdSmem), st>>>(a);
+  {
+    auto launch = [&](auto kern, size_t smem) -> int {
+      EDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)N, 128, smem, st>>>(a);
+      return 0;
+    };
+    int rc2;
+    if (E <= 8 && S <= 64) rc2 = launch(awp_ray_bwd_kernel<8, 64>, sizeof(RayBwdSmem<8, 64>));
+    else if (E <= 8 && S <= 128) rc2 = launch(awp_ray_bwd_kernel<8, 128>, sizeof(RayBwdSmem<8, 128>));
+    else rc2 = launch(awp_ray_bwd_kernel<kMaxE, kMaxS>, sizeof(RayBwdSmem<kMaxE, kMaxS>));
+    if (rc2) return rc2;
+  }
   // 3. motion MLP (awp.py:104-108) over the N*E sub-rays: x = relu(W1 relu(W0 IN + b0) + b1)
   awp_motion_input_kernel<<<blocks_for(NE * 112, 256), 256, 0, st>>>(a, IN);
   {   // zero-padded copy of motion_w[0] [32][111] -> [32][112]
@@ -617,7 +725,11 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   EDN_RC(gemm(false, false, NE, 112, 32, dH, 32, W0p, 112, 0.f, dIN, 112));
   awp_view_bwd_kernel<<<blocks_for(N, 128), 128, 0, st>>>(a, dIN);
   // 4. feature-integration backward -> d_h (=), d rays_d
-  {
+  if (S <= 128) {
+    const size_t smem4 = sizeof(float) * (128 * 64 + 129 * 64 + 64 + 16);
+    EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate4_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    awp_integrate4_bwd_kernel<<<(unsigned)NE, 512, smem4, st>>>(a, a.ws.act[3], dIN);
+  } else {
     const size_t smem_i = sizeof(float) * (size_t)(S * 3 * 65 + 64 + 4);
     EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
     awp_integrate_bwd_kernel<<<(unsigned)NE, 128, smem_i, st>>>(a, a.ws.act[3], dIN);

@@ -290,14 +290,23 @@ __global__ void head_bwd_kernel(const AT* __restrict__ dRGB, int nr, const float
   h.store(dH3 + m * hid + j);
 }
 
-// dSG[m][j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221)
+// dSG[m][j] += d_feat[m0 + m][j]   (upstream gradient of feature_map, voxnerf.py:221); 4 columns per thread (geo % 4 == 0),
+// scalar tail otherwise
 template <typename AT>
 __global__ void add_feat_grad_kernel(AT* __restrict__ dSG, int ldS, int geo, int64_t M, const float* __restrict__ d_feat) {
+  const int nq = (geo + 3) / 4;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = t / geo;
-  const int j = (int)(t % geo);
+  const int64_t m = t / nq;
+  const int j = (int)(t % nq) * 4;
   if (m >= M) return;
-  dSG[m * ldS + j] = from_f<AT>(to_f(dSG[m * ldS + j]) + d_feat[m * geo + j]);
+  if ((geo & 3) == 0) {
+    float4 d = ldv4(dSG + m * ldS + j);
+    const float4 f = __ldg(reinterpret_cast<const float4*>(d_feat + m * geo + j));
+    d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+    stv4(dSG + m * ldS + j, d);
+  } else {
+    for (int i = j; i < min(j + 4, geo); ++i) dSG[m * ldS + i] = from_f<AT>(to_f(dSG[m * ldS + i]) + d_feat[m * geo + i]);
+  }
 }
 
 // Compositing backward (voxnerf.py:153-201), one thread per ray of the chunk.
@@ -546,7 +555,7 @@ int field_bwd_run(const FieldBwdCall& c) {
     if (grad_w->color0_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D2, hid, hid, M, grad_w->color0_b);
     EDN_RC(gemm.run(false, false, M, D.ldS, hid, D2, hid, Wp[2], D.ldS, 0.f, dSG, D.ldS));                              // [d geo | 0 | d PE(dir)]
     set_sigma_grad_kernel<AT><<<blocks_for(M, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, dsig);
-    if (c.d_feat) add_feat_grad_kernel<AT><<<blocks_for(M * geo, 256), 256, 0, st>>>(dSG, D.ldS, geo, M, c.d_feat + m0 * geo);
+    if (c.d_feat) add_feat_grad_kernel<AT><<<blocks_for(M * ((geo + 3) / 4), 256), 256, 0, st>>>(dSG, D.ldS, geo, M, c.d_feat + m0 * geo);
     // ---- sigma_net backward ------------------------------------------------------------------------------------------------
     EDN_RC(gemm.run(true, false, D.sgn, hid, M, dSG, D.ldS, H1, hid, 1.f, gWp[1], hid));      // pad rows collect d PE(dir): dropped at fold-back
     EDN_RC(gemm.run(false, false, M, hid, D.sgn, dSG, D.ldS, Wp[1], hid, 0.f, D1, hid));                                // D1 = dH1 (pad rows of W are 0)
@@ -771,12 +780,12 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     colsum_kernel<<<blocks_for(M, 512), 128, 0, st>>>(dHV, kNHV, kNHV, M, g->views_b);
     EDN_RC(gemm(false, false, M, kNAF, kNHV, dHV, kNHV, Wp[3], kNAF, 0.f, dAF, kNAF));
     set_sigma_grad_kernel<<<blocks_for(M, 256), 256, 0, st>>>(dAF, kNAF, 256, M, dsig);
-    if (d_feat && feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * kNW, 256), 256, 0, st>>>(dAF, kNAF, kNW, M, d_feat + m0 * kNW);
+    if (d_feat && feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(dAF, kNAF, kNW, M, d_feat + m0 * kNW);
     EDN_RC(gemm(true, false, kNAFn, kNW, M, dAF, kNAF, H[7], kNW, 1.f, gWp[2], kNW));
     colsum_kernel<<<blocks_for(M, 512), 256, 0, st>>>(dAF, kNAF, kNW, M, g->feature_b);
     colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dAF + kNW, kNAF, 1, M, g->alpha_b);
     EDN_RC(gemm(false, false, M, kNW, kNAFn, dAF, kNAF, Wp[2], kNW, 0.f, D1, kNW));
-    if (d_feat && !feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * kNW, 256), 256, 0, st>>>(D1, kNW, kNW, M, d_feat + m0 * kNW);
+    if (d_feat && !feature_after_linear) add_feat_grad_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(D1, kNW, kNW, M, d_feat + m0 * kNW);
     // ---- the 8 x 256 trunk, layers 7..0 (D = gradient at the layer's post-activation) -------------------------------------------------
     float* D = D1;
     int ldD = kNW;
