@@ -144,6 +144,11 @@ SIGNATURES = {
     "edn_img2mse": (C.c_int, [_P, _P, _I64, _P, _P]),
     "edn_tv_loss_app": (C.c_int, [C.POINTER(C.c_void_p * 3), C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int32 * 3),
                                   C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _P, _P, _P]),
+    "edn_rays_from_pixels": (C.c_int, [_P, _P, _I32, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _I32, _P, _P]),
+    "edn_make_rgb_batch": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P,
+                                     _P, _P]),
+    "edn_gather_successor": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
+    "edn_interpolate_poses": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P, _I32, C.c_double, _P, _P, _P]),
     "edn_edi_prior": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _I32, _I32, _I32, _F, _F, _P, _P, _P]),
 }
 

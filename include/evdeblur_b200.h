@@ -430,6 +430,35 @@ int edn_edi_prior(const float* ev_x, const float* ev_y, const float* ev_p, const
                   int32_t n_seg, int64_t max_seg_events, const float* blurry, int32_t H, int32_t W, int32_t C, float c_pos,
                   float c_neg, float* bii, float* sharp, void* stream);
 
+/* ---- ray / event batch generation on the device -------------------------------------------------------------- */
+
+/* get_rays_pix (utils/rays.py:25-36): coords [n][2] = (x, y), poses [n][3][4] (or one [3][4] when broadcast_pose != 0)
+ * -> rays [n][3][2] (origin, direction).  No FMA contraction: bit-exact against the reference's torch arithmetic. */
+int edn_rays_from_pixels(const float* coords, const float* poses, int32_t broadcast_pose, int64_t n, double fx, double fy, double cx,
+                         double cy, int32_t add_halfpix, float* rays, void* stream);
+
+/* LLFFDataset.__getitem__ (data/loader.py:325-356): ray_ids [n] int64 over [n_img][H][W] -> rays [n][3][2], rays_x / rays_y [n]
+ * (pixel + 0.5), images_idx [n] int64, rgbsf [n][3] gathered from images [n_img][H][W][3], poses_out [n][3][4].  Every output
+ * except rays may be NULL. */
+int edn_make_rgb_batch(const int64_t* ray_ids, int64_t n, const float* images, const float* poses, int32_t n_img, int32_t H,
+                       int32_t W, double fx, double fy, double cx, double cy, float* rays, float* rays_x, float* rays_y,
+                       int64_t* images_idx, float* rgbsf, float* poses_out, void* stream);
+
+/* gather_successor (utils/events.py:221-257): follow successor_map query_hops[i] + 1 times from query_idx[i], summing the
+ * positive / negative polarities of the visited events; an out-of-range successor gives (-1, 0, 0). */
+int edn_gather_successor(const int64_t* query_idx, const int64_t* query_hops, int64_t n, const int64_t* successor_map,
+                         const int32_t* polarity, int64_t n_events, int64_t* succ_idx, int32_t* neg_cumsum, int32_t* pos_cumsum,
+                         void* stream);
+
+/* LLFFEventsDataset.interpolate_poses (data/loader_events.py:133-148, 175-183; utils/data.py:34-61, 167-183) without spherify:
+ * t [n] (float64, clipped to the key range); rotations = SLERP between key quaternions key_quats [n_keys][4] (x, y, z, w);
+ * translations = piecewise cubic trans_coef [n_breaks-1][4][3] (highest power first) in (t - trans_breaks[j]) -- the PPoly form
+ * of scipy's interp1d(kind="cubic") spline, computed once on the host; then the column reorder [c1, -c0, c2, T], T *= bd_scale
+ * and the left multiplication by recenter_inv [4][4] = inv(recenter c2w) (NULL = none) -> poses [n][3][4] fp32. */
+int edn_interpolate_poses(const double* t, int64_t n, const double* key_times, const double* key_quats, int32_t n_keys,
+                          const double* trans_breaks, const double* trans_coef, int32_t n_breaks, double bd_scale,
+                          const double* recenter_inv, float* poses, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

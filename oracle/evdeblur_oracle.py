@@ -594,3 +594,85 @@ def edi_prior_image(ev_x, ev_y, ev_t, ev_p, blurry, t_start, t_end, w, h, c_pos,
     bii = np.stack([edi_bii(ev_x[a:b], ev_y[a:b], ev_p[a:b], w, h, c_pos, c_neg) for a, b in zip(i0, i1)], 0)
     bii = np.repeat(bii[..., None], blurry.shape[-1], axis=-1) if blurry.ndim == 3 else bii
     return edi_deblur(blurry, bii)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# (f).2  ray / event batch generation     data/loader.py:325-356, utils/rays.py:25-36, data/loader_events.py:133-148,
+#        259-304, utils/events.py:221-257, utils/data.py:34-61, 167-183
+# --------------------------------------------------------------------------------------------------------------
+def rays_from_pixels(coords, K, c2ws, add_halfpix=True):
+    """get_rays_pix (utils/rays.py:25-36): coords [n,2] = (x, y), c2ws [n,3,4] (or [3,4]) -> rays [n,3,2]."""
+    half = 0.5 if add_halfpix else 0.0
+    x, y = coords[:, 0], coords[:, 1]
+    dirs = torch.stack([(x + (half - K[0][2])) / K[0][0], -(y + (half - K[1][2])) / K[1][1], -torch.ones_like(x)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2ws[..., :3, :3], -1)
+    rays_o = c2ws[..., :3, -1].expand(rays_d.shape)
+    return torch.stack([rays_o, rays_d], -1)
+
+
+def make_rgb_batch(ray_ids, images, poses, K):
+    """LLFFDataset.__getitem__ (data/loader.py:325-356): ray ids over [n_img, H, W] -> the training batch dict."""
+    n_img, Hh, Ww, _ = images.shape
+    img_id = ray_ids // (Hh * Ww)
+    ray_y = (ray_ids % (Hh * Ww)) // Ww
+    ray_x = ray_ids % Ww
+    c2w = poses[img_id]
+    rays = rays_from_pixels(torch.stack([ray_x, ray_y], -1).to(poses.dtype), K, c2w)
+    return {"rays": rays, "rays_x": (ray_x + 0.5).reshape(-1, 1), "rays_y": (ray_y + 0.5).reshape(-1, 1),
+            "images_idx": img_id.reshape(-1, 1), "rgbsf": images[img_id, ray_y, ray_x].reshape(-1, 3), "poses": c2w.reshape(-1, 3, 4)}
+
+
+def gather_successor(query_idx, query_hops, successor_map, polarities):
+    """utils/events.py:221-257: follow the per-pixel successor map `hops + 1` times, accumulating the polarities of the
+    visited events; an out-of-range successor invalidates the query (-1, 0, 0)."""
+    n_ev = successor_map.shape[0]
+    out_idx = query_idx.clone()
+    pos = torch.zeros_like(query_idx, dtype=polarities.dtype)
+    neg = torch.zeros_like(query_idx, dtype=polarities.dtype)
+    invalid = torch.zeros(query_idx.shape[0], dtype=torch.bool)
+    for i in range(query_idx.shape[0]):
+        cur = int(query_idx[i])
+        for _ in range(int(query_hops[i]) + 1):
+            nxt = int(successor_map[cur])
+            if nxt < 0 or nxt >= n_ev:
+                invalid[i] = True
+                break
+            p = int(polarities[nxt])
+            if p > 0:
+                pos[i] += p
+            elif p < 0:
+                neg[i] += p
+            cur = nxt
+        out_idx[i] = cur
+    out_idx[invalid] = -1
+    pos[invalid] = 0
+    neg[invalid] = 0
+    return out_idx, neg, pos
+
+
+def pose_interpolator(times, rots, trans):
+    """utils/data.py:34-61: SLERP of the rotations (scipy Slerp) + cubic-spline interpolation of the translations
+    (scipy interp1d(kind='cubic')), queries clipped to the known range.  Returns f(t [n]) -> (R [n,3,3], T [n,3])."""
+    from scipy.interpolate import interp1d
+    from scipy.spatial.transform import Rotation, Slerp
+    slerp = Slerp(times, Rotation.from_matrix(rots))
+    cubic = interp1d(x=times, y=trans, axis=0, kind="cubic", bounds_error=True)
+
+    def f(t):
+        t = np.clip(t, times[0], times[-1])
+        return slerp(t).as_matrix(), cubic(t)
+    return f
+
+
+def interpolate_event_poses(interp, t, bd_scale=1.0, recenter_c2w=None):
+    """LLFFEventsDataset.interpolate_poses (data/loader_events.py:133-148) without spherify: interpolated [R | T] -> column
+    reorder [c1, -c0, c2, T] -> T *= bd_scale -> inv(recenter_c2w) @ pose.  Returns [n,3,4] float32."""
+    Rm, T = interp(np.asarray(t, dtype=np.float64))
+    pose = np.concatenate([Rm, T[..., None]], -1)                                        # [n,3,4]
+    pose = np.concatenate([pose[..., 1:2], -pose[..., 0:1], pose[..., 2:]], -1).astype(np.float32)
+    pose[..., :3, 3] *= bd_scale
+    if recenter_c2w is not None:
+        bottom = np.tile(np.array([0, 0, 0, 1.0], dtype=np.float64).reshape(1, 1, 4), [pose.shape[0], 1, 1])
+        full = np.concatenate([pose[:, :3, :4], bottom], -2)
+        pose = (np.linalg.inv(recenter_c2w) @ full)[:, :3, :4]
+    return pose.astype(np.float32)

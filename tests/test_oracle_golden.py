@@ -99,3 +99,21 @@ def test_searchsorted_right_known_answer():
     u = torch.linspace(0, 1, 5)
     exp = torch.tensor([int((cdf <= x).sum()) for x in u])
     assert torch.equal(inds[0], exp)
+
+
+def test_batchgen_oracle_replays_reference_vectors():
+    """case7: the batch-generation restatements against the vectors written from the reference's own get_rays_pix,
+    gather_successor and SLERP / cubic-spline pose interpolator + recenter_poses."""
+    import numpy as np
+    import evdeblur_oracle as oc
+    from util import golden
+    g = golden("case7_batchgen")
+    K = g["K"].tolist()
+    b = oc.make_rgb_batch(g["ray_ids"], g["images"], g["poses"], K)
+    assert torch.equal(b["rays"], g["rays"]) and torch.equal(b["rgbsf"], g["rgbsf"]) and torch.equal(b["images_idx"], g["images_idx"])
+    idx, neg, pos = oc.gather_successor(g["q_idx"], g["q_hops"], g["succ"], g["pol"])
+    assert torch.equal(idx, g["succ_idx"]) and torch.equal(neg, g["neg"]) and torch.equal(pos, g["pos"])
+    poses = oc.interpolate_event_poses(oc.pose_interpolator(g["times"].numpy(), g["rots"].numpy(), g["trans"].numpy()), g["tq"].numpy(),
+                                       float(g["bd_scale"]), g["recenter_c2w"].numpy())
+    assert np.allclose(poses, g["event_poses"].numpy(), rtol=0, atol=1e-6)
+    assert torch.equal(oc.rays_from_pixels(g["ev_xy"], K, g["event_poses"]), g["ev_rays"])
