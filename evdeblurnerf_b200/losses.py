@@ -129,6 +129,11 @@ def img2mse(x, y):
     return out[0]
 
 
+def mse2psnr(x):
+    """utils/metrics.py:8: -10 log10(mse) (a scalar; host-side tensor op)."""
+    return -10.0 * torch.log(x) / 2.302585092994046
+
+
 def tv_loss_app(params, prefix):
     """VoxelNeRFBase.TV_loss_app (voxnerf.py:126-130) on the reference-layout parameters `prefix + app_plane.i / app_line.i`."""
     raw = [params[prefix + f"app_plane.{i}"] for i in range(3)] + [params[prefix + f"app_line.{i}"] for i in range(3)]
