@@ -180,6 +180,12 @@ class RenderSubRaysFn(torch.autograd.Function):
         else:
             from .renderer import build_ray_batch
             rb, weight, k = build_ray_batch(H, W, focal, rays, near, far, ndc), None, {}
+        extra_rays = kw.pop("extra_rays", None)
+        if extra_rays is not None and extra_rays.shape[0] > 0:
+            # rays rendered WITHOUT the blur kernel in the same launch (the event start / end rays of run_nerf.py:534-557): their
+            # rows follow the warped sub-rays; no gradient flows to their ray batch
+            from .renderer import build_ray_batch
+            rb = torch.cat([rb, build_ray_batch(H, W, focal, extra_rays, near, far, ndc)], 0)
         R, dev = rb.shape[0], rb.device
         Nc, Ni = int(kw["N_samples"]), int(kw.get("N_importance", 0))
         # draw the density noise here so that backward sees the very same tensors (voxnerf.py:175)

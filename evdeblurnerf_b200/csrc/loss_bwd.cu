@@ -10,8 +10,16 @@ namespace edn {
 namespace {
 
 // ---- CRF ----------------------------------------------------------------------------------------------------------------
-// parameter-gradient accumulator layout in shared memory
-constexpr int kCrfW0 = 0, kCrfB0 = 128, kCrfW1 = 144, kCrfB1 = 400, kCrfW2 = 416, kCrfB2 = 672, kCrfW3 = 688, kCrfB3 = 704, kCrfAcc = 705;
+// One thread per sample runs the 1 -> 16 -> 16 -> 16 -> 1 residual MLP forward and backward for its three colour channels.  The
+// parameter gradients are outer products summed over samples: each warp stages its 32 samples' activations / deltas in shared
+// memory and the lanes split the 705 parameters (22 each), looping over the 32 samples -- no shared-memory atomics (fp32 ones
+// are CAS loops: the first version of this kernel spent 1.4 ms per launch in them) -- then one global atomicAdd per
+// parameter and warp.
+constexpr int kCrfWarps = 2;
+struct CrfStage {          // per warp, per sample (column = lane)
+  float in[8][32], h0[16][32], h1[16][32], h2[16][32];
+  float d0[16][32], d1[16][32], d2[16][32], dout[32];
+};
 
 struct CrfBwdArgs {
   edn_crf_params p;
@@ -25,28 +33,38 @@ struct CrfBwdArgs {
   float* d_x;           // [M][3]
 };
 
-__global__ void crf_bwd_kernel(const CrfBwdArgs a) {
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_bwd_kernel(const CrfBwdArgs a) {
   __shared__ float w0[16 * 8], b0[16], w1[256], b1[16], w2[256], b2[16], w3[16], b3[1];
-  __shared__ float acc[kCrfAcc];
+  __shared__ CrfStage stage[kCrfWarps];
   const int F = a.p.extra_features, in_ch = 1 + F;
   const bool learn = (a.flags & EDN_CRF_LEARN) && !(a.flags & EDN_CRF_SKIP_LEARN);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (learn) {
     for (int i = threadIdx.x; i < 16 * in_ch; i += blockDim.x) w0[i] = a.p.w0[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { w1[i] = a.p.w1[i]; w2[i] = a.p.w2[i]; }
     for (int i = threadIdx.x; i < 16; i += blockDim.x) { b0[i] = a.p.b0[i]; b1[i] = a.p.b1[i]; b2[i] = a.p.b2[i]; w3[i] = a.p.w3[i]; }
     if (threadIdx.x == 0) b3[0] = a.p.b3[0];
-    for (int i = threadIdx.x; i < kCrfAcc; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
   }
+  const bool want_pg = learn && a.g.w0;
+  CrfStage& st = stage[warp];
+  // parameter p of this lane's share: index space [w0 (16*in_ch) | b0 16 | w1 256 | b1 16 | w2 256 | b2 16 | w3 16 | b3 1]
+  const int n_w0 = 16 * in_ch, n_par = n_w0 + 16 + 256 + 16 + 256 + 16 + 16 + 1;
+  constexpr int kPerLane = 23;                         // ceil(705 / 32)
+  float pg[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) pg[i] = 0.f;
   const int64_t mIdx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (mIdx < a.M) {
-    const float luma[3] = {0.299f, 0.587f, 0.114f};
+  const bool valid = mIdx < a.M;
+  const float luma[3] = {0.299f, 0.587f, 0.114f};
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-      const float x0 = a.x[mIdx * 3 + c];
-      float dy = (a.flags & EDN_CRF_LUMA) ? a.d_out[mIdx] * luma[c] : a.d_out[mIdx * 3 + c];
+  for (int c = 0; c < 3; ++c) {
+    float dxg = 0.f, x0 = 0.f;
+    if (valid) {
+      x0 = a.x[mIdx * 3 + c];
+      const float dy = (a.flags & EDN_CRF_LUMA) ? a.d_out[mIdx] * luma[c] : a.d_out[mIdx * 3 + c];
       const float xg = (a.flags & EDN_CRF_GAMMA) ? powf(x0, 1.0f / a.p.gamma) : x0;
-      float dxg = dy;
+      dxg = dy;
       if (learn) {
         float in[8], h0[16], h1[16], h2[16];
         in[0] = xg;
@@ -75,52 +93,85 @@ __global__ void crf_bwd_kernel(const CrfBwdArgs a) {
         const float dz = dy * y * (1.f - y);
         const float d_o = 0.1f * dz;
         dxg = dz;
-        atomicAdd(&acc[kCrfB3], d_o);
-        float dh1[16], dh0[16];
+        float d2[16], d1[16], d0[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dh1[k] = 0.f;
-        for (int j = 0; j < 16; ++j) {
-          atomicAdd(&acc[kCrfW3 + j], d_o * h2[j]);
-          const float dh2 = h2[j] > 0.f ? d_o * w3[j] : 0.f;
-          if (dh2 != 0.f) {
-            atomicAdd(&acc[kCrfB2 + j], dh2);
+        for (int j = 0; j < 16; ++j) d2[j] = h2[j] > 0.f ? d_o * w3[j] : 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { atomicAdd(&acc[kCrfW2 + j * 16 + k], dh2 * h1[k]); dh1[k] = fmaf(dh2, w2[j * 16 + k], dh1[k]); }
-          }
+        for (int k = 0; k < 16; ++k) {
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t = fmaf(d2[j], w2[j * 16 + k], t);
+          d1[k] = h1[k] > 0.f ? t : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dh0[k] = 0.f;
-        for (int j = 0; j < 16; ++j) {
-          const float dj = h1[j] > 0.f ? dh1[j] : 0.f;
-          if (dj != 0.f) {
-            atomicAdd(&acc[kCrfB1 + j], dj);
+        for (int k = 0; k < 16; ++k) {
+          float t = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { atomicAdd(&acc[kCrfW1 + j * 16 + k], dj * h0[k]); dh0[k] = fmaf(dj, w1[j * 16 + k], dh0[k]); }
-          }
+          for (int j = 0; j < 16; ++j) t = fmaf(d1[j], w1[j * 16 + k], t);
+          d0[k] = h0[k] > 0.f ? t : 0.f;
         }
-        for (int j = 0; j < 16; ++j) {
-          const float dj = h0[j] > 0.f ? dh0[j] : 0.f;
-          if (dj != 0.f) {
-            atomicAdd(&acc[kCrfB0 + j], dj);
-            for (int k = 0; k < in_ch; ++k) atomicAdd(&acc[kCrfW0 + j * in_ch + k], dj * in[k]);
-            dxg = fmaf(dj, w0[j * in_ch], dxg);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dxg = fmaf(d0[j], w0[j * in_ch], dxg);
+        if (want_pg) {
+          for (int k = 0; k < 8; ++k) st.in[k][lane] = k < in_ch ? in[k] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            st.h0[j][lane] = h0[j]; st.h1[j][lane] = h1[j]; st.h2[j][lane] = h2[j];
+            st.d0[j][lane] = d0[j]; st.d1[j][lane] = d1[j]; st.d2[j][lane] = d2[j];
           }
+          st.dout[lane] = d_o;
         }
       }
       float dx = dxg;
       if (a.flags & EDN_CRF_GAMMA) { const float ig = 1.0f / a.p.gamma; dx = dxg * ig * powf(x0, ig - 1.0f); }
       if (a.d_x) a.d_x[mIdx * 3 + c] = dx;
+    } else if (want_pg) {
+      for (int k = 0; k < 8; ++k) st.in[k][lane] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { st.h0[j][lane] = 0.f; st.h1[j][lane] = 0.f; st.h2[j][lane] = 0.f; st.d0[j][lane] = 0.f; st.d1[j][lane] = 0.f; st.d2[j][lane] = 0.f; }
+      st.dout[lane] = 0.f;
+    }
+    if (want_pg) {
+      __syncwarp();
+#pragma unroll 1
+      for (int i = 0; i < kPerLane; ++i) {
+        const int pi = lane + 32 * i;
+        if (pi >= n_par) break;
+        const float* A;      // delta row
+        const float* B;      // activation row (nullptr: bias -> 1)
+        int q = pi;
+        if (q < n_w0) { A = st.d0[q / in_ch]; B = st.in[q % in_ch]; }
+        else if ((q -= n_w0) < 16) { A = st.d0[q]; B = nullptr; }
+        else if ((q -= 16) < 256) { A = st.d1[q >> 4]; B = st.h0[q & 15]; }
+        else if ((q -= 256) < 16) { A = st.d1[q]; B = nullptr; }
+        else if ((q -= 16) < 256) { A = st.d2[q >> 4]; B = st.h1[q & 15]; }
+        else if ((q -= 256) < 16) { A = st.d2[q]; B = nullptr; }
+        else if ((q -= 16) < 16) { A = st.dout; B = st.h2[q]; }
+        else { A = st.dout; B = nullptr; }
+        float t = 0.f;
+#pragma unroll 8
+        for (int s2 = 0; s2 < 32; ++s2) t = fmaf(A[s2], B ? B[s2] : 1.0f, t);
+        pg[i] += t;
+      }
+      __syncwarp();
     }
   }
-  if (learn && a.g.w0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 16 * in_ch; i += blockDim.x) atomicAdd(a.g.w0 + i, acc[kCrfW0 + i]);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { atomicAdd(a.g.w1 + i, acc[kCrfW1 + i]); atomicAdd(a.g.w2 + i, acc[kCrfW2 + i]); }
-    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-      atomicAdd(a.g.b0 + i, acc[kCrfB0 + i]); atomicAdd(a.g.b1 + i, acc[kCrfB1 + i]); atomicAdd(a.g.b2 + i, acc[kCrfB2 + i]);
-      atomicAdd(a.g.w3 + i, acc[kCrfW3 + i]);
+  if (want_pg) {
+#pragma unroll 1
+    for (int i = 0; i < kPerLane; ++i) {
+      int q = lane + 32 * i;
+      if (q >= n_par) break;
+      float* dst;
+      if (q < n_w0) dst = a.g.w0 + q;
+      else if ((q -= n_w0) < 16) dst = a.g.b0 + q;
+      else if ((q -= 16) < 256) dst = a.g.w1 + q;
+      else if ((q -= 256) < 16) dst = a.g.b1 + q;
+      else if ((q -= 16) < 256) dst = a.g.w2 + q;
+      else if ((q -= 256) < 16) dst = a.g.b2 + q;
+      else if ((q -= 16) < 16) dst = a.g.w3 + q;
+      else dst = a.g.b3;
+      atomicAdd(dst, pg[i]);
     }
-    if (threadIdx.x == 0) atomicAdd(a.g.b3, acc[kCrfB3]);
   }
 }
 
@@ -210,7 +261,7 @@ extern "C" int edn_crf_bwd(const edn_crf_params* p, const float* x, const float*
   }
   if (m == 0) return EDN_OK;
   CrfBwdArgs a{*p, g, x, feat, feat_per_channel, flags, m, d_out, d_x};
-  crf_bwd_kernel<<<(unsigned)((m + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  crf_bwd_kernel<<<(unsigned)((m + kCrfWarps * 32 - 1) / (kCrfWarps * 32)), kCrfWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

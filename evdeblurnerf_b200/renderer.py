@@ -335,17 +335,44 @@ class NeRFAll:
 
     __call__ = forward
 
+    def forward_fused(self, H, W, K, rays, rays_info, naive_rays, **kwargs):
+        """Training-branch forward of the blurred rays (renderer.py:277-378) TOGETHER with the force_naive renders of the
+        ray sets in `naive_rays` (the event start / end rays, run_nerf.py:534-557): one fused render launch and one backward
+        instead of three -> (rgb, rgb0, other_loss, other_tensors, [(rgb_i, rgb0_i), ...]).  Autograd mode only."""
+        self._maybe_repack()
+        return_pts0_rgb = kwargs.pop("return_pts0_rgb", False)
+        want_tv = kwargs.pop("want_tv", True)
+        ndc, near, far = kwargs.pop("ndc", True), kwargs.pop("near", 0.), kwargs.pop("far", 1.)
+        kwargs.pop("use_viewdirs", None)
+        kwargs.pop("force_naive", None)
+        return self._forward_with_grad(H, W, K, rays, rays_info, False, return_pts0_rgb, kwargs.get("N_importance", 0), ndc, near, far,
+                                       kwargs, want_tv, naive_rays=list(naive_rays))
+
     def _forward_with_grad(self, H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far, kwargs,
-                           want_tv=True):
+                           want_tv=True, naive_rays=None):
         """Training branch of forward() (renderer.py:277-378) with outputs attached to the autograd graph."""
         other_loss, other_tensors = {}, {}
         blur = self.kernelsnet is not None and not force_baseline
+        if naive_rays:
+            kwargs = dict(kwargs, extra_rays=torch.cat([r.reshape(-1, 3, 2) for r in naive_rays], 0))
         rgb, depth, acc, rgb0, depth0, acc0, weight1, feat, rb, img_embed = self._render_sub_rays(
             H, W, K, rays, rays_info["images_idx"] if blur else None, near, far, ndc, kwargs, blur=blur)
+        naive_out = []
+        if naive_rays:     # rows of the extra rays follow the main sub-rays
+            n_main = rb.shape[0] - sum(r.reshape(-1, 3, 2).shape[0] for r in naive_rays)
+            lo = n_main
+            for r in naive_rays:
+                hi = lo + r.reshape(-1, 3, 2).shape[0]
+                naive_out.append((rgb[lo:hi], rgb0[lo:hi] if N_importance > 0 else None))
+                lo = hi
+            rgb, depth, acc, rgb0, depth0, acc0 = (t[:n_main] for t in (rgb, depth, acc, rgb0, depth0, acc0))
+            rb = rb[:n_main]
+            if feat.numel():
+                feat = feat[:n_main]
         if blur:
             N, E = weight1.shape
             if self.use_awp:     # renderer.py:310-330
-                ccw = self.awpnet(feat, self.last_render["z_vals"], rb[:, 3:6], img_embed)
+                ccw = self.awpnet(feat, self.last_render["z_vals"][:rb.shape[0]], rb[:, 3:6], img_embed)
                 ccw = normalize_ccw(ccw, self.awpnet.ccw_fine_scale)
                 other_tensors["rgb_awp"] = weighted_sum(rgb, ccw)
                 other_tensors["ccw_fine"] = ccw
@@ -363,6 +390,8 @@ class NeRFAll:
                 other_tensors["stage1_rgb1_pts0"] = rgb0
         if want_tv:
             other_loss["TV"] = self.tv_loss(N_importance > 0)
+        if naive_rays:
+            return rgb_b, rgb1, other_loss, other_tensors, naive_out
         return rgb_b, rgb1, other_loss, other_tensors
 
     def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):

@@ -90,6 +90,7 @@ class Trainer:
         Pc = {k[4:]: self.flat.views[k] for k in crf_train}
         self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision, use_awp=use_awp).train()
         self.awp_fine_loss_weight = awp_fine_loss_weight
+        self.fuse_event_renders = True      # one render + one backward for the blurred rays and both event ray sets
         self.crf = TonemappingTransform(Pc, **(crf_kwargs or dict(map_type_rgb="gamma", map_type_event="learn" if Pc else "gamma",
                                                                   extra_features_event=2)))
         self.hp = dict(lrate=lrate, decay=lrate_decay, warm_it=lrate_warmup_iters, warm_f=lrate_warmup_factor,
@@ -104,8 +105,16 @@ class Trainer:
     # run_nerf.py:438-504 (+ 539-557 when event rays are given)
     def loss(self, batch, H, W, K):
         out = {}
-        rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
-                                                        **self.render_kwargs)
+        events = self.hp["ev_w"] > 0 and "ev_rays_start" in batch
+        naive = None
+        if events and self.fuse_event_renders:
+            # the reference calls nerf() three times (blurred rays, event start rays, event end rays; run_nerf.py:438, 534, 547);
+            # the rays are independent, so one fused render + one backward gives the same result with a third of the launches
+            rgb, rgb0, extra_loss, extra_tensor, naive = self.nerf.forward_fused(
+                H, W, K, batch["rays"], batch, [batch["ev_rays_start"], batch["ev_rays_end"]], retraw=True, **self.render_kwargs)
+        else:
+            rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
+                                                            **self.render_kwargs)
         target = batch["rgbsf"].reshape(-1, 3)
         img_loss = img2mse(self.crf(rgb, mode="encode_rgb"), target)
         out["img_loss"] = img_loss.detach()
@@ -119,12 +128,15 @@ class Trainer:
             loss = loss + fine if flw is None else loss * (1 - flw) + fine * flw
         if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
             loss = loss + extra_loss["TV"] * self.hp["tv_w"]
-        if self.hp["ev_w"] > 0 and "ev_rays_start" in batch:
+        if events:
             feat = batch.get("ev_extra_feat")
             lum = []
-            for key in ("ev_rays_start", "ev_rays_end"):
-                c, c0, _, _ = self.nerf(H, W, K, rays=batch[key], rays_info=None, retraw=True, force_naive=True, want_tv=False,
-                                        **self.render_kwargs)   # TV of these calls is never used (run_nerf.py:500-501)
+            for i, key in enumerate(("ev_rays_start", "ev_rays_end")):
+                if naive is not None:
+                    c, c0 = naive[i]
+                else:
+                    c, c0, _, _ = self.nerf(H, W, K, rays=batch[key], rays_info=None, retraw=True, force_naive=True, want_tv=False,
+                                            **self.render_kwargs)   # TV of these calls is never used (run_nerf.py:500-501)
                 lum.append((self.crf(c, mode="encode_luma", ev_extra_feat=feat), self.crf(c0, mode="encode_luma", ev_extra_feat=feat)))
             ev = egm_loss(lum[0][0], lum[1][0], batch["bii"]) + egm_loss(lum[0][1], lum[1][1], batch["bii"])   # stage1 + stage0
             out["event_loss"] = ev.detach()

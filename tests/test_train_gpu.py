@@ -415,3 +415,30 @@ def test_awp_sync_batchnorm_two_shards_equal_full_batch():
     # without the exchange the shards normalise over their own rays: different numbers (the caveat is real)
     alone = torch.cat([fwd(lo, hi, awp.options(True, 0))[1] for lo, hi in shards])
     assert float((alone - ccw_full).abs().max()) > 1e-4
+
+
+def test_fused_event_render_equals_three_calls():
+    """Trainer.fuse_event_renders: one render + one backward for the blurred rays and both event-ray sets must give the same loss
+    and the same updated parameters as the reference's three nerf() calls (independent rays; deterministic settings)."""
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if v.is_floating_point()}
+    batch = _tiny_batch(20, 41)
+    M = 12
+    gen = torch.Generator().manual_seed(42)
+    ev0, _ = synthetic_rays(M, seed=43)
+    ev1, _ = synthetic_rays(M, seed=44)
+    batch.update(ev_rays_start=ev0.cuda(), ev_rays_end=ev1.cuda(), bii=torch.full((M,), 0.3).cuda(), ev_extra_feat=torch.rand(M, 2, generator=gen).cuda())
+    states, losses = [], []
+    for fuse in (True, False):
+        tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", lrate=1e-3, tv_loss_weight=0.02, event_loss_weight=0.7, use_awp=True,
+                     render_kwargs=dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.))
+        tr.fuse_event_renders = fuse
+        out = tr.step(batch, H, W, KMAT)
+        losses.append(float(out["loss"]))
+        states.append(tr.state_dict())
+    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[1])
+    for k in states[0]:
+        # Adam's first step moves every coordinate by ~lr * sign(g): compare the updates, tolerant to sign flips of ~0 gradients
+        frac = float(((states[0][k] - states[1][k]).abs() > 2e-4).float().mean())
+        assert frac < 0.01, (k, frac)
