@@ -88,13 +88,37 @@ __global__ void __launch_bounds__(kPdfWarpsPerBlock * 32) sample_pdf_merge_kerne
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) a.z_std[ray] = sqrtf(v / (float)ni);
   }
-  // stable rank sort of cat[z_coarse, z_samples]
+  // stable rank sort of cat[z_coarse, z_samples] (ties: lower index first, i.e. coarse before fine).  The coarse depths are
+  // non-decreasing (stratified placement), so a coarse key's rank among the coarse keys is its index and a sample's count
+  // of coarse keys <= it is a binary search: half the comparisons of the plain rank sort.  Unsorted coarse input (generic
+  // callers) falls back to the plain O(n^2) rank sort.
+  bool sorted = true;
+  for (int i = lane; i < nc - 1; i += 32) sorted = sorted && (keys[i] <= keys[i + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
+  const float* smp = keys + nc;
   for (int i = lane; i < nt; i += 32) {
     const float k = keys[i];
     int rank = 0;
-    for (int j = 0; j < nt; ++j) {
-      const float kj = keys[j];
-      rank += (kj < k) || (kj == k && j < i);
+    if (!sorted) {
+      for (int j = 0; j < nt; ++j) {
+        const float kj = keys[j];
+        rank += (kj < k) || (kj == k && j < i);
+      }
+    } else if (i < nc) {
+      rank = i;
+      for (int j = 0; j < ni; ++j) rank += smp[j] < k;
+    } else {
+      int lo = 0, hi = nc;                       // number of coarse keys <= k
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] <= k) lo = mid + 1; else hi = mid;
+      }
+      rank = lo;
+      const int js = i - nc;
+      for (int j = 0; j < ni; ++j) {
+        const float kj = smp[j];
+        rank += (kj < k) || (kj == k && j < js);
+      }
     }
     a.z_vals[ray * nt + rank] = k;
     if (a.order) a.order[ray * nt + rank] = i;
