@@ -43,6 +43,8 @@ struct alignas(16) GroupMisc {
   float rgb[kRows * 3];
   alignas(16) float bias[kMaxRpt][64];
   alignas(16) float headp[2][kRows][4];   // per column-half partial rgb (xyz) / sigma (w) heads
+  float red[4][8];        // per-warp partial ray sums (parallel compositing)
+  float wtot[4];          // per-warp products of (1 - alpha)
 };
 struct Misc {
   uint64_t bar_a[2], bar_acc[2], bar_w;
@@ -349,18 +351,59 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
           for (int i = 0; i < 3; ++i)
             gm->rgb[3 * r + i] = sigmoidf_(gm->headp[0][r][i] + gm->headp[1][r][i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
         }
-        named_bar_sync(bar_half, kRows);
-        if (r < rpt) {
-          const int64_t r2 = tile * rpt + r;
-          if (r2 < a.n_rays) {
-            float out[5];
-            composite_from_alpha(gm->sig + r * S, gm->rgb + 3 * r * S, gm->z + r * S, S, (a.flags & EDN_FLAG_RELU_RGB) != 0, gm->w + r * S, out);
-            a.rgb[r2 * 3 + 0] = out[0]; a.rgb[r2 * 3 + 1] = out[1]; a.rgb[r2 * 3 + 2] = out[2];
-            a.depth[r2] = out[3];
-            a.acc[r2] = out[4];
+        if ((S & 31) == 0) {
+          // rays are whole warps: transmittance by a warp-shuffle product scan + the per-warp totals of the ray's earlier warps
+          const float alpha = (r < rpt * S) ? gm->sig[r] : 0.f;
+          float t = 1.0f - alpha;
+#pragma unroll
+          for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const float y = __shfl_up_sync(0xffffffffu, t, dlt);
+            if (lane >= dlt) t *= y;
           }
+          float Tr = __shfl_up_sync(0xffffffffu, t, 1);
+          if (lane == 0) Tr = 1.0f;
+          if (lane == 31) gm->wtot[gwarp] = t;
+          named_bar_sync(bar_half, kRows);
+          const int wpr = S >> 5, first = (gwarp / wpr) * wpr;       // warps per ray, first warp of this row's ray
+          for (int w2 = first; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
+          const float wgt = alpha * Tr;
+          gm->w[r] = wgt;
+          float cr = gm->rgb[3 * r], cg = gm->rgb[3 * r + 1], cb = gm->rgb[3 * r + 2];
+          if (a.flags & EDN_FLAG_RELU_RGB) { cr = fmaxf(cr, 0.f); cg = fmaxf(cg, 0.f); cb = fmaxf(cb, 0.f); }
+          float red[5] = {wgt * cr, wgt * cg, wgt * cb, wgt * zv, wgt};
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], off);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
+          }
+          named_bar_sync(bar_half, kRows);
+          if (r < rpt * 5) {
+            const int rr = r / 5, i = r % 5;
+            const int64_t r2 = tile * rpt + rr;
+            if (r2 < a.n_rays) {
+              float sum = 0.f;
+              for (int w2 = rr * wpr; w2 < (rr + 1) * wpr; ++w2) sum += gm->red[w2][i];
+              if (i < 3) a.rgb[r2 * 3 + i] = sum; else if (i == 3) a.depth[r2] = sum; else a.acc[r2] = sum;
+            }
+          }
+        } else {
+          named_bar_sync(bar_half, kRows);
+          if (r < rpt) {
+            const int64_t r2 = tile * rpt + r;
+            if (r2 < a.n_rays) {
+              float out[5];
+              composite_from_alpha(gm->sig + r * S, gm->rgb + 3 * r * S, gm->z + r * S, S, (a.flags & EDN_FLAG_RELU_RGB) != 0, gm->w + r * S, out);
+              a.rgb[r2 * 3 + 0] = out[0]; a.rgb[r2 * 3 + 1] = out[1]; a.rgb[r2 * 3 + 2] = out[2];
+              a.depth[r2] = out[3];
+              a.acc[r2] = out[4];
+            }
+          }
+          named_bar_sync(bar_half, kRows);
         }
-        named_bar_sync(bar_half, kRows);
         if (live) {
           a.z_vals[ray * S + s] = zv;
           a.weights[ray * S + s] = gm->w[r];
