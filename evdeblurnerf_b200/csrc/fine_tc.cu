@@ -47,7 +47,11 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kRingFull = 20, kRingLean = 24;            // 16 KB ring stages per ray
 constexpr int kStepsFull = 2 + kRingFull, kStepsLean = kRingLean;
 constexpr int64_t kOffFull = kBasisBytes, kOffLean = kOffFull + (int64_t)kRingFull * kStageBytes;
-constexpr int64_t kBlobBytes = kOffLean + (int64_t)kRingLean * kStageBytes;
+// pair schedule (cta_group::2, lean layers only): each CTA of a pair streams its N half of every layer: [layer][rank][64 KB],
+// 4 stages of 4 K-steps (N/2 = 128 columns x 16 x 2 B = 4 KB each) per layer
+constexpr int kRingPair = 12;
+constexpr int64_t kOffPair = kOffLean + (int64_t)kRingLean * kStageBytes;
+constexpr int64_t kBlobBytes = kOffPair + 3 * 131072;
 
 struct StepDesc {
   uint8_t kind;      // 0 = basis coarse tile, 1 = basis fine tile, 2 = ring stage
@@ -94,6 +98,7 @@ struct alignas(16) GroupMisc {
 };
 struct Misc {
   uint64_t bar_a[2], bar_acc[2], full[2][kNst], empty[2][kNst], bar_basis;
+  uint64_t peer_full[2][kNst];    // pair mode, rank 0: the peer CTA's ring stage has landed
   GridDev grids[2];          // [0] coarse, [1] fine
   uint32_t tmem_base, skew_flag, pad[2];
   alignas(16) float wsig[256];           // sigma_net.1 row 0 (sigma head)
@@ -227,10 +232,20 @@ __device__ __forceinline__ void rows_signal_a(uint64_t* bar_a) {
   tc_fence_before();          // order our tcgen05.ld's before the MMAs that will overwrite those TMEM columns
   mbar_arrive(bar_a);
 }
+// pair mode: every row thread of BOTH CTAs arrives on the rank-0 CTA's barrier (its MMA issuer drives the pair)
+__device__ __forceinline__ void rows_signal_a_pair(uint32_t bar_a_rank0) {
+  asm volatile("fence.proxy.async;" ::: "memory");      // the peer CTA's tensor core reads this operand too: full async-proxy fence
+  tc_fence_before();
+  mbar_arrive_cluster(bar_a_rank0);
+}
 
-template <typename T, bool LEAN>
+// PAIR: two CTAs of a cluster (one TPC) drive cta_group::2 MMAs: M = 256 = both CTAs' 128-row tiles of ray group q, every CTA
+// streams only its N half of the weights (half the L2 -> smem weight traffic and twice the K extent per ring stage, which
+// is what the single-CTA kernel is latency-bound on).  Lean schedule only.
+template <typename T, bool LEAN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs a, const uint8_t* __restrict__ blob) {
-  constexpr int kRingStagesPerRay = LEAN ? kRingLean : kRingFull;
+  static_assert(!PAIR || LEAN, "the pair variant implements the lean schedule only");
+  constexpr int kRingStagesPerRay = PAIR ? kRingPair : (LEAN ? kRingLean : kRingFull);
   constexpr int kStepsPerRay = LEAN ? kStepsLean : kStepsFull;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB]
@@ -238,16 +253,17 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   uint8_t* Bs = Ws + 2 * kNst * kStageBytes;            // resident basis_mat operands
   Misc* m = reinterpret_cast<Misc*>(Bs + kBasisBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
 
   if (tid == 0) {
-    for (int q = 0; q < 2; ++q) { mbar_init(&m->bar_a[q], kGroupThreads); mbar_init(&m->bar_acc[q], 1); }
+    for (int q = 0; q < 2; ++q) { mbar_init(&m->bar_a[q], PAIR ? 2 * kGroupThreads : kGroupThreads); mbar_init(&m->bar_acc[q], 1); }
     for (int q = 0; q < 2; ++q)
-      for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[q][s], 1); mbar_init(&m->empty[q][s], 1); }
+      for (int s = 0; s < kNst; ++s) { mbar_init(&m->full[q][s], 1); mbar_init(&m->empty[q][s], 1); mbar_init(&m->peer_full[q][s], 1); }
     mbar_init(&m->bar_basis, 1);
     fence_barrier_init();
     m->skew_flag = 0;
   }
-  if (warp == kRowWarps) tmem_alloc(&m->tmem_base, kTmemCols);
+  if (warp == kRowWarps) { if (PAIR) tmem_alloc2(&m->tmem_base, kTmemCols); else tmem_alloc(&m->tmem_base, kTmemCols); }
   for (int i = tid; i < 256; i += kThreads) {
     m->wsig[i] = __ldg(a.mlp.sigma1_v + i);
     m->bias1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
@@ -257,10 +273,13 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = m->tmem_base;
   const int64_t n_pairs_total = (a.n_rays + 1) / 2;
-  const int64_t n_my = (n_pairs_total > (int64_t)blockIdx.x) ? (n_pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // pair mode: both CTAs of a cluster run the same number of iterations (the rank-1 CTA may replay a masked duplicate ray)
+  const int64_t first_cta = PAIR ? (int64_t)(blockIdx.x & ~1u) : (int64_t)blockIdx.x;
+  const int64_t n_my = (n_pairs_total > first_cta) ? (n_pairs_total - first_cta + gridDim.x - 1) / gridDim.x : 0;
   const int S = a.S;
   const int tpr = (S + kRows - 1) / kRows;                   // 128-row tiles per ray (rays longer than 128 samples span several)
   const int64_t n_it = n_my * tpr;
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     // =================================== weight-stream producer warp of ray group q ==================================
     const int q = warp - (kRowWarps + 2);
     if (lane == 0 && n_my > 0) {
-      const uint8_t* stream = blob + (LEAN ? kOffLean : kOffFull);
+      const uint8_t* stream = blob + (PAIR ? kOffPair : (LEAN ? kOffLean : kOffFull));
       if (q == 0 && !LEAN) { mbar_expect_tx(&m->bar_basis, kBasisBytes); bulk_g2s(Bs, blob, kBasisBytes, &m->bar_basis); }
       uint8_t* ring = Ws + q * kNst * kStageBytes;
       const uint32_t total_ring = (uint32_t)n_it * kRingStagesPerRay;
@@ -278,14 +297,49 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         const uint32_t use = g / kNst;
         if (use > 0) mbar_wait(&m->empty[q][s], (use - 1) & 1);   // the MMAs on the previous tenant completed
         mbar_expect_tx(&m->full[q][s], kStageBytes);
-        bulk_g2s(ring + s * kStageBytes, stream + (size_t)(g % kRingStagesPerRay) * kStageBytes, kStageBytes, &m->full[q][s]);
+        const uint32_t gs = g % kRingStagesPerRay;
+        const size_t src = PAIR ? (size_t)(gs >> 2) * 131072 + (size_t)rank * 65536 + (size_t)(gs & 3) * kStageBytes : (size_t)gs * kStageBytes;
+        bulk_g2s(ring + s * kStageBytes, stream + src, kStageBytes, &m->full[q][s]);
       }
     }
     __syncwarp();
   } else if (warp >= kRowWarps) {
     // =================================== MMA issuer warp of ray group q (one thread) ===================================
     const int q = warp - kRowWarps;
-    if (lane == 0 && n_my > 0) {
+    if (PAIR && lane == 0 && n_my > 0) {
+      const uint32_t total_ring = (uint32_t)n_it * kRingPair;
+      if (rank == 1) {
+        // ---- peer CTA: forward "my ring stage has landed" to the pair's MMA issuer (rank 0) ------------------------------
+        for (uint32_t g = 0; g < total_ring; ++g) {
+          const int s = g % kNst;
+          mbar_wait(&m->full[q][s], (g / kNst) & 1);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&m->peer_full[q][s]), 0));
+        }
+      } else {
+        // ---- rank 0: issue the pair's MMAs: M = 256 (128 rows per CTA), N = 256 (128 columns of B per CTA), K = 16 ----------
+        const uint32_t aq = smem_u32(As) + q * kABytes, w_base = smem_u32(Ws) + q * kNst * kStageBytes;
+        const uint32_t d_tmem = tmem + q * 256;
+        const uint32_t idesc = make_idesc_bf16(256, 256);
+        uint32_t pa = 0;
+        for (uint32_t g = 0; g < total_ring; ++g) {
+          const int s = g % kNst;
+          const uint32_t st4 = g & 3;                            // stage within the layer (4 stages of 4 K-steps)
+          mbar_wait(&m->full[q][s], (g / kNst) & 1);
+          mbar_wait_cluster(&m->peer_full[q][s], (g / kNst) & 1);
+          if (st4 == 0) { mbar_wait_cluster(&m->bar_a[q], pa); pa ^= 1; }
+          tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t kst = st4 * 4 + i;
+            const uint64_t adesc = make_smem_desc(aq + kst * 2 * kChunkA, kChunkA, 128);
+            const uint64_t bdesc = make_smem_desc(w_base + s * kStageBytes + i * 4096, 128 * 16, 128);
+            mma_bf16_ss2(d_tmem, adesc, bdesc, idesc, kst > 0);
+          }
+          mma_commit2(&m->empty[q][s]);
+          if (st4 == 3) mma_commit2(&m->bar_acc[q]);
+        }
+      }
+    } else if (!PAIR && lane == 0 && n_my > 0) {
       const uint32_t aq = smem_u32(As) + q * kABytes, w_base = smem_u32(Ws) + q * kNst * kStageBytes, b_base = smem_u32(Bs);
       const uint32_t d_tmem = tmem + q * 256;
       const int fine_tile_chunks[6] = {28, 30, 0, 2, 4, 6};
@@ -352,6 +406,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     float run_sum = 0.f;                    // half 0, thread r < 5: running ray sum (rgb, depth, acc) across the tiles of a ray
     int tile = -1;
     int64_t ray_raw = 2 * (int64_t)blockIdx.x + q - 2 * (int64_t)gridDim.x;
+    const uint32_t bar_a_rank0 = PAIR ? mapa_u32(smem_u32(&m->bar_a[q]), 0) : 0u;
+    auto signal_a = [&]() { if (PAIR) rows_signal_a_pair(bar_a_rank0); else rows_signal_a(&m->bar_a[q]); };
     for (int64_t it = 0; it < n_it; ++it) {
       stamp(it, 0);
       if (++tile == tpr || it == 0) { tile = 0; ray_raw += 2 * (int64_t)gridDim.x; }
@@ -417,14 +473,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       stamp(it, 1);
       // ---- VM gather: half 0 gathers the coarse grid, half 1 the fine grid -> two 128 x 96 bf16 tiles ------------------
       gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
-      rows_signal_a(&m->bar_a[q]);
+      signal_a();
       stamp(it, 2);
       if (!LEAN) {
         // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ----------------------------------------------
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 3);
         layer_epilogue(taddr_row, a_row, 32 * half, 32, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
-        rows_signal_a(&m->bar_a[q]);
+        signal_a();
         stamp(it, 4);
       }
       // ---- sigma_net.0 -> ReLU (+ sigma head: fp32 dot with sigma_net.1 row 0; partial per column half) -----------------
@@ -434,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         const float4 hd = layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb);
         gm->headp[half][r][3] = hd.x;
       }
-      rows_signal_a(&m->bar_a[q]);
+      signal_a();
       stamp(it, 6);
       if (!LEAN) {
         // ---- sigma_net.1 -> geo (128, linear) ----------------------------------------------------------------------------
@@ -442,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         stamp(it, 7);
         layer_epilogue(taddr_row, a_row, 64 * half, 64, kEpiPlain, 0u,
                        (a.feat && live && rg < S) ? a.feat + ((size_t)ray * S + rg) * 128 : nullptr, s_wsig, s_wrgb);
-        rows_signal_a(&m->bar_a[q]);
+        signal_a();
       }
       if (q == 0 && it == 0 && r == 0 && half == 0) *reinterpret_cast<volatile uint32_t*>(&m->skew_flag) = 1;
       stamp(it, 8);
@@ -450,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 9);
       layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
-      rows_signal_a(&m->bar_a[q]);
+      signal_a();
       stamp(it, 10);
       // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2; partial per column half) --------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
@@ -523,7 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kRowWarps) tmem_dealloc(tmem, kTmemCols);
+  if (PAIR) cluster_sync_all();     // the peer may still read this CTA's operands / signal its barriers
+  if (warp == kRowWarps) { if (PAIR) tmem_dealloc2(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols); }
 }
 
 int ensure_schedule() {
@@ -551,9 +608,28 @@ __global__ void fold_matmul_kernel(const float* __restrict__ A, int lda, const f
 
 template <typename T, bool LEAN>
 int launch_variant(const FineArgs& a, const uint8_t* blob, unsigned gx, cudaStream_t st) {
-  EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<T, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  fine_fwd_tc_kernel<T, LEAN><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
+  EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc_kernel<T, LEAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  fine_fwd_tc_kernel<T, LEAN, false><<<gx, kThreads, kSmemBytes, st>>>(a, blob);
   EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
+
+// cta_group::2 variant: clusters of 2 CTAs (one TPC), an even grid
+template <typename T>
+int launch_pair(const FineArgs& a, const uint8_t* blob, unsigned gx, cudaStream_t st) {
+  auto kern = fine_fwd_tc_kernel<T, true, true>;
+  EDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx & ~1u);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EDN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, blob));
   return EDN_OK;
 }
 
@@ -576,7 +652,9 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
     EDN_CUDA_OK(cudaMallocManaged(&buf, 8 * 16 * sizeof(long long)));
     memset(buf, 0, 8 * 16 * sizeof(long long));
     b.trace = buf;
-    rc = lean ? launch_variant<__nv_bfloat16, true>(b, blob, gx, st) : launch_variant<__nv_bfloat16, false>(b, blob, gx, st);
+    const char* pv2 = getenv("EDN_TC_PAIR");
+    if (lean && pv2 && pv2[0] == '1') rc = launch_pair<__nv_bfloat16>(b, blob, (unsigned)num_sms(), st);
+    else rc = lean ? launch_variant<__nv_bfloat16, true>(b, blob, gx, st) : launch_variant<__nv_bfloat16, false>(b, blob, gx, st);
     if (rc) return rc;
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     static const char* names[14] = {"start", "pe+bias", "gather", "w.basis", "e.ft", "w.L1", "e.L1", "w.L2", "e.L2", "w.L3", "e.L3", "w.L4", "e.L4", "composite"};
@@ -592,6 +670,13 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
     }
     cudaFree(buf);
     return EDN_OK;
+  }
+  const char* pv = getenv("EDN_TC_PAIR");                       // dev switch: CTA-pair (cta_group::2) variant of the lean schedule
+  if (lean && pv && pv[0] == '1' && gx >= 2 && num_sms() % 2 == 0) {
+    const unsigned gp = (unsigned)(n_pairs < (int64_t)num_sms() ? ((n_pairs + 1) & ~1ll) : (int64_t)num_sms());
+    static bool said = false;
+    if (!said) { fprintf(stderr, "[edn] fine pass: CTA-pair (cta_group::2) variant, grid %u\n", gp); said = true; }
+    return grid_dtype == EDN_BF16 ? launch_pair<__nv_bfloat16>(a, blob, gp, st) : launch_pair<float>(a, blob, gp, st);
   }
   if (grid_dtype == EDN_BF16)
     return lean ? launch_variant<__nv_bfloat16, true>(a, blob, gx, st) : launch_variant<__nv_bfloat16, false>(a, blob, gx, st);
@@ -633,6 +718,14 @@ extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_c
                                                                reinterpret_cast<__nv_bfloat16*>(b + off));
     off += (size_t)total * 2;
   }
+  // pair section: [layer][rank][K = 256 x N/2 = 128] halves of the three lean layers
+  const float* lean_src[3] = {f1, f23, mlp->color1_t};
+  for (int L = 0; L < 3; ++L)
+    for (int c = 0; c < 2; ++c) {
+      tc::pack_layer_kernel<<<(256 * 128 + 255) / 256, 256, 0, st>>>(lean_src[L] + 128 * c, 256, 256, 128, 256, 128, 0,
+                                                                     reinterpret_cast<__nv_bfloat16*>(b + off));
+      off += 256 * 128 * 2;
+    }
   EDN_REQUIRE((int64_t)off == kBlobBytes, "edn_pack_fine_tc: blob size mismatch");
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
