@@ -192,6 +192,52 @@ def cpu_reference_step(P_cpu, rays_cpu, idx_cpu, threads):
     return dt, out
 
 
+def gpu_eager_port(P_dev, dev, n_rays, steps=3):
+    """Baseline leg, second figure: the same oracle port run as EAGER PyTorch fp32 on the B200 itself -- the stand-in for
+    the reference's own single-GPU path (the reference is Python under /root/reference and cannot travel to the
+    GPU box).  Like the reference (run_nerf.py:779) it runs with CUDA as the default device.  Forward (no_grad) of the bench
+    workload, then forward + autograd backward of the image loss; CUDA-event timed, best of `steps` after one warm-up."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import evdeblur_oracle as oc
+    cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
+    rays, idx = make_rays(n_rays, seed=100)
+    rays, idx = rays.to(dev), idx.to(dev)
+    out = {"kind": "port", "what": "oracle restatement of the reference path as eager PyTorch fp32 on this GPU, whole batch in one chunk",
+           "rays": n_rays, "unit": "rays/s"}
+
+    def timed(fn):
+        best = None
+        for i in range(steps + 1):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                best = s.elapsed_time(e) if best is None else min(best, s.elapsed_time(e))
+        return best
+
+    with torch.device(dev):
+        def fwd():
+            with torch.no_grad():
+                oc.forward_train(P_dev, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+        ms = timed(fwd)
+        out.update(fwd_ms=ms, value=n_rays / (ms / 1e3))
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P_dev.items()}
+        target = torch.rand(n_rays, 3, device=dev)
+
+        def fwd_bwd():
+            o = oc.forward_train(leaves, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+            loss = oc.img2mse(o["rgb"], target) + oc.img2mse(o["rgb1"], target)
+            loss.backward()
+            for v in leaves.values():
+                v.grad = None
+        ms = timed(fwd_bwd)
+        out.update(fwd_bwd_ms=ms, fwd_bwd_value=n_rays / (ms / 1e3))
+    del leaves
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on the host cores, bounded sample per step."""
     import torch
@@ -237,6 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -380,6 +427,11 @@ def main():
         line["cpu_baseline"] = {"value": sample / best, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"{sample} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, same VM grids; "
                                           f"best of {i} after 1 warm-up"}
+    if not args.no_cpu_baseline and not args.no_gpu_eager_baseline and world == 1:
+        try:
+            line["gpu_eager_port"] = gpu_eager_port(P, dev, N_RAYS)
+        except Exception as exc:     # a reported extra, never the measured arm: an OOM here must not lose the bench line
+            line["gpu_eager_port"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

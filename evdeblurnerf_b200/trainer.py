@@ -16,6 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import check, stream_ptr
+from .schedules import annealing_interpolator, checkpoint_dict, exponential_scale_fine_loss_weight, load_checkpoint_dict, optimizer_groups
 from .losses import TonemappingTransform, egm_loss, img2mse
 from .renderer import NeRFAll
 
@@ -59,6 +60,10 @@ class FlatParams:
             v.grad = self.grad[self.offset[n]: self.offset[n] + t.numel()].view(t.shape)
             self.views[n] = v
 
+    def named(self, flat):
+        """name -> view of `flat` (a buffer laid out like `param`, e.g. exp_avg) with the parameter's shape."""
+        return {n: flat[self.offset[n]: self.offset[n] + v.numel()].view(v.shape) for n, v in self.views.items()}
+
     def all_reduce_mean(self, group=None):
         """The one gradient exchange of a step: sum over ranks of the flat gradient buffer, divided by the world size."""
         if torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
@@ -78,7 +83,7 @@ class Trainer:
     def __init__(self, state, crf_state, aabb_min, aabb_max, kernel_ptnum=5, precision="bf16", lrate=5e-4, lrate_decay=250,
                  lrate_warmup_iters=0, lrate_warmup_factor=1.0, colornet_weightdecay=0.0, tv_loss_weight=1e-2,
                  event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0,
-                 use_awp=False, awp_fine_loss_weight=None):
+                 use_awp=False, awp_fine_loss_weight=None, schedule=None):
         if not torch.cuda.is_available():
             raise RuntimeError("evdeblurnerf_b200.Trainer needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if device is not None else "cuda")
@@ -101,20 +106,51 @@ class Trainer:
         self.rank = torch.distributed.get_rank(process_group) if torch.distributed.is_initialized() else 0
         self.nerf.engine.seed(seed * 1000003 + self.rank)      # per-rank draw streams (SURVEY 8(e) caveat 2)
         self.global_step = 0
+        # run_nerf.py:121-142, 437-499 loss schedule.  Keys (reference option names, options.py:39,173-232): N_iters,
+        # kernel_start_iter, kernel_start_warmup_mode ("step" | "linear" | "cosine"), kernel_start_warmup_iters,
+        # kernel_awp_use_coarse_to_fine_opt, use_pts0_prior, pts0_target_{weight,weight_end,weight_steps,weight_scheduler,
+        # start_iter,end_iter}, blur_loss_after, event_egm_{weight,weight_end,weight_steps,weight_scheduler}, clip_grads_norm
+        sc = dict(kernel_start_iter=0, kernel_start_warmup_mode="step", kernel_start_warmup_iters=1, N_iters=200000,
+                  kernel_awp_use_coarse_to_fine_opt=False, use_pts0_prior=None, pts0_target_weight=0.1, pts0_target_weight_end=1.0,
+                  pts0_target_weight_steps=None, pts0_target_weight_scheduler="constant", pts0_target_start_iter=-1,
+                  pts0_target_end_iter=9999999, blur_loss_after=-1, event_egm_weight=event_loss_weight,
+                  event_egm_weight_end=event_loss_weight, event_egm_weight_steps=None, event_egm_weight_scheduler="constant",
+                  clip_grads_norm=None)
+        unknown = set(schedule or {}) - set(sc)
+        if unknown:
+            raise ValueError(f"unknown schedule keys {sorted(unknown)}")
+        sc.update(schedule or {})
+        self.schedule = sc
+        self.w_events_egm = annealing_interpolator(sc["event_egm_weight"], sc["event_egm_weight_end"], sc["event_egm_weight_steps"],
+                                                   sc["event_egm_weight_scheduler"])
+        self.w_pts0_target = annealing_interpolator(sc["pts0_target_weight"], sc["pts0_target_weight_end"],
+                                                    sc["pts0_target_weight_steps"], sc["pts0_target_weight_scheduler"])
+        self.w_kernel, self.kernel_end_warmup_iter = (lambda step: 1.0), -1
+        if sc["kernel_start_warmup_mode"] != "step":
+            self.kernel_end_warmup_iter = sc["kernel_start_iter"] + sc["kernel_start_warmup_iters"]
+            self.w_kernel = annealing_interpolator(0.0, 1.0, self.kernel_end_warmup_iter, sc["kernel_start_warmup_mode"],
+                                                   start_step=sc["kernel_start_iter"])
+        self._fine_loss_weight = None
+        self._names = {"net": list(trainable), "crf": list(crf_state or {})}
+        self._buffers = {k: v.detach().clone() for k, v in state.items() if isinstance(v, torch.Tensor) and k not in trainable}
 
     # run_nerf.py:438-504 (+ 539-557 when event rays are given)
     def loss(self, batch, H, W, K):
         out = {}
-        events = self.hp["ev_w"] > 0 and "ev_rays_start" in batch
+        sc, i = self.schedule, self.global_step           # the reference's loop index i == global_step while the step runs
+        events = "ev_rays_start" in batch and (self.w_events_egm(i) or 0.0) > 0
+        use_pts0 = sc["use_pts0_prior"] is not None and sc["pts0_target_start_iter"] <= i < sc["pts0_target_end_iter"]
+        warm = sc["kernel_start_warmup_mode"] != "step" and sc["kernel_start_iter"] <= i < self.kernel_end_warmup_iter
+        render_kwargs = dict(self.render_kwargs, return_pts0_rgb=True) if (use_pts0 or warm) else self.render_kwargs
         naive = None
         if events and self.fuse_event_renders:
             # the reference calls nerf() three times (blurred rays, event start rays, event end rays; run_nerf.py:438, 534, 547);
             # the rays are independent, so one fused render + one backward gives the same result with a third of the launches
             rgb, rgb0, extra_loss, extra_tensor, naive = self.nerf.forward_fused(
-                H, W, K, batch["rays"], batch, [batch["ev_rays_start"], batch["ev_rays_end"]], retraw=True, **self.render_kwargs)
+                H, W, K, batch["rays"], batch, [batch["ev_rays_start"], batch["ev_rays_end"]], retraw=True, **render_kwargs)
         else:
             rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
-                                                            **self.render_kwargs)
+                                                            **render_kwargs)
         target = batch["rgbsf"].reshape(-1, 3)
         img_loss = img2mse(self.crf(rgb, mode="encode_rgb"), target)
         out["img_loss"] = img_loss.detach()
@@ -125,7 +161,24 @@ class Trainer:
             fine = img2mse(self.crf(extra_tensor["rgb_awp"], mode="encode_rgb"), target)
             out["img_fine_loss"] = fine.detach()
             flw = self.awp_fine_loss_weight                   # kernel_awp_use_coarse_to_fine_opt: annealed mix, else plain sum
+            if flw is None and sc["kernel_awp_use_coarse_to_fine_opt"]:
+                if i % 10000 == 0 or self._fine_loss_weight is None:          # refreshed every 10 000 iterations (run_nerf.py:467-470)
+                    self._fine_loss_weight = exponential_scale_fine_loss_weight(sc["N_iters"], sc["kernel_start_iter"], 0.1, 0.9,
+                                                                                i - i % 10000)
+                flw = self._fine_loss_weight
             loss = loss + fine if flw is None else loss * (1 - flw) + fine * flw
+        if warm or use_pts0:                                  # run_nerf.py:475-499
+            tgt0 = batch["rgbsf_pts0"].reshape(-1, 3) if use_pts0 else target
+            pts0_loss = 0.0
+            for name in ("stage0_rgb_pts0", "stage1_rgb_pts0", "stage1_rgb1_pts0"):
+                if name in extra_tensor:
+                    pts0_loss = pts0_loss + img2mse(self.crf(extra_tensor[name], mode="encode_rgb"), tgt0)
+            out["pts0_loss"] = pts0_loss.detach()
+            if use_pts0:
+                w_pts0 = 1.0 if i <= sc["blur_loss_after"] else self.w_pts0_target(i)
+                loss = loss + pts0_loss * w_pts0
+            else:
+                loss = self.w_kernel(i) * loss + (1 - self.w_kernel(i)) * pts0_loss
         if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
             loss = loss + extra_loss["TV"] * self.hp["tv_w"]
         if events:
@@ -140,7 +193,7 @@ class Trainer:
                 lum.append((self.crf(c, mode="encode_luma", ev_extra_feat=feat), self.crf(c0, mode="encode_luma", ev_extra_feat=feat)))
             ev = egm_loss(lum[0][0], lum[1][0], batch["bii"]) + egm_loss(lum[0][1], lum[1][1], batch["bii"])   # stage1 + stage0
             out["event_loss"] = ev.detach()
-            loss = loss + ev * self.hp["ev_w"]
+            loss = loss + ev * self.w_events_egm(i)
         out["loss"] = loss
         return out
 
@@ -151,6 +204,12 @@ class Trainer:
         out = self.loss(batch, H, W, K)
         out["loss"].backward()
         self.flat.all_reduce_mean(self.group)
+        if self.schedule["clip_grads_norm"] is not None:       # run_nerf.py:596-599: over nerf.parameters() only (not the CRF)
+            grads = [self.flat.views[k].grad for k in self._names["net"]]
+            total = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+            coef = torch.clamp(self.schedule["clip_grads_norm"] / (total + 1e-6), max=1.0)
+            torch._foreach_mul_(grads, coef)
+            out["grad_norm"] = total.detach()
         self.global_step += 1
         # iteration g of the reference runs with the rate it set at the end of iteration g - 1 from global_step = g - 1
         lr = lr_at(max(self.global_step - 2, 0), hp["lrate"], hp["decay"], hp["warm_it"], hp["warm_f"])
@@ -163,3 +222,34 @@ class Trainer:
     def state_dict(self):
         """Reference-format tensors (run_nerf.py:628-634 saves network / optimizer state dicts)."""
         return {k: v.detach().clone() for k, v in self.flat.views.items()}
+
+    def _groups(self):
+        return optimizer_groups(self._names["net"], self._names["crf"], mode="c2f", colornet_weightdecay=self.hp["wd"])
+
+    def checkpoint(self):
+        """The dict run_nerf.py:628-634 passes to torch.save: network / crf state dicts (buffers included), a genuine
+        torch.optim.Adam state_dict in the reference's group order, global_step."""
+        views = self.flat.views
+        net = {**{k: views[k] for k in self._names["net"]}, **self._buffers}
+        crf = {k: views["crf." + k] for k in self._names["crf"]}
+        m, v = self.flat.named(self.flat.exp_avg), self.flat.named(self.flat.exp_avg_sq)
+        lr = lr_at(max(self.global_step - 1, 0), self.hp["lrate"], self.hp["decay"], self.hp["warm_it"], self.hp["warm_f"])
+        return checkpoint_dict(self.global_step, net, crf, m, v, self._groups(), lr=lr, initial_lr=self.hp["lrate"],
+                               colornet_weightdecay=self.hp["wd"])
+
+    def load_checkpoint(self, ckpt):
+        """Reload what `checkpoint()` -- or the reference itself -- saved (run_nerf.py:282-295)."""
+        step, net, crf, m, v, _ = load_checkpoint_dict(ckpt, self._groups())
+        views = self.flat.views
+        ma, va = self.flat.named(self.flat.exp_avg), self.flat.named(self.flat.exp_avg_sq)
+        with torch.no_grad():
+            for k in self._names["net"]:
+                views[k].copy_(net[k])
+            for k in self._names["crf"]:
+                views["crf." + k].copy_(crf[k])
+            for k, t in m.items():
+                ma[k].copy_(t)
+                va[k].copy_(v[k])
+        self._buffers.update({k: t.detach().clone() for k, t in net.items() if k in self._buffers})
+        self.global_step = step
+        self.nerf.repack()

@@ -442,3 +442,77 @@ def test_fused_event_render_equals_three_calls():
         # Adam's first step moves every coordinate by ~lr * sign(g): compare the updates, tolerant to sign flips of ~0 gradients
         frac = float(((states[0][k] - states[1][k]).abs() > 2e-4).float().mean())
         assert frac < 0.01, (k, frac)
+
+
+def test_trainer_loss_schedule_pts0_prior_and_kernel_warmup():
+    """run_nerf.py:437-499: EDI pts0-prior term with its annealed weight, cosine kernel warm-up mix, gradient clipping."""
+    from evdeblurnerf_b200 import NeRFAll, TonemappingTransform, img2mse
+    from evdeblurnerf_b200.schedules import annealing_interpolator
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if not k.startswith("awpnet.")}
+    batch = _tiny_batch(16, 41)
+    g = torch.Generator().manual_seed(5)
+    batch["rgbsf_pts0"] = torch.rand(16, 1, 3, generator=g).cuda()
+    rk = dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    sched = dict(use_pts0_prior="edi", pts0_target_weight=0.1, pts0_target_weight_end=1.0, pts0_target_weight_steps=10,
+                 pts0_target_weight_scheduler="linear", pts0_target_start_iter=0, clip_grads_norm=1e-3)
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", lrate=1e-3, tv_loss_weight=0.0, render_kwargs=rk, schedule=sched)
+    tr.global_step = 4
+    out = tr.loss(batch, H, W, KMAT)
+    nerf = NeRFAll({k: v.cuda() for k, v in P.items()}, *AABB, kernel_ptnum=5, precision="fp32").train()
+    crf = TonemappingTransform({k: v.cuda() for k, v in Pc.items()}, map_type_rgb="gamma", map_type_event="learn", extra_features_event=2)
+    rgb, rgb0, _, et = nerf(H, W, KMAT, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False, return_pts0_rgb=True, **rk)
+    enc = lambda x: crf(x, mode="encode_rgb")
+    base = img2mse(enc(rgb), batch["rgbsf"]) + img2mse(enc(rgb0), batch["rgbsf"])
+    tgt0 = batch["rgbsf_pts0"].reshape(-1, 3)
+    pts0 = img2mse(enc(et["stage1_rgb_pts0"]), tgt0) + img2mse(enc(et["stage1_rgb1_pts0"]), tgt0)
+    w = annealing_interpolator(0.1, 1.0, 10, "linear")(4)
+    assert_close(out["loss"], base + pts0 * w, "loss with pts0 prior", rtol=1e-6)
+    assert_close(out["pts0_loss"], pts0, "pts0 loss", rtol=1e-6)
+    res = tr.step(batch, H, W, KMAT)                 # clip: the update is bounded by lr (Adam) and the recorded norm is the pre-clip norm
+    assert float(res["grad_norm"]) > 1e-3
+    # cosine kernel warm-up (kernel_start_warmup_mode != "step"): loss = w * blur loss + (1 - w) * pts0 loss against the BLURRY target
+    tr2 = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk,
+                  schedule=dict(kernel_start_iter=2, kernel_start_warmup_mode="cosine", kernel_start_warmup_iters=8))
+    tr2.global_step = 5
+    out2 = tr2.loss(batch, H, W, KMAT)
+    pts0b = img2mse(enc(et["stage1_rgb_pts0"]), batch["rgbsf"]) + img2mse(enc(et["stage1_rgb1_pts0"]), batch["rgbsf"])
+    wk = annealing_interpolator(0.0, 1.0, 10, "cosine", start_step=2)(5)
+    assert 0.0 < wk < 1.0
+    assert_close(out2["loss"], wk * base + (1 - wk) * pts0b, "kernel warm-up mix", rtol=1e-6)
+    tr2.global_step = 10                              # past the warm-up: plain loss, no pts0 render requested
+    assert "pts0_loss" not in tr2.loss(batch, H, W, KMAT)
+    with pytest.raises(ValueError):
+        Trainer(P, Pc, *AABB, schedule=dict(not_an_option=1))
+
+
+def test_trainer_checkpoint_round_trip_in_reference_format():
+    """checkpoint() is the run_nerf.py:628-634 payload (loadable by torch.optim.Adam in the reference's group order); a second
+    trainer restored from it continues bit-identically."""
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if not k.startswith("awpnet.")}
+    batch = _tiny_batch(16, 43)
+    rk = dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    kw = dict(kernel_ptnum=5, precision="fp32", lrate=1e-3, colornet_weightdecay=1e-2, tv_loss_weight=0.01, render_kwargs=rk)
+    a = Trainer(P, Pc, *AABB, **kw)
+    for _ in range(3):
+        a.step(batch, H, W, KMAT)
+    ck = a.checkpoint()
+    assert set(ck) == {"wandb_id", "global_step", "crf_state_dict", "network_state_dict", "optimizer_state_dict"} and ck["global_step"] == 3
+    assert [len(g["params"]) for g in ck["optimizer_state_dict"]["param_groups"]] == [6, len(P) - 6 - 12, 12, len(Pc)]
+    assert ck["optimizer_state_dict"]["param_groups"][0]["weight_decay"] == 1e-2
+    import io
+    buf = io.BytesIO()
+    torch.save(ck, buf)
+    buf.seek(0)
+    ck2 = torch.load(buf, weights_only=False)
+    b = Trainer({k: torch.zeros_like(v) for k, v in P.items()}, {k: torch.zeros_like(v) for k, v in Pc.items()}, *AABB, **kw)
+    b.load_checkpoint(ck2)
+    assert b.global_step == 3
+    ra, rb = a.step(batch, H, W, KMAT), b.step(batch, H, W, KMAT)
+    assert float(ra["loss"]) == float(rb["loss"]) and ra["lr"] == rb["lr"]
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert_close(sb[k], sa[k], "restored + 1 step: " + k, rtol=1e-6, atol=1e-9)
