@@ -411,7 +411,7 @@ def main():
                      "whole_step_tflops": flops_per_subray() * R / (ms_per_step / 1e3) / 1e12},
         "wall_s_timed_region": t_wall,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N = 1 only
         threads = os.cpu_count() or 1
         sample = 512
         Pc = {k: v.cpu() for k, v in P.items()}

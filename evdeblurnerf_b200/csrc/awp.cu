@@ -368,12 +368,13 @@ struct RaySmem {
   float inter_n[kMaxE][16];
   float x_inter[kMaxE][kMaxE];
   float cf[kMaxE][32];
-  float intra[32][kMaxS];         // later reused as intra_b [16][S] / intra_l [S][16]
+  float intra[32][kMaxS + 1];     // padded (written channel-major, read sample-major); later reused flat as intra_l [S][16]
   float intra_b[16][kMaxS];
   float x_intra[kMaxE][kMaxS];
 };
 
-__global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
+constexpr int kRayThreads = 512;   // short shared-memory-latency-bound phases: more warps per CTA hide them
+__global__ void __launch_bounds__(kRayThreads) awp_ray_kernel(const AwpArgs a) {
   extern __shared__ __align__(16) float smraw[];
   RaySmem& s = *reinterpret_cast<RaySmem*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S;
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
   }
   __syncthreads();
   // motion_feature_embed_layer: [gint(64) | view(47)] = 111 -> 32 -> 32, ReLU both (awp.py:104-108)
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayThreads) {
     const int e = i >> 5, j = i & 31;
     float acc = a.p.motion_b[0][j];
     const float* w = a.p.motion_w[0] + j * 111;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
     s.cf[e][j] = fmaxf(acc, 0.f);     // staging
   }
   __syncthreads();
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayThreads) {
     const int e = i >> 5, j = i & 31;
     float acc = a.p.motion_b[1][j];
     const float* w = a.p.motion_w[1] + j * 32;
@@ -409,20 +410,23 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
     s.x[e][j] = fmaxf(acc, 0.f);
   }
   // "intra": sum_e xl[e][s][:] * softmax_e(att[:, s])   (mam.py:35)
-  for (int sp = tid; sp < S; sp += 128) {
+  for (int sp = tid; sp < S; sp += kRayThreads) {           // softmax over exposures -> x_intra (free until the logits below)
     float mx = -INFINITY, pe[kMaxE];
     for (int e = 0; e < E; ++e) { pe[e] = a.att[(n * E + e) * S + sp]; mx = fmaxf(mx, pe[e]); }
     float sum = 0.f;
     for (int e = 0; e < E; ++e) { pe[e] = expf(pe[e] - mx); sum += pe[e]; }
-    for (int c = 0; c < 32; ++c) {
-      float acc = 0.f;
-      for (int e = 0; e < E; ++e) acc = fmaf(a.xl[((n * E + e) * S + sp) * 32 + c], pe[e] / sum, acc);
-      s.intra[c][sp] = acc;
-    }
+    for (int e = 0; e < E; ++e) s.x_intra[e][sp] = pe[e] / sum;
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * S; i += kRayThreads) {         // lanes = channels: coalesced reads of xl
+    const int c = i & 31, sp = i >> 5;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(a.xl[((n * E + e) * S + sp) * 32 + c], s.x_intra[e][sp], acc);
+    s.intra[c][sp] = acc;
   }
   __syncthreads();
   // conva on inter (mam.py:37), convc on x (mam.py:40)
-  for (int i = tid; i < 16 * E; i += 128) {
+  for (int i = tid; i < 16 * E; i += kRayThreads) {
     const int k = i / E, e = i % E;
     float acc = 0.f, acc2 = 0.f;
     for (int c = 0; c < 32; ++c) { acc = fmaf(a.p.conva[k * 32 + c], a.inter[(n * E + e) * 32 + c], acc); acc2 = fmaf(a.p.convc[k * 32 + c], s.x[e][c], acc2); }
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
     s.xlog[e][k] = acc2;
   }
   // convb on intra (mam.py:38)
-  for (int i = tid; i < 16 * S; i += 128) {
+  for (int i = tid; i < 16 * S; i += kRayThreads) {
     const int k = i / S, sp = i % S;
     float acc = 0.f;
     for (int c = 0; c < 32; ++c) acc = fmaf(a.p.convb[k * 32 + c], s.intra[c][sp], acc);
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
     }
   }
   // x_intra logits (mam.py:42): [E][S]
-  for (int i = tid; i < E * S; i += 128) {
+  for (int i = tid; i < E * S; i += kRayThreads) {
     const int e = i / S, sp = i % S;
     float t = 0.f;
     for (int k = 0; k < 16; ++k) t = fmaf(s.xlog[e][k], s.intra_b[k][sp], t);
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
   __syncthreads();
   {  // softmax over samples, one warp per exposure row
     const int warp = tid >> 5, lane = tid & 31;
-    for (int e = warp; e < E; e += 4) {
+    for (int e = warp; e < E; e += kRayThreads / 32) {
       float mx = -INFINITY;
       for (int sp = lane; sp < S; sp += 32) mx = fmaxf(mx, s.x_intra[e][sp]);
 #pragma unroll
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
   // convl on intra_b (mam.py:45): intra_l[s][k] -> reuse s.intra as [S][16]
   float* intra_l = &s.intra[0][0];
   __syncthreads();
-  for (int i = tid; i < S * 16; i += 128) {
+  for (int i = tid; i < S * 16; i += kRayThreads) {
     const int sp = i >> 4, k = i & 15;
     float t = 0.f;
     for (int c = 0; c < 16; ++c) t = fmaf(a.p.convl[k * 16 + c], s.intra_b[c][sp], t);
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
   }
   __syncthreads();
   // curve features (mam.py:47-50): cf[e] = [x_inter . inter_n | x_intra . intra_l]
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayThreads) {
     const int e = i >> 5, j = i & 31;
     float t = 0.f;
     if (j < 16) { for (int e2 = 0; e2 < E; ++e2) t = fmaf(s.x_inter[e][e2], s.inter_n[e2][j], t); }
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(128) awp_ray_kernel(const AwpArgs a) {
   }
   __syncthreads();
   // convd.0 (mam.py:51, before BatchNorm): y[e][c]; also export x
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayThreads) {
     const int e = i >> 5, c = i & 31;
     float t = 0.f;
     for (int k = 0; k < 32; ++k) t = fmaf(a.p.convd_w[c * 32 + k], s.cf[e][k], t);
@@ -615,7 +619,7 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
   }
   const size_t smem2 = sizeof(RaySmem);
   EDN_CUDA_OK(cudaFuncSetAttribute(awp_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  awp_ray_kernel<<<(unsigned)n_rays, 128, smem2, st>>>(a);
+  awp_ray_kernel<<<(unsigned)n_rays, kRayThreads, smem2, st>>>(a);
   awp_bn_stats_kernel<<<1, 256, 0, st>>>(a.y, NE, a.stats);
   if (phase == 0) awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
   EDN_CUDA_OK(cudaGetLastError());

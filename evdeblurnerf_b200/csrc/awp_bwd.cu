@@ -120,7 +120,7 @@ struct RayBwdSmem {
   float att[EMAX][SMAX];        // logits, later d att
   float pE[EMAX][SMAX];         // softmax over exposures
   float pS[EMAX][SMAX];         // softmax over samples
-  float intra[32][SMAX];        // later d intra
+  float intra[32][SMAX + 1];    // later d intra (padded: read and written both channel-major and sample-major)
   float intra_b[16][SMAX], dintra_b[16][SMAX];
   float x_intra[EMAX][SMAX];    // later d logits
   float intra_l[SMAX][16], dintra_l[SMAX][16];
@@ -141,15 +141,16 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // EMAX / SMAX bound the exposure / sample counts of this instantiation (shared memory: 88 KB for E <= 8, S <= 128 -> two CTAs per
 // SM; 200 KB for the largest one)
+constexpr int kRayBwdThreads = 512;   // the kernel is a chain of short shared-memory-latency-bound phases: more warps per CTA hide it
 template <int EMAX, int SMAX>
-__global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kRayBwdThreads) awp_ray_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float smraw[];
   RayBwdSmem<EMAX, SMAX>& s = *reinterpret_cast<RayBwdSmem<EMAX, SMAX>*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S, warp = tid >> 5, lane = tid & 31;
   const int64_t n = blockIdx.x;
   const double rows = a.bn_rows;
   // ---- load / recompute the forward intermediates --------------------------------------------------------------------
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayBwdThreads) {
     const int e = i >> 5, c = i & 31;
     s.x[e][c] = a.ws.x[(n * E + e) * 32 + c];
     s.inter[e][c] = a.ws.inter[(n * E + e) * 32 + c];
@@ -161,26 +162,28 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     const float m1 = (float)(a.bn_sums[2 * c] / rows), m2 = (float)(a.bn_sums[2 * c + 1] / rows);
     s.dy[e][c] = a.p.bn_weight[c] * inv * (a.d_yn[(n * E + e) * 32 + c] - m1 - yh * m2);
   }
-  for (int i = tid; i < E * S; i += 128) s.att[i / S][i % S] = a.ws.att[(n * E + i / S) * S + i % S];
-  for (int i = tid; i < 32 * 32; i += 128) s.g_convd[i] = 0.f;
-  for (int i = tid; i < 16 * 32; i += 128) { s.g_conva[i] = 0.f; s.g_convb[i] = 0.f; s.g_convc[i] = 0.f; }
-  for (int i = tid; i < 16 * 16; i += 128) { s.g_convn[i] = 0.f; s.g_convl[i] = 0.f; }
+  for (int i = tid; i < E * S; i += kRayBwdThreads) s.att[i / S][i % S] = a.ws.att[(n * E + i / S) * S + i % S];
+  for (int i = tid; i < 32 * 32; i += kRayBwdThreads) s.g_convd[i] = 0.f;
+  for (int i = tid; i < 16 * 32; i += kRayBwdThreads) { s.g_conva[i] = 0.f; s.g_convb[i] = 0.f; s.g_convc[i] = 0.f; }
+  for (int i = tid; i < 16 * 16; i += kRayBwdThreads) { s.g_convn[i] = 0.f; s.g_convl[i] = 0.f; }
   if (tid < 32) s.g_latt[tid] = 0.f;
   __syncthreads();
   // softmax over exposures (per sample) and "intra"
-  for (int sp = tid; sp < S; sp += 128) {
+  for (int sp = tid; sp < S; sp += kRayBwdThreads) {
     float mx = -INFINITY, pe[EMAX], sum = 0.f;
     for (int e = 0; e < E; ++e) { pe[e] = s.att[e][sp]; mx = fmaxf(mx, pe[e]); }
     for (int e = 0; e < E; ++e) { pe[e] = expf(pe[e] - mx); sum += pe[e]; }
     for (int e = 0; e < E; ++e) s.pE[e][sp] = pe[e] / sum;
-    for (int c = 0; c < 32; ++c) {
-      float acc = 0.f;
-      for (int e = 0; e < E; ++e) acc = fmaf(a.ws.xl[((n * E + e) * S + sp) * 32 + c], s.pE[e][sp], acc);
-      s.intra[c][sp] = acc;
-    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * S; i += kRayBwdThreads) {        // lanes = channels: coalesced reads of xl
+    const int c = i & 31, sp = i >> 5;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(a.ws.xl[((n * E + e) * S + sp) * 32 + c], s.pE[e][sp], acc);
+    s.intra[c][sp] = acc;
   }
   // softmax over samples (per exposure), one warp per exposure row
-  for (int e = warp; e < E; e += 4) {
+  for (int e = warp; e < E; e += kRayBwdThreads / 32) {
     float mx = -INFINITY, sum = 0.f;
     for (int sp = lane; sp < S; sp += 32) mx = fmaxf(mx, s.att[e][sp]);
     mx = warp_max(mx);
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     sum = warp_sum(sum);
     for (int sp = lane; sp < S; sp += 32) s.pS[e][sp] /= sum;
   }
-  for (int i = tid; i < 16 * E; i += 128) {
+  for (int i = tid; i < 16 * E; i += kRayBwdThreads) {
     const int k = i / E, e = i % E;
     float acc = 0.f, acc2 = 0.f;
     for (int c = 0; c < 32; ++c) { acc = fmaf(a.p.conva[k * 32 + c], s.inter[e][c], acc); acc2 = fmaf(a.p.convc[k * 32 + c], s.x[e][c], acc2); }
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     s.xlog[e][k] = acc2;
   }
   __syncthreads();
-  for (int i = tid; i < 16 * S; i += 128) {
+  for (int i = tid; i < 16 * S; i += kRayBwdThreads) {
     const int k = i / S, sp = i % S;
     float acc = 0.f;
     for (int c = 0; c < 32; ++c) acc = fmaf(a.p.convb[k * 32 + c], s.intra[c][sp], acc);
@@ -219,20 +222,20 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     }
   }
   __syncthreads();
-  for (int i = tid; i < E * S; i += 128) {
+  for (int i = tid; i < E * S; i += kRayBwdThreads) {
     const int e = i / S, sp = i % S;
     float t = 0.f;
     for (int k = 0; k < 16; ++k) t = fmaf(s.xlog[e][k], s.intra_b[k][sp], t);
     s.x_intra[e][sp] = t;
   }
-  for (int i = tid; i < S * 16; i += 128) {
+  for (int i = tid; i < S * 16; i += kRayBwdThreads) {
     const int sp = i >> 4, k = i & 15;
     float t = 0.f;
     for (int c = 0; c < 16; ++c) t = fmaf(a.p.convl[k * 16 + c], s.intra_b[c][sp], t);
     s.intra_l[sp][k] = t;
   }
   __syncthreads();
-  for (int e = warp; e < E; e += 4) {
+  for (int e = warp; e < E; e += kRayBwdThreads / 32) {
     float mx = -INFINITY, sum = 0.f;
     for (int sp = lane; sp < S; sp += 32) mx = fmaxf(mx, s.x_intra[e][sp]);
     mx = warp_max(mx);
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     for (int sp = lane; sp < S; sp += 32) s.x_intra[e][sp] /= sum;
   }
   __syncthreads();
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayBwdThreads) {
     const int e = i >> 5, j = i & 31;
     float t = 0.f;
     if (j < 16) { for (int e2 = 0; e2 < E; ++e2) t = fmaf(s.x_inter[e][e2], s.inter_n[e2][j], t); }
@@ -251,13 +254,13 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   __syncthreads();
   // ---- backward --------------------------------------------------------------------------------------------------------
   // convd: y[e][c] = sum_k convd[c][k] cf[e][k]
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayBwdThreads) {
     const int e = i >> 5, k = i & 31;
     float t = 0.f;
     for (int c = 0; c < 32; ++c) t = fmaf(s.dy[e][c], a.p.convd_w[c * 32 + k], t);
     s.dcf[e][k] = t;
   }
-  for (int i = tid; i < 32 * 32; i += 128) {
+  for (int i = tid; i < 32 * 32; i += kRayBwdThreads) {
     const int c = i >> 5, k = i & 31;
     float t = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.dy[e][c], s.cf[e][k], t);
@@ -265,19 +268,19 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // cf[e][j<16] = sum_e2 x_inter[e][e2] inter_n[e2][j];  cf[e][16+j] = sum_sp x_intra[e][sp] intra_l[sp][j]
-  for (int i = tid; i < E * E; i += 128) {
+  for (int i = tid; i < E * E; i += kRayBwdThreads) {
     const int e = i / E, e2 = i % E;
     float t = 0.f;
     for (int j = 0; j < 16; ++j) t = fmaf(s.dcf[e][j], s.inter_n[e2][j], t);
     s.dlg_inter[e][e2] = t;                                  // d x_inter for now
   }
-  for (int i = tid; i < E * 16; i += 128) {
+  for (int i = tid; i < E * 16; i += kRayBwdThreads) {
     const int e2 = i >> 4, j = i & 15;
     float t = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.x_inter[e][e2], s.dcf[e][j], t);
     s.dinter_n[e2][j] = t;
   }
-  for (int i = tid; i < S * 16; i += 128) {
+  for (int i = tid; i < S * 16; i += kRayBwdThreads) {
     const int sp = i >> 4, j = i & 15;
     float t = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.x_intra[e][sp], s.dcf[e][16 + j], t);
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     for (int e2 = 0; e2 < E; ++e2) dot = fmaf(s.x_inter[e][e2], s.dlg_inter[e][e2], dot);
     for (int e2 = 0; e2 < E; ++e2) s.dlg_inter[e][e2] = s.x_inter[e][e2] * (s.dlg_inter[e][e2] - dot);
   }
-  for (int e = warp; e < E; e += 4) {
+  for (int e = warp; e < E; e += kRayBwdThreads / 32) {
     float dot = 0.f;
     for (int sp = lane; sp < S; sp += 32) {
       float t = 0.f;
@@ -304,28 +307,28 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // logits: lg_inter[e][e2] = sum_k xlog[e][k] inter_a[k][e2];  lg_intra[e][sp] = sum_k xlog[e][k] intra_b[k][sp]
-  for (int i = tid; i < E * 16; i += 128) {
+  for (int i = tid; i < E * 16; i += kRayBwdThreads) {
     const int e = i >> 4, k = i & 15;
     float t = 0.f;
     for (int e2 = 0; e2 < E; ++e2) t = fmaf(s.dlg_inter[e][e2], s.inter_a[k][e2], t);
     for (int sp = 0; sp < S; ++sp) t = fmaf(s.x_intra[e][sp], s.intra_b[k][sp], t);
     s.dxlog[e][k] = t;
   }
-  for (int i = tid; i < 16 * E; i += 128) {
+  for (int i = tid; i < 16 * E; i += kRayBwdThreads) {
     const int k = i / E, e2 = i % E;
     float t = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.dlg_inter[e][e2], s.xlog[e][k], t);
     for (int k2 = 0; k2 < 16; ++k2) t = fmaf(a.p.convn[k2 * 16 + k], s.dinter_n[e2][k2], t);     // inter_n = convn . inter_a
     s.dinter_a[k][e2] = t;
   }
-  for (int i = tid; i < 16 * S; i += 128) {
+  for (int i = tid; i < 16 * S; i += kRayBwdThreads) {
     const int k = i / S, sp = i % S;
     float t = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.x_intra[e][sp], s.xlog[e][k], t);
     for (int k2 = 0; k2 < 16; ++k2) t = fmaf(a.p.convl[k2 * 16 + k], s.dintra_l[sp][k2], t);      // intra_l = convl . intra_b
     s.dintra_b[k][sp] = t;
   }
-  for (int i = tid; i < 16 * 16; i += 128) {
+  for (int i = tid; i < 16 * 16; i += kRayBwdThreads) {
     const int k2 = i >> 4, c = i & 15;
     float t = 0.f, u = 0.f;
     for (int e = 0; e < E; ++e) t = fmaf(s.dinter_n[e][k2], s.inter_a[c][e], t);
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // 1x1 convs: xlog = convc . x, inter_a = conva . inter, intra_b = convb . intra
-  for (int i = tid; i < 16 * 32; i += 128) {
+  for (int i = tid; i < 16 * 32; i += kRayBwdThreads) {
     const int k = i >> 5, c = i & 31;
     float tc = 0.f, ta = 0.f, tb = 0.f;
     for (int e = 0; e < E; ++e) { tc = fmaf(s.dxlog[e][k], s.x[e][c], tc); ta = fmaf(s.dinter_a[k][e], s.inter[e][c], ta); }
@@ -343,14 +346,14 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
     s.g_convc[i] = tc; s.g_conva[i] = ta; s.g_convb[i] = tb;
   }
   __syncthreads();          // g_convb read intra before it is overwritten below
-  for (int i = tid; i < E * 32; i += 128) {
+  for (int i = tid; i < E * 32; i += kRayBwdThreads) {
     const int e = i >> 5, c = i & 31;
     float tx = 0.f, ti = 0.f;
     for (int k = 0; k < 16; ++k) { tx = fmaf(a.p.convc[k * 32 + c], s.dxlog[e][k], tx); ti = fmaf(a.p.conva[k * 32 + c], s.dinter_a[k][e], ti); }
     a.d_x[(n * E + e) * 32 + c] += tx;        // residual-path gradient was written by awp_out_bwd_kernel
     s.dinter[e][c] = ti;
   }
-  for (int i = tid; i < 32 * S; i += 128) {
+  for (int i = tid; i < 32 * S; i += kRayBwdThreads) {
     const int c = i / S, sp = i % S;
     float t = 0.f;
     for (int k = 0; k < 16; ++k) t = fmaf(a.p.convb[k * 32 + c], s.dintra_b[k][sp], t);
@@ -358,23 +361,21 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // d pE, d pS -> d att (both softmaxes); att scratch holds d pS first, x_intra holds d pE
-  for (int i = tid; i < E * S; i += 128) {
-    const int e = i / S, sp = i % S;
-    const float* xl = a.ws.xl + ((n * E + e) * S + sp) * 32;
-    float dpe = 0.f, dps = 0.f;
-    for (int c = 0; c < 32; ++c) { const float v = xl[c]; dpe = fmaf(s.intra[c][sp], v, dpe); dps = fmaf(s.dinter[e][c], v, dps); }
-    s.x_intra[e][sp] = dpe;
-    s.att[e][sp] = dps;
+  for (int r = warp; r < E * S; r += kRayBwdThreads / 32) {      // one warp per (exposure, sample) row, lanes = channels
+    const int e = r / S, sp = r % S;
+    const float v = a.ws.xl[((n * E + e) * S + sp) * 32 + lane];
+    const float dpe = warp_sum(s.intra[lane][sp] * v), dps = warp_sum(s.dinter[e][lane] * v);
+    if (lane == 0) { s.x_intra[e][sp] = dpe; s.att[e][sp] = dps; }
   }
   __syncthreads();
-  for (int e = warp; e < E; e += 4) {           // row dot products of the softmax over samples
+  for (int e = warp; e < E; e += kRayBwdThreads / 32) {           // row dot products of the softmax over samples
     float dot = 0.f;
     for (int sp = lane; sp < S; sp += 32) dot = fmaf(s.pS[e][sp], s.att[e][sp], dot);
     dot = warp_sum(dot);
     if (lane == 0) s.red[e] = dot;
   }
   __syncthreads();
-  for (int sp = tid; sp < S; sp += 128) {
+  for (int sp = tid; sp < S; sp += kRayBwdThreads) {
     float dotE = 0.f;
     for (int e = 0; e < E; ++e) dotE = fmaf(s.pE[e][sp], s.x_intra[e][sp], dotE);
     for (int e = 0; e < E; ++e)
@@ -383,18 +384,25 @@ __global__ void __launch_bounds__(128) awp_ray_bwd_kernel(const BwdArgs a) {
   __syncthreads();
   // d xl = d intra * pE + d inter * pS + d att * latt;  d latt += d att * xl
   float glatt = 0.f;      // thread c = tid & 31 accumulates channel c over its (e, sp) subset
-  for (int i = tid; i < E * S * 32; i += 128) {
+  for (int i = tid; i < E * S * 32; i += kRayBwdThreads) {
     const int c = i & 31, r = i >> 5, e = r / S, sp = r % S;
     const int64_t off = ((n * E + e) * S + sp) * 32 + c;
     const float da = s.att[e][sp];
     a.d_xl[off] = s.intra[c][sp] * s.pE[e][sp] + s.dinter[e][c] * s.pS[e][sp] + da * a.p.line_conv_att[c];
     glatt = fmaf(da, a.ws.xl[off], glatt);
   }
-  atomicAdd(&s.g_latt[tid & 31], glatt);
+  float* part = &s.dintra_b[0][0];      // free since the d intra pass; [warp][channel] partials instead of shared-memory atomics
+  part[warp * 32 + lane] = glatt;
   __syncthreads();
-  for (int i = tid; i < 32 * 32; i += 128) atomicAdd(a.g.convd_w + i, s.g_convd[i]);
-  for (int i = tid; i < 16 * 32; i += 128) { atomicAdd(a.g.conva + i, s.g_conva[i]); atomicAdd(a.g.convb + i, s.g_convb[i]); atomicAdd(a.g.convc + i, s.g_convc[i]); }
-  for (int i = tid; i < 16 * 16; i += 128) { atomicAdd(a.g.convn + i, s.g_convn[i]); atomicAdd(a.g.convl + i, s.g_convl[i]); }
+  if (tid < 32) {
+    float t = 0.f;
+    for (int w = 0; w < kRayBwdThreads / 32; ++w) t += part[w * 32 + tid];
+    s.g_latt[tid] = t;
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * 32; i += kRayBwdThreads) atomicAdd(a.g.convd_w + i, s.g_convd[i]);
+  for (int i = tid; i < 16 * 32; i += kRayBwdThreads) { atomicAdd(a.g.conva + i, s.g_conva[i]); atomicAdd(a.g.convb + i, s.g_convb[i]); atomicAdd(a.g.convc + i, s.g_convc[i]); }
+  for (int i = tid; i < 16 * 16; i += kRayBwdThreads) { atomicAdd(a.g.convn + i, s.g_convn[i]); atomicAdd(a.g.convl + i, s.g_convl[i]); }
   if (tid < 32) atomicAdd(a.g.line_conv_att + tid, s.g_latt[tid]);
 }
 
@@ -697,7 +705,7 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   {
     auto launch = [&](auto kern, size_t smem) -> int {
       EDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<(unsigned)N, 128, smem, st>>>(a);
+      kern<<<(unsigned)N, kRayBwdThreads, smem, st>>>(a);
       return 0;
     };
     int rc2;
