@@ -44,7 +44,7 @@ def main():
                 print(json.dumps({"rays": n, "exposures": E, "samples": [nc, ni], "ms": ms, "rays_per_s": n / (ms / 1e3),
                                   "subrays_per_s": n * E / (ms / 1e3), "tflops_algorithmic": flops / (ms / 1e3) / 1e12,
                                   "frac_of_measured_bf16_peak": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
-                                  "fine_path": "tcgen05 bf16" if nc + ni <= 128 else "fp32 SIMT (S > 128)"}), flush=True)
+                                  "fine_path": f"tcgen05 bf16, {(nc + ni + 127) // 128} x 128-row tile(s) per ray"}), flush=True)
 
 
 if __name__ == "__main__":
