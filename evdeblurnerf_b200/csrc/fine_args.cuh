@@ -20,6 +20,8 @@ struct FineArgs {
   float* acc;
   float* feat;
   long long* trace;   // dev tooling (EDN_TC_TRACE=1): per-phase clock64 stamps of CTA 0, NULL otherwise
+  int ablate;         // dev tooling (EDN_TC_ABLATE=bits): TIMING-ONLY ablations, results are garbage: 1 no VM gather, 2 no layer
+                      // epilogues, 4 no weight stream (the MMAs read stale shared memory), 8 no PE / view-bias phase
 };
 
 }  // namespace edn

@@ -191,7 +191,7 @@ extern "C" int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_
               "edn_render_fine_fwd: null weight");
   EDN_REQUIRE(grid_coarse && grid_fine && grid_coarse->dtype == grid_fine->dtype, "edn_render_fine_fwd: grids must share a dtype");
   EDN_REQUIRE(grid_fine->dtype == EDN_F32 || grid_fine->dtype == EDN_BF16, "edn_render_fine_fwd: bad grid dtype");
-  FineArgs a;
+  FineArgs a{};
   int rc = make_grid_dev(grid_coarse, &a.gc);
   if (rc) return rc;
   rc = make_grid_dev(grid_fine, &a.gf);

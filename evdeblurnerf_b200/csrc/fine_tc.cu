@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         const int s = g % kNst;
         const uint32_t use = g / kNst;
         if (use > 0) mbar_wait(&m->empty[q][s], (use - 1) & 1);   // the MMAs on the previous tenant completed
+        if (a.ablate & 4) { mbar_expect_tx(&m->full[q][s], 0); continue; }
         mbar_expect_tx(&m->full[q][s], kStageBytes);
         const uint32_t gs = g % kRingStagesPerRay;
         const size_t src = PAIR ? (size_t)(gs >> 2) * 131072 + (size_t)rank * 65536 + (size_t)(gs & 3) * kStageBytes : (size_t)gs * kStageBytes;
@@ -400,6 +401,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       uint32_t spins = 0;
       while (*reinterpret_cast<volatile uint32_t*>(&m->skew_flag) == 0) { if (++spins > (1u << 22)) break; }   // a scheduling hint only: never a correctness dependency
     }
+    auto epi = [&](uint32_t taddr, uint8_t* arow, int col_begin, int ncols, int mode, uint32_t bias_s, float* gout, uint32_t wsig,
+                   uint32_t wrgb) {
+      return (a.ablate & 2) ? make_float4(0.f, 0.f, 0.f, 0.f) : layer_epilogue(taddr, arow, col_begin, ncols, mode, bias_s, gout, wsig, wrgb);
+    };
     auto stamp = [&](int64_t it, int k) {
       if (a.trace && blockIdx.x == 0 && r == 0 && half == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
     };
@@ -418,7 +423,9 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
       const float zv = a.z_vals[ray * S + min(rg, S - 1)];
-      if (half == 0) {
+      if (a.ablate & 8) {
+        if (half == 0) gm->z[r] = zv;
+      } else if (half == 0) {
         gm->z[r] = zv;
         if (tile == 0 && r == 0) gm->tcarry = 1.0f;
         // ---- PE(pts) -> 64 A columns (full: chunks 8..15, lean: 24..31); the last column is the zero pad of K = 127 -> 128.
@@ -472,14 +479,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       named_bar_sync(bar_id, kGroupThreads);      // z[] (and bias[]) visible to the whole group
       stamp(it, 1);
       // ---- VM gather: half 0 gathers the coarse grid, half 1 the fine grid -> two 128 x 96 bf16 tiles ------------------
-      gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
+      if (!(a.ablate & 1)) gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
       signal_a();
       stamp(it, 2);
       if (!LEAN) {
         // ---- basis_mat outputs (coarse 32 | fine 32) -> A columns 0..63 ----------------------------------------------
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 3);
-        layer_epilogue(taddr_row, a_row, 32 * half, 32, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
+        epi(taddr_row, a_row, 32 * half, 32, kEpiPlain, 0u, nullptr, s_wsig, s_wrgb);
         signal_a();
         stamp(it, 4);
       }
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 5);
       {
-        const float4 hd = layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb);
+        const float4 hd = epi(taddr_row, a_row, 128 * half, 128, kEpiReluSigma, 0u, nullptr, s_wsig, s_wrgb);
         gm->headp[half][r][3] = hd.x;
       }
       signal_a();
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         // ---- sigma_net.1 -> geo (128, linear) ----------------------------------------------------------------------------
         mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
         stamp(it, 7);
-        layer_epilogue(taddr_row, a_row, 64 * half, 64, kEpiPlain, 0u,
+        epi(taddr_row, a_row, 64 * half, 64, kEpiPlain, 0u,
                        (a.feat && live && rg < S) ? a.feat + ((size_t)ray * S + rg) * 128 : nullptr, s_wsig, s_wrgb);
         signal_a();
       }
@@ -505,14 +512,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       // ---- color_net.0 (+ per-ray view-dir bias) -> ReLU ------------------------------------------------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 9);
-      layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
+      epi(taddr_row, a_row, 128 * half, 128, kEpiRelu, smem_u32(gm->bias), nullptr, s_wsig, s_wrgb);
       signal_a();
       stamp(it, 10);
       // ---- color_net.1 -> ReLU -> rgb head (fp32 dot with color_net.2; partial per column half) --------------------------
       mbar_wait(&m->bar_acc[q], pacc); pacc ^= 1; tc_fence_after();
       stamp(it, 11);
       {
-        const float4 hd = layer_epilogue(taddr_row, a_row, 128 * half, 128, kEpiReluRgb, a.mlp.color1_b ? smem_u32(m->bias1) : 0u, nullptr,
+        const float4 hd = epi(taddr_row, a_row, 128 * half, 128, kEpiReluRgb, a.mlp.color1_b ? smem_u32(m->bias1) : 0u, nullptr,
                                          s_wsig, s_wrgb);
         gm->headp[half][r][0] = hd.x; gm->headp[half][r][1] = hd.y; gm->headp[half][r][2] = hd.z;
       }
@@ -635,7 +642,8 @@ int launch_pair(const FineArgs& a, const uint8_t* blob, unsigned gx, cudaStream_
 
 }  // namespace
 
-int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
+int launch_fine_tc(const FineArgs& a_in, int grid_dtype, cudaStream_t st) {
+  FineArgs a = a_in;
   EDN_REQUIRE(a.S >= 2, "edn_render_fine_fwd(bf16): n_samples must be >= 2, got %d", a.S);
   EDN_REQUIRE(a.mlp.tc_blob != nullptr, "edn_render_fine_fwd(bf16): edn_field_mlp.tc_blob is NULL (call edn_pack_fine_tc)");
   int rc = ensure_schedule();
@@ -645,6 +653,12 @@ int launch_fine_tc(const FineArgs& a, int grid_dtype, cudaStream_t st) {
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
   const char* fv = getenv("EDN_TC_FULL");                       // dev switch: force the unfolded schedule
   const bool lean = (a.feat == nullptr) && !(fv && fv[0] == '1');   // depth_feature (geo) only exists in the full schedule
+  static const int ablate = [] { const char* e = getenv("EDN_TC_ABLATE"); return e ? atoi(e) : 0; }();
+  a.ablate = ablate;
+  if (ablate) {
+    static bool told = false;
+    if (!told) { fprintf(stderr, "[evdeblur_b200] EDN_TC_ABLATE=%d: fine tensor-core kernel runs a TIMING-ONLY ablation, outputs are invalid\n", ablate); told = true; }
+  }
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;
