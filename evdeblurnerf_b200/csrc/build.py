@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "libevdeblur_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v"]
+FLAGS += os.environ.get("EDN_NVCC_EXTRA", "").split()        # dev builds, e.g. -DEDN_TC_ABLATE_BUILD=1
 
 
 def sources():

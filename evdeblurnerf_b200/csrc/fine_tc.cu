@@ -26,6 +26,10 @@
 #include "tc_common.cuh"
 #include "tc_rows.cuh"
 
+#ifndef EDN_TC_ABLATE_BUILD
+#define EDN_TC_ABLATE_BUILD 0      // dev builds only (tools/fine_tc_ablate.sh): compile the EDN_TC_ABLATE timing ablations in
+#endif
+
 namespace edn {
 namespace {
 
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
   if (PAIR) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = m->tmem_base;
+  const int ablate_bits = EDN_TC_ABLATE_BUILD ? a.ablate : 0;     // compile-time gate: the shipped kernel carries no ablation branches
   const int64_t n_pairs_total = (a.n_rays + 1) / 2;
   // pair mode: both CTAs of a cluster run the same number of iterations (the rank-1 CTA may replay a masked duplicate ray)
   const int64_t first_cta = PAIR ? (int64_t)(blockIdx.x & ~1u) : (int64_t)blockIdx.x;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
         const int s = g % kNst;
         const uint32_t use = g / kNst;
         if (use > 0) mbar_wait(&m->empty[q][s], (use - 1) & 1);   // the MMAs on the previous tenant completed
-        if (a.ablate & 4) { mbar_expect_tx(&m->full[q][s], 0); continue; }
+        if (ablate_bits & 4) { mbar_expect_tx(&m->full[q][s], 0); continue; }
         mbar_expect_tx(&m->full[q][s], kStageBytes);
         const uint32_t gs = g % kRingStagesPerRay;
         const size_t src = PAIR ? (size_t)(gs >> 2) * 131072 + (size_t)rank * 65536 + (size_t)(gs & 3) * kStageBytes : (size_t)gs * kStageBytes;
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
     }
     auto epi = [&](uint32_t taddr, uint8_t* arow, int col_begin, int ncols, int mode, uint32_t bias_s, float* gout, uint32_t wsig,
                    uint32_t wrgb) {
-      return (a.ablate & 2) ? make_float4(0.f, 0.f, 0.f, 0.f) : layer_epilogue(taddr, arow, col_begin, ncols, mode, bias_s, gout, wsig, wrgb);
+      return (ablate_bits & 2) ? make_float4(0.f, 0.f, 0.f, 0.f) : layer_epilogue(taddr, arow, col_begin, ncols, mode, bias_s, gout, wsig, wrgb);
     };
     auto stamp = [&](int64_t it, int k) {
       if (a.trace && blockIdx.x == 0 && r == 0 && half == 0 && it >= 8 && it < 12) a.trace[((it - 8) * 2 + q) * 16 + k] = clock64();
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
       const float zv = a.z_vals[ray * S + min(rg, S - 1)];
-      if (a.ablate & 8) {
+      if (ablate_bits & 8) {
         if (half == 0) gm->z[r] = zv;
       } else if (half == 0) {
         gm->z[r] = zv;
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc_kernel(const FineArgs
       named_bar_sync(bar_id, kGroupThreads);      // z[] (and bias[]) visible to the whole group
       stamp(it, 1);
       // ---- VM gather: half 0 gathers the coarse grid, half 1 the fine grid -> two 128 x 96 bf16 tiles ------------------
-      if (!(a.ablate & 1)) gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
+      if (!(ablate_bits & 1)) gather_tiles<T>(m->grids, Aq, gm->z, gwarp, lane, o, d, LEAN, half);
       signal_a();
       stamp(it, 2);
       if (!LEAN) {
@@ -654,10 +659,14 @@ int launch_fine_tc(const FineArgs& a_in, int grid_dtype, cudaStream_t st) {
   const char* fv = getenv("EDN_TC_FULL");                       // dev switch: force the unfolded schedule
   const bool lean = (a.feat == nullptr) && !(fv && fv[0] == '1');   // depth_feature (geo) only exists in the full schedule
   static const int ablate = [] { const char* e = getenv("EDN_TC_ABLATE"); return e ? atoi(e) : 0; }();
-  a.ablate = ablate;
+  a.ablate = EDN_TC_ABLATE_BUILD ? ablate : 0;
   if (ablate) {
     static bool told = false;
-    if (!told) { fprintf(stderr, "[evdeblur_b200] EDN_TC_ABLATE=%d: fine tensor-core kernel runs a TIMING-ONLY ablation, outputs are invalid\n", ablate); told = true; }
+    if (!told) {
+      fprintf(stderr, EDN_TC_ABLATE_BUILD ? "[evdeblur_b200] EDN_TC_ABLATE=%d: fine tensor-core kernel runs a TIMING-ONLY ablation, outputs are invalid\n"
+                                          : "[evdeblur_b200] EDN_TC_ABLATE=%d ignored: library built without -DEDN_TC_ABLATE_BUILD=1\n", ablate);
+      told = true;
+    }
   }
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
