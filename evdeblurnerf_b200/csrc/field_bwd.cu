@@ -136,14 +136,18 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
     float gx = 0.f, gy = 0.f, gv = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+#if !defined(EDN_SCATTER_ABLATE) || EDN_SCATTER_ABLATE != 2
       if (tp.pt.w[k] != 0.f) atomicAdd(reinterpret_cast<float4*>(gg.plane[comp] + (size_t)tp.pt.off[k] * C + c), scale4(dpl, tp.pt.w[k]));
+#endif
       const float dv = dot4(dpl, v[k]);
       gx = fmaf(tp.dwx[k], dv, gx);
       gy = fmaf(tp.dwy[k], dv, gy);
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
+#if !defined(EDN_SCATTER_ABLATE) || EDN_SCATTER_ABLATE != 1      // dev timing ablation: 1 = no line reds, 2 = no plane reds
       if (tp.lt.w[k] != 0.f) atomicAdd(reinterpret_cast<float4*>(gg.line[comp] + (size_t)tp.lt.off[k] * C + c), scale4(dln, tp.lt.w[k]));
+#endif
       gv = fmaf(tp.dl[k], dot4(dln, l[k]), gv);
     }
     part[threadIdx.x][tp.ax] = gx * tp.sx;      // (ax, ay, av) is a permutation of the three point axes
