@@ -600,9 +600,11 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
     const float* X = depth_feature;
     int K = 128;
     for (int l = 0; l < 4; ++l) {
-      int rc = gemm(false, false, M, 64, K, X, K, p->sample_t[l], 64, 0.f, ws.act[l], 64);
+      float* act = ws.act[l];
+      const float* bias = p->sample_b[l];
+      int rc = gemm.relu_linear(M, 64, K, X, K, p->sample_t[l], 64, bias, act, 64, st,
+                                [&] { relu_bias_kernel<<<blocks_for(M * 16, 256), 256, 0, st>>>(act, 64, 64, M, bias); }, /*w_kn=*/true);
       if (rc) return rc;
-      relu_bias_kernel<<<blocks_for(M * 16, 256), 256, 0, st>>>(ws.act[l], 64, 64, M, p->sample_b[l]);
       X = ws.act[l];
       K = 64;
     }

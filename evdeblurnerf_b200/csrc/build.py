@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         # cuBLAS carries the plain tall GEMMs of the backward pass (field_bwd.cu); resolved from the CUDA toolkit or, when
         # torch is already imported, from the libcublas.so.12 torch loaded
         r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                            "-L/usr/local/cuda/lib64", "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"],
+                            "-L/usr/local/cuda/lib64", "-lcublas", "-lcublasLt", "-Xlinker", "-rpath=/usr/local/cuda/lib64"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

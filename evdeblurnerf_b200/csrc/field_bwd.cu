@@ -535,14 +535,14 @@ int field_bwd_run(const FieldBwdCall& c) {
       EDN_RC(gemm.run(false, true, M, kAppDim, kAppComp, P[g], kAppComp, Wb[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
     }
     pe_kernel<AT><<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
-    EDN_RC(gemm.run(false, true, M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, 0.f, H1, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr);
+    EDN_RC(gemm.relu_linear(M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, (const float*)nullptr, H1, hid, st,
+                            [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr); }));
     EDN_RC(gemm.run(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
     pe_kernel<AT><<<blocks_for(M * (kPeFreqDir + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
-    EDN_RC(gemm.run(false, true, M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, 0.f, H2, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b);
-    EDN_RC(gemm.run(false, true, M, hid, hid, H2, hid, Wc1, hid, 0.f, H3, hid));
-    relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b);
+    EDN_RC(gemm.relu_linear(M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, w->color0_b, H2, hid, st,
+                            [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b); }));
+    EDN_RC(gemm.relu_linear(M, hid, hid, H2, hid, Wc1, hid, w->color1_b, H3, hid, st,
+                            [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H3, hid, hid, M, w->color1_b); }));
     EDN_RC(gemm.run(false, true, M, D.nr, hid, H3, hid, Wp[3], hid, 0.f, RGB, D.nr));
     // ---- compositing backward ------------------------------------------------------------------------------------------
     composite_bwd_kernel<AT><<<blocks_for(Rc, 64), 64, 0, st>>>(SG + geo, D.ldS, RGB, D.nr, w->color2_b, ray_batch, z_vals, c.noise, r0, Rc, S, c.d_rgb,
@@ -764,14 +764,17 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     for (int l = 0; l < 8; ++l) {
       const float* X = (l == 0 || l == 5) ? XH : H[l - 1];
       const int ldx = (l == 0 || l == 5) ? kNXH : ldH[l - 1];
-      EDN_RC(gemm(false, true, M, kNW, Kl[l], X, ldx, Wl[l], Kl[l], 0.f, H[l], ldH[l]));
-      relu_bias_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(H[l], ldH[l], kNW, M, w->pts_b[l]);
+      float* Hl = H[l];
+      const int ldh = ldH[l];
+      const float* bl = w->pts_b[l];
+      EDN_RC(gemm.relu_linear(M, kNW, Kl[l], X, ldx, Wl[l], Kl[l], bl, Hl, ldh, st,
+                              [&] { relu_bias_kernel<<<blocks_for(M * (kNW / 4), 256), 256, 0, st>>>(Hl, ldh, kNW, M, bl); }));
     }
     EDN_RC(gemm(false, true, M, kNAFn, kNW, H[7], kNW, Wp[2], kNW, 0.f, AF, kNAF));
     add_bias_ld_kernel<<<blocks_for(M * 257, 256), 256, 0, st>>>(AF, kNAF, 257, M, Wp[5]);
     pe_kernel<<<blocks_for(M * (kPeFreqDir + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, XH, kNXH, 0, 0, AF, kNAF, 256, 1);
-    EDN_RC(gemm(false, true, M, kNHV, kNAF, AF, kNAF, Wp[3], kNAF, 0.f, HV, kNHV));
-    relu_bias_kernel<<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(HV, kNHV, kNHV, M, w->views_b);
+    EDN_RC(gemm.relu_linear(M, kNHV, kNAF, AF, kNAF, Wp[3], kNAF, w->views_b, HV, kNHV, st,
+                            [&] { relu_bias_kernel<<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(HV, kNHV, kNHV, M, w->views_b); }));
     EDN_RC(gemm(false, true, M, 4, kNHV, HV, kNHV, Wp[4], kNHV, 0.f, RGB, 4));
     // ---- compositing backward (nerf.py:74-129: sigma = channel 3, rgb = sigmoid) ------------------------------------------------
     composite_bwd_kernel<float><<<blocks_for(Rc, 64), 64, 0, st>>>(AF + 256, kNAF, RGB, 4, w->rgb_b, ray_batch, z_vals, noise, r0, Rc, S, d_rgb, d_depth,
