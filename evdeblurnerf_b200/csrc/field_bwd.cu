@@ -201,6 +201,40 @@ __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict_
   }
 }
 
+// bf16 storage, PE(pts) only: one thread per sample writes the whole [PE (63) | 0] block as eight 16-byte vectors.  Base
+// frequency by sincosf, higher octaves by the double-angle recurrence -- the same recipe as the tensor-core forward (abs
+// error <= 2^9 * 1e-7, far below the bf16 resolution of the stored operand).  Needs nf * 2 and ldX * 2 multiples of 16 bytes.
+__global__ void pe_pts_bf16_kernel(const float* __restrict__ rb, const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
+                                   __nv_bfloat16* __restrict__ X0, int ldX, int nf) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mc) return;
+  float pe[64];
+  sample_point(rb, z_vals, m0 + m, S, pe);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sincosf(pe[i], &pe[3 + i], &pe[6 + i]);
+#pragma unroll
+  for (int f = 1; f < kPeFreqPts; ++f) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float sp = pe[3 + 6 * (f - 1) + i], cp = pe[6 + 6 * (f - 1) + i];
+      pe[3 + 6 * f + i] = 2.0f * sp * cp;
+      pe[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+    }
+  }
+  pe[63] = 0.f;
+  uint4* out = reinterpret_cast<uint4*>(X0 + m * ldX + nf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(pe[8 * j + 2 * i], pe[8 * j + 2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    out[j] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // Weight re-layout between the reference nn.Linear tensors and the aligned copies the GEMMs read (to_padded = 1), and the
 // fold-back of their gradients (to_padded = 0: ref += padded).  One thread per padded element.
 //   mode 0: zero-pad columns            ref [rows][cols_r]      -> pad [rows][cols_p]
@@ -534,7 +568,14 @@ int field_bwd_run(const FieldBwdCall& c) {
       else vm_products_kernel<__nv_bfloat16, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], ray_batch, z_vals, m0, M, S, P[g]);
       EDN_RC(gemm.run(false, true, M, kAppDim, kAppComp, P[g], kAppComp, Wb[g], kAppComp, 0.f, X0 + 32 * g, D.ldX));
     }
-    pe_kernel<AT><<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
+    if constexpr (sizeof(AT) == 2) {
+      if (D.ldX - D.nf == 64 && D.nf % 8 == 0 && D.ldX % 8 == 0)
+        pe_pts_bf16_kernel<<<blocks_for(M, 128), 128, 0, st>>>(ray_batch, z_vals, m0, M, S, reinterpret_cast<__nv_bfloat16*>(X0), D.ldX, D.nf);
+      else
+        pe_kernel<AT><<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
+    } else {
+      pe_kernel<AT><<<blocks_for(M * (kPeFreqPts + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, D.ldX - D.nf, SG, D.ldS, geo, 0);
+    }
     EDN_RC(gemm.relu_linear(M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, (const float*)nullptr, H1, hid, st,
                             [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr); }));
     EDN_RC(gemm.run(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
