@@ -252,6 +252,35 @@ __global__ void pe_kernel(const float* __restrict__ rb, const float* __restrict_
   }
 }
 
+// PE(viewdir) is constant along a ray: one block per ray computes the 27 values once (same sincosf arguments as pe_kernel, so the
+// stored values are identical) and copies them, with the zero padding, into the S sample rows: SG[m][geo + 1 : ldS).
+template <typename AT>
+__global__ void __launch_bounds__(128) pe_dirs_ray_kernel(const float* __restrict__ rb, int64_t r0, int S, AT* __restrict__ SG, int ldS, int geo) {
+  __shared__ float pe[64];
+  const int width = ldS - 1 - geo;       // [PE (27) | zero padding]
+  const float* row = rb + (r0 + blockIdx.x) * 11 + 8;
+  for (int j = threadIdx.x; j < width && j < 64; j += blockDim.x) pe[j] = 0.f;
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int i = threadIdx.x;
+    const float x = __ldg(row + i);
+    pe[i] = x;
+#pragma unroll
+    for (int f = 0; f < kPeFreqDir; ++f) {
+      float sn, cs;
+      sincosf(x * (float)(1 << f), &sn, &cs);
+      pe[3 + 6 * f + i] = sn;
+      pe[6 + 6 * f + i] = cs;
+    }
+  }
+  __syncthreads();
+  AT* out = SG + (int64_t)blockIdx.x * S * ldS + geo + 1;
+  for (int idx = threadIdx.x; idx < S * width; idx += blockDim.x) {
+    const int sp = idx / width, j = idx - sp * width;
+    out[(int64_t)sp * ldS + j] = from_f<AT>(j < 64 ? pe[j] : 0.f);
+  }
+}
+
 // bf16 storage, PE(pts) only: one thread per sample writes the whole [PE (63) | 0] block as eight 16-byte vectors.  Base
 // frequency by sincosf, higher octaves by the double-angle recurrence -- the same recipe as the tensor-core forward (abs
 // error <= 2^9 * 1e-7, far below the bf16 resolution of the stored operand).  Needs nf * 2 and ldX * 2 multiples of 16 bytes.
@@ -630,7 +659,7 @@ int field_bwd_run(const FieldBwdCall& c) {
     EDN_RC(gemm.relu_linear(M, hid, D.ldX, X0, D.ldX, Wp[0], D.ldX, (const float*)nullptr, H1, hid, st,
                             [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H1, hid, hid, M, nullptr); }));
     EDN_RC(gemm.run(false, true, M, D.sgn, hid, H1, hid, Wp[1], hid, 0.f, SG, D.ldS));                               // [geo | sigma | 0..]
-    pe_kernel<AT><<<blocks_for(M * (kPeFreqDir + 1), 256), 256, 0, st>>>(ray_batch, z_vals, m0, M, S, X0, D.ldX, D.nf, 0, SG, D.ldS, geo, 1);
+    pe_dirs_ray_kernel<AT><<<(unsigned)Rc, 128, 0, st>>>(ray_batch, r0, S, SG, D.ldS, geo);
     EDN_RC(gemm.relu_linear(M, hid, D.ldS, SG, D.ldS, Wp[2], D.ldS, w->color0_b, H2, hid, st,
                             [&] { relu_bias_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(H2, hid, hid, M, w->color0_b); }));
     EDN_RC(gemm.relu_linear(M, hid, hid, H2, hid, Wc1, hid, w->color1_b, H3, hid, st,
