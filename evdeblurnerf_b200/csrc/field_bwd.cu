@@ -392,7 +392,7 @@ __global__ void pe_bwd_kernel(const float* __restrict__ rb, const float* __restr
 // vector of H3 / dH3 per thread
 template <typename AT>
 __global__ void head_bwd_kernel(const AT* __restrict__ dRGB, int nr, const float* __restrict__ W2, const AT* __restrict__ H3, int hid,
-                                int64_t M, AT* __restrict__ dH3) {
+                                int64_t M, AT* __restrict__ dH3, bool w2_vec) {
   constexpr int V = Vec16<AT>::n;
   const int nq = hid / V;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,9 +402,21 @@ __global__ void head_bwd_kernel(const AT* __restrict__ dRGB, int nr, const float
   const float4 g = ldv4(dRGB + m * nr);
   Vec16<AT> h;
   h.load(H3 + m * hid + j);
+  if (w2_vec) {        // W2 16-byte aligned (uniform): the three weight rows as float4 loads
 #pragma unroll
-  for (int i = 0; i < V; ++i)
-    h.v[i] = h.v[i] > 0.f ? g.x * __ldg(W2 + j + i) + g.y * __ldg(W2 + hid + j + i) + g.z * __ldg(W2 + 2 * hid + j + i) : 0.f;
+    for (int i = 0; i < V; i += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(W2 + j + i)), b = __ldg(reinterpret_cast<const float4*>(W2 + hid + j + i)),
+                   c = __ldg(reinterpret_cast<const float4*>(W2 + 2 * hid + j + i));
+      h.v[i] = h.v[i] > 0.f ? g.x * a.x + g.y * b.x + g.z * c.x : 0.f;
+      h.v[i + 1] = h.v[i + 1] > 0.f ? g.x * a.y + g.y * b.y + g.z * c.y : 0.f;
+      h.v[i + 2] = h.v[i + 2] > 0.f ? g.x * a.z + g.y * b.z + g.z * c.z : 0.f;
+      h.v[i + 3] = h.v[i + 3] > 0.f ? g.x * a.w + g.y * b.w + g.z * c.w : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      h.v[i] = h.v[i] > 0.f ? g.x * __ldg(W2 + j + i) + g.y * __ldg(W2 + hid + j + i) + g.z * __ldg(W2 + 2 * hid + j + i) : 0.f;
+  }
   h.store(dH3 + m * hid + j);
 }
 
@@ -671,7 +683,8 @@ int field_bwd_run(const FieldBwdCall& c) {
     // ---- color_net backward ----------------------------------------------------------------------------------------------
     EDN_RC(gemm.run(true, false, D.nr, hid, M, dRGB, D.nr, H3, hid, 1.f, gWp[3], hid));
     if (grad_w->color2_b) colsum_kernel<AT><<<blocks_for(M, 512), 32, 0, st>>>(dRGB, D.nr, 3, M, grad_w->color2_b);
-    head_bwd_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(dRGB, D.nr, w->color2, H3, hid, M, D1);               // D1 = dH3
+    head_bwd_kernel<AT><<<blocks_for(M * (hid / al), 256), 256, 0, st>>>(dRGB, D.nr, w->color2, H3, hid, M, D1,
+                                                                           (reinterpret_cast<uintptr_t>(w->color2) & 15) == 0 && hid % 4 == 0);   // D1 = dH3
     EDN_RC(gemm.run(true, false, hid, hid, M, D1, hid, H2, hid, 1.f, grad_w->color1, hid));
     if (grad_w->color1_b) colsum_kernel<AT><<<blocks_for(M, 512), 256, 0, st>>>(D1, hid, hid, M, grad_w->color1_b);
     EDN_RC(gemm.run(false, false, M, hid, hid, D1, hid, Wc1, hid, 0.f, D2, hid));                                       // D2 = dH2
@@ -903,7 +916,7 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
     // ---- heads ------------------------------------------------------------------------------------------------------------
     EDN_RC(gemm(true, false, 4, kNHV, M, dRGB, 4, HV, kNHV, 1.f, gWp[4], kNHV));
     if (g->rgb_b) colsum_kernel<<<blocks_for(M, 512), 32, 0, st>>>(dRGB, 4, 3, M, g->rgb_b);
-    head_bwd_kernel<float><<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(dRGB, 4, w->rgb_w, HV, kNHV, M, dHV);
+    head_bwd_kernel<float><<<blocks_for(M * (kNHV / 4), 256), 256, 0, st>>>(dRGB, 4, w->rgb_w, HV, kNHV, M, dHV, (reinterpret_cast<uintptr_t>(w->rgb_w) & 15) == 0);
     EDN_RC(gemm(true, false, kNHV, kNAF, M, dHV, kNHV, AF, kNAF, 1.f, gWp[3], kNAF));
     colsum_kernel<<<blocks_for(M, 512), 128, 0, st>>>(dHV, kNHV, kNHV, M, g->views_b);
     EDN_RC(gemm(false, false, M, kNAF, kNHV, dHV, kNHV, Wp[3], kNAF, 0.f, dAF, kNAF));
