@@ -373,8 +373,8 @@ struct RaySmem {
   float x_intra[kMaxE][kMaxS];
 };
 
-constexpr int kRayThreads = 512;   // short shared-memory-latency-bound phases: more warps per CTA hide them
-__global__ void __launch_bounds__(kRayThreads) awp_ray_kernel(const AwpArgs a) {
+constexpr int kRayThreads = 256;   // short shared-memory-latency-bound phases with few busy threads each: 3 CTAs of 8 warps per SM
+__global__ void __launch_bounds__(kRayThreads, 3) awp_ray_kernel(const AwpArgs a) {
   extern __shared__ __align__(16) float smraw[];
   RaySmem& s = *reinterpret_cast<RaySmem*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S;
