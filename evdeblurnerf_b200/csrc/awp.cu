@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(128) awp_integrate_kernel(const AwpArgs a, con
 // Same computation for S <= 128 with FOUR threads per sample (16 channels each, 512 threads): the channel cumprod is a local
 // prefix product + a 3-step shuffle across the row's four lanes, the sums over samples are warp-shuffle + shared-memory
 // reductions.  (The products are associated differently from the sequential kernels: last-bit differences.)
-__global__ void __launch_bounds__(512) awp_integrate4_kernel(const AwpArgs a, const float* __restrict__ h_all) {
+__global__ void __launch_bounds__(512, 2) awp_integrate4_kernel(const AwpArgs a, const float* __restrict__ h_all) {
   __shared__ float Qs[128][64];
   __shared__ float atts[128];
   __shared__ float red[16][64];

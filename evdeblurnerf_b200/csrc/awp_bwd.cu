@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(128) awp_integrate_bwd_kernel(const BwdArgs a,
 
 // S <= 128: four threads per sample (16 channels each); the suffix recursion over the channels runs locally and is stitched
 // across the row's four lanes with three dependent shuffles.
-__global__ void __launch_bounds__(512) awp_integrate4_bwd_kernel(const BwdArgs a, const float* __restrict__ h_all, const float* __restrict__ dIN) {
+__global__ void __launch_bounds__(512, 2) awp_integrate4_bwd_kernel(const BwdArgs a, const float* __restrict__ h_all, const float* __restrict__ dIN) {
   extern __shared__ __align__(16) float sm4[];
   float (*Qs)[64] = reinterpret_cast<float (*)[64]>(sm4);                 // [128][64]
   float (*AH)[64] = reinterpret_cast<float (*)[64]>(sm4 + 128 * 64);      // [129][64]: al * h of each row (row s needs row s + 1); row 128 = 0
