@@ -2,9 +2,10 @@
 // Replaces utils/rays.py:149-193 (sample_pdf) as called at networks/renderer.py:199-203, the torch.sort at
 // renderer.py:205 and torch.std at renderer.py:250.
 //
-// Index contract (DESIGN.md "Numerics contract"): the pdf normaliser and the cdf prefix sums are accumulated
-// sequentially in fp64 and rounded to fp32 once per entry -- what torch's CPU cumsum does -- so `inds` is platform
-// independent and bit-exact against the oracle.  The merge is a stable rank sort (ties: coarse sample first).
+// Index contract (DESIGN.md "Numerics contract"): the pdf normaliser and the cdf prefix sums are accumulated in fp64 and
+// rounded to fp32 once per entry -- what torch's CPU cumsum does -- so `inds` is platform independent and bit-exact
+// against the oracle.  The fp64 sums of these fp32 terms are exact (terms within 2^29 of each other), so the warp-parallel
+// scan below returns the same bits as the sequential sum.  The merge is a stable rank sort (ties: coarse sample first).
 #include "common.cuh"
 
 namespace edn {
@@ -41,16 +42,28 @@ __global__ void __launch_bounds__(kPdfWarpsPerBlock * 32) sample_pdf_merge_kerne
   for (int i = lane; i < nc; i += 32) keys[i] = z0[i];
   __syncwarp();
   for (int i = lane; i < nb; i += 32) bins[i] = 0.5f * __fadd_rn(keys[i + 1], keys[i]);   // z_vals_mid, renderer.py:199
-  if (lane == 0) {
-    // weights[..., 1:-1] + 1e-5 -> nc-2 terms; normaliser and prefix sums in sequential fp64 (see header comment)
-    double tot = 0.0;
-    for (int i = 0; i < nc - 2; ++i) tot += (double)__fadd_rn(w0[i + 1], 1e-5f);
-    const float norm = (float)tot;
-    double run = 0.0;
-    cdf[0] = 0.0f;
-    for (int i = 0; i < nc - 2; ++i) {
-      const float pdf = __fdiv_rn(__fadd_rn(w0[i + 1], 1e-5f), norm);
-      run += (double)pdf;
+  {
+    // weights[..., 1:-1] + 1e-5 -> nc-2 terms; normaliser and prefix sums in fp64, rounded to fp32 once per entry.  The terms are
+    // fp32 values within a factor 2^17 of each other (1e-5 <= w + 1e-5 <= ~1), so every fp64 partial sum of up to 1024 of them
+    // is EXACT and the association order cannot matter: a warp scan gives the bits of the sequential sum (header comment).
+    const int n = nc - 2, per = (n + 31) / 32, lo = lane * per, hi = min(lo + per, n);
+    double part = 0.0;
+    for (int i = lo; i < hi; ++i) part += (double)__fadd_rn(w0[i + 1], 1e-5f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float norm = (float)part;
+    double loc = 0.0;
+    for (int i = lo; i < hi; ++i) loc += (double)__fdiv_rn(__fadd_rn(w0[i + 1], 1e-5f), norm);
+    double incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    double run = incl - loc;                 // exclusive prefix of this lane's chunk (exact)
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int i = lo; i < hi; ++i) {
+      run += (double)__fdiv_rn(__fadd_rn(w0[i + 1], 1e-5f), norm);
       cdf[i + 1] = (float)run;
     }
   }

@@ -92,6 +92,25 @@ def test_sample_pdf_ragged_sizes(engine, nc, ni):
     assert torch.equal(m["z_vals"].cpu(), zv) and torch.equal(m["order"].cpu(), order)
 
 
+@pytest.mark.parametrize("nc,ni", [(64, 64), (517, 200), (1024, 1024)])
+def test_sample_pdf_wide_dynamic_range_stays_bit_exact(engine, nc, ni):
+    """The sampler's warp-parallel fp64 scan must return the bits of the sequential fp64 cumsum the oracle (torch CPU) runs: weights
+    spanning 0 .. 1 with denormal-small, 1e-30, 1e-7-sized and O(1) entries, long rows, ragged tails (nc - 2 not a multiple of 32)."""
+    g = torch.Generator().manual_seed(nc + ni)
+    R = 64
+    z0 = torch.sort(torch.rand(R, nc, generator=g), -1)[0]
+    w0 = torch.rand(R, nc, generator=g)
+    scale = torch.tensor([0.0, 1e-38, 1e-30, 1e-7, 1e-3, 1.0])[torch.randint(0, 6, (R, nc), generator=g)]
+    w0 = w0 * scale
+    w0[0] = 1.0                                # all-equal row
+    w0[1, ::2] = 0.0
+    u = torch.rand(R, ni, generator=g)
+    m = engine.sample_pdf_merge(z0.cuda(), w0.cuda(), ni, u=u.cuda())
+    zs, inds = oc.sample_pdf(.5 * (z0[..., 1:] + z0[..., :-1]), w0[..., 1:-1], ni, u=u)
+    assert torch.equal(m["inds"].cpu(), inds)
+    assert torch.equal(m["z_samples"].cpu(), zs)
+
+
 def test_case1_c2f_render(engine):
     P, _ = small_params()
     g = golden("case1_train48x5")
