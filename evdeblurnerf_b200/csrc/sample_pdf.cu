@@ -109,10 +109,25 @@ __global__ void __launch_bounds__(kPdfWarpsPerBlock * 32) sample_pdf_merge_kerne
   for (int i = lane; i < nc - 1; i += 32) sorted = sorted && (keys[i] <= keys[i + 1]);
   sorted = __all_sync(0xffffffffu, sorted);
   const float* smp = keys + nc;
+  // deterministic u (perturb == 0) is increasing, so the samples come out non-decreasing as well: both halves are sorted runs and
+  // the stable merge rank of every key is its own index plus one binary search in the other run
+  bool smp_sorted = true;
+  for (int j = lane; j < ni - 1; j += 32) smp_sorted = smp_sorted && (smp[j] <= smp[j + 1]);
+  smp_sorted = __all_sync(0xffffffffu, smp_sorted) && sorted;
   for (int i = lane; i < nt; i += 32) {
     const float k = keys[i];
     int rank = 0;
-    if (!sorted) {
+    if (smp_sorted) {
+      if (i < nc) {                               // coarse key: its index + number of samples strictly below it
+        int lo = 0, hi = ni;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (smp[mid] < k) lo = mid + 1; else hi = mid; }
+        rank = i + lo;
+      } else {                                    // sample: its index among the samples + number of coarse keys <= it
+        int lo = 0, hi = nc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] <= k) lo = mid + 1; else hi = mid; }
+        rank = (i - nc) + lo;
+      }
+    } else if (!sorted) {
       for (int j = 0; j < nt; ++j) {
         const float kj = keys[j];
         rank += (kj < k) || (kj == k && j < i);
