@@ -7,6 +7,12 @@ One "step" = one forward pass of the hot path over one synthetic batch: 4096 pri
 sub-rays) -> coarse pass (64 samples) -> hierarchical sampling -> fine pass (128 samples) -> composited colours.
 N > 1 (torchrun): every rank renders its own 4096-ray batch (weak scaling, no data-path collective); value = all
 rays / max-over-ranks time.  Prints ONE JSON line on rank 0.
+
+Beside the headline (kept as in round 1 for continuity) the line carries, at EVERY N:
+  "shipped_forward": the training-branch forward of the shipped configuration (AWP on, perturb = 1, raw_noise_std = 1);
+  "train_step":      BASELINE config 4 -- forward + losses + backward + the NCCL gradient all-reduce (+ the synchronised-BatchNorm
+                     exchange of the AWP branch) + Adam, weak scaling, with `loss_finite` and the all-reduce's share;
+  "strong":          SURVEY 8(e)'s own partition -- the SAME 4096-ray batch split across the N ranks -- forward and training.
 """
 import argparse
 import json
@@ -81,6 +87,35 @@ def make_params(device, seed=0):
     for h, n_out in (("r", 3 * (N_EXPOSURE - 1)), ("v", 3 * (N_EXPOSURE - 1)), ("w", N_EXPOSURE)):
         P[pre + f"{h}_linear.weight"] = (0.05 * torch.randn(n_out, 32, generator=g)).to(device)
         P[pre + f"{h}_linear.bias"] = torch.zeros(n_out, device=device)
+    return P
+
+
+def awp_params(device, E=N_EXPOSURE, seed=7):
+    """AdaptiveWeightProposal parameters (dpnerf/awp.py:9-47, mam.py) with nn.Linear / Conv1d default-init scales."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+
+    def lin(name, o, i, bias=True, extra=()):
+        b = 1.0 / (i ** 0.5)
+        P[name + ".weight"] = ((torch.rand(o, i, *extra, generator=g) * 2 - 1) * b).to(device)
+        if bias:
+            P[name + ".bias"] = ((torch.rand(o, generator=g) * 2 - 1) * b).to(device)
+
+    pre = "awpnet."
+    lin(pre + "sample_feature_embed_layer.0", 64, 128)
+    for l in (1, 2, 3):
+        lin(pre + f"sample_feature_embed_layer.{l}", 64, 64)
+    lin(pre + "motion_feature_embed_layer.0", 32, 111)
+    lin(pre + "motion_feature_embed_layer.1", 32, 32)
+    lin(pre + "MAM.linear", 32, 64)
+    P[pre + "MAM.Corr.line_conv_att.weight"] = (torch.randn(1, 32, 1, 1, generator=g) * 0.2).to(device)
+    for n, (o, i) in (("conva", (16, 32)), ("convb", (16, 32)), ("convc", (16, 32)), ("convn", (16, 16)), ("convl", (16, 16))):
+        lin(pre + "MAM.Corr." + n, o, i, bias=False, extra=(1,))
+    lin(pre + "MAM.Corr.convd.0", 32, 32, bias=False, extra=(1,))
+    P[pre + "MAM.Corr.convd.1.weight"] = torch.ones(32, device=device)
+    P[pre + "MAM.Corr.convd.1.bias"] = torch.zeros(32, device=device)
+    lin(pre + "w_linear", E, 32)
     return P
 
 
@@ -177,34 +212,65 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def cpu_reference_step(P_cpu, rays_cpu, idx_cpu, threads):
-    """One bounded CPU step of the reference algorithm (oracle port; the reference is Python and cannot travel):
-    blur-kernel warp -> NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum."""
-    import torch
+def _reference_kwargs(perturb=0., raw_noise_std=0.):
+    """render_kwargs_train of run_nerf.py:306-330 for the blurfactory configs (ndc, near 0, far 1, use_viewdirs)."""
+    return dict(retraw=True, force_naive=False, perturb=perturb, N_importance=NI, N_samples=NC, use_viewdirs=True,
+                white_bkgd=False, raw_noise_std=raw_noise_std, inference=False, near=0., far=1.)
+
+
+def _harness():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import evdeblur_oracle as oc
+    import reference_harness as rh
+    return rh
+
+
+def cpu_reference_arm(sample_rays, steps, warmup, threads):
+    """The reference's own CPU path on the host cores: the UNMODIFIED reference (oracle/_ref staged copy, or /root/reference in the
+    build container; kind "reference") through its public NeRFAll.forward in training mode -- its chunk loop, NaN checks and
+    per-exposure Python included -- else the oracle port (kind "port").  Returns (kind, ms per step)."""
+    import torch
     torch.set_num_threads(threads)
-    cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
-    with torch.no_grad():
+    rh = _harness()
+    P = make_params("cpu")
+    rays, idx = make_rays(sample_rays, seed=100)
+    if rh.reference_available():
+        nerf = rh.build_bench_reference(P, N_EXPOSURE, False, "cpu")
+        kw = _reference_kwargs()
+
+        def one():
+            with torch.no_grad():
+                nerf(H, W, KMAT, chunk=1024 * 32, rays=rays, rays_info={"images_idx": idx}, **kw)
+        kind = "reference"
+    else:
+        import evdeblur_oracle as oc
+        cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
+
+        def one():
+            with torch.no_grad():
+                oc.forward_train(P, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+        kind = "port"
+    times = []
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = oc.forward_train(P_cpu, cfg, H, W, FOCAL, rays_cpu, idx_cpu, N_EXPOSURE, NC, NI, use_awp=False)
-        dt = time.perf_counter() - t0
-    return dt, out
+        one()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return kind, 1e3 * sum(times) / max(len(times), 1)
 
 
-def gpu_eager_port(P_dev, dev, n_rays, steps=3):
-    """Baseline leg, second figure: the same oracle port run as EAGER PyTorch fp32 on the B200 itself -- the stand-in for
-    the reference's own single-GPU path (the reference is Python under /root/reference and cannot travel to the
-    GPU box).  Like the reference (run_nerf.py:779) it runs with CUDA as the default device.  Forward (no_grad) of the bench
-    workload, then forward + autograd backward of the image loss; CUDA-event timed, best of `steps` after one warm-up."""
+def gpu_eager_reference(P_dev, dev, n_rays, steps=3):
+    """Baseline leg, second figure: the reference's own single-GPU PyTorch path ON the B200 (north star: >= 10x this) -- the
+    UNMODIFIED reference from oracle/_ref with CUDA as the default device (run_nerf.py:779), eager fp32, its own chunk loop
+    (chunk = 32768) and host-synchronising NaN checks; the oracle port as eager PyTorch when nothing is staged.  Forward
+    (no_grad) of the bench workload, then forward + autograd backward of the image loss; CUDA-event timed, best of `steps`."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import evdeblur_oracle as oc
-    cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
+    rh = _harness()
     rays, idx = make_rays(n_rays, seed=100)
     rays, idx = rays.to(dev), idx.to(dev)
-    out = {"kind": "port", "what": "oracle restatement of the reference path as eager PyTorch fp32 on this GPU, whole batch in one chunk",
-           "rays": n_rays, "unit": "rays/s"}
+    real = rh.reference_available()
+    out = {"kind": "reference" if real else "port", "rays": n_rays, "unit": "rays/s",
+           "what": ("UNMODIFIED reference (oracle/_ref) NeRFAll.forward, training branch, eager fp32, default device = this GPU, chunk 32768"
+                    if real else "oracle restatement of the reference path as eager PyTorch fp32 on this GPU, whole batch in one chunk")}
 
     def timed(fn):
         best = None
@@ -217,50 +283,60 @@ def gpu_eager_port(P_dev, dev, n_rays, steps=3):
         return best
 
     with torch.device(dev):
-        def fwd():
-            with torch.no_grad():
-                oc.forward_train(P_dev, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+        target = torch.rand(n_rays, 3, device=dev)
+        if real:
+            nerf = rh.build_bench_reference(P_dev, N_EXPOSURE, False, dev)
+            kw = _reference_kwargs()
+            call = lambda: nerf(H, W, KMAT, chunk=1024 * 32, rays=rays, rays_info={"images_idx": idx}, **kw)
+
+            def fwd():
+                with torch.no_grad():
+                    call()
+
+            def fwd_bwd():
+                rgb, rgb0, _, _ = call()
+                loss = torch.mean((rgb - target) ** 2) + torch.mean((rgb0 - target) ** 2)
+                loss.backward()
+                nerf.zero_grad(set_to_none=True)
+        else:
+            import evdeblur_oracle as oc
+            cfg = {"aabb_min": AABB[0], "aabb_max": AABB[1], "rmnearplane": 0}
+            leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P_dev.items()}
+
+            def fwd():
+                with torch.no_grad():
+                    oc.forward_train(P_dev, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+
+            def fwd_bwd():
+                o = oc.forward_train(leaves, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
+                loss = oc.img2mse(o["rgb"], target) + oc.img2mse(o["rgb1"], target)
+                loss.backward()
+                for v in leaves.values():
+                    v.grad = None
         ms = timed(fwd)
         out.update(fwd_ms=ms, value=n_rays / (ms / 1e3))
-        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P_dev.items()}
-        target = torch.rand(n_rays, 3, device=dev)
-
-        def fwd_bwd():
-            o = oc.forward_train(leaves, cfg, H, W, FOCAL, rays, idx, N_EXPOSURE, NC, NI, use_awp=False)
-            loss = oc.img2mse(o["rgb"], target) + oc.img2mse(o["rgb1"], target)
-            loss.backward()
-            for v in leaves.values():
-                v.grad = None
         ms = timed(fwd_bwd)
         out.update(fwd_bwd_ms=ms, fwd_bwd_value=n_rays / (ms / 1e3))
-    del leaves
     torch.cuda.empty_cache()
     return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores, bounded sample per step."""
-    import torch
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_rays = 512
-    P = make_params("cpu")
-    rays, idx = make_rays(sample_rays, seed=100)
-    times = []
-    for i in range(args.warmup + args.steps):
-        dt, _ = cpu_reference_step(P, rays, idx, threads)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / max(len(times), 1)
+    sample_rays = args.sample_rays
+    kind, ms = cpu_reference_arm(sample_rays, args.steps, args.warmup, threads)
     val = sample_rays / (ms / 1e3)
     line = {"impl": "reference", "metric": "primary_rays_per_sec_fwd", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config("fp32", sample=f"{sample_rays} primary rays x {N_EXPOSURE} exposures per step"),
-            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample_rays} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, full-size VM grids"},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
+                             "sample": f"{sample_rays} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, full-size VM grids"
+                                       + ("; UNMODIFIED reference NeRFAll.forward (training branch, AWP off) from oracle/_ref" if kind == "reference" else "")},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -275,6 +351,70 @@ def workload_config(precision, **extra):
     return cfg
 
 
+def timed_steps(fn, steps, warmup, world, dev, before_each=None):
+    """W untimed + K timed calls of fn(i); barrier + synchronize on both sides; CUDA events; MAX over ranks -> ms per step."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = []
+    for i in range(steps):
+        if before_each is not None:
+            before_each()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn(warmup + i)
+        e.record()
+        ev.append((s, e))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def train_leg(P_all, dev, precision, n_rays_rank, world, rank, steps, warmup, flush):
+    """BASELINE config 4: Trainer.step on this rank's rays -- forward (AWP on, perturb = 1, raw_noise_std = 1) + MSE (fine, coarse,
+    AWP) + TV losses + backward + ONE flat gradient all-reduce over NCCL (+ the synchronised-BatchNorm exchange) + fused Adam."""
+    import torch
+    from evdeblurnerf_b200.trainer import Trainer
+    tr = Trainer(P_all, None, *AABB, kernel_ptnum=N_EXPOSURE, precision=precision, tv_loss_weight=1e-2, device=dev, use_awp=True,
+                 render_kwargs=dict(N_samples=NC, N_importance=NI, perturb=1., raw_noise_std=1.), check_numerics_every=0)
+    tr.nerf.backward_chunk_rays = 20480
+    batches = []
+    for s_ in range(steps + warmup):
+        rays, idx = make_rays(n_rays_rank, seed=5000 + 1000 * rank + s_)
+        g = torch.Generator().manual_seed(s_)
+        batches.append({"rays": rays.to(dev), "images_idx": idx.to(dev), "rgbsf": torch.rand(n_rays_rank, 3, generator=g).to(dev)})
+    last = {}
+    tr.flat.profile = []
+
+    def one(i):
+        last["out"] = tr.step(batches[i], H, W, KMAT)
+    ms = timed_steps(one, steps, warmup, world, dev, before_each=lambda: flush.fill_(1))
+    ar = tr.flat.profile[-steps:] if world > 1 else []
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar) / max(len(ar), 1) if ar else 0.0
+    loss = float(last["out"]["loss"])
+    errs = tr.nerf.engine.numerical_errors()
+    finite = torch.tensor([1.0 if (loss == loss and abs(loss) != float("inf") and not errs and bool(torch.isfinite(tr.flat.param).all())) else 0.0],
+                          device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+    res = {"ms_per_step": ms, "value": world * n_rays_rank / (ms / 1e3), "unit": "rays/s", "rays_per_rank": n_rays_rank, "loss": loss,
+           "loss_finite": bool(finite.item() > 0.5), "numerical_errors": errs, "all_reduce_ms": ar_ms,
+           "all_reduce_share": ar_ms / ms if ms else None, "all_reduce_bytes": tr.flat.numel * 4 if world > 1 else 0}
+    del tr, batches
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,6 +424,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the shipped-config / training / strong-scaling legs")
+    ap.add_argument("--sample-rays", type=int, default=512, help="--impl reference: primary rays per CPU step (bounded sample)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -359,11 +501,50 @@ def main():
         ev2.append((s, e))
     barrier()
     e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
+    headline_errs = eng.numerical_errors()
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = t.tolist()
+
+    # ---- the legs beside the headline, at every N (all ranks take part) ------------------------------------------------------
+    extra = {}
+    if not args.no_train:
+        k2, w2 = max(4, min(args.steps, 8)), 3
+        flush_fn = lambda: flush.fill_(1)
+        # (a) shipped configuration, forward: training branch with the AWP branch on, perturb = 1, raw_noise_std = 1
+        P_all = dict(P)
+        P_all.update(awp_params(dev))
+        nerf_awp = NeRFAll(P_all, *AABB, kernel_ptnum=N_EXPOSURE, precision=args.precision, use_awp=True).train()
+        kw_ship = dict(force_naive=False, retraw=True, N_samples=NC, N_importance=NI, perturb=1., raw_noise_std=1.)
+
+        def ship(i):
+            with torch.no_grad():
+                nerf_awp(H, W, KMAT, rays=rays_dev, rays_info={"images_idx": idx_dev}, **kw_ship)
+        ms = timed_steps(ship, k2, w2, world, dev, before_each=flush_fn)
+        extra["shipped_forward"] = {"ms_per_step": ms, "value": world * N_RAYS / (ms / 1e3), "unit": "rays/s",
+                                    "what": "NeRFAll.forward training branch: RBK warp -> c2f render emitting depth_feature -> AWP -> "
+                                            "exposure blends + TV; kernel_use_awp, perturb = 1, raw_noise_std = 1 (every shipped config)",
+                                    "numerical_errors": nerf_awp.engine.numerical_errors()}
+        del nerf_awp
+        torch.cuda.empty_cache()
+        # (b) config 4: full training step, weak scaling (4096 rays per rank), the gradient all-reduce inside
+        extra["train_step"] = dict(train_leg(P_all, dev, args.precision, N_RAYS, world, rank, k2, w2, flush), scaling="weak", n_gpus=world,
+                                   what="Trainer.step: fwd (AWP on, perturb / noise on) + MSE x3 + TV + bwd + flat gradient all-reduce "
+                                        "(NCCL, avg) + sync-BN exchange + Adam over 36.9M parameters")
+        # (c) SURVEY 8(e)'s partition: the SAME 4096-ray batch split across the ranks (strong scaling), forward and training
+        n_loc = N_RAYS // world
+        rays_s, idx_s = make_rays(N_RAYS, seed=4242)
+        rays_s, idx_s = rays_s[rank * n_loc:(rank + 1) * n_loc].to(dev), idx_s[rank * n_loc:(rank + 1) * n_loc].to(dev)
+        ms = timed_steps(lambda i: step(rays_s, idx_s), k2, w2, world, dev, before_each=flush_fn)
+        strong = {"rays_total": n_loc * world, "rays_per_rank": n_loc, "fwd_ms_per_step": ms, "fwd_value": n_loc * world / (ms / 1e3), "unit": "rays/s"}
+        tl = train_leg(P_all, dev, args.precision, n_loc, world, rank, k2, w2, flush)
+        strong.update(train_ms_per_step=tl["ms_per_step"], train_value=tl["value"], train_loss_finite=tl["loss_finite"],
+                      train_all_reduce_ms=tl["all_reduce_ms"])
+        extra["strong"] = strong
+        del P_all
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -381,18 +562,20 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
     R = N_RAYS * N_EXPOSURE
     fine_ms = kern_ms.get("fine", float("nan"))
-    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of the fine kernel from the committed ncu --set full capture
-    try:
-        txt = open(os.path.join(ROOT, "profiles", "r1_tc_kernels_ncu_summary.txt")).read().split("=" * 100)
-        blk = next(b for b in txt if "fine_fwd_tc_kernel" in b)
-        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-        tot = 0.0
-        for key in ("dram__bytes_read.sum ", "dram__bytes_write.sum "):
-            ln = next(l for l in blk.splitlines() if l.startswith(key)).split()
-            tot += float(ln[1]) * unit[ln[2]]
-        traffic = tot if args.precision == "bf16" else None
-    except Exception:
-        traffic = None
+    traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of the fine kernel: committed ncu --set full capture
+    for name in ("r2_tc_kernels_ncu_summary.txt", "r1_tc_kernels_ncu_summary.txt"):
+        try:
+            txt = open(os.path.join(ROOT, "profiles", name)).read().split("=" * 100)
+            blk = next(b for b in txt if "fine_fwd_tc_kernel" in b)
+            unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            tot = 0.0
+            for key in ("dram__bytes_read.sum ", "dram__bytes_write.sum "):
+                ln = next(l for l in blk.splitlines() if l.startswith(key)).split()
+                tot += float(ln[1]) * unit[ln[2]]
+            traffic, traffic_src = (tot if args.precision == "bf16" else None), "profiles/" + name
+            break
+        except Exception:
+            continue
     achieved = flops_fine_kernel_per_subray() * R / (fine_ms / 1e3) / 1e12
     line = {
         "metric": "primary_rays_per_sec_fwd", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -401,37 +584,37 @@ def main():
         "config": workload_config(args.precision),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rays_host.numel() * 4 + idx_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": 6 * args.steps,   # rbk_warp_ndc, coarse, sample_pdf_merge, fine, 2 x weighted_sum
+        "gpu_launches": 7 * args.steps,   # rbk_warp_ndc, coarse, sample_pdf_merge, fine, NaN/Inf guard, 2 x weighted_sum
         "clocks": clocks,
         "kernels_ms": kern_ms,
+        "numerical_errors": headline_errs,
         "roofline": {"bound": "tensor", "kernel": "edn_render_fine_fwd", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-                     "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                     "traffic_unit": "bytes/launch (ncu dram read+write, parsed from the committed capture, not measured in this run)",
+                     "traffic_source": traffic_src, "peak_source": peak_src,
+                     "peak_note": "a burst figure against the burst peak: the timed region is tens of ms, power never reaches the cap",
                      "flops_per_launch": flops_fine_kernel_per_subray() * R, "ms_per_launch": fine_ms,
                      "whole_step_tflops": flops_per_subray() * R / (ms_per_step / 1e3) / 1e12},
         "wall_s_timed_region": t_wall,
     }
+    line.update(extra)
+    del nerf
+    torch.cuda.empty_cache()
     if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N = 1 only
-        threads = os.cpu_count() or 1
-        sample = 512
-        Pc = {k: v.cpu() for k, v in P.items()}
-        rays_c, idx_c = make_rays(sample, seed=100)
-        best, t_spent = None, 0.0
-        for i in range(4):
-            dt, _ = cpu_reference_step(Pc, rays_c, idx_c, threads)
-            t_spent += dt
-            if i > 0:
-                best = dt if best is None else min(best, dt)
-            if t_spent > 25.0 and best is not None:
-                break
-        line["cpu_baseline"] = {"value": sample / best, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"{sample} primary rays x {N_EXPOSURE} exposures, {NC}+{NI} samples, same VM grids; "
-                                          f"best of {i} after 1 warm-up"}
+        # the reference's CPU path in a FRESH process (its harness turns Tensor.cuda into a no-op: never in this process)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                               capture_output=True, text=True, timeout=600)
+            ref_line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            line["cpu_baseline"] = dict(ref_line["cpu_baseline"], ms_per_step=ref_line["ms_per_step"])
+            line["cpu_baseline"]["sample"] += "; mean of 3 steps after 1 warm-up, all host threads"
+        except Exception as exc:
+            line["cpu_baseline"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     if not args.no_cpu_baseline and not args.no_gpu_eager_baseline and world == 1:
         try:
-            line["gpu_eager_port"] = gpu_eager_port(P, dev, N_RAYS)
+            line["gpu_eager_reference"] = gpu_eager_reference(P, dev, N_RAYS)
         except Exception as exc:     # a reported extra, never the measured arm: an OOM here must not lose the bench line
-            line["gpu_eager_port"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            line["gpu_eager_reference"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

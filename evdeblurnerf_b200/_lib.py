@@ -87,6 +87,7 @@ class AwpGrads(AwpParams):
 
 
 CRF_GAMMA, CRF_LEARN, CRF_SKIP_LEARN, CRF_LUMA = 1, 2, 4, 8
+CRF_LUMA_REC709, CRF_LUMA_AVG = 16, 32
 FLAG_WHITE_BKGD = 8
 
 # name -> (restype, argtypes); must list every symbol include/evdeblur_b200.h declares (tests/test_abi.py checks)
@@ -97,6 +98,7 @@ SIGNATURES = {
     "edn_pack_vm_plane": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "edn_fill_random": (C.c_int, [_P, _I64, C.c_uint64, C.c_uint32, _I32, _F, _P]),
     "edn_vm_sample": (C.c_int, [C.POINTER(VmGrid), _P, _P, _I64, _P]),
+    "edn_check_finite": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I32, _P, _P]),
     "edn_render_coarse_fwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(FieldMlp), _P, _P, _P, _P, _I64, _I32, _I32, _F,
                                         _I32, _P, _P, _P, _P, _P, _P, _P]),
     "edn_coarse_tc_blob_bytes": (C.c_int64, []),

@@ -314,11 +314,12 @@ class AwpFn(torch.autograd.Function):
         d_vf = torch.empty_like(vf)
         ws, ctx.ws = ctx.ws, None
         world = awp._world()
-        phases = [awp.options(True)] if world == 1 else [awp.options(True, 1), awp.options(True, 2, NE * world)]
+        # phases 1 / 2: BatchNorm row count = the all-reduced one the forward left in the workspace (bn_rows_total = 0)
+        phases = [awp.options(True)] if world == 1 else [awp.options(True, 1), awp.options(True, 2)]
         dcc = _c(d_ccw)
         for o in phases:      # the forward's workspace still holds the activations and the (all-reduced) batch sums
             check(lib.edn_awp_bwd(C.byref(awp.p), ptr(df), ptr(z), ptr(rd), 3, ptr(vf), N, E, S, awp.bn_eps, C.byref(o), 1, ptr(dcc),
                                   C.byref(g), ptr(d_df), ptr(d_rd), 3, ptr(d_vf), ptr(ws), stream_ptr()), "edn_awp_bwd")
             if o.phase == 1:
-                awp._all_reduce_block(ws, int(lib.edn_awp_bwd_sums_offset_floats(N, E, S)))
+                awp._all_reduce_block(ws, int(lib.edn_awp_bwd_sums_offset_floats(N, E, S)), 64)
         return (None, d_df, None, d_rd, d_vf) + tuple(awp_grads_to_reference(bufs))

@@ -521,13 +521,14 @@ __global__ void awp_bn_stats_kernel(const float* __restrict__ y, int64_t rows, d
     for (int p = 1; p < 8; ++p) { s1 += sh[0][p][c]; s2 += sh[1][p][c]; }
     stats[2 * c] = s1; stats[2 * c + 1] = s2;
   }
+  if (threadIdx.x == 0) { stats[64] = (double)rows; stats[65] = 0.0; }     // the row count travels (and is all-reduced) with the sums
 }
 
 __global__ void awp_out_kernel(const AwpArgs a, float bn_eps) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.N) return;
   const int E = a.E;
-  const double rows = a.bn_rows;
+  const double rows = a.bn_rows > 0.0 ? a.bn_rows : a.stats[64];
   float pooled[32];
   for (int c = 0; c < 32; ++c) {
     const double mean = a.stats[2 * c] / rows;
@@ -578,7 +579,7 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
   a.view_feature = view_feature; a.N = n_rays; a.E = n_exposure; a.S = n_samples; a.ccw = ccw;
   const AwpWs ws = awp_ws_carve(workspace, n_rays, n_exposure, n_samples, gemm_path);
   a.gint = ws.gint; a.inter = ws.inter; a.xl = ws.xl; a.att = ws.att; a.x = ws.x; a.y = ws.y; a.stats = ws.stats;
-  a.bn_rows = (double)(bn_rows_total > 0 ? bn_rows_total : NE);
+  a.bn_rows = (double)(bn_rows_total > 0 ? bn_rows_total : (phase == 0 ? NE : 0));   // 0: read the all-reduced count from the workspace
   if (phase == 2) {      // finish from the (all-reduced) batch sums already in the workspace
     awp_out_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(a, bn_eps);
     EDN_CUDA_OK(cudaGetLastError());

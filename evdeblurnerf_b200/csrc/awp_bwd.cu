@@ -43,7 +43,7 @@ struct BwdArgs {
 __global__ void __launch_bounds__(128) awp_out_bwd_kernel(const BwdArgs a) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int E = a.E, lane = threadIdx.x & 31;
-  const double rows = a.bn_rows;
+  const double rows = a.bn_rows > 0.0 ? a.bn_rows : a.ws.stats[64];
   float s1[32], s2[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kRayBwdThreads) awp_ray_bwd_kernel(const BwdAr
   RayBwdSmem<EMAX, SMAX>& s = *reinterpret_cast<RayBwdSmem<EMAX, SMAX>*>(smraw);
   const int tid = threadIdx.x, E = a.E, S = a.S, warp = tid >> 5, lane = tid & 31;
   const int64_t n = blockIdx.x;
-  const double rows = a.bn_rows;
+  const double rows = a.bn_rows > 0.0 ? a.bn_rows : a.ws.stats[64];
   // ---- load / recompute the forward intermediates --------------------------------------------------------------------
   for (int i = tid; i < E * 32; i += kRayBwdThreads) {
     const int e = i >> 5, c = i & 31;
@@ -673,7 +673,7 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   a.p = *p; a.g = *grads; a.ws = awp_ws_carve(workspace, N, E, S, true);
   a.z_vals = z_vals; a.rays_d = rays_d; a.rays_d_stride = rays_d_stride; a.view_feature = view_feature;
   a.N = N; a.E = E; a.S = S; a.bn_eps = bn_eps; a.d_ccw = d_ccw;
-  a.bn_rows = (double)(opt->bn_rows_total > 0 ? opt->bn_rows_total : NE);
+  a.bn_rows = (double)(opt->bn_rows_total > 0 ? opt->bn_rows_total : (phase == 0 ? NE : 0));   // 0: the forward's all-reduced count (ws.stats[64])
   a.d_rays_d = d_rays_d; a.d_rays_d_stride = d_rays_d_stride; a.d_view_feature = d_view_feature;
   a.d_yn = head.d_yn;
   a.d_x = head.d_x;

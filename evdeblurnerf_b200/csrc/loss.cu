@@ -79,7 +79,9 @@ __global__ void crf_kernel(const CrfArgs a) {
     y[c] = x;
   }
   if (a.flags & EDN_CRF_LUMA) {
-    a.out[mIdx] = 0.299f * y[0] + 0.587f * y[1] + 0.114f * y[2];   // rec601, tonemapping.py:128-129
+    if (a.flags & EDN_CRF_LUMA_REC709) a.out[mIdx] = 0.2126f * y[0] + 0.7152f * y[1] + 0.0722f * y[2];   // tonemapping.py:130-131
+    else if (a.flags & EDN_CRF_LUMA_AVG) a.out[mIdx] = (y[0] + y[1] + y[2]) / 3.0f;                      // x.mean(-1), tonemapping.py:132-133
+    else a.out[mIdx] = 0.299f * y[0] + 0.587f * y[1] + 0.114f * y[2];                                   // rec601, tonemapping.py:128-129
   } else {
     a.out[mIdx * 3 + 0] = y[0]; a.out[mIdx * 3 + 1] = y[1]; a.out[mIdx * 3 + 2] = y[2];
   }

@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_bwd_kernel(const CrfBwdArg
   for (int i = 0; i < kPerLane; ++i) pg[i] = 0.f;
   const int64_t mIdx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = mIdx < a.M;
-  const float luma[3] = {0.299f, 0.587f, 0.114f};
+  const float third = 1.0f / 3.0f;
+  const float luma[3] = {(a.flags & EDN_CRF_LUMA_REC709) ? 0.2126f : (a.flags & EDN_CRF_LUMA_AVG) ? third : 0.299f,
+                         (a.flags & EDN_CRF_LUMA_REC709) ? 0.7152f : (a.flags & EDN_CRF_LUMA_AVG) ? third : 0.587f,
+                         (a.flags & EDN_CRF_LUMA_REC709) ? 0.0722f : (a.flags & EDN_CRF_LUMA_AVG) ? third : 0.114f};
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     float dxg = 0.f, x0 = 0.f;

@@ -147,6 +147,39 @@ class SamplerHost:
         self.device = torch.device(device if device is not None else "cuda")
         self._lin = {}
         self.profile = None     # set to {} to collect (start, end) CUDA events per kernel (bench.py roofline leg)
+        # NaN / Inf guard (renderer.py:259-263): True = every returned tensor except depth_feature (a non-finite feature reaches
+        # rgb_map through color_net anyway), "full" = depth_feature too (1.3 GB scan on the headline batch), False = off
+        self.check_numerics = True
+        self._err_flags = torch.zeros((2,), dtype=torch.int32, device=self.device)
+
+    GUARD_KEYS = ("rgb_map", "depth_map", "acc_map", "z_vals", "weights", "rgb0", "depth0", "acc0", "z_std", "z_vals0", "weights0",
+                  "depth_feature")
+
+    def _guard(self, ret):
+        """One launch ORs a bit per result tensor into the device flag words; nothing is read back here."""
+        if not self.check_numerics:
+            return ret
+        keys = [k for k in self.GUARD_KEYS if k in ret and ret[k] is not None and ret[k].numel() > 0
+                and (k != "depth_feature" or self.check_numerics == "full")]
+        ts = [ret[k] if ret[k].is_contiguous() else ret[k].contiguous() for k in keys]
+        ptrs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        sizes = (C.c_int64 * len(ts))(*[t.numel() for t in ts])
+        # bit t of the flag words = position of the key in GUARD_KEYS: pad the call with empty slots to keep positions fixed
+        idx = [self.GUARD_KEYS.index(k) for k in keys]
+        n = (max(idx) + 1) if idx else 0
+        full_p, full_n = (C.c_void_p * max(n, 1))(), (C.c_int64 * max(n, 1))()
+        for j, i in enumerate(idx):
+            full_p[i], full_n[i] = ptrs[j], sizes[j]
+        check(_lib.load().edn_check_finite(full_p, full_n, n, ptr(self._err_flags), stream_ptr()), "edn_check_finite")
+        return ret
+
+    def numerical_errors(self, reset=True):
+        """Reads the guard's flag words (synchronises) -> the reference's messages, e.g. ['rgb_map contains nan.']."""
+        nan_bits, inf_bits = (int(v) & 0xFFFFFFFF for v in self._err_flags.tolist())
+        if reset and (nan_bits or inf_bits):
+            self._err_flags.zero_()
+        msgs = [f"{k} contains nan." for i, k in enumerate(self.GUARD_KEYS) if nan_bits >> i & 1]
+        return msgs + [f"{k} contains inf." for i, k in enumerate(self.GUARD_KEYS) if inf_bits >> i & 1]
 
 
 class RenderEngine(SamplerHost):
@@ -317,7 +350,7 @@ class RenderEngine(SamplerHost):
                 ret["z_vals"], ret["weights"] = z0, w0
             if want_feat:
                 ret["depth_feature"], ret["z_vals"] = feat0, z0
-            return ret
+            return self._guard(ret)
 
         if self.fine is None:
             raise RuntimeError("render_rays: N_importance > 0 needs mlp_fine.* parameters")
@@ -350,7 +383,7 @@ class RenderEngine(SamplerHost):
             ret["depth_feature"], ret["z_vals"] = feat1, m["z_vals"]
         if want_indices:
             ret["inds"], ret["order"], ret["z_samples"] = m["inds"], m["order"], m["z_samples"]
-        return ret
+        return self._guard(ret)
 
 
 # the sampler / launch helpers do not depend on the VM fields: share them with the nerf-mode renderer
@@ -400,4 +433,4 @@ class NerfRenderEngine(SamplerHost):
         from .nerf_mode import render_rays_nerf
         kw.pop("pytest", None)
         kw.pop("want_indices", None)
-        return render_rays_nerf(self, self.mlp_coarse, self.mlp_fine, ray_batch, N_samples, **kw)
+        return self._guard(render_rays_nerf(self, self.mlp_coarse, self.mlp_fine, ray_batch, N_samples, **kw))

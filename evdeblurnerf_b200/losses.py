@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CRF_GAMMA, CRF_LEARN, CRF_LUMA, CRF_SKIP_LEARN, CrfParams, check, ptr, stream_ptr
+from ._lib import CRF_GAMMA, CRF_LEARN, CRF_LUMA, CRF_LUMA_AVG, CRF_LUMA_REC709, CRF_SKIP_LEARN, CrfParams, check, ptr, stream_ptr
 
 
 def _f32c(t):
@@ -20,8 +20,9 @@ class TonemappingTransform:
 
     def __init__(self, params, map_type_rgb="gamma", map_type_event="learn", extra_features_event=2,
                  extra_features_rgb=0, gamma=2.2, luma_standard="rec601"):
-        if luma_standard != "rec601":
-            raise NotImplementedError("only luma_standard='rec601' (the reference default) is built")
+        if luma_standard not in ("rec601", "rec709", "avg"):
+            raise ValueError(f"Unknown luma_standard {luma_standard}")          # tonemapping.py:134-135
+        self.luma_standard = luma_standard
         self.map_type = {"rgb": map_type_rgb, "event": map_type_event}
         self.extra = {"rgb": extra_features_rgb, "event": extra_features_event}
         self.gamma = float(gamma)
@@ -51,9 +52,10 @@ class TonemappingTransform:
         if mt not in ("none", "gamma", "learn"):
             raise NotImplementedError(f"map_type {mt!r}")
         flags = (CRF_GAMMA if "gamma" in mt else 0) | (CRF_LEARN if mt == "learn" else 0)
-        flags |= (CRF_SKIP_LEARN if skip_learn else 0) | (CRF_LUMA if luma else 0)
+        luma_bits = (CRF_LUMA | {"rec601": 0, "rec709": CRF_LUMA_REC709, "avg": CRF_LUMA_AVG}[self.luma_standard]) if luma else 0
+        flags |= (CRF_SKIP_LEARN if skip_learn else 0) | luma_bits
         if mt == "none":
-            flags = CRF_LUMA if luma else 0
+            flags = luma_bits
         shape = x.shape
         xf = _f32c(x).reshape(-1, 3)
         M = xf.shape[0]

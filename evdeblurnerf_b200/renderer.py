@@ -128,23 +128,24 @@ class AdaptiveWeightProposal:
             return AwpFn.apply(self, depth_feature, z_vals, rays_d, view_feature, *ps)
         return self.run(depth_feature, z_vals, rays_d, view_feature)
 
-    # ---- synchronised BatchNorm: with torch.distributed initialised and world_size > 1 the batch sums of
-    #      CorrelationModule's BatchNorm1d are all-reduced between two phases of the pass, so N ranks x N/world rays reproduce
-    #      the single-GPU statistics (equal shard sizes assumed) --------------------------------------------------------------
-    sync_bn = True
+    # ---- synchronised BatchNorm: when `sync_bn` is set (the Trainer does, for the process group it trains on)
+    #      the batch sums of CorrelationModule's BatchNorm1d -- and the row count behind them, so ragged shards are fine -- are
+    #      all-reduced between two phases of the pass: N ranks x N/world rays reproduce the single-GPU statistics.  Off by
+    #      default: a stand-alone (e.g. rank-0-only validation) call must not enter a collective -------------------------------
+    sync_bn = False
+    group = None            # torch.distributed process group of the exchange (None = default group)
 
     def _world(self):
         import torch.distributed as dist
-        return dist.get_world_size() if (self.sync_bn and dist.is_available() and dist.is_initialized()) else 1
+        return dist.get_world_size(self.group) if (self.sync_bn and dist.is_available() and dist.is_initialized()) else 1
 
     def options(self, keep_activations=False, phase=0, bn_rows_total=0):
         return _lib.AwpOptions(self.precision, 1 if keep_activations else 0, int(phase), int(bn_rows_total))
 
-    @staticmethod
-    def _all_reduce_block(ws, offset_floats):
+    def _all_reduce_block(self, ws, offset_floats, n_doubles):
         import torch.distributed as dist
-        block = ws[offset_floats: offset_floats + 128].view(torch.float64)
-        dist.all_reduce(block)
+        block = ws[offset_floats: offset_floats + 2 * n_doubles].view(torch.float64)
+        dist.all_reduce(block, group=self.group)
 
     def run(self, depth_feature, z_vals, rays_d, view_feature, workspace=None, keep_activations=False):
         df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
@@ -163,12 +164,14 @@ class AdaptiveWeightProposal:
                                                                  dtype=torch.float32, device=df.device)
         ccw = torch.empty((N, E), dtype=torch.float32, device=df.device)
         world = self._world()
-        phases = [self.options(keep_activations)] if world == 1 else [self.options(keep_activations, 1), self.options(keep_activations, 2, NE * world)]
+        # phases 1 / 2 with bn_rows_total = 0: the kernels take the row count from the all-reduced block (sums + count)
+        phases = [self.options(keep_activations)] if world == 1 else [self.options(keep_activations, 1), self.options(keep_activations, 2)]
         for o in phases:
             check(lib.edn_awp_fwd(C.byref(self.p), ptr(df), ptr(z), rd.data_ptr(), int(rd.stride(0)), ptr(vf), N, E, S, self.bn_eps,
                                   C.byref(o), ptr(ws), ptr(ccw), stream_ptr()), "edn_awp_fwd")
             if o.phase == 1:
-                self._all_reduce_block(ws, int(lib.edn_awp_stats_offset_floats(N, E, S)))
+                self._all_reduce_block(ws, int(lib.edn_awp_stats_offset_floats(N, E, S)), 66)
+        self.last_stats = ws[int(lib.edn_awp_stats_offset_floats(N, E, S)):][:132].view(torch.float64)   # sums, sums of squares, rows
         return ccw
 
 
@@ -238,7 +241,9 @@ class NeRFAll:
         """Refresh the render-layout copies after the parameters changed (optimizer.step(), load_state_dict)."""
         self.engine.repack(self.params)
         if self.use_awp:
-            self.awpnet = AdaptiveWeightProposal(self.params, self.awpnet.E - 1, precision=self.awpnet.precision)
+            old = self.awpnet
+            self.awpnet = AdaptiveWeightProposal(self.params, old.E - 1, precision=old.precision)
+            self.awpnet.sync_bn, self.awpnet.group = old.sync_bn, old.group
         self._packed_version = self._param_version()
 
     def _maybe_repack(self):

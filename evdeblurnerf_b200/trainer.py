@@ -21,6 +21,7 @@ from .losses import TonemappingTransform, egm_loss, img2mse
 from .renderer import NeRFAll
 
 _WD_RE = re.compile(r"\.color_net\.[0-9]+\.weight$")     # run_nerf.py:246
+_BUFFER_SUFFIXES = (".running_mean", ".running_var", ".num_batches_tracked")
 
 
 def lr_at(step, lrate, decay_k, warmup_iters=0, warmup_factor=1.0):
@@ -64,11 +65,25 @@ class FlatParams:
         """name -> view of `flat` (a buffer laid out like `param`, e.g. exp_avg) with the parameter's shape."""
         return {n: flat[self.offset[n]: self.offset[n] + v.numel()].view(v.shape) for n, v in self.views.items()}
 
+    profile = None      # set to [] to collect (start, end) CUDA events around the gradient exchange (bench.py)
+
     def all_reduce_mean(self, group=None):
-        """The one gradient exchange of a step: sum over ranks of the flat gradient buffer, divided by the world size."""
-        if torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
-            torch.distributed.all_reduce(self.grad, group=group)
-            self.grad.div_(torch.distributed.get_world_size(group))
+        """The one gradient exchange of a step: mean over ranks of the flat gradient buffer, in place.  NCCL averages inside the
+        collective (ReduceOp.AVG: no separate division sweep over the 147 MB buffer); gloo (CPU tests) sums, then divides."""
+        dist = torch.distributed
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            ev = None
+            if self.profile is not None and self.grad.is_cuda:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.grad, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.grad, group=group)
+                self.grad.div_(dist.get_world_size(group))
+            if ev is not None:
+                ev[1].record()
+                self.profile.append(ev)
 
     def adam(self, lr, step, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
         lib = _lib.load()
@@ -83,17 +98,22 @@ class Trainer:
     def __init__(self, state, crf_state, aabb_min, aabb_max, kernel_ptnum=5, precision="bf16", lrate=5e-4, lrate_decay=250,
                  lrate_warmup_iters=0, lrate_warmup_factor=1.0, colornet_weightdecay=0.0, tv_loss_weight=1e-2,
                  event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0,
-                 use_awp=False, awp_fine_loss_weight=None, schedule=None):
+                 use_awp=False, awp_fine_loss_weight=None, schedule=None, check_numerics_every=100):
         if not torch.cuda.is_available():
             raise RuntimeError("evdeblurnerf_b200.Trainer needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if device is not None else "cuda")
+        # nn.Module buffers (the BatchNorm running statistics of awpnet.MAM) are state, not parameters: they stay out of the flat
+        # parameter buffer, the optimizer groups and the Adam state (run_nerf.py:243-261 iterates named_parameters())
         trainable = {k: v for k, v in state.items() if isinstance(v, torch.Tensor) and v.is_floating_point()
-                     and k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.") + (("awpnet.",) if use_awp else ()))}
+                     and k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet.") + (("awpnet.",) if use_awp else ()))
+                     and not k.endswith(_BUFFER_SUFFIXES)}
         crf_train = {"crf." + k: v for k, v in (crf_state or {}).items() if isinstance(v, torch.Tensor) and v.is_floating_point()}
         self.flat = FlatParams({**trainable, **crf_train}, dev)
         P = {k: self.flat.views[k] for k in trainable}
         Pc = {k[4:]: self.flat.views[k] for k in crf_train}
         self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision, use_awp=use_awp).train()
+        if use_awp:     # BatchNorm statistics over the WHOLE batch, as on one GPU (SURVEY 8(e) caveat 1)
+            self.nerf.awpnet.sync_bn, self.nerf.awpnet.group = True, process_group
         self.awp_fine_loss_weight = awp_fine_loss_weight
         self.fuse_event_renders = True      # one render + one backward for the blurred rays and both event ray sets
         self.crf = TonemappingTransform(Pc, **(crf_kwargs or dict(map_type_rgb="gamma", map_type_event="learn" if Pc else "gamma",
@@ -106,16 +126,23 @@ class Trainer:
         self.rank = torch.distributed.get_rank(process_group) if torch.distributed.is_initialized() else 0
         self.nerf.engine.seed(seed * 1000003 + self.rank)      # per-rank draw streams (SURVEY 8(e) caveat 2)
         self.global_step = 0
+        # NaN / Inf guard (renderer.py:259-263): the render kernels' flag words are read back -- one host synchronisation -- every
+        # `check_numerics_every` steps (0 = never); findings are printed like the reference's and kept in `numerical_errors`
+        self.check_numerics_every, self.numerical_errors = int(check_numerics_every), []
         # run_nerf.py:121-142, 437-499 loss schedule.  Keys (reference option names, options.py:39,173-232): N_iters,
         # kernel_start_iter, kernel_start_warmup_mode ("step" | "linear" | "cosine"), kernel_start_warmup_iters,
         # kernel_awp_use_coarse_to_fine_opt, use_pts0_prior, pts0_target_{weight,weight_end,weight_steps,weight_scheduler,
-        # start_iter,end_iter}, blur_loss_after, event_egm_{weight,weight_end,weight_steps,weight_scheduler}, clip_grads_norm
+        # start_iter,end_iter}, blur_loss_after, event_egm_{weight,weight_end,weight_steps,weight_scheduler}, clip_grads_norm,
+        # tone_mapping_start_learn_iter, add_event_egm_startiter, add_event_egm_stages, event_egm_use_color_weights,
+        # event_egm_color_weights_start_iter, kernel_awp_fine_loss_start_ratio
         sc = dict(kernel_start_iter=0, kernel_start_warmup_mode="step", kernel_start_warmup_iters=1, N_iters=200000,
                   kernel_awp_use_coarse_to_fine_opt=False, use_pts0_prior=None, pts0_target_weight=0.1, pts0_target_weight_end=1.0,
                   pts0_target_weight_steps=None, pts0_target_weight_scheduler="constant", pts0_target_start_iter=-1,
                   pts0_target_end_iter=9999999, blur_loss_after=-1, event_egm_weight=event_loss_weight,
                   event_egm_weight_end=event_loss_weight, event_egm_weight_steps=None, event_egm_weight_scheduler="constant",
-                  clip_grads_norm=None)
+                  clip_grads_norm=None, tone_mapping_start_learn_iter=0, add_event_egm_startiter=None,
+                  add_event_egm_stages=("stage0", "stage1"), event_egm_use_color_weights=None, event_egm_color_weights_start_iter=-1,
+                  kernel_awp_fine_loss_start_ratio=0.1)
         unknown = set(schedule or {}) - set(sc)
         if unknown:
             raise ValueError(f"unknown schedule keys {sorted(unknown)}")
@@ -134,37 +161,48 @@ class Trainer:
         self._names = {"net": list(trainable), "crf": list(crf_state or {})}
         self._buffers = {k: v.detach().clone() for k, v in state.items() if isinstance(v, torch.Tensor) and k not in trainable}
 
-    # run_nerf.py:438-504 (+ 539-557 when event rays are given)
+    # run_nerf.py:438-504 (+ 506-592 when event rays are given)
     def loss(self, batch, H, W, K):
         out = {}
-        sc, i = self.schedule, self.global_step           # the reference's loop index i == global_step while the step runs
-        events = "ev_rays_start" in batch and (self.w_events_egm(i) or 0.0) > 0
+        sc, g = self.schedule, self.global_step
+        i = g + 1      # the reference's loop index: `start = global_step; for i in range(start + 1, ...)` (run_nerf.py:421-423), so
+        #                comparisons written against `i` see global_step + 1 and the schedule functions see global_step
+        force_naive = i < sc["kernel_start_iter"]                       # run_nerf.py:440: the blur kernel is off at first
+        skip_crf = i < sc["tone_mapping_start_learn_iter"]              # run_nerf.py:443: the learnt CRF is bypassed at first
+        w_ev = self.w_events_egm(g)
+        events = ("ev_rays_start" in batch and (w_ev or 0.0) > 0
+                  and (sc["add_event_egm_startiter"] is None or i >= sc["add_event_egm_startiter"]))
         use_pts0 = sc["use_pts0_prior"] is not None and sc["pts0_target_start_iter"] <= i < sc["pts0_target_end_iter"]
-        warm = sc["kernel_start_warmup_mode"] != "step" and sc["kernel_start_iter"] <= i < self.kernel_end_warmup_iter
-        render_kwargs = dict(self.render_kwargs, return_pts0_rgb=True) if (use_pts0 or warm) else self.render_kwargs
+        warm = sc["kernel_start_warmup_mode"] != "step" and sc["kernel_start_iter"] <= g < self.kernel_end_warmup_iter
+        want_pts0 = g < self.kernel_end_warmup_iter or use_pts0        # run_nerf.py:441
+        render_kwargs = dict(self.render_kwargs, return_pts0_rgb=True) if want_pts0 else self.render_kwargs
+        crf = lambda x, **kw: self.crf(x, skip_learn_crf=skip_crf, **kw)
         naive = None
-        if events and self.fuse_event_renders:
+        if events and self.fuse_event_renders and not force_naive:
             # the reference calls nerf() three times (blurred rays, event start rays, event end rays; run_nerf.py:438, 534, 547);
             # the rays are independent, so one fused render + one backward gives the same result with a third of the launches
             rgb, rgb0, extra_loss, extra_tensor, naive = self.nerf.forward_fused(
                 H, W, K, batch["rays"], batch, [batch["ev_rays_start"], batch["ev_rays_end"]], retraw=True, **render_kwargs)
         else:
-            rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False,
-                                                            **render_kwargs)
+            rgb, rgb0, extra_loss, extra_tensor = self.nerf(H, W, K, rays=batch["rays"], rays_info=batch, retraw=True,
+                                                            force_naive=force_naive, **render_kwargs)
         target = batch["rgbsf"].reshape(-1, 3)
-        img_loss = img2mse(self.crf(rgb, mode="encode_rgb"), target)
-        out["img_loss"] = img_loss.detach()
-        if rgb0 is not None:
-            img_loss = img_loss + img2mse(self.crf(rgb0, mode="encode_rgb"), target)
-        loss = img_loss
+        loss = 0.0
+        if i > sc["blur_loss_after"]:                          # run_nerf.py:452-462: no photometric term before blur_loss_after
+            img_loss = img2mse(crf(rgb, mode="encode_rgb"), target)
+            out["img_loss"] = img_loss.detach()
+            if rgb0 is not None:
+                img_loss = img_loss + img2mse(crf(rgb0, mode="encode_rgb"), target)
+            loss = img_loss
         if extra_tensor.get("rgb_awp") is not None:          # run_nerf.py:464-475
-            fine = img2mse(self.crf(extra_tensor["rgb_awp"], mode="encode_rgb"), target)
+            fine = img2mse(crf(extra_tensor["rgb_awp"], mode="encode_rgb"), target)
             out["img_fine_loss"] = fine.detach()
             flw = self.awp_fine_loss_weight                   # kernel_awp_use_coarse_to_fine_opt: annealed mix, else plain sum
             if flw is None and sc["kernel_awp_use_coarse_to_fine_opt"]:
-                if i % 10000 == 0 or self._fine_loss_weight is None:          # refreshed every 10 000 iterations (run_nerf.py:467-470)
-                    self._fine_loss_weight = exponential_scale_fine_loss_weight(sc["N_iters"], sc["kernel_start_iter"], 0.1, 0.9,
-                                                                                i - i % 10000)
+                if self._fine_loss_weight is None:            # run_nerf.py:416: starts at kernel_awp_fine_loss_start_ratio
+                    self._fine_loss_weight = sc["kernel_awp_fine_loss_start_ratio"]
+                if i % 10000 == 0:                            # refreshed every 10 000 iterations (run_nerf.py:467-470; N_iters + 1 there)
+                    self._fine_loss_weight = exponential_scale_fine_loss_weight(sc["N_iters"] + 1, sc["kernel_start_iter"], 0.1, 0.9, i)
                 flw = self._fine_loss_weight
             loss = loss + fine if flw is None else loss * (1 - flw) + fine * flw
         if warm or use_pts0:                                  # run_nerf.py:475-499
@@ -172,28 +210,36 @@ class Trainer:
             pts0_loss = 0.0
             for name in ("stage0_rgb_pts0", "stage1_rgb_pts0", "stage1_rgb1_pts0"):
                 if name in extra_tensor:
-                    pts0_loss = pts0_loss + img2mse(self.crf(extra_tensor[name], mode="encode_rgb"), tgt0)
+                    pts0_loss = pts0_loss + img2mse(crf(extra_tensor[name], mode="encode_rgb"), tgt0)
             out["pts0_loss"] = pts0_loss.detach()
             if use_pts0:
-                w_pts0 = 1.0 if i <= sc["blur_loss_after"] else self.w_pts0_target(i)
+                w_pts0 = 1.0 if i <= sc["blur_loss_after"] else self.w_pts0_target(g)
                 loss = loss + pts0_loss * w_pts0
             else:
-                loss = self.w_kernel(i) * loss + (1 - self.w_kernel(i)) * pts0_loss
+                loss = self.w_kernel(g) * loss + (1 - self.w_kernel(g)) * pts0_loss
         if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
             loss = loss + extra_loss["TV"] * self.hp["tv_w"]
         if events:
             feat = batch.get("ev_extra_feat")
+            cmask = batch.get("ev_color_map")
+            cweight = sc["event_egm_use_color_weights"] if i > sc["event_egm_color_weights_start_iter"] else None
+            ev_kw = {"tonemap_only": True} if cmask is not None else {}      # event_egm_use_colorevents (run_nerf.py:522)
             lum = []
-            for i, key in enumerate(("ev_rays_start", "ev_rays_end")):
+            for j, key in enumerate(("ev_rays_start", "ev_rays_end")):
                 if naive is not None:
-                    c, c0 = naive[i]
+                    c, c0 = naive[j]
                 else:
                     c, c0, _, _ = self.nerf(H, W, K, rays=batch[key], rays_info=None, retraw=True, force_naive=True, want_tv=False,
                                             **self.render_kwargs)   # TV of these calls is never used (run_nerf.py:500-501)
-                lum.append((self.crf(c, mode="encode_luma", ev_extra_feat=feat), self.crf(c0, mode="encode_luma", ev_extra_feat=feat)))
-            ev = egm_loss(lum[0][0], lum[1][0], batch["bii"]) + egm_loss(lum[0][1], lum[1][1], batch["bii"])   # stage1 + stage0
-            out["event_loss"] = ev.detach()
-            loss = loss + ev * self.w_events_egm(i)
+                lum.append((crf(c, mode="encode_luma", ev_extra_feat=feat, **ev_kw),
+                            crf(c0, mode="encode_luma", ev_extra_feat=feat, **ev_kw) if c0 is not None else None))
+            ev = 0.0
+            if "stage0" in sc["add_event_egm_stages"] and lum[0][1] is not None:          # run_nerf.py:562-567
+                ev = ev + egm_loss(lum[0][1], lum[1][1], batch["bii"], color_mask=cmask, color_weight=cweight)
+            if "stage1" in sc["add_event_egm_stages"]:                                     # run_nerf.py:568-571
+                ev = ev + egm_loss(lum[0][0], lum[1][0], batch["bii"], color_mask=cmask, color_weight=cweight)
+            out["event_loss"] = ev.detach() if isinstance(ev, torch.Tensor) else ev
+            loss = loss + ev * w_ev
         out["loss"] = loss
         return out
 
@@ -217,7 +263,17 @@ class Trainer:
         self.nerf.repack()
         out["loss"] = out["loss"].detach()
         out["lr"] = lr
+        if self.check_numerics_every > 0 and self.global_step % self.check_numerics_every == 0:
+            out["numerical_errors"] = self.poll_numerics()
         return out
+
+    def poll_numerics(self):
+        """Lazy read of the device NaN / Inf flags (synchronises) -> messages, printed in the reference's format."""
+        msgs = self.nerf.engine.numerical_errors()
+        for m_ in msgs:
+            print(f"! [Numerical Error] {m_}")            # renderer.py:260-263
+        self.numerical_errors += [(self.global_step, m_) for m_ in msgs]
+        return msgs
 
     def state_dict(self):
         """Reference-format tensors (run_nerf.py:628-634 saves network / optimizer state dicts)."""

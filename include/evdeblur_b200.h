@@ -134,6 +134,14 @@ int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_
                         int32_t n_samples, int32_t flags, float rmnearplane, int32_t precision, float* weights,
                         float* rgb, float* depth, float* acc, float* feat, void* stream);
 
+/* NaN / Inf guard of render_rays' result dict (renderer.py:259-263: `torch.isnan(ret[k]).any()` / `isinf` per returned tensor,
+ * printed, not raised).  One launch scans n_tensors (<= EDN_GUARD_MAX_TENSORS) fp32 device tensors -- pointer and element-count
+ * arrays live on the HOST -- and ORs bit t into flags[0] if tensor t holds a NaN, into flags[1] if it holds an Inf.  flags:
+ * 2 x uint32 in device memory, zeroed by the caller once; it is read back lazily (no synchronisation here). */
+#define EDN_GUARD_MAX_TENSORS 16
+int edn_check_finite(const float* const* tensors_host, const int64_t* sizes_host, int32_t n_tensors, uint32_t* flags,
+                     void* stream);
+
 /* ---- backward of the render path (the reference relies on torch autograd: loss.backward() at run_nerf.py:594) -------- */
 
 /* One PDRF field's weights -- or their gradients -- in the reference's own nn.Linear layout ([out][in], fp32), i.e. the
@@ -314,10 +322,12 @@ typedef struct edn_awp_options {
   int32_t keep_activations;  /* forward: run the per-sample MLP as GEMMs (fp32 ones under EDN_F32) and keep the layer activations
                                 in the workspace, so that edn_awp_bwd(forward_in_workspace = 1) does not recompute them */
   int32_t phase;             /* synchronised BatchNorm across ranks: 0 = whole pass with this call's batch sums;
-                                1 = stop after the local batch sums (64 doubles at edn_awp_stats_offset_floats /
-                                edn_awp_bwd_sums_offset_floats inside the workspace; the caller all-reduces them in place);
+                                1 = stop after the local batch sums (forward: 66 doubles at edn_awp_stats_offset_floats --
+                                64 sums, the row count behind them, one pad; backward: 64 doubles at
+                                edn_awp_bwd_sums_offset_floats -- inside the workspace; the caller all-reduces them in place);
                                 2 = finish from the sums in the workspace */
-  int64_t bn_rows_total;     /* rows behind the batch sums = N * E summed over all ranks; 0 = this call's N * E */
+  int64_t bn_rows_total;     /* rows behind the batch sums = N * E summed over all ranks; 0 = this call's N * E in phase 0 and, in
+                                phases 1 / 2, the all-reduced row count the forward left in the workspace (ragged shards are fine) */
 } edn_awp_options;
 
 int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples, const edn_awp_options* opt);
@@ -358,7 +368,9 @@ int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, const float
 int edn_weighted_sum(const float* x, const float* w, float* out, int64_t n, int32_t n_exposure, int64_t channels,
                      void* stream);
 
-enum { EDN_CRF_GAMMA = 1, EDN_CRF_LEARN = 2, EDN_CRF_SKIP_LEARN = 4, EDN_CRF_LUMA = 8 };
+/* EDN_CRF_LUMA alone = rec601; or-ed with EDN_CRF_LUMA_REC709 / EDN_CRF_LUMA_AVG for the other luma_standard values
+ * (tonemapping.py:128-135). */
+enum { EDN_CRF_GAMMA = 1, EDN_CRF_LEARN = 2, EDN_CRF_SKIP_LEARN = 4, EDN_CRF_LUMA = 8, EDN_CRF_LUMA_REC709 = 16, EDN_CRF_LUMA_AVG = 32 };
 
 /* CRF residual MLP (tonemapping.py:7-57): linear.0 [16][1+extra], linear.2 [16][16], linear.4 [16][16], linear.6 [1][16]. */
 typedef struct edn_crf_params {
@@ -373,7 +385,7 @@ typedef struct edn_crf_params {
 /* CRF.forward + TonemappingTransform.encode_rgb / encode_luma (tonemapping.py:59-93, 111-139).
  *   x [M][3]; feat [M][F] (feat_per_channel = 0), [M][3][F] (= 1) or NULL (zero padded, tonemapping.py:83-86)
  *   flags: EDN_CRF_GAMMA (map_type contains 'gamma'), EDN_CRF_LEARN (map_type == 'learn'), EDN_CRF_SKIP_LEARN,
- *          EDN_CRF_LUMA (rec601 luma, out [M][1]; otherwise out [M][3]). */
+ *          EDN_CRF_LUMA (luma, out [M][1]; otherwise out [M][3]; rec601 unless EDN_CRF_LUMA_REC709 / _AVG is set too). */
 int edn_crf_fwd(const edn_crf_params* p, const float* x, const float* feat, int32_t feat_per_channel, int32_t flags,
                 int64_t m, float* out, void* stream);
 

@@ -511,10 +511,17 @@ def encode_rgb(P, x, map_type_rgb="gamma", gamma=2.2):
 
 
 def encode_luma(P, x, map_type_event="learn", gamma=2.2, ev_extra_feat=None, extra_features=2, skip_learn=False,
-                tonemap_only=False):
+                tonemap_only=False, luma_standard="rec601"):
     x = crf_apply(P, "tonemapping_event.", x, map_type_event, gamma, ev_extra_feat, extra_features, skip_learn)
     if not tonemap_only:
-        x = 0.299 * x[..., [0]] + 0.587 * x[..., [1]] + 0.114 * x[..., [2]]  # rec601, tonemapping.py:128-129
+        if luma_standard == "rec601":
+            x = 0.299 * x[..., [0]] + 0.587 * x[..., [1]] + 0.114 * x[..., [2]]  # tonemapping.py:128-129
+        elif luma_standard == "rec709":
+            x = 0.2126 * x[..., [0]] + 0.7152 * x[..., [1]] + 0.0722 * x[..., [2]]  # tonemapping.py:130-131
+        elif luma_standard == "avg":
+            x = x.mean(axis=-1, keepdims=True)  # tonemapping.py:132-133
+        else:
+            raise ValueError(f"Unknown luma_standard {luma_standard}")
     return x
 
 

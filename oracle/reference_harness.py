@@ -1,9 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference from /root/reference (this container only).
+"""TEST / BENCH INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference: from /root/reference in the build container, else from
+the byte-for-byte staged copy under oracle/_ref/EvDeblurNeRF (oracle/stage_reference.py; git-ignored, travels to the GPU box).
 
 Builds the reference's own modules (NeRFAll + RigidBlurringModel + AdaptiveWeightProposal +
-TonemappingTransform) on CPU so that `oracle/make_golden.py` can (a) pin the oracle restatement in
-`oracle/evdeblur_oracle.py` against the real reference and (b) write the golden fixtures under `tests/golden/`.
-`/root/reference` does not exist on the GPU box, so nothing under tests/, bench.py or smoke() imports this file.
+TonemappingTransform) so that `oracle/make_golden.py` can (a) pin the oracle restatement in
+`oracle/evdeblur_oracle.py` against the real reference and (b) write the golden fixtures under `tests/golden/`, and so that
+`bench.py --impl reference` and bench.py's eager-GPU baseline leg can TIME the reference's own code (never the product path).
 
 Shims; no reference file is modified:
   * kornia / imageio / h5py / configargparse / tensorboardX / skimage / numba -> empty stub modules
@@ -16,10 +17,20 @@ from types import SimpleNamespace
 
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "EvDeblurNeRF")
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference/networks") else _STAGED
 
 
-def _install_shims():
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "networks"))
+
+
+def _install_shims(cpu=True):
+    """cpu = True additionally turns Tensor.cuda / Module.cuda into no-ops (CPU-only process!); with cpu = False the reference
+    runs on the GPU as it does in production: the caller wraps construction and calls in `torch.device("cuda")`, the modern
+    spelling of run_nerf.py:779's torch.set_default_tensor_type('torch.cuda.FloatTensor')."""
     for name in ("kornia", "imageio", "h5py", "configargparse", "tensorboardX", "wandb", "skimage",
                  "skimage.metrics", "numba"):
         if name not in sys.modules:
@@ -32,8 +43,9 @@ def _install_shims():
                     m.njit = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
                     m.jit = m.njit
                 sys.modules[name] = m
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
+    if cpu:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
 
@@ -67,9 +79,9 @@ def blurfactory_args(E=5, mode="c2f", n_imgs=30, aabb=((-1.5, -1.5, -1.0), (1.5,
     return a
 
 
-def build_reference(args, seed=0, nontrivial_rbk=True):
+def build_reference(args, seed=0, nontrivial_rbk=True, cpu=True):
     """Construct the reference modules exactly as run_nerf.py:166-244 does (RBK + AWP + CRF + NeRFAll)."""
-    _install_shims()
+    _install_shims(cpu)
     from networks.embedding import ViewEmbedding
     from networks.dpnerf.blurmodel import RigidBlurringModel
     from networks.dpnerf.awp import AdaptiveWeightProposal
@@ -110,3 +122,26 @@ def synthetic_rays(N, seed=0, n_imgs=30, H=400, W=400):
     rays = torch.stack([o, d], -1)  # [N,3,2]
     images_idx = torch.randint(0, n_imgs, (N, 1), generator=g)
     return rays, images_idx
+
+
+def build_bench_reference(P, E=5, use_awp=False, device="cpu"):
+    """The reference's NeRFAll for bench.py's synthetic blurfactory workload: constructed by the reference's own code, then
+    loaded with the bench parameters `P` (reference state_dict names; tensors missing from P -- e.g. awpnet.* -- keep the
+    reference's own initialisation).  device = "cpu": Tensor.cuda shimmed away; "cuda[:i]": CUDA is the default device."""
+    import contextlib
+    cpu = str(device) == "cpu"
+    args = blurfactory_args(E=E, use_awp=use_awp)
+    ctx = contextlib.nullcontext() if cpu else torch.device(device)
+    with ctx:
+        args.bounding_box = (args.bounding_box[0].to(device), args.bounding_box[1].to(device))
+        nerf, _ = build_reference(args, nontrivial_rbk=False, cpu=cpu)
+        sd = nerf.state_dict()
+        bad = [k for k, v in P.items() if k in sd and tuple(sd[k].shape) != tuple(v.shape)]
+        if bad:
+            raise RuntimeError(f"bench parameters do not fit the reference model: {bad[:4]}")
+        missing = [k for k in sd if k not in P and not k.startswith("awpnet.")]
+        if missing:
+            raise RuntimeError(f"bench parameters miss reference tensors: {missing[:4]}")
+        nerf.load_state_dict({k: v.to(device) for k, v in P.items() if k in sd}, strict=False)
+        nerf = nerf.to(device)
+    return nerf.train()

@@ -1,0 +1,104 @@
+"""Run under torchrun with 2 ranks (tests/test_train_gpu.py::test_nccl_two_ranks_half_batch_equal_one_rank_full_batch, or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 tests/nccl_train_equiv.py
+
+SURVEY 8(e): the ray batch is split across ranks, parameters are replicated, ONE all-reduce on the flat gradient buffer (+ the
+synchronised-BatchNorm exchange of the AWP branch).  Checks, over NCCL:
+  * loss and every gradient of 2 ranks x half batch == 1 rank x full batch (the full batch is computed on rank 0 in the same
+    process with the collectives switched off),
+  * several optimisation steps stay finite and keep the two ranks' parameters bit-identical."""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+sys.path.insert(0, HERE)
+
+from util import AABB, FOCAL, H, W, small_params, synthetic_rays  # noqa: E402
+
+KMAT = [[FOCAL, 0, 200.0], [0, FOCAL, 200.0], [0, 0, 1.0]]
+
+
+def batch_of(n, seed, dev, lo=None, hi=None):
+    rays, idx = synthetic_rays(n, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    b = {"rays": rays, "images_idx": idx, "rgbsf": torch.rand(n, 1, 3, generator=g)}
+    return {k: v[lo:hi].to(dev) for k, v in b.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--rays", type=int, default=32)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    from evdeblurnerf_b200.parallel import shard_bounds
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if v.is_floating_point()}
+    rk = dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    kw = dict(kernel_ptnum=5, precision=args.precision, lrate=1e-3, tv_loss_weight=0.01, use_awp=True, render_kwargs=rk, device=dev,
+              check_numerics_every=1)
+    n = args.rays
+    lo, hi = shard_bounds(n, rank, world)
+
+    # ---- (1) one step's loss + gradients: sharded over NCCL vs the full batch on one rank ---------------------------------------
+    tr = Trainer(P, Pc, *AABB, **kw)
+    tr.flat.grad.zero_()
+    out = tr.loss(batch_of(n, 5, dev, lo, hi), H, W, KMAT)
+    out["loss"].backward()
+    tr.flat.all_reduce_mean(tr.group)
+    loss_mean = out["loss"].detach().clone()
+    dist.all_reduce(loss_mean)
+    loss_mean /= world                      # the TV term is replicated, the ray means average: same as the full-batch loss
+    g_sharded = tr.flat.grad.clone()
+
+    ref = Trainer(P, Pc, *AABB, **kw)
+    ref.nerf.awpnet.sync_bn = False         # full batch on this rank alone: no collective anywhere
+    ref.flat.grad.zero_()
+    out_ref = ref.loss(batch_of(n, 5, dev), H, W, KMAT)
+    out_ref["loss"].backward()
+    g_full = ref.flat.grad
+    tol = 2e-4 if args.precision == "fp32" else 3e-2
+    rel_loss = abs(float(loss_mean) - float(out_ref["loss"])) / abs(float(out_ref["loss"]))
+    worst = ("", 0.0)
+    for name in tr.flat.order:
+        a, b = tr.flat.named(g_sharded)[name], ref.flat.named(g_full)[name]
+        scale = float(b.abs().max())
+        if scale == 0.0:
+            continue
+        err = float((a - b).abs().max()) / scale
+        if err > worst[1]:
+            worst = (name, err)
+    print(f"[rank {rank}] loss sharded {float(loss_mean):.8f} full {float(out_ref['loss']):.8f} rel {rel_loss:.2e}; "
+          f"worst gradient {worst[0]} rel-to-max {worst[1]:.2e} (tol {tol:.0e})", flush=True)
+    assert rel_loss < (1e-5 if args.precision == "fp32" else 2e-3), rel_loss
+    assert worst[1] < tol, worst
+    del ref
+
+    # ---- (2) a few real steps: finite, ranks stay in lock-step -------------------------------------------------------------------
+    tr = Trainer(P, Pc, *AABB, **dict(kw, render_kwargs=dict(rk, perturb=1., raw_noise_std=1.)))
+    for s in range(6):
+        o = tr.step(batch_of(n, 100 + s, dev, lo, hi), H, W, KMAT)
+        assert bool(torch.isfinite(o["loss"])), (s, float(o["loss"]))
+        assert o.get("numerical_errors", []) == [], o["numerical_errors"]
+    mine = tr.flat.param.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other), "ranks diverged"
+    assert bool(torch.isfinite(mine).all())
+    dist.barrier()
+    if rank == 0:
+        print("NCCL_EQUIV_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

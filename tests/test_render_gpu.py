@@ -257,3 +257,28 @@ def test_perturbed_render_is_reproducible_and_valid(engine):
     z = a["z_vals"]
     assert bool((z[:, 1:] >= z[:, :-1]).all()) and bool((a["z_vals0"][:, 1:] > a["z_vals0"][:, :-1]).all())
     assert_close(a["weights"].sum(-1), a["acc_map"], "acc", rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("perturb", [0.0, 1.0])
+def test_lindisp_sample_placement(precision, perturb):
+    """renderer.py:166-167 (`lindisp`, only reachable with --no_ndc: near must be > 0): samples linear in inverse depth.  Placement is
+    bit-exact in both precisions (with and without the stratified jitter); the fp32 render follows the oracle at the usual bar."""
+    from evdeblurnerf_b200 import RenderEngine
+    P, _ = small_params()
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=precision)
+    rays, _ = synthetic_rays(40, seed=91)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays, near=0.5, far=2.0, ndc=False)
+    g = torch.Generator().manual_seed(92)
+    rand = {"t_rand": torch.rand(40, 64, generator=g)} if perturb > 0 else {}
+    out = eng.render_rays(rb.cuda(), 64, retraw=True, lindisp=True, perturb=perturb, rand={k: v.cuda() for k, v in rand.items()})
+    ref = oc.render_rays(P, CFG, rb, 64, 0, perturb=perturb, lindisp=True, rand=rand)
+    lin = oc.render_rays(P, CFG, rb, 64, 0, perturb=perturb, lindisp=False, rand=rand)
+    assert torch.equal(out["z_vals"].cpu(), ref["z_vals"]), "lindisp placement must be bit-exact"
+    assert float((ref["z_vals"] - lin["z_vals"]).abs().max()) > 0.05          # the flag changes the placement
+    if precision == "fp32":
+        for k in ("rgb_map", "depth_map", "acc_map", "weights"):
+            assert_close(out[k], ref[k], k)
+    else:
+        for k in ("rgb_map", "acc_map"):
+            assert_close(out[k], ref[k], k, rtol=0, atol=4e-2)

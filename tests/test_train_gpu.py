@@ -341,9 +341,13 @@ def test_trainer_with_event_loss_trains_crf_and_fields():
     assert all(float((tr.flat.views[k].detach() - v).abs().max()) > 0 for k, v in crf0.items()), "CRF parameters must receive gradients"
 
 
-def test_awp_sync_batchnorm_two_shards_equal_full_batch():
+@pytest.mark.parametrize("split", [8, 6])
+def test_awp_sync_batchnorm_two_shards_equal_full_batch(split):
     """SURVEY 8(e) caveat 1: AWP's BatchNorm uses batch statistics over ALL rays.  Two half shards whose batch sums are summed
-    between the two phases of the pass (what `all_reduce` does across ranks) must reproduce the full-batch ccw and gradients."""
+    between the two phases of the pass (what `all_reduce` does across ranks) must reproduce the full-batch ccw and gradients --
+    equal (8 + 8) and ragged (6 + 10) shards: the row count behind the sums travels in the same all-reduced block.  The phased
+    calls pass bn_rows_total = 0 exactly like AwpFn / AdaptiveWeightProposal.run do on NCCL (the round-1 N = 8 NaN was a phase-1
+    backward normalising all-rank sums by the LOCAL row count)."""
     import ctypes as C
     from evdeblurnerf_b200 import _lib
     from evdeblurnerf_b200.autograd import AWP_PARAM_NAMES, awp_grad_buffers, awp_grads_to_reference
@@ -378,8 +382,8 @@ def test_awp_sync_batchnorm_two_shards_equal_full_batch():
                                    vf[lo:hi].data_ptr(), n, E, S, awp.bn_eps, C.byref(opt), 1, cot[lo:hi].contiguous().data_ptr(), C.byref(g),
                                    d_df[lo * E:hi * E].data_ptr(), d_rd[lo * E:hi * E].data_ptr(), 3, d_vf[lo:hi].data_ptr(), ws.data_ptr(), st), "bwd")
 
-    def block(ws, off):
-        return ws[off: off + 128].view(torch.float64)
+    def block(ws, off, n_doubles):
+        return ws[off: off + 2 * n_doubles].view(torch.float64)
 
     new_outs = lambda: (torch.zeros_like(df), torch.zeros_like(rd), torch.zeros_like(vf))
     # full batch, single phase
@@ -388,24 +392,26 @@ def test_awp_sync_batchnorm_two_shards_equal_full_batch():
     outs_full = new_outs()
     bwd(0, N, awp.options(True, 0), ws_full, g_full, outs_full)
     # two shards, batch sums exchanged between the phases
-    h = N // 2
+    h = split
     shards = [(0, h), (h, N)]
-    off_f, off_b = int(lib.edn_awp_stats_offset_floats(h, E, S)), int(lib.edn_awp_bwd_sums_offset_floats(h, E, S))
+    off_f = [int(lib.edn_awp_stats_offset_floats(hi - lo, E, S)) for lo, hi in shards]
+    off_b = [int(lib.edn_awp_bwd_sums_offset_floats(hi - lo, E, S)) for lo, hi in shards]
     wss = [fwd(lo, hi, awp.options(True, 1))[0] for lo, hi in shards]
-    tot = block(wss[0], off_f) + block(wss[1], off_f)
-    for w in wss:
-        block(w, off_f).copy_(tot)
-    ccw = torch.cat([fwd(lo, hi, awp.options(True, 2, N * E), w)[1] for (lo, hi), w in zip(shards, wss)])
+    tot = block(wss[0], off_f[0], 66) + block(wss[1], off_f[1], 66)
+    assert float(tot[64]) == N * E
+    for w, o in zip(wss, off_f):
+        block(w, o, 66).copy_(tot)
+    ccw = torch.cat([fwd(lo, hi, awp.options(True, 2), w)[1] for (lo, hi), w in zip(shards, wss)])
     assert_close(ccw, ccw_full, "ccw (2 shards, summed batch sums)", rtol=2e-5, atol=1e-7)
     g2, bufs2 = awp_grad_buffers(shapes, "cuda")
     outs2 = new_outs()
     for (lo, hi), w in zip(shards, wss):
-        bwd(lo, hi, awp.options(True, 1, N * E), w, g2, outs2)
-    tot = block(wss[0], off_b) + block(wss[1], off_b)
-    for w in wss:
-        block(w, off_b).copy_(tot)
+        bwd(lo, hi, awp.options(True, 1), w, g2, outs2)
+    tot = block(wss[0], off_b[0], 64) + block(wss[1], off_b[1], 64)
+    for w, o in zip(wss, off_b):
+        block(w, o, 64).copy_(tot)
     for (lo, hi), w in zip(shards, wss):
-        bwd(lo, hi, awp.options(True, 2, N * E), w, g2, outs2)
+        bwd(lo, hi, awp.options(True, 2), w, g2, outs2)
     for name, a, b in zip(("d depth_feature", "d rays_d", "d view_feature"), outs2, outs_full):
         grad_close(a, b, name, tol=2e-5)
     for name, a, b in zip(AWP_PARAM_NAMES, awp_grads_to_reference(bufs2), awp_grads_to_reference(bufs_full)):
@@ -516,3 +522,168 @@ def test_trainer_checkpoint_round_trip_in_reference_format():
     sa, sb = a.state_dict(), b.state_dict()
     for k in sa:
         assert_close(sb[k], sa[k], "restored + 1 step: " + k, rtol=1e-6, atol=1e-9)
+
+
+def test_trainer_awp_parameter_groups_match_reference_layout():
+    """BatchNorm buffers are state, not parameters.  With use_awp the optimizer groups must equal the reference's
+    (run_nerf.py:243-261 over named_parameters(); golden written by the unmodified reference) and a torch.optim.Adam built the
+    reference way must accept the checkpoint."""
+    import json
+    import os
+    from util import GOLDEN
+    from evdeblurnerf_b200.trainer import Trainer
+    lay = json.load(open(os.path.join(GOLDEN, "case8_optimizer_layout.json")))["c2f_wd0"]
+    P, Pc = small_params()
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", use_awp=True,
+                 render_kwargs=dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.))
+    want = [[n[4:] if n.startswith("crf.") else n for n in g] for g in lay["groups"]]
+    assert tr._groups() == want
+    assert not any(k.endswith(("running_mean", "running_var", "num_batches_tracked")) for k in tr.flat.views)
+    tr.step(_tiny_batch(16, 45), H, W, KMAT)
+    ck = tr.checkpoint()
+    assert "awpnet.MAM.Corr.convd.1.running_mean" in ck["network_state_dict"]          # buffers still travel in the state dict
+    params = [[torch.nn.Parameter(torch.zeros_like(tr.flat.views[("crf." + n) if gi == len(want) - 1 else n])) for n in g]
+              for gi, g in enumerate(want)]
+    opt = torch.optim.Adam([{"params": g, "lr": 5e-4} for g in params], lr=5e-4, betas=(0.9, 0.999))
+    opt.load_state_dict(ck["optimizer_state_dict"])                                     # would raise on a shifted / longer layout
+    tr2 = Trainer({k: torch.zeros_like(v) if v.is_floating_point() else v for k, v in P.items()}, {k: torch.zeros_like(v) for k, v in Pc.items()},
+                  *AABB, kernel_ptnum=5, precision="fp32", use_awp=True)
+    tr2.load_checkpoint(ck)
+    for k, v in tr.state_dict().items():
+        assert torch.equal(tr2.state_dict()[k], v), k
+
+
+def _event_batch(n=16, m=12, seed=51):
+    batch = _tiny_batch(n, seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    ev0, _ = synthetic_rays(m, seed=seed + 2)
+    ev1, _ = synthetic_rays(m, seed=seed + 3)
+    batch.update(ev_rays_start=ev0.cuda(), ev_rays_end=ev1.cuda(), bii=torch.full((m,), 0.3).cuda(), ev_extra_feat=torch.rand(m, 2, generator=gen).cuda())
+    return batch
+
+
+def test_trainer_event_weight_follows_global_step():
+    """the event weight is w_events_egm(global_step) (run_nerf.py:592), not the value at step 1: with a linear
+    schedule the loss difference between two global steps is event_loss * (w(g2) - w(g1))."""
+    from evdeblurnerf_b200.schedules import annealing_interpolator
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if v.is_floating_point() and not k.startswith("awpnet.")}
+    batch = _event_batch()
+    rk = dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    sched = dict(event_egm_weight=0.1, event_egm_weight_end=1.0, event_egm_weight_steps=10, event_egm_weight_scheduler="linear")
+    for fuse in (True, False):
+        tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk, schedule=sched)
+        tr.fuse_event_renders = fuse
+        outs = {}
+        for g in (1, 7):
+            tr.global_step = g
+            outs[g] = {k: float(v) for k, v in tr.loss(batch, H, W, KMAT).items()}
+        w = annealing_interpolator(0.1, 1.0, 10, "linear")
+        assert outs[1]["event_loss"] == pytest.approx(outs[7]["event_loss"], rel=1e-6)
+        assert outs[7]["loss"] - outs[1]["loss"] == pytest.approx(outs[7]["event_loss"] * (w(7) - w(1)), rel=1e-4)
+    # add_event_egm_stages / add_event_egm_startiter (run_nerf.py:506, 562-571)
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk, event_loss_weight=1.0,
+                 schedule=dict(add_event_egm_stages=("stage1",), add_event_egm_startiter=4))
+    tr.global_step = 2                                # i = 3 < 4: no event term yet
+    assert "event_loss" not in tr.loss(batch, H, W, KMAT)
+    tr.global_step = 3
+    one = float(tr.loss(batch, H, W, KMAT)["event_loss"])
+    tr.schedule["add_event_egm_stages"] = ("stage0", "stage1")
+    both = float(tr.loss(batch, H, W, KMAT)["event_loss"])
+    assert 0 < one < both
+
+
+def test_trainer_kernel_start_and_blur_loss_after_phases():
+    """i = global_step + 1 is the reference's loop index.  Before kernel_start_iter the render is the blur-free one
+    (force_naive, run_nerf.py:440) and the learnt CRF is bypassed before tone_mapping_start_learn_iter (:443); while
+    i <= blur_loss_after the photometric term is dropped and the pts0 prior weighs 1 (:452-462, 489-495)."""
+    from evdeblurnerf_b200 import NeRFAll, TonemappingTransform, img2mse
+    from evdeblurnerf_b200.trainer import Trainer
+    P, Pc = small_params()
+    P = {k: v for k, v in P.items() if not k.startswith("awpnet.")}
+    batch = _tiny_batch(16, 61)
+    g = torch.Generator().manual_seed(6)
+    batch["rgbsf_pts0"] = torch.rand(16, 1, 3, generator=g).cuda()
+    rk = dict(N_samples=32, N_importance=32, perturb=0., raw_noise_std=0.)
+    nerf = NeRFAll({k: v.cuda() for k, v in P.items()}, *AABB, kernel_ptnum=5, precision="fp32").train()
+    crf = TonemappingTransform({k: v.cuda() for k, v in Pc.items()}, map_type_rgb="gamma", map_type_event="learn", extra_features_event=2)
+    enc = lambda x: crf(x, mode="encode_rgb")
+    tgt, tgt0 = batch["rgbsf"].reshape(-1, 3), batch["rgbsf_pts0"].reshape(-1, 3)
+    # (a) kernel_start_iter = 4: global_step 2 -> i = 3 < 4 renders naively; global_step 3 -> i = 4 renders through the blur kernel
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk, schedule=dict(kernel_start_iter=4))
+    with torch.no_grad():
+        n_rgb, n_rgb0, _, _ = nerf(H, W, KMAT, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=True, **rk)
+        b_rgb, b_rgb0, _, et = nerf(H, W, KMAT, rays=batch["rays"], rays_info=batch, retraw=True, force_naive=False, return_pts0_rgb=True, **rk)
+        naive = img2mse(enc(n_rgb), tgt) + img2mse(enc(n_rgb0), tgt)
+        blur = img2mse(enc(b_rgb), tgt) + img2mse(enc(b_rgb0), tgt)
+        pts0 = img2mse(enc(et["stage1_rgb_pts0"]), tgt0) + img2mse(enc(et["stage1_rgb1_pts0"]), tgt0)
+    assert abs(float(naive) - float(blur)) > 1e-6 * float(blur)
+    tr.global_step = 2
+    assert_close(tr.loss(batch, H, W, KMAT)["loss"], naive, "blur-free phase (i < kernel_start_iter)", rtol=1e-6)
+    tr.global_step = 3
+    assert_close(tr.loss(batch, H, W, KMAT)["loss"], blur, "blur phase (i == kernel_start_iter)", rtol=1e-6)
+    # (b) blur_loss_after = 5 with the pts0 prior: i <= 5 -> pts0 loss only, weight 1; i = 6 -> photometric + annealed pts0 weight
+    tr = Trainer(P, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk,
+                 schedule=dict(use_pts0_prior="edi", pts0_target_weight=0.25, pts0_target_start_iter=0, blur_loss_after=5))
+    tr.global_step = 4
+    out = tr.loss(batch, H, W, KMAT)
+    assert "img_loss" not in out
+    assert_close(out["loss"], pts0, "i <= blur_loss_after: pts0 term only", rtol=1e-6)
+    tr.global_step = 5
+    assert_close(tr.loss(batch, H, W, KMAT)["loss"], blur + 0.25 * pts0, "i > blur_loss_after", rtol=1e-6)
+    # (c) tone_mapping_start_learn_iter: the event CRF is skipped at first (encode_luma(skip_learn_crf=True))
+    batch_ev = _event_batch(16, 12, 63)
+    Pn = {k: v for k, v in P.items() if v.is_floating_point()}
+    tr = Trainer(Pn, Pc, *AABB, kernel_ptnum=5, precision="fp32", tv_loss_weight=0.0, render_kwargs=rk, event_loss_weight=1.0,
+                 schedule=dict(tone_mapping_start_learn_iter=3))
+    tr.global_step = 1
+    skipped = float(tr.loss(batch_ev, H, W, KMAT)["event_loss"])
+    tr.global_step = 2
+    learnt = float(tr.loss(batch_ev, H, W, KMAT)["event_loss"])
+    assert abs(skipped - learnt) > 1e-7 * abs(learnt)
+
+
+def test_numerical_guard_flags_nan_and_inf_lazily():
+    """renderer.py:259-263 as a device flag word: a NaN planted in the fine colour head must be reported for rgb_map only, an Inf in
+    the coarse one for rgb0; nothing is reported for a healthy render; reading the flags resets them."""
+    from evdeblurnerf_b200 import RenderEngine
+    P, _ = small_params()
+    rays, _ = synthetic_rays(32, seed=71)
+    rb = oc.build_ray_batch(H, W, FOCAL, rays).cuda()
+    for precision in ("fp32", "bf16"):
+        eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=precision)
+        eng.render_rays(rb, 32, retraw=True, N_importance=32)
+        assert eng.numerical_errors() == []
+        bad = {k: v.clone().cuda() for k, v in P.items()}
+        bad["mlp_fine.color_net.2.weight"][0, 0] = float("nan")
+        eng = RenderEngine(bad, *AABB, precision=precision)
+        eng.render_rays(rb, 32, retraw=True, N_importance=32)
+        assert eng.numerical_errors() == ["rgb_map contains nan."]
+        assert eng.numerical_errors() == []
+        bad = {k: v.clone().cuda() for k, v in P.items()}
+        bad["mlp_coarse.app_plane.0"].fill_(float("inf"))
+        eng = RenderEngine(bad, *AABB, precision=precision)
+        eng.render_rays(rb, 32, retraw=True, N_importance=32)
+        msgs = eng.numerical_errors()
+        assert any(m.startswith("rgb0 contains") for m in msgs) and any(m.startswith("weights0 contains") for m in msgs), msgs
+
+
+def _n_gpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs (NCCL)")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_nccl_two_ranks_half_batch_equal_one_rank_full_batch(precision):
+    """1 GPU x full batch vs 2 ranks x half batch over NCCL -> equal loss, equal gradients (AWP branch on: the
+    synchronised BatchNorm exchange and the flat gradient all-reduce are both on the path), finite loss after several steps."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(here, "nccl_train_equiv.py"), "--precision", precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "NCCL_EQUIV_OK" in r.stdout, r.stdout[-3000:]

@@ -14,31 +14,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 
-def awp_params(device, E, seed=7):
-    g = torch.Generator().manual_seed(seed)
-    P = {}
-
-    def lin(name, o, i, bias=True, extra=()):
-        b = 1.0 / (i ** 0.5)
-        P[name + ".weight"] = ((torch.rand(o, i, *extra, generator=g) * 2 - 1) * b).to(device)
-        if bias:
-            P[name + ".bias"] = ((torch.rand(o, generator=g) * 2 - 1) * b).to(device)
-
-    pre = "awpnet."
-    lin(pre + "sample_feature_embed_layer.0", 64, 128)
-    for l in (1, 2, 3):
-        lin(pre + f"sample_feature_embed_layer.{l}", 64, 64)
-    lin(pre + "motion_feature_embed_layer.0", 32, 111)
-    lin(pre + "motion_feature_embed_layer.1", 32, 32)
-    lin(pre + "MAM.linear", 32, 64)
-    P[pre + "MAM.Corr.line_conv_att.weight"] = (torch.randn(1, 32, 1, 1, generator=g) * 0.2).to(device)
-    for n, (o, i) in (("conva", (16, 32)), ("convb", (16, 32)), ("convc", (16, 32)), ("convn", (16, 16)), ("convl", (16, 16))):
-        lin(pre + "MAM.Corr." + n, o, i, bias=False, extra=(1,))
-    lin(pre + "MAM.Corr.convd.0", 32, 32, bias=False, extra=(1,))
-    P[pre + "MAM.Corr.convd.1.weight"] = torch.ones(32, device=device)
-    P[pre + "MAM.Corr.convd.1.bias"] = torch.zeros(32, device=device)
-    lin(pre + "w_linear", E, 32)
-    return P
+awp_params = bench.awp_params      # moved to bench.py (the bench line reports the AWP-on figures too)
 
 
 def main():
