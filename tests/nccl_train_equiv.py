@@ -68,15 +68,20 @@ def main():
     g_full = ref.flat.grad
     tol = 2e-4 if args.precision == "fp32" else 3e-2
     rel_loss = abs(float(loss_mean) - float(out_ref["loss"])) / abs(float(out_ref["loss"]))
-    worst = ("", 0.0)
+    errs = []
     for name in tr.flat.order:
+        if name.endswith("MAM.linear.bias"):
+            continue      # softmax over the samples is invariant to this bias: its gradient is pure cancellation noise (~1e-9), as in
+            #               test_awp_sync_batchnorm_two_shards_equal_full_batch
         a, b = tr.flat.named(g_sharded)[name], ref.flat.named(g_full)[name]
         scale = float(b.abs().max())
         if scale == 0.0:
             continue
-        err = float((a - b).abs().max()) / scale
-        if err > worst[1]:
-            worst = (name, err)
+        errs.append((float((a - b).abs().max()) / scale, name))
+    errs.sort(reverse=True)
+    worst = (errs[0][1], errs[0][0])
+    if rank == 0:
+        print("worst gradients (rel to each tensor's max):", [(n, f"{e:.1e}") for e, n in errs[:4]], flush=True)
     print(f"[rank {rank}] loss sharded {float(loss_mean):.8f} full {float(out_ref['loss']):.8f} rel {rel_loss:.2e}; "
           f"worst gradient {worst[0]} rel-to-max {worst[1]:.2e} (tol {tol:.0e})", flush=True)
     assert rel_loss < (1e-5 if args.precision == "fp32" else 2e-3), rel_loss
