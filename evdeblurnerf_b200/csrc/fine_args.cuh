@@ -24,4 +24,8 @@ struct FineArgs {
                       // epilogues, 4 no weight stream (the MMAs read stale shared memory), 8 no PE / view-bias phase
 };
 
+// fine_tc2.cu: second-generation tensor-core fine kernel (lean schedule, rays of <= 128 samples); wblob = the lean section of the
+// fine tensor-core blob ([layer][K-step][256 x 16] bf16, edn_pack_fine_tc)
+int launch_fine_tc2(const FineArgs& a, int grid_dtype, const uint8_t* wblob, cudaStream_t st);
+
 }  // namespace edn

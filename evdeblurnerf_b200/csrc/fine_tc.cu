@@ -668,6 +668,8 @@ int launch_fine_tc(const FineArgs& a_in, int grid_dtype, cudaStream_t st) {
       told = true;
     }
   }
+  static const bool force_v1 = [] { const char* e = getenv("EDN_TC_V1"); return e && e[0] == '1'; }();   // dev switch: round-1 kernel
+  if (lean && a.S <= kRows && !force_v1 && !ablate) return launch_fine_tc2(a, grid_dtype, blob + kOffLean, st);   // same lean weight stream
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;

@@ -1,0 +1,578 @@
+// Fine pass of render_rays on tcgen05 / TMEM, second generation ("v2"): decoupled gather, activations chained through TMEM.
+// Replaces networks/renderer.py:190-217 + networks/pdrf/voxnerf.py:203-259,153-201 for the FVR field (lean schedule: basis_mat
+// folded into sigma_net.0, sigma_net.1(geo) folded into color_net.0 -> three 256 -> 256 layers; see fine_tc.cu).
+//
+// What round 1's kernel (fine_tc.cu) was bound by: a ray group's VM gather, its three layer epilogues and its MMAs form ONE serial
+// chain, and shared memory (2 x 64 KB A operands + rings) / TMEM (2 x 256 accumulator columns) capped it at two such chains per SM.
+// Here the chain is cut in two and the hidden activations never touch shared memory:
+//   gather warps (8):   ray k+1: PE + view-direction bias + cooperative VM gather of both grids -> A_in[(k+1) & 1] (64 KB, UMMA
+//                       K-major layout) WHILE ray k is in the MLP: the gather is off the critical chain, double buffered.
+//   MMA issuer (1 thr): layer 1 reads A_in from shared memory (SS), layers 2 / 3 read their A operand from TENSOR MEMORY (TS): the
+//                       epilogue writes relu(acc) as packed bf16 straight back into TMEM (tcgen05.st), so shared memory holds only
+//                       layer-1 inputs and the weight ring.  Every layer is issued as four N = 64 quarters into four 64-column
+//                       accumulators, and the next layer's K-steps 4i..4i+3 only wait for quarter i's epilogue (K-chunk hand-over).
+//   epilogue warps (8): two threads per sample row; per quarter: tcgen05.ld 32 columns -> bias / ReLU -> sigma / rgb head partials ->
+//                       bf16x2 -> tcgen05.st into the next layer's A operand; finally sigma -> alpha compositing (warp-shuffle scan).
+//   weight stream (1 thr): the three layers' weights, quarter-major ([layer][quarter][K-step][64 x 16]), through a 4 x 16 KB ring
+//                       with cp.async.bulk (TMA engine); stages are released by tcgen05.commit.
+// TMEM map (512 columns): [0,128) A operand of layer 2, [128,256) A operand of layer 3, [256,512) four 64-column accumulators.
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "fine_args.cuh"
+#include "tc_common.cuh"
+#include "tc_rows.cuh"
+
+namespace edn {
+namespace {
+
+using namespace tc;
+
+constexpr int kRows = 128;
+constexpr int kGatherWarps = 8, kEpiWarps = 8;
+constexpr int kWarpMma = kGatherWarps + kEpiWarps, kWarpLoad = kWarpMma + 1;
+constexpr int kThreads = (kGatherWarps + kEpiWarps + 2) * 32;      // 576
+constexpr int kRoleThreads = 256;
+constexpr int kNst = 4;                    // weight ring stages
+constexpr int kStageBytes = 16384;         // 2 K-steps of a layer (N = 256 rows x 16 x 2 B = 8 KB per K-step): the lean section of the blob
+constexpr int kKstepBytes = 8192;
+constexpr int kABytes = 65536;
+constexpr int kStagesPerRay = 3 * 8;       // layers x (16 K-steps / 2)
+constexpr uint32_t kTmemCols = 512;
+// TMEM: [0,128) A operand of layers 2 / 3 (rewritten in place), [128,512) THREE 128-column accumulator slots.  A layer accumulates
+// into two slots (output columns 0..127 | 128..255, issued K-major as two independent chains); layer n uses slots (2n % 3,
+// (2n + 1) % 3), so the next layer's first slot is the spare one and its second slot is this layer's first, which the epilogue
+// drains first: the next layer's K-steps 0..7 (they only read the first half of the new A operand) overlap the second half of
+// this layer's epilogue.
+constexpr uint32_t kColA = 0, kColAcc = 128;
+constexpr int kNQ = 2;                     // N = 128 per instruction: 86 (TS) / 119 (SS) cycles each, measured (fine_tc2 ablate 16 / 48)
+
+struct alignas(16) RaySlot {              // per-ray data produced by the gather warps, read by the epilogue warps
+  float z[kRows];
+  alignas(16) float bias[256];             // color_net.0 bias + W0[:, 128:155] . PE(viewdir)
+};
+struct Misc {
+  uint64_t a_full[2], a_empty[2], slot_free[2];
+  uint64_t w_full[kNst], w_empty[kNst];
+  uint64_t acc_full, hand[2];           // hand[h]: the epilogue finished half h of a layer (slot drained + A' columns 64h.. written)
+  GridDev grids[2];
+  uint32_t tmem_base, pad[3];
+  alignas(16) float wsig[256];
+  alignas(16) float wrgb[3][256];          // color_net.2, channel-major (float4 = 4 consecutive hidden units of one channel)
+  alignas(16) float bias1[256];
+  RaySlot slot[2];
+  alignas(16) float headp[2][kRows][4];
+  float red[4][8];
+  float wtot[4];
+};
+static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 && offsetof(Misc, bias1) % 16 == 0 &&
+              offsetof(Misc, slot) % 16 == 0 && offsetof(Misc, headp) % 16 == 0, "float4 alignment");
+constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + (int)sizeof(Misc);
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// ---- TMEM store: 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread ------------------------------------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 16 step (A: 128 lanes x 8 packed-bf16x2 columns), issued by ONE thread.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+
+// One lane of a CONVERGED warp (all operands warp-uniform): lets the compiler keep descriptors in uniform registers and emit a
+// plainly predicated UTCHMMA / UTCBAR instead of the per-active-lane retry loop it wraps around them inside `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Packed fp32 FMA (sm_100 FFMA2): d = a * b + c on two lanes at once; halves the issue slots of the epilogue's head dot products.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
+// Cooperative gather of ONE grid for the 32 points of this warp (lean A layout: coarse chunks 0..11, fine chunks 12..23).
+// Component 0 (64 channels = one 128-byte line per texel): lane (p4 = lane & 3, c = lane >> 2) reads chunk c of points 8 gi + p4 and
+// 8 gi + 4 + p4, so every warp-wide load covers FOUR WHOLE lines (round 1: eight half lines -- the L1 wavefront count per byte is
+// what bounds the gather).  Components 1 / 2 (16 channels): lane (q = lane >> 3, j = lane & 7) -> point 8 gi + j, component 1 + q / 2,
+// chunk q & 1.
+template <typename T>
+__device__ __forceinline__ void gather_tiles2(const GridDev& g, uint8_t* As, const float* z_s, int gwarp, int lane, const float o[3],
+                                              const float d[3], const int fine_tile) {
+  const int base = fine_tile ? 12 : 0;
+  const int p4 = lane & 3, c8 = lane >> 2, q = lane >> 3;
+#pragma unroll 1
+  for (int gi = 0; gi < 4; ++gi) {
+    {  // component 0: plane (x,y), line z
+      GatherTask<T> t0, t1;
+      const T* pl = reinterpret_cast<const T*>(g.plane[0]);
+      const T* ln = reinterpret_cast<const T*>(g.line[0]);
+      const int ptA = gwarp * 32 + gi * 8 + p4, ptB = ptA + 4;
+      {
+        const float zv = z_s[ptA];
+        float p[3], n[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+        normalize_pt(g, p, n);
+        Taps2 pt2; Taps1 lt1;
+        plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
+        line_taps(n[2], g.ll[0], lt1);
+        t0.issue(pl, ln, 64, c8, pt2, lt1);
+      }
+      {
+        const float zv = z_s[ptB];
+        float p[3], n[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+        normalize_pt(g, p, n);
+        Taps2 pt2; Taps1 lt1;
+        plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
+        line_taps(n[2], g.ll[0], lt1);
+        t1.issue(pl, ln, 64, c8, pt2, lt1);
+      }
+      t0.finish(As + ptA * 16 + (base + c8) * kChunkA);
+      t1.finish(As + ptB * 16 + (base + c8) * kChunkA);
+    }
+    {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
+      GatherTask<T> t2;
+      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
+      const float zv = z_s[pt];
+      float p[3], n[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+      normalize_pt(g, p, n);
+      const int comp = 1 + (q >> 1);
+      Taps2 pt2; Taps1 lt1;
+      plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], pt2);
+      line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
+      t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
+      t2.finish(As + pt * 16 + (base + 8 + q) * kChunkA);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* As = smem;                                   // [2][64 KB] layer-1 operands (double buffered)
+  uint8_t* Ws = smem + 2 * kABytes;                     // weight ring
+  Misc* m = reinterpret_cast<Misc*>(Ws + kNst * kStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); mbar_init(&m->slot_free[b], kRoleThreads); }
+    for (int s = 0; s < kNst; ++s) { mbar_init(&m->w_full[s], 1); mbar_init(&m->w_empty[s], 1); }
+    mbar_init(&m->acc_full, 1); mbar_init(&m->hand[0], kRoleThreads); mbar_init(&m->hand[1], kRoleThreads);
+    fence_barrier_init();
+  }
+  if (warp == kWarpMma) tmem_alloc(&m->tmem_base, kTmemCols);
+  for (int i = tid; i < 256; i += kThreads) {
+    m->wsig[i] = __ldg(a.mlp.sigma1_v + i);
+    m->bias1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) m->wrgb[j][i] = __ldg(a.mlp.color2_t + i * 4 + j);
+  }
+  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = m->tmem_base;
+  const int S = a.S;
+  // dev tooling (EDN_TC_TRACE=1): clock64 stamps of CTA 0 for iterations 8..11: trace[role][it - 8][slot], role 0 gather, 1 MMA, 2 epilogue
+  auto stamp = [&](int role, int64_t it, int k) {
+    if (a.trace && blockIdx.x == 0 && it >= 8 && it < 12) a.trace[(role * 4 + (it - 8)) * 16 + k] = clock64();
+  };
+  const int64_t n_my = (a.n_rays > (int64_t)blockIdx.x) ? (a.n_rays - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (a.ablate & 16) {      // dev microbenchmark: ONLY the MMA warp runs, no waits at all -> pure tcgen05.mma issue / execution rate
+    if (warp == kWarpMma && n_my > 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256 / kNQ);
+      const uint32_t w_base = smem_u32(Ws), a_in = smem_u32(As);
+      const bool ts = (a.ablate & 32) != 0;
+      for (int64_t it = 0; it < n_my * 3; ++it) {
+        for (int st8 = 0; st8 < 8; ++st8) {
+          const uint64_t bd0 = make_smem_desc(w_base + (st8 & 3) * kStageBytes, 256 * 16, 128);
+          const uint64_t ad0 = make_smem_desc(a_in + st8 * 2 * 2 * kChunkA, kChunkA, 128);
+          if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int q = 0; q < kNQ; ++q) {
+                if (ts) mma_bf16_ts(tmem + kColAcc + q * (256 / kNQ), tmem + kColA + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes + q * (256 / kNQ) * 16) >> 4), idesc, 1);
+                else mma_bf16_ss(tmem + kColAcc + q * (256 / kNQ), ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes + q * (256 / kNQ) * 16) >> 4), idesc, 1);
+              }
+            if (a.ablate & 64) mma_commit(&m->w_empty[st8 & 3]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) mma_commit(&m->acc_full);
+      __syncwarp();
+      mbar_wait(&m->acc_full, 0);
+    }
+  } else if (warp == kWarpLoad) {
+    // =================================== weight stream =====================================================================
+    if (n_my > 0) {      // converged warp, one elected lane issues (uniform operands: no per-lane retry loop around UBLKCP)
+      const uint32_t total = (uint32_t)n_my * kStagesPerRay;
+      for (uint32_t g = 0; g < total; ++g) {
+        const int s = g % kNst;
+        const uint32_t use = g / kNst;
+        if (use > 0) mbar_wait(&m->w_empty[s], (use - 1) & 1);
+        if (elect_one()) {
+          if (a.ablate & 2) {
+            mbar_expect_tx(&m->w_full[s], 0);
+          } else {
+            mbar_expect_tx(&m->w_full[s], kStageBytes);
+            bulk_g2s(Ws + s * kStageBytes, wblob + (size_t)(g % kStagesPerRay) * kStageBytes, kStageBytes, &m->w_full[s]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpMma) {
+    // =================================== MMA issuer (converged warp, one elected lane issues) ==============================
+    if (n_my > 0) {
+      // K-major issue with kNQ INDEPENDENT accumulator chains per K-step: back-to-back MMAs into the same accumulator serialise on
+      // the tensor pipe's accumulate latency (~140 cycles, measured: N = 64 MMAs issued quarter by quarter ran at 140 cycles each
+      // instead of 32), so consecutive instructions always target different TMEM columns.
+      constexpr int kNsub = 256 / kNQ;
+      const uint32_t idesc = make_idesc_bf16(128, kNsub);
+      const uint32_t w_base = smem_u32(Ws);
+      uint32_t g = 0;                       // ring stage counter
+      uint32_t n_layer = 0;                 // layers issued so far (3 per ray)
+      for (int64_t it = 0; it < n_my; ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t a_in = smem_u32(As) + buf * kABytes;
+        if (lane == 0) stamp(1, it, 0);
+#pragma unroll 1
+        for (int L = 0; L < 3; ++L) {
+          const uint32_t dx = tmem + kColAcc + ((2 * n_layer) % 3) * 128, dy = tmem + kColAcc + ((2 * n_layer + 1) % 3) * 128;
+          const uint32_t a_tm = tmem + kColA;
+          if (n_layer > 0) mbar_wait(&m->hand[0], (n_layer - 1) & 1);       // slot dy drained (dx is the spare); A' K 0..127 written
+          if (L == 0) mbar_wait(&m->a_full[buf], (uint32_t)(it >> 1) & 1);
+#pragma unroll 1
+          for (int st8 = 0; st8 < 8; ++st8) {
+            if (st8 == 4 && n_layer > 0) mbar_wait(&m->hand[1], (n_layer - 1) & 1);   // A' K 128..255 written
+            const int s = g % kNst;
+            mbar_wait(&m->w_full[s], (g / kNst) & 1);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(w_base + s * kStageBytes, 256 * 16, 128);
+            if (elect_one()) {
+              if (L == 0) {
+                const uint64_t ad0 = make_smem_desc(a_in + st8 * 2 * 2 * kChunkA, kChunkA, 128);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  mma_bf16_ss(dx, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
+                  mma_bf16_ss(dy, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  mma_bf16_ts(dx, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
+                  mma_bf16_ts(dy, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
+                }
+              }
+              mma_commit(&m->w_empty[s]);
+            }
+            __syncwarp();
+            ++g;
+          }
+          if (elect_one()) {
+            mma_commit(&m->acc_full);
+            if (L == 0) mma_commit(&m->a_empty[buf]);      // layer 1 has consumed A_in[buf]: the gather warps may refill it
+          }
+          __syncwarp();
+          ++n_layer;
+          if (lane == 0) stamp(1, it, 1 + L);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < kGatherWarps) {
+    // =================================== gather warps: TWO threads per sample row ===========================================
+    // half 0: PE + coarse grid; half 1: view-direction bias + fine grid.  Runs one ray ahead of the MLP.
+    const int half = warp >> 2, gwarp = warp & 3;
+    const int r = gwarp * 32 + lane;
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      if (tid == 0) stamp(0, it, 0);
+      if (use > 0) { mbar_wait(&m->a_empty[buf], (use - 1) & 1); mbar_wait(&m->slot_free[buf], (use - 1) & 1); }
+      if (tid == 0) stamp(0, it, 1);
+      uint8_t* Aq = As + buf * kABytes;
+      uint8_t* a_row = Aq + r * 16;
+      RaySlot* slot = &m->slot[buf];
+      const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
+      const float* rb = a.ray_batch + ray * 11;
+      const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
+      const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+      if (half == 0) {
+        const float zv = a.z_vals[ray * S + min(r, S - 1)];
+        slot->z[r] = zv;
+        // PE(pts) -> A chunks 24..31 (64 columns, the last one is the zero pad of K = 127 -> 128)
+        float pe[64];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pe[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+          fast_sincos(pe[i], &pe[3 + i], &pe[6 + i]);
+        }
+#pragma unroll
+        for (int f = 1; f < kPeFreqPts; ++f) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float sp = pe[3 + 6 * (f - 1) + i], cp = pe[6 + 6 * (f - 1) + i];
+            pe[3 + 6 * f + i] = 2.0f * sp * cp;
+            pe[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+          }
+        }
+        pe[63] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(a_row + (24 + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
+                       pack_bf16x2(pe[8 * j + 4], pe[8 * j + 5]), pack_bf16x2(pe[8 * j + 6], pe[8 * j + 7]));
+      } else {
+        const float vd[3] = {__ldg(rb + 8), __ldg(rb + 9), __ldg(rb + 10)};
+        float ped[kPeDir];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { ped[i] = vd[i]; fast_sincos(vd[i], &ped[3 + i], &ped[6 + i]); }
+#pragma unroll
+        for (int f = 1; f < kPeFreqDir; ++f) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float sp = ped[3 + 6 * (f - 1) + i], cp = ped[6 + 6 * (f - 1) + i];
+            ped[3 + 6 * f + i] = 2.0f * sp * cp;
+            ped[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+          }
+        }
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          const int col = r + hc * kRows;
+          float b = a.mlp.color0_b ? __ldg(a.mlp.color0_b + col) : 0.f;
+          const float* w = a.mlp.color0_t + (size_t)128 * 256 + col;
+#pragma unroll
+          for (int j = 0; j < kPeDir; ++j) b = fmaf(__ldg(w + j * 256), ped[j], b);
+          slot->bias[col] = b;
+        }
+      }
+      named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
+      if (tid == 0) stamp(0, it, 2);
+      if (!(a.ablate & 1)) gather_tiles2<T>(m->grids[half], Aq, slot->z, gwarp, lane, o, d, half);
+      fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&m->a_full[buf]);
+      if (tid == 0) stamp(0, it, 3);
+    }
+  } else {
+    // =================================== epilogue warps: TWO threads per sample row ============================================
+    const int ew = warp - kGatherWarps;
+    const int half = ew >> 2, gwarp = ew & 3;     // both halves of a row read the same TMEM lane quarter (warp % 4)
+    const int r = gwarp * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(gwarp * 32) << 16);
+    const uint32_t s_wsig = smem_u32(m->wsig), s_wrgb = smem_u32(m->wrgb), s_bias1 = smem_u32(m->bias1);
+    const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
+    const float near_thr = a.rmnearplane / 128.0f;
+    const bool has_bias1 = a.mlp.color1_b != nullptr;
+    uint32_t n_use = 0;                            // completed accumulator uses (3 per ray)
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int buf = (int)(it & 1);
+      RaySlot* slot = &m->slot[buf];
+      const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
+      const uint32_t s_bias = smem_u32(slot->bias);
+      float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
+      const bool st0 = (ew == 0 && lane == 0);
+      if (st0) stamp(2, it, 0);
+#pragma unroll 1
+      for (int L = 0; L < 3; ++L) {
+        mbar_wait(&m->acc_full, n_use & 1);
+        if (st0) stamp(2, it, 1 + 2 * L);
+        tc_fence_after();
+        const uint32_t acc_x = lane_base + kColAcc + ((2 * n_use) % 3) * 128 + half * 32;
+        const uint32_t acc_y = lane_base + kColAcc + ((2 * n_use + 1) % 3) * 128 + half * 32;
+        // 32 accumulator columns [col0, col0 + 32) of this thread's row
+        auto process = [&](const uint32_t (&v)[32], const int q) {
+          const int col0 = q * 64 + half * 32;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (L == 1 || (L == 2 && has_bias1)) {
+            const uint32_t bs = (L == 1) ? s_bias : s_bias1;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = ld_shared_f4(bs + (col0 + i) * 4);
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+          }
+          if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (two packed accumulator pairs)
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 w = ld_shared_f4(s_wsig + (col0 + i) * 4);
+              s0 = ffma2(make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), make_float2(w.x, w.y), s0);
+              s1 = ffma2(make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f)), make_float2(w.z, w.w), s1);
+            }
+            sig_part += (s0.x + s0.y) + (s1.x + s1.y);
+          }
+          if (L < 2) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(f[2 * i], f[2 * i + 1]);
+            if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + q * 32 + half * 16, pk);   // in place: the layer's MMAs are complete
+          } else {             // rgb head: fp32 dot of relu(h3) with color_net.2, packed FMAs over column pairs
+            float2 r2 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 wr = ld_shared_f4(s_wrgb + (col0 + i) * 4), wg = ld_shared_f4(s_wrgb + (256 + col0 + i) * 4),
+                           wb = ld_shared_f4(s_wrgb + (512 + col0 + i) * 4);
+              const float2 x01 = make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), x23 = make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f));
+              r2 = ffma2(x01, make_float2(wr.x, wr.y), r2); r2 = ffma2(x23, make_float2(wr.z, wr.w), r2);
+              g2 = ffma2(x01, make_float2(wg.x, wg.y), g2); g2 = ffma2(x23, make_float2(wg.z, wg.w), g2);
+              b2 = ffma2(x01, make_float2(wb.x, wb.y), b2); b2 = ffma2(x23, make_float2(wb.z, wb.w), b2);
+            }
+            rr += r2.x + r2.y; rg_ += g2.x + g2.y; rbl += b2.x + b2.y;
+          }
+        };
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          uint32_t v[32];
+          if (a.ablate & 4) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          } else {
+            tmem_ld32(((q >> 1) ? acc_y : acc_x) + (q & 1) * 64, v);
+            tmem_ld_wait();
+          }
+          process(v, q);
+          if (q & 1) {         // half (q >> 1) of the layer is done: its accumulator slot is drained, its A' columns are written
+            if (L < 2) tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&m->hand[q >> 1]);
+          }
+        }
+        ++n_use;
+        if (st0) stamp(2, it, 2 + 2 * L);
+      }
+      m->headp[half][r][0] = rr; m->headp[half][r][1] = rg_; m->headp[half][r][2] = rbl; m->headp[half][r][3] = sig_part;
+      named_bar_sync(2, kRoleThreads);              // both halves' head partials visible
+      if (half == 0) {
+        // ---- compositing (voxnerf.py:153-201), one thread per sample row ---------------------------------------------------
+        const float* rb = a.ray_batch + ray * 11;
+        const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+        const float zv = slot->z[r];
+        float col[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          col[i] = sigmoidf_(m->headp[0][r][i] + m->headp[1][r][i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+        const float sig_raw = m->headp[0][r][3] + m->headp[1][r][3];
+        float alpha = 0.f;
+        if (r < S - 1) {
+          const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+          const float znext = slot->z[r + 1];
+          const float dist = __fmul_rn(znext - zv, dnorm);
+          float sg = sig_raw;
+          if (a.noise) sg += __ldg(a.noise + ray * (S - 1) + r);
+          sg = fmaxf(sg, 0.f);
+          if (mask_near && !(znext > near_thr)) sg = 0.f;
+          alpha = 1.0f - expf(-__fmul_rn(sg, dist));
+        } else if (r == S - 1) {
+          alpha = 1.0f;
+        }
+        float t = 1.0f - alpha;                 // inclusive product scan of (1 - alpha) over the warp
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const float y = __shfl_up_sync(0xffffffffu, t, dlt);
+          if (lane >= dlt) t *= y;
+        }
+        float Tr = __shfl_up_sync(0xffffffffu, t, 1);
+        if (lane == 0) Tr = 1.0f;
+        if (lane == 31) m->wtot[gwarp] = t;
+        named_bar_sync(3, kRows);
+        for (int w2 = 0; w2 < gwarp; ++w2) Tr *= m->wtot[w2];
+        const float wgt = alpha * Tr;
+        if (r < S) a.weights[ray * S + r] = wgt;
+        float red[5] = {wgt * col[0], wgt * col[1], wgt * col[2], wgt * zv, wgt};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) m->red[gwarp][i] = red[i];
+        }
+        named_bar_sync(3, kRows);
+        if (r < 5) {
+          const float tot = m->red[0][r] + m->red[1][r] + m->red[2][r] + m->red[3][r];
+          if (r < 3) a.rgb[ray * 3 + r] = tot; else if (r == 3) a.depth[ray] = tot; else a.acc[ray] = tot;
+        }
+      }
+      named_bar_sync(2, kRoleThreads);              // headp / red / wtot free for the next ray
+      if (st0) stamp(2, it, 7);
+      mbar_arrive(&m->slot_free[buf]);              // slot[buf] (z, bias) may be rewritten by the gather warps
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace
+
+int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, cudaStream_t st) {
+  FineArgs a = a_in;
+  static const int ablate = [] { const char* e = getenv("EDN_TC2_ABLATE"); return e ? atoi(e) : 0; }();   // dev: TIMING-ONLY ablations (outputs invalid)
+  a.ablate = ablate;
+  const unsigned gx = (unsigned)(a.n_rays < (int64_t)num_sms() ? a.n_rays : (int64_t)num_sms());
+  const char* tr = getenv("EDN_TC_TRACE");
+  if (tr && tr[0] == '1' && grid_dtype == EDN_BF16) {   // dev tooling: print the role time lines of CTA 0 (synchronises!)
+    long long* buf = nullptr;
+    EDN_CUDA_OK(cudaMallocManaged(&buf, 3 * 4 * 16 * sizeof(long long)));
+    memset(buf, 0, 3 * 4 * 16 * sizeof(long long));
+    a.trace = buf;
+    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+    EDN_CUDA_OK(cudaStreamSynchronize(st));
+    const long long t0 = buf[16];   // MMA role, it = 8, slot 0
+    static const char* role[3] = {"gather", "mma", "epi"};
+    for (int r = 0; r < 3; ++r)
+      for (int i = 0; i < 4; ++i) {
+        fprintf(stderr, "[trace2 %s it=%d]", role[r], 8 + i);
+        for (int k = 0; k < 8; ++k) if (buf[(r * 4 + i) * 16 + k]) fprintf(stderr, " s%d=%lld", k, buf[(r * 4 + i) * 16 + k] - t0);
+        fprintf(stderr, "\n");
+      }
+    cudaFree(buf);
+    return EDN_OK;
+  }
+  if (grid_dtype == EDN_BF16) {
+    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+  } else {
+    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    fine_fwd_tc2_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+  }
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
+
+}  // namespace edn
