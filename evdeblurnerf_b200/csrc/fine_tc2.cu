@@ -32,10 +32,17 @@ namespace {
 using namespace tc;
 
 constexpr int kRows = 128;
-constexpr int kGatherWarps = 8, kEpiWarps = 8;
+// Warp roles (7 warpgroups = 896 threads, launched at 72 registers per thread, then re-balanced with setmaxnreg):
+//   warps 0-7   gather   (2 warpgroups, raised to 96 registers: 18 sixteen-byte loads in flight per thread)
+//   warps 8-23  epilogue (4 warpgroups, 72 registers): FOUR threads per sample row, 64 columns of a layer each -- the epilogue is a
+//               per-warp dependent instruction stream (~5 cycles per instruction), so its latency halves with twice the warps
+//   warp 24 MMA issuer, warp 25 weight stream, warps 26-27 idle (the warpgroup drops to 24 registers and donates the rest)
+constexpr int kGatherWarps = 8, kEpiWarps = 16;
 constexpr int kWarpMma = kGatherWarps + kEpiWarps, kWarpLoad = kWarpMma + 1;
-constexpr int kThreads = (kGatherWarps + kEpiWarps + 2) * 32;      // 576
-constexpr int kRoleThreads = 256;
+constexpr int kThreads = (kGatherWarps + kEpiWarps + 4) * 32;      // 896
+constexpr int kRoleThreads = 256;                                   // gather threads
+constexpr int kEpiThreads = kEpiWarps * 32;                         // 512
+constexpr int kQuarterThreads = 128;                                // epilogue threads serving one 64-column quarter of a layer
 constexpr int kNst = 4;                    // weight ring stages
 constexpr int kStageBytes = 16384;         // 2 K-steps of a layer (N = 256 rows x 16 x 2 B = 8 KB per K-step): the lean section of the blob
 constexpr int kKstepBytes = 8192;
@@ -48,6 +55,9 @@ constexpr uint32_t kTmemCols = 512;
 // drains first: the next layer's K-steps 0..7 (they only read the first half of the new A operand) overlap the second half of
 // this layer's epilogue.
 constexpr uint32_t kColA = 0, kColAcc = 128;
+#ifndef EDN_TC2_PACKED
+#define EDN_TC2_PACKED 1                   // fp32x2 packed arithmetic in the gather / epilogue (same results as scalar)
+#endif
 constexpr int kNQ = 2;                     // N = 128 per instruction: 86 (TS) / 119 (SS) cycles each, measured (fine_tc2 ablate 16 / 48)
 
 struct alignas(16) RaySlot {              // per-ray data produced by the gather warps, read by the epilogue warps
@@ -57,14 +67,14 @@ struct alignas(16) RaySlot {              // per-ray data produced by the gather
 struct Misc {
   uint64_t a_full[2], a_empty[2], slot_free[2];
   uint64_t w_full[kNst], w_empty[kNst];
-  uint64_t acc_full, hand[2];           // hand[h]: the epilogue finished half h of a layer (slot drained + A' columns 64h.. written)
+  uint64_t acc_full, hand[4];           // hand[q]: the epilogue finished quarter q of a layer (A' K 64q..64q+63 written; q = 1 / 3: slot x / y drained)
   GridDev grids[2];
   uint32_t tmem_base, pad[3];
   alignas(16) float wsig[256];
   alignas(16) float wrgb[3][256];          // color_net.2, channel-major (float4 = 4 consecutive hidden units of one channel)
   alignas(16) float bias1[256];
   RaySlot slot[2];
-  alignas(16) float headp[2][kRows][4];
+  alignas(16) float headp[4][kRows][4];   // per column quarter: partial rgb (xyz) / sigma (w) heads
   float red[4][8];
   float wtot[4];
 };
@@ -104,20 +114,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Packed fp32 FMA (sm_100 FFMA2): d = a * b + c on two lanes at once; halves the issue slots of the epilogue's head dot products.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-
 // Cooperative gather of ONE grid for the 32 points of this warp (lean A layout: coarse chunks 0..11, fine chunks 12..23).
 // Component 0 (64 channels = one 128-byte line per texel): lane (p4 = lane & 3, c = lane >> 2) reads chunk c of points 8 gi + p4 and
 // 8 gi + 4 + p4, so every warp-wide load covers FOUR WHOLE lines (round 1: eight half lines -- the L1 wavefront count per byte is
 // what bounds the gather).  Components 1 / 2 (16 channels): lane (q = lane >> 3, j = lane & 7) -> point 8 gi + j, component 1 + q / 2,
 // chunk q & 1.
+#if EDN_TC2_PACKED
+#define FIN finish2
+#else
+#define FIN finish
+#endif
 template <typename T>
 __device__ __forceinline__ void gather_tiles2(const GridDev& g, uint8_t* As, const float* z_s, int gwarp, int lane, const float o[3],
                                               const float d[3], const int fine_tile) {
@@ -125,50 +131,49 @@ __device__ __forceinline__ void gather_tiles2(const GridDev& g, uint8_t* As, con
   const int p4 = lane & 3, c8 = lane >> 2, q = lane >> 3;
 #pragma unroll 1
   for (int gi = 0; gi < 4; ++gi) {
-    {  // component 0: plane (x,y), line z
-      GatherTask<T> t0, t1;
-      const T* pl = reinterpret_cast<const T*>(g.plane[0]);
-      const T* ln = reinterpret_cast<const T*>(g.line[0]);
-      const int ptA = gwarp * 32 + gi * 8 + p4, ptB = ptA + 4;
-      {
-        const float zv = z_s[ptA];
-        float p[3], n[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
-        normalize_pt(g, p, n);
-        Taps2 pt2; Taps1 lt1;
-        plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
-        line_taps(n[2], g.ll[0], lt1);
-        t0.issue(pl, ln, 64, c8, pt2, lt1);
-      }
-      {
-        const float zv = z_s[ptB];
-        float p[3], n[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
-        normalize_pt(g, p, n);
-        Taps2 pt2; Taps1 lt1;
-        plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
-        line_taps(n[2], g.ll[0], lt1);
-        t1.issue(pl, ln, 64, c8, pt2, lt1);
-      }
-      t0.finish(As + ptA * 16 + (base + c8) * kChunkA);
-      t1.finish(As + ptB * 16 + (base + c8) * kChunkA);
-    }
-    {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
-      GatherTask<T> t2;
-      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
-      const float zv = z_s[pt];
+    // Tap offsets / weights are computed ONCE per (point, component) -- lane 8 c + j: component c (0, 1, 2) of point 8 gi + j; lanes
+    // 24..31 idle -- and handed to the lanes that load with warp shuffles: 36 SHFL instead of three redundant ~70-instruction tap
+    // computations per lane (the gather warps' instruction count is what the kernel is bound by).
+    Taps2 mp; Taps1 ml;
+    {
+      const int comp = min(lane >> 3, 2);
+      const float zv = z_s[gwarp * 32 + gi * 8 + (lane & 7)];
       float p[3], n[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
       normalize_pt(g, p, n);
+      // matMode = [[0,1],[0,2],[1,2]], vecMode = [2,1,0]
+      const float px = comp == 2 ? n[1] : n[0], py = comp == 0 ? n[1] : n[2], lv = comp == 0 ? n[2] : (comp == 1 ? n[1] : n[0]);
+      plane_taps(px, py, g.ph[comp], g.pw[comp], mp);
+      line_taps(lv, g.ll[comp], ml);
+    }
+    auto fetch = [&](int src, Taps2& pt2, Taps1& lt1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { pt2.off[k] = __shfl_sync(0xffffffffu, mp.off[k], src); pt2.w[k] = __shfl_sync(0xffffffffu, mp.w[k], src); }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { lt1.off[k] = __shfl_sync(0xffffffffu, ml.off[k], src); lt1.w[k] = __shfl_sync(0xffffffffu, ml.w[k], src); }
+    };
+    {  // component 0: plane (x,y), line z -- whole 128-byte lines: lane (p4, c8) reads chunk c8 of points p4 and p4 + 4
+      GatherTask<T> t0, t1;
+      const T* pl = reinterpret_cast<const T*>(g.plane[0]);
+      const T* ln = reinterpret_cast<const T*>(g.line[0]);
+      const int ptA = gwarp * 32 + gi * 8 + p4, ptB = ptA + 4;
+      Taps2 pt2; Taps1 lt1;
+      fetch(p4, pt2, lt1);
+      t0.issue(pl, ln, 64, c8, pt2, lt1);
+      fetch(p4 + 4, pt2, lt1);
+      t1.issue(pl, ln, 64, c8, pt2, lt1);
+      t0.FIN(As + ptA * 16 + (base + c8) * kChunkA);
+      t1.FIN(As + ptB * 16 + (base + c8) * kChunkA);
+    }
+    {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
+      GatherTask<T> t2;
+      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
       const int comp = 1 + (q >> 1);
       Taps2 pt2; Taps1 lt1;
-      plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], pt2);
-      line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
+      fetch(comp * 8 + (lane & 7), pt2, lt1);
       t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
-      t2.finish(As + pt * 16 + (base + 8 + q) * kChunkA);
+      t2.FIN(As + pt * 16 + (base + 8 + q) * kChunkA);
     }
   }
 }
@@ -182,9 +187,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); mbar_init(&m->slot_free[b], kRoleThreads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); mbar_init(&m->slot_free[b], kEpiThreads); }
     for (int s = 0; s < kNst; ++s) { mbar_init(&m->w_full[s], 1); mbar_init(&m->w_empty[s], 1); }
-    mbar_init(&m->acc_full, 1); mbar_init(&m->hand[0], kRoleThreads); mbar_init(&m->hand[1], kRoleThreads);
+    mbar_init(&m->acc_full, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&m->hand[q], kQuarterThreads);
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(&m->tmem_base, kTmemCols);
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   tc_fence_after();
   const uint32_t tmem = m->tmem_base;
   const int S = a.S;
+  // register re-balancing (first statement of every role branch): the MMA / loader warpgroup donates, the gather warpgroups take
   // dev tooling (EDN_TC_TRACE=1): clock64 stamps of CTA 0 for iterations 8..11: trace[role][it - 8][slot], role 0 gather, 1 MMA, 2 epilogue
   auto stamp = [&](int role, int64_t it, int k) {
     if (a.trace && blockIdx.x == 0 && it >= 8 && it < 12) a.trace[(role * 4 + (it - 8)) * 16 + k] = clock64();
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
     }
   } else if (warp == kWarpLoad) {
     // =================================== weight stream =====================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (n_my > 0) {      // converged warp, one elected lane issues (uniform operands: no per-lane retry loop around UBLKCP)
       const uint32_t total = (uint32_t)n_my * kStagesPerRay;
       for (uint32_t g = 0; g < total; ++g) {
@@ -252,8 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       }
     }
     __syncwarp();
+  } else if (warp > kWarpLoad) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle warps of the donor warpgroup
   } else if (warp == kWarpMma) {
     // =================================== MMA issuer (converged warp, one elected lane issues) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (n_my > 0) {
       // K-major issue with kNQ INDEPENDENT accumulator chains per K-step: back-to-back MMAs into the same accumulator serialise on
       // the tensor pipe's accumulate latency (~140 cycles, measured: N = 64 MMAs issued quarter by quarter ran at 140 cycles each
@@ -271,35 +282,53 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         for (int L = 0; L < 3; ++L) {
           const uint32_t dx = tmem + kColAcc + ((2 * n_layer) % 3) * 128, dy = tmem + kColAcc + ((2 * n_layer + 1) % 3) * 128;
           const uint32_t a_tm = tmem + kColA;
-          if (n_layer > 0) mbar_wait(&m->hand[0], (n_layer - 1) & 1);       // slot dy drained (dx is the spare); A' K 0..127 written
+          // Issue order of a layer (chain x -> slot dx = the spare one, chain y -> slot dy = the previous layer's x slot):
+          //   after hand[0] (A' K 0..63):            x.K0-3
+          //   after hand[1] (dy drained, K 64..127): y.K0-3, then x / y alternating K4-7
+          //   after hand[2] / hand[3]:               K8-11 / K12-15
+          // so only the first quarter of the previous epilogue and the last quarter of this layer's MMAs are exposed.
+          const uint32_t hp = (n_layer - 1) & 1;
+          if (n_layer > 0) mbar_wait(&m->hand[0], hp);
           if (L == 0) mbar_wait(&m->a_full[buf], (uint32_t)(it >> 1) & 1);
-#pragma unroll 1
-          for (int st8 = 0; st8 < 8; ++st8) {
-            if (st8 == 4 && n_layer > 0) mbar_wait(&m->hand[1], (n_layer - 1) & 1);   // A' K 128..255 written
-            const int s = g % kNst;
-            mbar_wait(&m->w_full[s], (g / kNst) & 1);
-            tc_fence_after();
+          const uint32_t g0 = g;
+          auto issue = [&](int st8, bool do_x, bool do_y) {      // the two K-steps of ring stage g0 + st8
+            const int s = (g0 + st8) % kNst;
             const uint64_t bd0 = make_smem_desc(w_base + s * kStageBytes, 256 * 16, 128);
-            if (elect_one()) {
-              if (L == 0) {
-                const uint64_t ad0 = make_smem_desc(a_in + st8 * 2 * 2 * kChunkA, kChunkA, 128);
+            if (L == 0) {
+              const uint64_t ad0 = make_smem_desc(a_in + st8 * 2 * 2 * kChunkA, kChunkA, 128);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  mma_bf16_ss(dx, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
-                  mma_bf16_ss(dy, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  mma_bf16_ts(dx, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
-                  mma_bf16_ts(dy, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
-                }
+              for (int i = 0; i < 2; ++i) {
+                if (do_x) mma_bf16_ss(dx, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
+                if (do_y) mma_bf16_ss(dy, ad0 + (uint64_t)(i * (2 * kChunkA >> 4)), bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
               }
-              mma_commit(&m->w_empty[s]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                if (do_x) mma_bf16_ts(dx, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes) >> 4), idesc, (st8 | i) > 0);
+                if (do_y) mma_bf16_ts(dy, a_tm + (st8 * 2 + i) * 8, bd0 + (uint64_t)((i * kKstepBytes + 128 * 16) >> 4), idesc, (st8 | i) > 0);
+              }
             }
-            __syncwarp();
-            ++g;
+          };
+          auto wait_stage = [&](int st8) { mbar_wait(&m->w_full[(g0 + st8) % kNst], ((g0 + st8) / kNst) & 1); };
+          wait_stage(0); wait_stage(1);
+          tc_fence_after();
+          if (elect_one()) { issue(0, true, false); issue(1, true, false); }
+          __syncwarp();
+          if (n_layer > 0) { mbar_wait(&m->hand[1], hp); tc_fence_after(); }
+          if (elect_one()) {
+            issue(0, false, true); mma_commit(&m->w_empty[(g0 + 0) % kNst]);
+            issue(1, false, true); mma_commit(&m->w_empty[(g0 + 1) % kNst]);
           }
+          __syncwarp();
+#pragma unroll 1
+          for (int st8 = 2; st8 < 8; ++st8) {
+            if (n_layer > 0 && (st8 == 4 || st8 == 6)) mbar_wait(&m->hand[st8 >> 1], hp);
+            wait_stage(st8);
+            tc_fence_after();
+            if (elect_one()) { issue(st8, true, true); mma_commit(&m->w_empty[(g0 + st8) % kNst]); }
+            __syncwarp();
+          }
+          g += 8;
           if (elect_one()) {
             mma_commit(&m->acc_full);
             if (L == 0) mma_commit(&m->a_empty[buf]);      // layer 1 has consumed A_in[buf]: the gather warps may refill it
@@ -314,13 +343,17 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   } else if (warp < kGatherWarps) {
     // =================================== gather warps: TWO threads per sample row ===========================================
     // half 0: PE + coarse grid; half 1: view-direction bias + fine grid.  Runs one ray ahead of the MLP.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     const int half = warp >> 2, gwarp = warp & 3;
     const int r = gwarp * 32 + lane;
     for (int64_t it = 0; it < n_my; ++it) {
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       if (tid == 0) stamp(0, it, 0);
-      if (use > 0) { mbar_wait(&m->a_empty[buf], (use - 1) & 1); mbar_wait(&m->slot_free[buf], (use - 1) & 1); }
+      if (use > 0) {      // one polling warp, the rest of the gather group blocks in a named barrier (see the epilogue warps)
+        if (warp == 0) { mbar_wait(&m->a_empty[buf], (use - 1) & 1); mbar_wait(&m->slot_free[buf], (use - 1) & 1); }
+        named_bar_sync(5, kRoleThreads);
+      }
       if (tid == 0) stamp(0, it, 1);
       uint8_t* Aq = As + buf * kABytes;
       uint8_t* a_row = Aq + r * 16;
@@ -387,10 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   } else {
     // =================================== epilogue warps: TWO threads per sample row ============================================
     const int ew = warp - kGatherWarps;
-    const int half = ew >> 2, gwarp = ew & 3;     // both halves of a row read the same TMEM lane quarter (warp % 4)
+    const int tq = ew >> 2, gwarp = ew & 3;       // tq: the 64-column quarter of every layer this thread serves; TMEM lane quarter = warp % 4
     const int r = gwarp * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(gwarp * 32) << 16);
-    const uint32_t s_wsig = smem_u32(m->wsig), s_wrgb = smem_u32(m->wrgb), s_bias1 = smem_u32(m->bias1);
+    // plain shared-memory loads (the compiler may batch them; a `volatile` asm load per float4 serialises on its 29-cycle latency)
+    const float4* s_wsig = reinterpret_cast<const float4*>(m->wsig);
+    const float4* s_wrgb = reinterpret_cast<const float4*>(&m->wrgb[0][0]);
+    const float4* s_bias1 = reinterpret_cast<const float4*>(m->bias1);
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
     const bool has_bias1 = a.mlp.color1_b != nullptr;
@@ -399,38 +435,57 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       const int buf = (int)(it & 1);
       RaySlot* slot = &m->slot[buf];
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
-      const uint32_t s_bias = smem_u32(slot->bias);
+      const float4* s_bias = reinterpret_cast<const float4*>(slot->bias);
       float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
       const bool st0 = (ew == 0 && lane == 0);
       if (st0) stamp(2, it, 0);
 #pragma unroll 1
       for (int L = 0; L < 3; ++L) {
-        mbar_wait(&m->acc_full, n_use & 1);
+        // ONE warp polls the mbarrier, the other 15 block in a named barrier: a polling warp re-issues its try_wait loop every ~35
+        // cycles, and sixteen of them took ~40 % of the SM's issue slots from the warps doing the work (ncu source page, round 2)
+        if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
+        named_bar_sync(4, kEpiThreads);
         if (st0) stamp(2, it, 1 + 2 * L);
         tc_fence_after();
-        const uint32_t acc_x = lane_base + kColAcc + ((2 * n_use) % 3) * 128 + half * 32;
-        const uint32_t acc_y = lane_base + kColAcc + ((2 * n_use + 1) % 3) * 128 + half * 32;
+        // quarters 0, 1 live in slot x, quarters 2, 3 in slot y
+        const uint32_t acc_q = lane_base + kColAcc + ((2 * n_use + (tq >> 1)) % 3) * 128 + (tq & 1) * 64;
         // 32 accumulator columns [col0, col0 + 32) of this thread's row
-        auto process = [&](const uint32_t (&v)[32], const int q) {
-          const int col0 = q * 64 + half * 32;
+        auto process = [&](const uint32_t (&v)[32], const int c) {
+          const int col0 = tq * 64 + c * 32;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (L == 1 || (L == 2 && has_bias1)) {
-            const uint32_t bs = (L == 1) ? s_bias : s_bias1;
+          if (L == 2 && has_bias1) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = ld_shared_f4(bs + (col0 + i) * 4);
+              const float4 b4 = s_bias1[(col0 + i) >> 2];
               f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+          }
+          if (L == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = s_bias[(col0 + i) >> 2];
+#if EDN_TC2_PACKED
+              const float2 lo = fadd2(make_float2(f[i], f[i + 1]), make_float2(b4.x, b4.y)), hi = fadd2(make_float2(f[i + 2], f[i + 3]), make_float2(b4.z, b4.w));
+              f[i] = lo.x; f[i + 1] = lo.y; f[i + 2] = hi.x; f[i + 3] = hi.y;
+#else
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+#endif
             }
           }
           if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (two packed accumulator pairs)
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 w = ld_shared_f4(s_wsig + (col0 + i) * 4);
+              const float4 w = s_wsig[(col0 + i) >> 2];
+#if EDN_TC2_PACKED
               s0 = ffma2(make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), make_float2(w.x, w.y), s0);
               s1 = ffma2(make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f)), make_float2(w.z, w.w), s1);
+#else
+              s0.x = fmaf(fmaxf(f[i], 0.f), w.x, s0.x); s0.y = fmaf(fmaxf(f[i + 1], 0.f), w.y, s0.y);
+              s1.x = fmaf(fmaxf(f[i + 2], 0.f), w.z, s1.x); s1.y = fmaf(fmaxf(f[i + 3], 0.f), w.w, s1.y);
+#endif
             }
             sig_part += (s0.x + s0.y) + (s1.x + s1.y);
           }
@@ -438,44 +493,58 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(f[2 * i], f[2 * i + 1]);
-            if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + q * 32 + half * 16, pk);   // in place: the layer's MMAs are complete
+            if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + (col0 >> 1), pk);   // in place: the layer's MMAs are complete
           } else {             // rgb head: fp32 dot of relu(h3) with color_net.2, packed FMAs over column pairs
             float2 r2 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 wr = ld_shared_f4(s_wrgb + (col0 + i) * 4), wg = ld_shared_f4(s_wrgb + (256 + col0 + i) * 4),
-                           wb = ld_shared_f4(s_wrgb + (512 + col0 + i) * 4);
+              const float4 wr = s_wrgb[(col0 + i) >> 2], wg = s_wrgb[(256 + col0 + i) >> 2], wb = s_wrgb[(512 + col0 + i) >> 2];
               const float2 x01 = make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), x23 = make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f));
+#if EDN_TC2_PACKED
               r2 = ffma2(x01, make_float2(wr.x, wr.y), r2); r2 = ffma2(x23, make_float2(wr.z, wr.w), r2);
               g2 = ffma2(x01, make_float2(wg.x, wg.y), g2); g2 = ffma2(x23, make_float2(wg.z, wg.w), g2);
               b2 = ffma2(x01, make_float2(wb.x, wb.y), b2); b2 = ffma2(x23, make_float2(wb.z, wb.w), b2);
+#else
+              r2.x = fmaf(x01.x, wr.x, r2.x); r2.y = fmaf(x01.y, wr.y, r2.y); r2.x = fmaf(x23.x, wr.z, r2.x); r2.y = fmaf(x23.y, wr.w, r2.y);
+              g2.x = fmaf(x01.x, wg.x, g2.x); g2.y = fmaf(x01.y, wg.y, g2.y); g2.x = fmaf(x23.x, wg.z, g2.x); g2.y = fmaf(x23.y, wg.w, g2.y);
+              b2.x = fmaf(x01.x, wb.x, b2.x); b2.y = fmaf(x01.y, wb.y, b2.y); b2.x = fmaf(x23.x, wb.z, b2.x); b2.y = fmaf(x23.y, wb.w, b2.y);
+#endif
             }
             rr += r2.x + r2.y; rg_ += g2.x + g2.y; rbl += b2.x + b2.y;
           }
         };
+        long long t_ld = 0, t_pr = 0, t_st = 0;
+        const bool tr_on = st0 && a.trace && blockIdx.x == 0 && it >= 8 && it < 12;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
+          long long c0 = tr_on ? clock64() : 0;
           if (a.ablate & 4) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0u;
           } else {
-            tmem_ld32(((q >> 1) ? acc_y : acc_x) + (q & 1) * 64, v);
+            tmem_ld32(acc_q + c * 32, v);
             tmem_ld_wait();
           }
-          process(v, q);
-          if (q & 1) {         // half (q >> 1) of the layer is done: its accumulator slot is drained, its A' columns are written
-            if (L < 2) tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&m->hand[q >> 1]);
-          }
+          long long c1 = tr_on ? clock64() : 0;
+          process(v, c);
+          if (tr_on) { const long long c2 = clock64(); t_ld += c1 - c0; t_pr += c2 - c1; }
         }
+        {
+          long long c2 = tr_on ? clock64() : 0;
+          // quarter tq of the layer is done: its A' columns are written (and with quarter tq ^ 1 its accumulator slot is drained)
+          if (L < 2) tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&m->hand[tq]);
+          if (tr_on) t_st = clock64() - c2;
+        }
+        if (tr_on) { a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 0] = t_ld; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 1] = t_pr; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 2] = t_st; }
         ++n_use;
         if (st0) stamp(2, it, 2 + 2 * L);
       }
-      m->headp[half][r][0] = rr; m->headp[half][r][1] = rg_; m->headp[half][r][2] = rbl; m->headp[half][r][3] = sig_part;
-      named_bar_sync(2, kRoleThreads);              // both halves' head partials visible
-      if (half == 0) {
+      m->headp[tq][r][0] = rr; m->headp[tq][r][1] = rg_; m->headp[tq][r][2] = rbl; m->headp[tq][r][3] = sig_part;
+      named_bar_sync(2, kEpiThreads);               // all four quarters' head partials visible
+      if (tq == 0) {
         // ---- compositing (voxnerf.py:153-201), one thread per sample row ---------------------------------------------------
         const float* rb = a.ray_batch + ray * 11;
         const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
@@ -483,8 +552,9 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         float col[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          col[i] = sigmoidf_(m->headp[0][r][i] + m->headp[1][r][i] + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
-        const float sig_raw = m->headp[0][r][3] + m->headp[1][r][3];
+          col[i] = sigmoidf_((m->headp[0][r][i] + m->headp[1][r][i]) + (m->headp[2][r][i] + m->headp[3][r][i]) +
+                             (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+        const float sig_raw = (m->headp[0][r][3] + m->headp[1][r][3]) + (m->headp[2][r][3] + m->headp[3][r][3]);
         float alpha = 0.f;
         if (r < S - 1) {
           const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
@@ -527,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           if (r < 3) a.rgb[ray * 3 + r] = tot; else if (r == 3) a.depth[ray] = tot; else a.acc[ray] = tot;
         }
       }
-      named_bar_sync(2, kRoleThreads);              // headp / red / wtot free for the next ray
+      named_bar_sync(2, kEpiThreads);               // headp / red / wtot free for the next ray
       if (st0) stamp(2, it, 7);
       mbar_arrive(&m->slot_free[buf]);              // slot[buf] (z, bias) may be rewritten by the gather warps
     }
@@ -547,8 +617,8 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1' && grid_dtype == EDN_BF16) {   // dev tooling: print the role time lines of CTA 0 (synchronises!)
     long long* buf = nullptr;
-    EDN_CUDA_OK(cudaMallocManaged(&buf, 3 * 4 * 16 * sizeof(long long)));
-    memset(buf, 0, 3 * 4 * 16 * sizeof(long long));
+    EDN_CUDA_OK(cudaMallocManaged(&buf, 4 * 4 * 16 * sizeof(long long)));
+    memset(buf, 0, 4 * 4 * 16 * sizeof(long long));
     a.trace = buf;
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
@@ -561,6 +631,11 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
         for (int k = 0; k < 8; ++k) if (buf[(r * 4 + i) * 16 + k]) fprintf(stderr, " s%d=%lld", k, buf[(r * 4 + i) * 16 + k] - t0);
         fprintf(stderr, "\n");
       }
+    for (int i = 0; i < 4; ++i) {
+      fprintf(stderr, "[trace2 epi-split it=%d] (ld, process, st+arrive) per layer:", 8 + i);
+      for (int k = 0; k < 9; ++k) fprintf(stderr, " %lld%s", buf[(3 * 4 + i) * 16 + k], k % 3 == 2 ? " |" : "");
+      fprintf(stderr, "\n");
+    }
     cudaFree(buf);
     return EDN_OK;
   }

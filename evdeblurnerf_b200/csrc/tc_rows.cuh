@@ -32,6 +32,27 @@ __device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
   *c = __cosf(r);
 }
 
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per instruction, same rounding as the scalar ones.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // Raw 16-byte channel chunk of a bf16 texel row / 2 x 16 bytes of an fp32 one.
 template <typename T> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> {
@@ -85,6 +106,31 @@ struct GatherTask {
 #pragma unroll
     for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
     st_shared_v4(dst, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+  }
+  // Same arithmetic (fp32, one rounding per operation, identical results) on the packed fp32x2 pipe: 28 FMUL2 / FFMA2 instead of 56
+  // scalar operations -- the gather warps' FMA-pipe time is what the epilogue warps compete with (fine_tc2.cu).
+  __device__ __forceinline__ void finish2(uint8_t* dst) const {
+    float2 p[4], l[4];
+    float t[8];
+    pv[0].get(t);
+    const float2 w0 = make_float2(pw[0], pw[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fmul2(make_float2(t[2 * i], t[2 * i + 1]), w0);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      pv[k].get(t);
+      const float2 wk = make_float2(pw[k], pw[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = ffma2(make_float2(t[2 * i], t[2 * i + 1]), wk, p[i]);
+    }
+    lv[0].get(t);
+    const float2 l0 = make_float2(lw[0], lw[0]), l1 = make_float2(lw[1], lw[1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = fmul2(make_float2(t[2 * i], t[2 * i + 1]), l0);
+    lv[1].get(t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fmul2(p[i], ffma2(make_float2(t[2 * i], t[2 * i + 1]), l1, l[i]));
+    st_shared_v4(dst, pack_bf16x2(p[0].x, p[0].y), pack_bf16x2(p[1].x, p[1].y), pack_bf16x2(p[2].x, p[2].y), pack_bf16x2(p[3].x, p[3].y));
   }
 };
 
