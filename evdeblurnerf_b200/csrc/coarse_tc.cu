@@ -144,17 +144,22 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
 
   if (warp >= kRowWarps) {
     // =================================== MMA issuer warp of group q (one thread) =======================================
+    // (converged warp, one elected lane issues: uniform descriptors, no per-lane retry loop around UTCHMMA)
     const int q = warp - kRowWarps;
-    if (lane == 0 && n_my > 0) {
-      if (q == 0) { mbar_expect_tx(&m->bar_w, kWBytes); bulk_g2s(Wsm, blob, kWBytes, &m->bar_w); }
+    if (n_my > 0) {
+      if (q == 0 && elect_one()) { mbar_expect_tx(&m->bar_w, kWBytes); bulk_g2s(Wsm, blob, kWBytes, &m->bar_w); }
+      __syncwarp();
       const uint32_t aq = smem_u32(As) + q * kABytes, wb = smem_u32(Wsm);
       const uint32_t d_tmem = tmem + q * 64;
       uint32_t pa = 0;
       mbar_wait(&m->bar_w, 0);
       auto stage = [&](uint32_t a_base, uint32_t b_off, int ksteps, int n, uint32_t b_step) {
         mbar_wait(&m->bar_a[q], pa); pa ^= 1; tc_fence_after();
-        issue_layer(d_tmem, a_base, wb + b_off, ksteps, n, b_step);
-        mma_commit(&m->bar_acc[q]);
+        if (elect_one()) {
+          issue_layer(d_tmem, a_base, wb + b_off, ksteps, n, b_step);
+          mma_commit(&m->bar_acc[q]);
+        }
+        __syncwarp();
       };
       for (int64_t it = 0; it < n_my; ++it) {
         if (LEAN) {
@@ -245,42 +250,15 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
       named_bar_sync(bar_id, kGroupThreads);
       // ---- VM gather of the coarse grid -> 128 x 96 bf16 tile; half h handles point groups gi = 2h, 2h + 1 ----------------
       {
-        const GridDev& g = m->grid;
-        const int qq = lane >> 3;
-#pragma unroll 1
-        for (int gi = 2 * half; gi < 2 * half + 2; ++gi) {
-          const int pt = gwarp * 32 + gi * 8 + (lane & 7);
+        const float* z_s = gm->z;
+        gather_points<T>(m->grid, Aq, kTileChunk, gwarp, lane, 2 * half, 2 * half + 2, [&](int pt, float (&p)[3]) {
           const int plr = min(pt / S, rpt - 1);
           const int64_t pray = min(tile * rpt + plr, a.n_rays - 1);   // the point's own ray (rays of a tile are adjacent)
           const float* rbp = a.ray_batch + pray * 11;
-          const float zp = gm->z[pt];
-          float p[3], n[3];
+          const float zp = z_s[pt];
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(__ldg(rbp + i), __fmul_rn(__ldg(rbp + 3 + i), zp));
-          normalize_pt(g, p, n);
-          uint8_t* row = Aq + pt * 16;
-          {
-            GatherTask<T> t0, t1;
-            Taps2 pt2; Taps1 lt1;
-            plane_taps(n[0], n[1], g.ph[0], g.pw[0], pt2);
-            line_taps(n[2], g.ll[0], lt1);
-            const T* pl = reinterpret_cast<const T*>(g.plane[0]);
-            const T* ln = reinterpret_cast<const T*>(g.line[0]);
-            t0.issue(pl, ln, 64, qq, pt2, lt1);
-            t1.issue(pl, ln, 64, qq + 4, pt2, lt1);
-            t0.finish(row + (kTileChunk + qq) * kChunkA);
-            t1.finish(row + (kTileChunk + 4 + qq) * kChunkA);
-          }
-          {
-            GatherTask<T> t2;
-            const int comp = 1 + (qq >> 1);
-            Taps2 pt2; Taps1 lt1;
-            plane_taps(comp == 1 ? n[0] : n[1], n[2], g.ph[comp], g.pw[comp], pt2);
-            line_taps(comp == 1 ? n[1] : n[0], g.ll[comp], lt1);
-            t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, qq & 1, pt2, lt1);
-            t2.finish(row + (kTileChunk + 8 + qq) * kChunkA);
-          }
-        }
+        });
       }
       rows_signal(&m->bar_a[q]);
       float sig_raw = 0.f;

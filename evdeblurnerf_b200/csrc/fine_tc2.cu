@@ -106,78 +106,6 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
 }
 
-// One lane of a CONVERGED warp (all operands warp-uniform): lets the compiler keep descriptors in uniform registers and emit a
-// plainly predicated UTCHMMA / UTCBAR instead of the per-active-lane retry loop it wraps around them inside `if (lane == 0)`.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
-// Cooperative gather of ONE grid for the 32 points of this warp (lean A layout: coarse chunks 0..11, fine chunks 12..23).
-// Component 0 (64 channels = one 128-byte line per texel): lane (p4 = lane & 3, c = lane >> 2) reads chunk c of points 8 gi + p4 and
-// 8 gi + 4 + p4, so every warp-wide load covers FOUR WHOLE lines (round 1: eight half lines -- the L1 wavefront count per byte is
-// what bounds the gather).  Components 1 / 2 (16 channels): lane (q = lane >> 3, j = lane & 7) -> point 8 gi + j, component 1 + q / 2,
-// chunk q & 1.
-#if EDN_TC2_PACKED
-#define FIN finish2
-#else
-#define FIN finish
-#endif
-template <typename T>
-__device__ __forceinline__ void gather_tiles2(const GridDev& g, uint8_t* As, const float* z_s, int gwarp, int lane, const float o[3],
-                                              const float d[3], const int fine_tile) {
-  const int base = fine_tile ? 12 : 0;
-  const int p4 = lane & 3, c8 = lane >> 2, q = lane >> 3;
-#pragma unroll 1
-  for (int gi = 0; gi < 4; ++gi) {
-    // Tap offsets / weights are computed ONCE per (point, component) -- lane 8 c + j: component c (0, 1, 2) of point 8 gi + j; lanes
-    // 24..31 idle -- and handed to the lanes that load with warp shuffles: 36 SHFL instead of three redundant ~70-instruction tap
-    // computations per lane (the gather warps' instruction count is what the kernel is bound by).
-    Taps2 mp; Taps1 ml;
-    {
-      const int comp = min(lane >> 3, 2);
-      const float zv = z_s[gwarp * 32 + gi * 8 + (lane & 7)];
-      float p[3], n[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
-      normalize_pt(g, p, n);
-      // matMode = [[0,1],[0,2],[1,2]], vecMode = [2,1,0]
-      const float px = comp == 2 ? n[1] : n[0], py = comp == 0 ? n[1] : n[2], lv = comp == 0 ? n[2] : (comp == 1 ? n[1] : n[0]);
-      plane_taps(px, py, g.ph[comp], g.pw[comp], mp);
-      line_taps(lv, g.ll[comp], ml);
-    }
-    auto fetch = [&](int src, Taps2& pt2, Taps1& lt1) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { pt2.off[k] = __shfl_sync(0xffffffffu, mp.off[k], src); pt2.w[k] = __shfl_sync(0xffffffffu, mp.w[k], src); }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) { lt1.off[k] = __shfl_sync(0xffffffffu, ml.off[k], src); lt1.w[k] = __shfl_sync(0xffffffffu, ml.w[k], src); }
-    };
-    {  // component 0: plane (x,y), line z -- whole 128-byte lines: lane (p4, c8) reads chunk c8 of points p4 and p4 + 4
-      GatherTask<T> t0, t1;
-      const T* pl = reinterpret_cast<const T*>(g.plane[0]);
-      const T* ln = reinterpret_cast<const T*>(g.line[0]);
-      const int ptA = gwarp * 32 + gi * 8 + p4, ptB = ptA + 4;
-      Taps2 pt2; Taps1 lt1;
-      fetch(p4, pt2, lt1);
-      t0.issue(pl, ln, 64, c8, pt2, lt1);
-      fetch(p4 + 4, pt2, lt1);
-      t1.issue(pl, ln, 64, c8, pt2, lt1);
-      t0.FIN(As + ptA * 16 + (base + c8) * kChunkA);
-      t1.FIN(As + ptB * 16 + (base + c8) * kChunkA);
-    }
-    {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
-      GatherTask<T> t2;
-      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
-      const int comp = 1 + (q >> 1);
-      Taps2 pt2; Taps1 lt1;
-      fetch(comp * 8 + (lane & 7), pt2, lt1);
-      t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
-      t2.FIN(As + pt * 16 + (base + 8 + q) * kChunkA);
-    }
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -412,7 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       }
       named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
       if (tid == 0) stamp(0, it, 2);
-      if (!(a.ablate & 1)) gather_tiles2<T>(m->grids[half], Aq, slot->z, gwarp, lane, o, d, half);
+      if (!(a.ablate & 1)) {      // lean A layout: coarse-grid products in chunks 0..11, fine-grid products in chunks 12..23
+        const float* z_s = slot->z;
+        gather_points<T>(m->grids[half], Aq, half ? 12 : 0, gwarp, lane, 0, 4, [&](int pt, float (&p)[3]) {
+          const float zv = z_s[pt];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+        });
+      }
       fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&m->a_full[buf]);
       if (tid == 0) stamp(0, it, 3);

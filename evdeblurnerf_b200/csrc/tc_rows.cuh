@@ -135,5 +135,69 @@ struct GatherTask {
 };
 
 
+// Cooperative VM gather of ONE grid for point groups gi_begin .. gi_end - 1 (8 points each) of this warp's 32 points; `pos(pt, p)`
+// returns the world position of tile row pt.  Results: (plane (.) line) products as bf16 into A chunks base .. base + 11 of row pt.
+//   * Tap offsets / weights are computed ONCE per (point, component) -- lane 8 c + j: component c (0, 1, 2) of point 8 gi + j; lanes
+//     24..31 idle -- and handed to the loading lanes with warp shuffles (36 SHFL instead of three ~70-instruction tap computations).
+//   * Component 0 (64 channels = one 128-byte line per texel): lane (p4 = lane & 3, c8 = lane >> 2) reads chunk c8 of points
+//     8 gi + p4 and 8 gi + 4 + p4, so every warp-wide load covers FOUR WHOLE lines (round 1: eight half lines; the L1 wavefront
+//     count per byte bounds the gather).  Components 1 / 2 (16 channels): lane (q = lane >> 3, j = lane & 7) -> point 8 gi + j,
+//     component 1 + q / 2, chunk q & 1.
+template <typename T, typename Pos>
+__device__ __forceinline__ void gather_points(const GridDev& g, uint8_t* As, const int base, const int gwarp, const int lane,
+                                              const int gi_begin, const int gi_end, Pos pos) {
+  const int p4 = lane & 3, c8 = lane >> 2, q = lane >> 3;
+#pragma unroll 1
+  for (int gi = gi_begin; gi < gi_end; ++gi) {
+    Taps2 mp; Taps1 ml;
+    {
+      const int comp = min(lane >> 3, 2);
+      float p[3], n[3];
+      pos(gwarp * 32 + gi * 8 + (lane & 7), p);
+      normalize_pt(g, p, n);
+      // matMode = [[0,1],[0,2],[1,2]], vecMode = [2,1,0]   (voxnerf.py:99-100)
+      const float px = comp == 2 ? n[1] : n[0], py = comp == 0 ? n[1] : n[2], lv = comp == 0 ? n[2] : (comp == 1 ? n[1] : n[0]);
+      plane_taps(px, py, g.ph[comp], g.pw[comp], mp);
+      line_taps(lv, g.ll[comp], ml);
+    }
+    auto fetch = [&](int src, Taps2& pt2, Taps1& lt1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { pt2.off[k] = __shfl_sync(0xffffffffu, mp.off[k], src); pt2.w[k] = __shfl_sync(0xffffffffu, mp.w[k], src); }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { lt1.off[k] = __shfl_sync(0xffffffffu, ml.off[k], src); lt1.w[k] = __shfl_sync(0xffffffffu, ml.w[k], src); }
+    };
+    {  // component 0: plane (x,y), line z
+      GatherTask<T> t0, t1;
+      const T* pl = reinterpret_cast<const T*>(g.plane[0]);
+      const T* ln = reinterpret_cast<const T*>(g.line[0]);
+      const int ptA = gwarp * 32 + gi * 8 + p4, ptB = ptA + 4;
+      Taps2 pt2; Taps1 lt1;
+      fetch(p4, pt2, lt1);
+      t0.issue(pl, ln, 64, c8, pt2, lt1);
+      fetch(p4 + 4, pt2, lt1);
+      t1.issue(pl, ln, 64, c8, pt2, lt1);
+      t0.finish2(As + ptA * 16 + (base + c8) * kChunkA);
+      t1.finish2(As + ptB * 16 + (base + c8) * kChunkA);
+    }
+    {  // components 1 (plane (x,z), line y) and 2 (plane (y,z), line x): 16 channels each = 2 chunks each
+      GatherTask<T> t2;
+      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
+      const int comp = 1 + (q >> 1);
+      Taps2 pt2; Taps1 lt1;
+      fetch(comp * 8 + (lane & 7), pt2, lt1);
+      t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
+      t2.finish2(As + pt * 16 + (base + 8 + q) * kChunkA);
+    }
+  }
+}
+
+// One lane of a CONVERGED warp (all operands warp-uniform): lets the compiler keep descriptors in uniform registers and emit a
+// plainly predicated UTCHMMA / UTCBAR / UBLKCP instead of the per-active-lane retry loop it wraps around them inside `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 }  // namespace tc
 }  // namespace edn
