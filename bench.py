@@ -421,7 +421,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("EDN_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16", "tc32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the shipped-config / training / strong-scaling legs")
@@ -580,7 +580,7 @@ def main():
     line = {
         "metric": "primary_rays_per_sec_fwd", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "tc32": "f32 via bf16x3 split operands on tcgen05"}[args.precision], "data": "synthetic",
         "config": workload_config(args.precision),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rays_host.numel() * 4 + idx_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 4},

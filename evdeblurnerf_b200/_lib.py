@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libevdeblur_b200.so")
 
-EDN_F32, EDN_BF16 = 0, 1
+EDN_F32, EDN_BF16, EDN_TC32 = 0, 1, 2
 FLAG_LINDISP, FLAG_TRAIN, FLAG_RELU_RGB = 1, 2, 4
 
 c_float_p = C.c_void_p   # device pointers travel as plain integers

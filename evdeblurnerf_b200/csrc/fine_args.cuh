@@ -28,4 +28,9 @@ struct FineArgs {
 // fine tensor-core blob ([layer][K-step][256 x 16] bf16, edn_pack_fine_tc)
 int launch_fine_tc2(const FineArgs& a, int grid_dtype, const uint8_t* wblob, cudaStream_t st);
 
+// fine_tc3.cu: bf16 x 3 tensor-core parity mode (EDN_TC32) and its blob section packer (scratch: 128 KB)
+int launch_fine_tc3(const FineArgs& a, int grid_dtype, const uint8_t* wblob, cudaStream_t st);
+int pack_fine_tc3_section(const float* f1, const float* f23, const float* color1_t, uint8_t* scratch, uint8_t* dst, cudaStream_t st);
+int64_t fine_tc3_blob_offset();
+
 }  // namespace edn

@@ -204,6 +204,10 @@ extern "C" int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == EDN_F32) return launch_fine_f32(a, grid_fine->dtype, st);
   if (precision == EDN_BF16) return launch_fine_tc(a, grid_fine->dtype, st);
+  if (precision == EDN_TC32) {
+    EDN_REQUIRE(mlp->tc_blob != nullptr, "edn_render_fine_fwd(tc32): edn_field_mlp.tc_blob is NULL (call edn_pack_fine_tc)");
+    return launch_fine_tc3(a, grid_fine->dtype, reinterpret_cast<const uint8_t*>(mlp->tc_blob) + fine_tc3_blob_offset(), st);
+  }
   set_error("edn_render_fine_fwd: bad precision %d", precision);
   return EDN_E_INVALID;
 }

@@ -55,7 +55,8 @@ constexpr int64_t kOffFull = kBasisBytes, kOffLean = kOffFull + (int64_t)kRingFu
 // 4 stages of 4 K-steps (N/2 = 128 columns x 16 x 2 B = 4 KB each) per layer
 constexpr int kRingPair = 12;
 constexpr int64_t kOffPair = kOffLean + (int64_t)kRingLean * kStageBytes;
-constexpr int64_t kBlobBytes = kOffPair + 3 * 131072;
+constexpr int64_t kOffTc3 = kOffPair + 3 * 131072;     // fine_tc3.cu: hi / lo split weights of the three lean layers (768 KB)
+constexpr int64_t kBlobBytes = kOffTc3 + 3 * 262144;
 
 struct StepDesc {
   uint8_t kind;      // 0 = basis coarse tile, 1 = basis fine tile, 2 = ring stage
@@ -712,7 +713,8 @@ int launch_fine_tc(const FineArgs& a_in, int grid_dtype, cudaStream_t st) {
 
 extern "C" int64_t edn_fine_tc_blob_bytes(void) { return edn::kBlobBytes; }
 
-extern "C" int64_t edn_fine_tc_pack_workspace_floats(void) { return 2 * 256 * 256; }
+extern "C" int64_t edn_fine_tc_pack_workspace_floats(void) { return 2 * 256 * 256 + 32768; }
+namespace edn { int64_t fine_tc3_blob_offset() { return kOffTc3; } }
 
 extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, const float* basis_t_fine, float* workspace,
                                 void* blob, void* stream) {
@@ -751,7 +753,11 @@ extern "C" int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_c
                                                                      reinterpret_cast<__nv_bfloat16*>(b + off));
       off += 256 * 128 * 2;
     }
-  EDN_REQUIRE((int64_t)off == kBlobBytes, "edn_pack_fine_tc: blob size mismatch");
+  EDN_REQUIRE((int64_t)off == kOffTc3, "edn_pack_fine_tc: blob size mismatch");
+  {
+    int rc3 = pack_fine_tc3_section(f1, f23, mlp->color1_t, reinterpret_cast<uint8_t*>(workspace + 2 * 256 * 256), b + kOffTc3, st);
+    if (rc3) return rc3;
+  }
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

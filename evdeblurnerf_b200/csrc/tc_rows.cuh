@@ -53,6 +53,13 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// (x0, x1) fp32 -> packed bf16x2 hi = rn(x) and lo = rn(x - hi): x = hi + lo up to 2^-17 |x| (the operand split of the bf16 x 3 mode)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
+
 // Raw 16-byte channel chunk of a bf16 texel row / 2 x 16 bytes of an fp32 one.
 template <typename T> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> {
@@ -106,6 +113,31 @@ struct GatherTask {
 #pragma unroll
     for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
     st_shared_v4(dst, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+  }
+  // fp32-grade variant (bf16 x 3 tensor-core parity mode): the fp32 product p is written as TWO bf16 operands, hi = bf16(p) and
+  // lo = bf16(p - hi) (|p - hi - lo| <= 2^-17 |p|), 16 bytes each
+  __device__ __forceinline__ void finish_split(uint8_t* dst_hi, uint8_t* dst_lo) const {
+    float p[8], l[8], t[8];
+    pv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = t[i] * pw[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      pv[k].get(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fmaf(t[i], pw[k], p[i]);
+    }
+    lv[0].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = t[i] * lw[0];
+    lv[1].get(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] *= fmaf(t[i], lw[1], l[i]);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(p[2 * i], p[2 * i + 1], hi[i], lo[i]);
+    st_shared_v4(dst_hi, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(dst_lo, lo[0], lo[1], lo[2], lo[3]);
   }
   // Same arithmetic (fp32, one rounding per operation, identical results) on the packed fp32x2 pipe: 28 FMUL2 / FFMA2 instead of 56
   // scalar operations -- the gather warps' FMA-pipe time is what the epilogue warps compete with (fine_tc2.cu).
@@ -187,6 +219,53 @@ __device__ __forceinline__ void gather_points(const GridDev& g, uint8_t* As, con
       fetch(comp * 8 + (lane & 7), pt2, lt1);
       t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
       t2.finish2(As + pt * 16 + (base + 8 + q) * kChunkA);
+    }
+  }
+}
+
+// gather_points for the bf16 x 3 parity mode: fp32 (or bf16) grids, ONE task in flight per lane (an fp32 task holds 48 registers of
+// raw taps), products written as hi / lo operand pairs into As_hi / As_lo.  Same lane mapping and shared tap computation.
+template <typename T, typename Pos>
+__device__ __forceinline__ void gather_points_split(const GridDev& g, uint8_t* As_hi, uint8_t* As_lo, const int base, const int gwarp,
+                                                    const int lane, const int gi_begin, const int gi_end, Pos pos) {
+  const int p4 = lane & 3, c8 = lane >> 2, q = lane >> 3;
+#pragma unroll 1
+  for (int gi = gi_begin; gi < gi_end; ++gi) {
+    Taps2 mp; Taps1 ml;
+    {
+      const int comp = min(lane >> 3, 2);
+      float p[3], n[3];
+      pos(gwarp * 32 + gi * 8 + (lane & 7), p);
+      normalize_pt(g, p, n);
+      const float px = comp == 2 ? n[1] : n[0], py = comp == 0 ? n[1] : n[2], lv = comp == 0 ? n[2] : (comp == 1 ? n[1] : n[0]);
+      plane_taps(px, py, g.ph[comp], g.pw[comp], mp);
+      line_taps(lv, g.ll[comp], ml);
+    }
+    auto fetch = [&](int src, Taps2& pt2, Taps1& lt1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { pt2.off[k] = __shfl_sync(0xffffffffu, mp.off[k], src); pt2.w[k] = __shfl_sync(0xffffffffu, mp.w[k], src); }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { lt1.off[k] = __shfl_sync(0xffffffffu, ml.off[k], src); lt1.w[k] = __shfl_sync(0xffffffffu, ml.w[k], src); }
+    };
+    const T* pl = reinterpret_cast<const T*>(g.plane[0]);
+    const T* ln = reinterpret_cast<const T*>(g.line[0]);
+#pragma unroll 1
+    for (int ab = 0; ab < 2; ++ab) {     // component 0: chunk c8 of points 8 gi + p4 and 8 gi + 4 + p4
+      GatherTask<T> t;
+      const int pt = gwarp * 32 + gi * 8 + p4 + 4 * ab;
+      Taps2 pt2; Taps1 lt1;
+      fetch(p4 + 4 * ab, pt2, lt1);
+      t.issue(pl, ln, 64, c8, pt2, lt1);
+      t.finish_split(As_hi + pt * 16 + (base + c8) * kChunkA, As_lo + pt * 16 + (base + c8) * kChunkA);
+    }
+    {
+      GatherTask<T> t2;
+      const int pt = gwarp * 32 + gi * 8 + (lane & 7);
+      const int comp = 1 + (q >> 1);
+      Taps2 pt2; Taps1 lt1;
+      fetch(comp * 8 + (lane & 7), pt2, lt1);
+      t2.issue(reinterpret_cast<const T*>(g.plane[comp]), reinterpret_cast<const T*>(g.line[comp]), 16, q & 1, pt2, lt1);
+      t2.finish_split(As_hi + pt * 16 + (base + 8 + q) * kChunkA, As_lo + pt * 16 + (base + 8 + q) * kChunkA);
     }
   }
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EDN_BF16, EDN_F32, FLAG_LINDISP, FLAG_RELU_RGB, FLAG_TRAIN, FieldMlp, VmGrid, check, ptr, stream_ptr
+from ._lib import EDN_BF16, EDN_F32, EDN_TC32, FLAG_LINDISP, FLAG_RELU_RGB, FLAG_TRAIN, FieldMlp, VmGrid, check, ptr, stream_ptr
 
 MATMODE = ((0, 1), (0, 2), (1, 2))   # voxnerf.py:99
 VECMODE = (2, 1, 0)                  # voxnerf.py:100
@@ -186,6 +186,8 @@ class RenderEngine(SamplerHost):
     """Fused c2f renderer over a reference `NeRFAll.state_dict()`-style parameter dict.
 
     precision: "fp32" -> fp32 SIMT kernels everywhere (parity mode, 1e-4 rel against the reference);
+               "tc32" -> tensor-core parity mode: the fine pass's GEMMs on tcgen05 with bf16 x 3 split operands and fp32 TMEM
+                         accumulation (fp32-grade, same tolerances as "fp32"); fp32 VM planes, fp32 coarse pass / backward;
                "bf16" -> tcgen05 tensor-core fine pass with bf16 operands / fp32 accumulation and bf16 VM planes.
     """
 
@@ -193,10 +195,10 @@ class RenderEngine(SamplerHost):
         if not torch.cuda.is_available():
             raise RuntimeError("evdeblurnerf_b200.RenderEngine needs a CUDA device (no CPU fallback)")
         _lib.load()
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if precision not in ("fp32", "bf16", "tc32"):
+            raise ValueError(f"precision must be 'fp32', 'tc32' or 'bf16', got {precision!r}")
         self.precision = precision
-        self.prec_code = EDN_F32 if precision == "fp32" else EDN_BF16
+        self.prec_code = EDN_BF16 if precision == "bf16" else EDN_F32      # storage / backward precision
         self._init_host(device)
         self.rmnearplane = float(rmnearplane)
         self.aabb_min, self.aabb_max = [float(x) for x in aabb_min], [float(x) for x in aabb_max]
@@ -237,7 +239,7 @@ class RenderEngine(SamplerHost):
         self.fine = None
         if "mlp_fine.sigma_net.0.weight" in P:
             self.fine = PackedField(P, "mlp_fine.", self.aabb_min, self.aabb_max, False, grid_dtype)
-            if self.prec_code == EDN_BF16:
+            if self.prec_code == EDN_BF16 or self.precision == "tc32":
                 self.fine.pack_tensor_core_operands(self.coarse)
 
     @staticmethod
@@ -257,8 +259,11 @@ class RenderEngine(SamplerHost):
             ret["z_vals"] = torch.empty((0, S), **f32)
         return ret
 
-    def _fine_precision(self, n_total):
-        # the tensor-core fine kernel maps a ray to ceil(S / 128) UMMA M tiles (e.g. 96 + 96 samples = 128 + 64 rows)
+    def _fine_precision(self, n_total, want_feat=False):
+        # the bf16 tensor-core fine kernel maps a ray to ceil(S / 128) UMMA M tiles (e.g. 96 + 96 samples = 128 + 64 rows); the
+        # bf16 x 3 parity kernel handles rays of <= 128 samples without depth_feature, everything else stays on the fp32 SIMT kernel
+        if self.precision == "tc32":
+            return EDN_TC32 if (n_total <= 128 and not want_feat) else EDN_F32
         return self.prec_code
 
     def _coarse_precision(self, n_samples):
@@ -371,7 +376,7 @@ class RenderEngine(SamplerHost):
         feat1 = torch.empty((R, S, 128), **f32) if want_feat else None
         check(self._launch("fine", lambda: lib.edn_render_fine_fwd(
             C.byref(self.coarse.grid), C.byref(self.fine.grid), C.byref(self.fine.mlp), ptr(rb), ptr(m["z_vals"]),
-            ptr(noise1), R, S, flags, self.rmnearplane, self._fine_precision(S), ptr(w1), ptr(rgb1), ptr(depth1), ptr(acc1),
+            ptr(noise1), R, S, flags, self.rmnearplane, self._fine_precision(S, want_feat), ptr(w1), ptr(rgb1), ptr(depth1), ptr(acc1),
             ptr(feat1), stream_ptr())), "edn_render_fine_fwd")
         ret = {"rgb_map": rgb1, "depth_map": depth1, "acc_map": acc1}
         if retraw:

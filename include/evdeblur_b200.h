@@ -28,7 +28,9 @@ enum {
   EDN_E_UNSUPPORTED = -3
 };
 
-enum { EDN_F32 = 0, EDN_BF16 = 1 };
+/* precision / storage codes.  EDN_TC32 (edn_render_fine_fwd only): the tensor-core PARITY mode -- bf16 x 3 operand splitting
+ * (hi.hi + lo.hi + hi.lo into fp32 TMEM accumulators), fp32 everywhere else: fp32-grade results on tcgen05. */
+enum { EDN_F32 = 0, EDN_BF16 = 1, EDN_TC32 = 2 };
 
 /* flags for the render entry points */
 enum {
@@ -126,7 +128,8 @@ int edn_pack_fine_tc(const edn_field_mlp* mlp, const float* basis_t_coarse, cons
                      void* blob, void* stream);
 
 /* Fine pass of render_rays (renderer.py:190-217): VM lookup of both grids at the merged samples, PE, FVR field,
- * compositing.  precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path.
+ * compositing.  precision: EDN_F32 = fp32 SIMT parity path, EDN_BF16 = tcgen05 tensor-core path (bf16 operands), EDN_TC32 =
+ * tcgen05 parity path (bf16 x 3 split operands, fp32-grade; n_samples <= 128, feat must be NULL; needs mlp->tc_blob).
  *   z_vals [R][S] sorted merged depths;  noise [R][S-1] or NULL.
  * outputs: weights [R][S], rgb [R][3], depth [R], acc [R], feat [R][S][128] or NULL (depth_feature for AWP). */
 int edn_render_fine_fwd(const edn_vm_grid* grid_coarse, const edn_vm_grid* grid_fine, const edn_field_mlp* mlp,

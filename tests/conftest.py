@@ -21,3 +21,17 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Achieved errors of every assert_close (tests/util.py), beside the bounds: gpurun_out/parity_achieved.json."""
+    try:
+        import json
+        import util
+        if util.ACHIEVED:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_achieved.json"), "w") as f:
+                json.dump(util.ACHIEVED, f, indent=1, sort_keys=True)
+    except Exception:
+        pass

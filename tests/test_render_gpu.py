@@ -14,11 +14,13 @@ Z_ATOL = 5e-4
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
+# every test of this file runs in BOTH parity-grade precisions: "fp32" (SIMT kernels) and "tc32" (the fine pass's GEMMs on tcgen05
+# with bf16 x 3 split operands, fp32 TMEM accumulation) -- same tolerances
+@pytest.fixture(scope="module", params=["fp32", "tc32"])
+def engine(request):
     from evdeblurnerf_b200 import RenderEngine
     P, _ = small_params()
-    return RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32")
+    return RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=request.param)
 
 
 def test_vm_sample_known_answers(engine):
@@ -156,11 +158,12 @@ def test_case2_injected_randomness(engine):
         assert_close(out[k], g[k], "golden " + k, rtol=1e-4, atol=5e-4)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tc32"])
 @pytest.mark.parametrize("nc,ni,R", [(32, 32, 70), (96, 96, 19), (64, 0, 5), (48, 80, 3)])
-def test_ragged_sample_counts(nc, ni, R):
+def test_ragged_sample_counts(nc, ni, R, prec):
     from evdeblurnerf_b200 import RenderEngine
     P = random_params(7)
-    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32")
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=prec)
     rays, _ = synthetic_rays(R, seed=nc + ni)
     rb = oc.build_ray_batch(H, W, FOCAL, rays)
     out = eng.render_rays(rb.cuda(), nc, retraw=True, N_importance=ni)
@@ -184,10 +187,11 @@ def test_empty_batch(engine):
     assert out["rgb_map"].shape == (0, 3) and out["weights"].shape == (0, 128)
 
 
-def test_eval_mode_near_plane_mask():
+@pytest.mark.parametrize("prec", ["fp32", "tc32"])
+def test_eval_mode_near_plane_mask(prec):
     from evdeblurnerf_b200 import RenderEngine
     P, _ = small_params()
-    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32", rmnearplane=40)
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=prec, rmnearplane=40)
     rays, _ = synthetic_rays(16, seed=2)
     rb = oc.build_ray_batch(H, W, FOCAL, rays)
     out = eng.render_rays(rb.cuda(), 64, retraw=True, N_importance=64, is_train=False)
@@ -201,11 +205,12 @@ def test_eval_mode_near_plane_mask():
         assert_close(out[k], ref[k], k, rtol=1e-4, atol=5e-4)
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("prec", ["fp32", "tc32"])
+def test_full_size_properties(prec):
     """BASELINE config[1] size (4096 rays x 5 exposures, 64+64): size-independent properties."""
     from evdeblurnerf_b200 import RenderEngine
     P = random_params(11, coarse_grid=(96, 96, 64), fine_grid=(192, 192, 128))
-    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32")
+    eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision=prec)
     rays, _ = synthetic_rays(20480, seed=5)
     rb = oc.build_ray_batch(H, W, FOCAL, rays).cuda()
     out = eng.render_rays(rb, 64, retraw=True, N_importance=64, want_indices=True)

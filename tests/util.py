@@ -27,6 +27,9 @@ def small_params():
     return P, Pc
 
 
+ACHIEVED = {}      # test id -> {comparison name: achieved error}: written to gpurun_out/parity_achieved.json at session end (conftest.py)
+
+
 def assert_close(a, b, name, rtol=RTOL, atol=ATOL):
     a = torch.as_tensor(a).detach().cpu().double()
     b = torch.as_tensor(b).detach().cpu().double()
@@ -34,6 +37,11 @@ def assert_close(a, b, name, rtol=RTOL, atol=ATOL):
     if a.numel() == 0:
         return
     err = (a - b).abs()
+    # the ACHIEVED error is recorded beside the bound (max |diff|, max |diff| / max |ref|, and the worst ratio err / allowed)
+    test_id = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    ACHIEVED.setdefault(test_id, {})[name] = {
+        "max_abs": float(err.max()), "max_abs_over_ref_max": float(err.max() / b.abs().max().clamp_min(1e-30)),
+        "worst_err_over_allowed": float((err / (atol + rtol * b.abs())).max()), "rtol": rtol, "atol": atol}
     tol = atol + rtol * b.abs()
     bad = err > tol
     assert not bool(bad.any()), (f"{name}: {int(bad.sum())}/{a.numel()} out of tolerance, max|diff|={err.max().item():.3e} "
