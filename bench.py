@@ -513,6 +513,17 @@ def main():
     if not args.no_train:
         k2, w2 = max(4, min(args.steps, 8)), 3
         flush_fn = lambda: flush.fill_(1)
+        # (0) the same headline render in the tensor-core PARITY mode (bf16 x 3 split operands: fp32-grade, tests/test_render_gpu.py)
+        if args.precision != "tc32":
+            nerf_p = NeRFAll(P, *AABB, kernel_ptnum=N_EXPOSURE, precision="tc32").eval()
+            ms = timed_steps(lambda i: nerf_p.render_blurred(H, W, KMAT, rays_dev, idx_dev, N_samples=NC, N_importance=NI, perturb=0., raw_noise_std=0.),
+                             k2, w2, world, dev, before_each=flush_fn)
+            extra["parity_mode"] = {"precision": "tc32", "ms_per_step": ms, "value": world * N_RAYS / (ms / 1e3), "unit": "rays/s",
+                                    "what": "same workload, fine pass on tcgen05 with bf16 x 3 split operands + fp32 TMEM accumulation (meets the 1e-4 "
+                                            "parity bar: tests/test_render_gpu.py runs in this precision), fp32 coarse pass",
+                                    "numerical_errors": nerf_p.engine.numerical_errors()}
+            del nerf_p
+            torch.cuda.empty_cache()
         # (a) shipped configuration, forward: training branch with the AWP branch on, perturb = 1, raw_noise_std = 1
         P_all = dict(P)
         P_all.update(awp_params(dev))

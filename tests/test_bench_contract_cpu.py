@@ -36,5 +36,5 @@ def test_bench_line_keys_are_all_produced_by_the_gpu_arm_source():
     for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"steps"', '"warmup"', '"ms_per_step"', '"higher_is_better"', '"scaling"',
                 '"vs_baseline"', '"dtype"', '"data"', '"config"', '"e2e"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"gpu_launches"',
                 '"clocks"', '"roofline"', '"bound"', '"achieved"', '"peak"', '"frac"', '"traffic"', '"cpu_baseline"', '"cores"', '"kind"',
-                '"sample"', '"train_step"', '"loss_finite"', '"all_reduce_ms"', '"shipped_forward"', '"strong"'):
+                '"sample"', '"train_step"', '"loss_finite"', '"all_reduce_ms"', '"shipped_forward"', '"strong"', '"parity_mode"'):
         assert key in src, key
