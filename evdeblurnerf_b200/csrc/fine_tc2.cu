@@ -60,6 +60,13 @@ constexpr uint32_t kColA = 0, kColAcc = 128;
 #endif
 constexpr int kNQ = 2;                     // N = 128 per instruction: 86 (TS) / 119 (SS) cycles each, measured (fine_tc2 ablate 16 / 48)
 
+// Head weights (sigma_net.1 row 0: [0,256); color_net.2 channel-major: [256,1024)) in CONSTANT memory: every lane of an epilogue warp
+// reads the same element, so the FFMAs take them as constant-bank operands -- no load instruction, no shared-memory latency (the
+// epilogue's top stall was the short scoreboard behind LDS under the gather's LSU traffic).  A few slots, rotated per launch, so
+// that launches in flight on different streams / models do not overwrite each other's copy.
+constexpr int kHeadSlots = 8, kHeadFloats = 1024;
+__constant__ float c_heads[kHeadSlots][kHeadFloats];
+
 struct alignas(16) RaySlot {              // per-ray data produced by the gather warps, read by the epilogue warps
   float z[kRows];
   alignas(16) float bias[256];             // color_net.0 bias + W0[:, 128:155] . PE(viewdir)
@@ -70,15 +77,13 @@ struct Misc {
   uint64_t acc_full, hand[4];           // hand[q]: the epilogue finished quarter q of a layer (A' K 64q..64q+63 written; q = 1 / 3: slot x / y drained)
   GridDev grids[2];
   uint32_t tmem_base, pad[3];
-  alignas(16) float wsig[256];
-  alignas(16) float wrgb[3][256];          // color_net.2, channel-major (float4 = 4 consecutive hidden units of one channel)
   alignas(16) float bias1[256];
   RaySlot slot[2];
   alignas(16) float headp[4][kRows][4];   // per column quarter: partial rgb (xyz) / sigma (w) heads
   float red[4][8];
   float wtot[4];
 };
-static_assert(offsetof(Misc, wsig) % 16 == 0 && offsetof(Misc, wrgb) % 16 == 0 && offsetof(Misc, bias1) % 16 == 0 &&
+static_assert(offsetof(Misc, bias1) % 16 == 0 &&
               offsetof(Misc, slot) % 16 == 0 && offsetof(Misc, headp) % 16 == 0, "float4 alignment");
 constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -107,7 +112,7 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob) {
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob, const int hslot) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB] layer-1 operands (double buffered)
   uint8_t* Ws = smem + 2 * kABytes;                     // weight ring
@@ -123,10 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   }
   if (warp == kWarpMma) tmem_alloc(&m->tmem_base, kTmemCols);
   for (int i = tid; i < 256; i += kThreads) {
-    m->wsig[i] = __ldg(a.mlp.sigma1_v + i);
     m->bias1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) m->wrgb[j][i] = __ldg(a.mlp.color2_t + i * 4 + j);
   }
   if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
   tc_fence_before();
@@ -354,13 +356,13 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
     }
   } else {
     // =================================== epilogue warps: TWO threads per sample row ============================================
-    const int ew = warp - kGatherWarps;
+    // (the warp index through a shuffle: provably warp-uniform, so that tq-derived constant-bank addresses stay in uniform registers)
+    const int ew = __shfl_sync(0xffffffffu, warp, 0) - kGatherWarps;
     const int tq = ew >> 2, gwarp = ew & 3;       // tq: the 64-column quarter of every layer this thread serves; TMEM lane quarter = warp % 4
+    const float* __restrict__ cw = c_heads[hslot];
     const int r = gwarp * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(gwarp * 32) << 16);
     // plain shared-memory loads (the compiler may batch them; a `volatile` asm load per float4 serialises on its 29-cycle latency)
-    const float4* s_wsig = reinterpret_cast<const float4*>(m->wsig);
-    const float4* s_wrgb = reinterpret_cast<const float4*>(&m->wrgb[0][0]);
     const float4* s_bias1 = reinterpret_cast<const float4*>(m->bias1);
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
@@ -409,43 +411,30 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
 #endif
             }
           }
-          if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (two packed accumulator pairs)
-            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+          if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (constant-bank operands, 4 accumulators)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 w = s_wsig[(col0 + i) >> 2];
-#if EDN_TC2_PACKED
-              s0 = ffma2(make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), make_float2(w.x, w.y), s0);
-              s1 = ffma2(make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f)), make_float2(w.z, w.w), s1);
-#else
-              s0.x = fmaf(fmaxf(f[i], 0.f), w.x, s0.x); s0.y = fmaf(fmaxf(f[i + 1], 0.f), w.y, s0.y);
-              s1.x = fmaf(fmaxf(f[i + 2], 0.f), w.z, s1.x); s1.y = fmaf(fmaxf(f[i + 3], 0.f), w.w, s1.y);
-#endif
+              s0 = fmaf(fmaxf(f[i], 0.f), cw[col0 + i], s0); s1 = fmaf(fmaxf(f[i + 1], 0.f), cw[col0 + i + 1], s1);
+              s2 = fmaf(fmaxf(f[i + 2], 0.f), cw[col0 + i + 2], s2); s3 = fmaf(fmaxf(f[i + 3], 0.f), cw[col0 + i + 3], s3);
             }
-            sig_part += (s0.x + s0.y) + (s1.x + s1.y);
+            sig_part += (s0 + s1) + (s2 + s3);
           }
           if (L < 2) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(f[2 * i], f[2 * i + 1]);
             if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + (col0 >> 1), pk);   // in place: the layer's MMAs are complete
-          } else {             // rgb head: fp32 dot of relu(h3) with color_net.2, packed FMAs over column pairs
-            float2 r2 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+          } else {             // rgb head: fp32 dot of relu(h3) with color_net.2 (constant-bank operands, 2 accumulators per channel)
+            float r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 wr = s_wrgb[(col0 + i) >> 2], wg = s_wrgb[(256 + col0 + i) >> 2], wb = s_wrgb[(512 + col0 + i) >> 2];
-              const float2 x01 = make_float2(fmaxf(f[i], 0.f), fmaxf(f[i + 1], 0.f)), x23 = make_float2(fmaxf(f[i + 2], 0.f), fmaxf(f[i + 3], 0.f));
-#if EDN_TC2_PACKED
-              r2 = ffma2(x01, make_float2(wr.x, wr.y), r2); r2 = ffma2(x23, make_float2(wr.z, wr.w), r2);
-              g2 = ffma2(x01, make_float2(wg.x, wg.y), g2); g2 = ffma2(x23, make_float2(wg.z, wg.w), g2);
-              b2 = ffma2(x01, make_float2(wb.x, wb.y), b2); b2 = ffma2(x23, make_float2(wb.z, wb.w), b2);
-#else
-              r2.x = fmaf(x01.x, wr.x, r2.x); r2.y = fmaf(x01.y, wr.y, r2.y); r2.x = fmaf(x23.x, wr.z, r2.x); r2.y = fmaf(x23.y, wr.w, r2.y);
-              g2.x = fmaf(x01.x, wg.x, g2.x); g2.y = fmaf(x01.y, wg.y, g2.y); g2.x = fmaf(x23.x, wg.z, g2.x); g2.y = fmaf(x23.y, wg.w, g2.y);
-              b2.x = fmaf(x01.x, wb.x, b2.x); b2.y = fmaf(x01.y, wb.y, b2.y); b2.x = fmaf(x23.x, wb.z, b2.x); b2.y = fmaf(x23.y, wb.w, b2.y);
-#endif
+            for (int i = 0; i < 32; i += 2) {
+              const float x0 = fmaxf(f[i], 0.f), x1 = fmaxf(f[i + 1], 0.f);
+              r0 = fmaf(x0, cw[256 + col0 + i], r0); r1 = fmaf(x1, cw[256 + col0 + i + 1], r1);
+              g0 = fmaf(x0, cw[512 + col0 + i], g0); g1 = fmaf(x1, cw[512 + col0 + i + 1], g1);
+              b0 = fmaf(x0, cw[768 + col0 + i], b0); b1 = fmaf(x1, cw[768 + col0 + i + 1], b1);
             }
-            rr += r2.x + r2.y; rg_ += g2.x + g2.y; rbl += b2.x + b2.y;
+            rr += r0 + r1; rg_ += g0 + g1; rbl += b0 + b1;
           }
         };
         long long t_ld = 0, t_pr = 0, t_st = 0;
@@ -544,8 +533,23 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
 
 }  // namespace
 
+// sigma / rgb head weights of the model -> [wsig 256 | r 256 | g 256 | b 256] fp32 (staged in global memory, then copied to a constant slot)
+static __global__ void heads_stage_kernel(const float* __restrict__ sigma1_v, const float* __restrict__ color2_t, float* __restrict__ dst) {
+  const int i = threadIdx.x;
+  dst[i] = sigma1_v[i];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) dst[256 + j * 256 + i] = color2_t[i * 4 + j];
+}
+
 int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, cudaStream_t st) {
   FineArgs a = a_in;
+  static float* stage = nullptr;
+  static unsigned launch_no = 0;
+  if (!stage) EDN_CUDA_OK(cudaMalloc(&stage, sizeof(float) * kHeadSlots * kHeadFloats));
+  const int hslot = (int)(launch_no++ % kHeadSlots);
+  heads_stage_kernel<<<1, 256, 0, st>>>(a.mlp.sigma1_v, a.mlp.color2_t, stage + hslot * kHeadFloats);
+  EDN_CUDA_OK(cudaMemcpyToSymbolAsync(c_heads, stage + hslot * kHeadFloats, sizeof(float) * kHeadFloats, sizeof(float) * kHeadFloats * hslot,
+                                      cudaMemcpyDeviceToDevice, st));
   static const int ablate = [] { const char* e = getenv("EDN_TC2_ABLATE"); return e ? atoi(e) : 0; }();   // dev: TIMING-ONLY ablations (outputs invalid)
   a.ablate = ablate;
   const unsigned gx = (unsigned)(a.n_rays < (int64_t)num_sms() ? a.n_rays : (int64_t)num_sms());
@@ -556,7 +560,7 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
     memset(buf, 0, 4 * 4 * 16 * sizeof(long long));
     a.trace = buf;
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     const long long t0 = buf[16];   // MMA role, it = 8, slot 0
     static const char* role[3] = {"gather", "mma", "epi"};
@@ -576,10 +580,10 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
   }
   if (grid_dtype == EDN_BF16) {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
   } else {
     EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, wblob);
+    fine_fwd_tc2_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
   }
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
