@@ -37,11 +37,11 @@ constexpr int kRows = 128;
 //   warps 8-23  epilogue (4 warpgroups, 72 registers): FOUR threads per sample row, 64 columns of a layer each -- the epilogue is a
 //               per-warp dependent instruction stream (~5 cycles per instruction), so its latency halves with twice the warps
 //   warp 24 MMA issuer, warp 25 weight stream, warps 26-27 idle (the warpgroup drops to 24 registers and donates the rest)
-constexpr int kGatherWarps = 8, kEpiWarps = 16;
+constexpr int kGatherWarps = 16, kEpiWarps = 8;
 constexpr int kWarpMma = kGatherWarps + kEpiWarps, kWarpLoad = kWarpMma + 1;
 constexpr int kThreads = (kGatherWarps + kEpiWarps + 4) * 32;      // 896
-constexpr int kRoleThreads = 256;                                   // gather threads
-constexpr int kEpiThreads = kEpiWarps * 32;                         // 512
+constexpr int kRoleThreads = kGatherWarps * 32;                     // gather threads (512)
+constexpr int kEpiThreads = kEpiWarps * 32;                         // 256
 constexpr int kQuarterThreads = 128;                                // epilogue threads serving one 64-column quarter of a layer
 constexpr int kNst = 4;                    // weight ring stages
 constexpr int kStageBytes = 16384;         // 2 K-steps of a layer (N = 256 rows x 16 x 2 B = 8 KB per K-step): the lean section of the blob
@@ -69,7 +69,6 @@ __constant__ float c_heads[kHeadSlots][kHeadFloats];
 
 struct alignas(16) RaySlot {              // per-ray data produced by the gather warps, read by the epilogue warps
   float z[kRows];
-  alignas(16) float bias[256];             // color_net.0 bias + W0[:, 128:155] . PE(viewdir)
 };
 struct Misc {
   uint64_t a_full[2], a_empty[2], slot_free[2];
@@ -85,7 +84,12 @@ struct Misc {
 };
 static_assert(offsetof(Misc, bias1) % 16 == 0 &&
               offsetof(Misc, slot) % 16 == 0 && offsetof(Misc, headp) % 16 == 0, "float4 alignment");
-constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + (int)sizeof(Misc);
+// The per-ray bias of color_net.0 (b0 + W0[:, 128:155] . PE(viewdir), the same for all 128 rows) is added BY THE TENSOR CORE: one
+// extra K-step whose A operand is a constant tile with 1.0 in K columns 0, 1 and whose B operand holds (bf16 hi, bf16 lo) of the
+// bias in those two K columns -- exact to 2^-17, and the epilogue of that layer needs no shared-memory loads at all.
+constexpr int kOneBytes = 4096;            // A: 128 rows x 16 K bf16
+constexpr int kBiasBBytes = 8192;          // B: 256 rows x 16 K bf16, one per ray slot
+constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kOneBytes + 2 * kBiasBBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // ---- TMEM store: 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread ------------------------------------
@@ -116,8 +120,15 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB] layer-1 operands (double buffered)
   uint8_t* Ws = smem + 2 * kABytes;                     // weight ring
-  Misc* m = reinterpret_cast<Misc*>(Ws + kNst * kStageBytes);
+  uint8_t* A_one = Ws + kNst * kStageBytes;
+  uint8_t* B_bias = A_one + kOneBytes;                  // [2][8 KB]
+  Misc* m = reinterpret_cast<Misc*>(B_bias + 2 * kBiasBBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (kOneBytes + 2 * kBiasBBytes) / 16; i += kThreads) {      // zero, then 1.0 | 1.0 in K columns 0, 1 of every A row
+    const bool one = i < kRows;                          // 16-byte piece i < 128 of A_one = (row i, K 0..7)
+    st_shared_v4(A_one + i * 16, one ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();                              // these tiles are read by the tensor core (async proxy)
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); mbar_init(&m->slot_free[b], kEpiThreads); }
@@ -259,6 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
             __syncwarp();
           }
           g += 8;
+          if (L == 1) {      // + per-ray bias: [1 1 0 ..] x [hi lo 0 ..]^T into both chains
+            if (elect_one()) {
+              const uint64_t ad = make_smem_desc(smem_u32(A_one), kChunkA, 128);
+              const uint64_t bd = make_smem_desc(smem_u32(B_bias) + buf * kBiasBBytes, 256 * 16, 128);
+              mma_bf16_ss(dx, ad, bd, idesc, 1);
+              mma_bf16_ss(dy, ad, bd + (uint64_t)((128 * 16) >> 4), idesc, 1);
+            }
+            __syncwarp();
+          }
           if (elect_one()) {
             mma_commit(&m->acc_full);
             if (L == 0) mma_commit(&m->a_empty[buf]);      // layer 1 has consumed A_in[buf]: the gather warps may refill it
@@ -273,8 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   } else if (warp < kGatherWarps) {
     // =================================== gather warps: TWO threads per sample row ===========================================
     // half 0: PE + coarse grid; half 1: view-direction bias + fine grid.  Runs one ray ahead of the MLP.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-    const int half = warp >> 2, gwarp = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    // warp = (grid 1 bit, row group 2 bits, gi half 1 bit): FOUR threads per sample row
+    const int half = warp >> 3, gwarp = (warp >> 1) & 3, gsub = warp & 1;
     const int r = gwarp * 32 + lane;
     for (int64_t it = 0; it < n_my; ++it) {
       const int buf = (int)(it & 1);
@@ -292,7 +313,9 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
-      if (half == 0) {
+      if (gsub != 0) {
+        // (the second warp of a (grid, row group) only gathers)
+      } else if (half == 0) {
         const float zv = a.z_vals[ray * S + min(r, S - 1)];
         slot->z[r] = zv;
         // PE(pts) -> A chunks 24..31 (64 columns, the last one is the zero pad of K = 127 -> 128)
@@ -337,14 +360,16 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           const float* w = a.mlp.color0_t + (size_t)128 * 256 + col;
 #pragma unroll
           for (int j = 0; j < kPeDir; ++j) b = fmaf(__ldg(w + j * 256), ped[j], b);
-          slot->bias[col] = b;
+          uint32_t hi, lo;
+          split_bf16x2(b, 0.f, hi, lo);                   // low halves: bf16 hi / lo of b
+          *reinterpret_cast<uint32_t*>(B_bias + buf * kBiasBBytes + col * 16) = (hi & 0xffffu) | (lo << 16);     // K column 0: hi, 1: lo
         }
       }
       named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
       if (tid == 0) stamp(0, it, 2);
       if (!(a.ablate & 1)) {      // lean A layout: coarse-grid products in chunks 0..11, fine-grid products in chunks 12..23
         const float* z_s = slot->z;
-        gather_points<T>(m->grids[half], Aq, half ? 12 : 0, gwarp, lane, 0, 4, [&](int pt, float (&p)[3]) {
+        gather_points<T>(m->grids[half], Aq, half ? 12 : 0, gwarp, lane, 2 * gsub, 2 * gsub + 2, [&](int pt, float (&p)[3]) {
           const float zv = z_s[pt];
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
@@ -357,8 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   } else {
     // =================================== epilogue warps: TWO threads per sample row ============================================
     // (the warp index through a shuffle: provably warp-uniform, so that tq-derived constant-bank addresses stay in uniform registers)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int ew = __shfl_sync(0xffffffffu, warp, 0) - kGatherWarps;
-    const int tq = ew >> 2, gwarp = ew & 3;       // tq: the 64-column quarter of every layer this thread serves; TMEM lane quarter = warp % 4
+    const int th = ew >> 2, gwarp = ew & 3;       // th: this thread serves the 64-column quarters th and th + 2 of every layer
     const float* __restrict__ cw = c_heads[hslot];
     const int r = gwarp * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(gwarp * 32) << 16);
@@ -372,7 +398,6 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       const int buf = (int)(it & 1);
       RaySlot* slot = &m->slot[buf];
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
-      const float4* s_bias = reinterpret_cast<const float4*>(slot->bias);
       float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
       const bool st0 = (ew == 0 && lane == 0);
       if (st0) stamp(2, it, 0);
@@ -384,10 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         named_bar_sync(4, kEpiThreads);
         if (st0) stamp(2, it, 1 + 2 * L);
         tc_fence_after();
-        // quarters 0, 1 live in slot x, quarters 2, 3 in slot y
-        const uint32_t acc_q = lane_base + kColAcc + ((2 * n_use + (tq >> 1)) % 3) * 128 + (tq & 1) * 64;
         // 32 accumulator columns [col0, col0 + 32) of this thread's row
-        auto process = [&](const uint32_t (&v)[32], const int c) {
+        auto process = [&](const uint32_t (&v)[32], const int tq, const int c) {
           const int col0 = tq * 64 + c * 32;
           float f[32];
 #pragma unroll
@@ -397,18 +420,6 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
             for (int i = 0; i < 32; i += 4) {
               const float4 b4 = s_bias1[(col0 + i) >> 2];
               f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-            }
-          }
-          if (L == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = s_bias[(col0 + i) >> 2];
-#if EDN_TC2_PACKED
-              const float2 lo = fadd2(make_float2(f[i], f[i + 1]), make_float2(b4.x, b4.y)), hi = fadd2(make_float2(f[i + 2], f[i + 3]), make_float2(b4.z, b4.w));
-              f[i] = lo.x; f[i + 1] = lo.y; f[i + 2] = hi.x; f[i + 3] = hi.y;
-#else
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-#endif
             }
           }
           if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (constant-bank operands, 4 accumulators)
@@ -440,35 +451,38 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         long long t_ld = 0, t_pr = 0, t_st = 0;
         const bool tr_on = st0 && a.trace && blockIdx.x == 0 && it >= 8 && it < 12;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          long long c0 = tr_on ? clock64() : 0;
-          if (a.ablate & 4) {
+        for (int pass = 0; pass < 2; ++pass) {       // quarters th (slot x) then th + 2 (slot y)
+          const int tq = th + 2 * pass;
+          const uint32_t acc_q = lane_base + kColAcc + ((2 * n_use + pass) % 3) * 128 + th * 64;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            long long c0 = tr_on ? clock64() : 0;
+            if (a.ablate & 4) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-          } else {
-            tmem_ld32(acc_q + c * 32, v);
-            tmem_ld_wait();
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            } else {
+              tmem_ld32(acc_q + c * 32, v);
+              tmem_ld_wait();
+            }
+            long long c1 = tr_on ? clock64() : 0;
+            process(v, tq, c);
+            if (tr_on) { const long long c2 = clock64(); t_ld += c1 - c0; t_pr += c2 - c1; }
           }
-          long long c1 = tr_on ? clock64() : 0;
-          process(v, c);
-          if (tr_on) { const long long c2 = clock64(); t_ld += c1 - c0; t_pr += c2 - c1; }
-        }
-        {
           long long c2 = tr_on ? clock64() : 0;
           // quarter tq of the layer is done: its A' columns are written (and with quarter tq ^ 1 its accumulator slot is drained)
           if (L < 2) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&m->hand[tq]);
-          if (tr_on) t_st = clock64() - c2;
+          if (tr_on) t_st += clock64() - c2;
         }
         if (tr_on) { a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 0] = t_ld; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 1] = t_pr; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 2] = t_st; }
         ++n_use;
         if (st0) stamp(2, it, 2 + 2 * L);
       }
-      m->headp[tq][r][0] = rr; m->headp[tq][r][1] = rg_; m->headp[tq][r][2] = rbl; m->headp[tq][r][3] = sig_part;
+      m->headp[th][r][0] = rr; m->headp[th][r][1] = rg_; m->headp[th][r][2] = rbl; m->headp[th][r][3] = sig_part;
       named_bar_sync(2, kEpiThreads);               // all four quarters' head partials visible
-      if (tq == 0) {
+      if (th == 0) {
         // ---- compositing (voxnerf.py:153-201), one thread per sample row ---------------------------------------------------
         const float* rb = a.ray_batch + ray * 11;
         const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
@@ -476,9 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         float col[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          col[i] = sigmoidf_((m->headp[0][r][i] + m->headp[1][r][i]) + (m->headp[2][r][i] + m->headp[3][r][i]) +
-                             (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
-        const float sig_raw = (m->headp[0][r][3] + m->headp[1][r][3]) + (m->headp[2][r][3] + m->headp[3][r][3]);
+          col[i] = sigmoidf_((m->headp[0][r][i] + m->headp[1][r][i]) + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + i) : 0.f));
+        const float sig_raw = m->headp[0][r][3] + m->headp[1][r][3];
         float alpha = 0.f;
         if (r < S - 1) {
           const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
