@@ -43,7 +43,9 @@ constexpr int kThreads = (kGatherWarps + kEpiWarps + 4) * 32;      // 896
 constexpr int kRoleThreads = kGatherWarps * 32;                     // gather threads (512)
 constexpr int kEpiThreads = kEpiWarps * 32;                         // 256
 constexpr int kQuarterThreads = 128;                                // epilogue threads serving one 64-column quarter of a layer
-constexpr int kNst = 4;                    // weight ring stages
+constexpr int kNst = 3;                    // weight ring stages (the stream is far from limiting: removing it changes nothing, ablation bit 2)
+constexpr int kSlots = 3;                  // per-ray slots (z, bias operand): one more than A_in buffers, so that the gather of ray k
+                                           // only waits for layer 1 of ray k - 2 (A_in free), not for its compositing
 constexpr int kStageBytes = 16384;         // 2 K-steps of a layer (N = 256 rows x 16 x 2 B = 8 KB per K-step): the lean section of the blob
 constexpr int kKstepBytes = 8192;
 constexpr int kABytes = 65536;
@@ -71,13 +73,13 @@ struct alignas(16) RaySlot {              // per-ray data produced by the gather
   float z[kRows];
 };
 struct Misc {
-  uint64_t a_full[2], a_empty[2], slot_free[2];
+  uint64_t a_full[2], a_empty[2], slot_free[kSlots];
   uint64_t w_full[kNst], w_empty[kNst];
   uint64_t acc_full, hand[4];           // hand[q]: the epilogue finished quarter q of a layer (A' K 64q..64q+63 written; q = 1 / 3: slot x / y drained)
   GridDev grids[2];
   uint32_t tmem_base, pad[3];
   alignas(16) float bias1[256];
-  RaySlot slot[2];
+  RaySlot slot[kSlots];
   alignas(16) float headp[4][kRows][4];   // per column quarter: partial rgb (xyz) / sigma (w) heads
   float red[4][8];
   float wtot[4];
@@ -89,7 +91,7 @@ static_assert(offsetof(Misc, bias1) % 16 == 0 &&
 // bias in those two K columns -- exact to 2^-17, and the epilogue of that layer needs no shared-memory loads at all.
 constexpr int kOneBytes = 4096;            // A: 128 rows x 16 K bf16
 constexpr int kBiasBBytes = 8192;          // B: 256 rows x 16 K bf16, one per ray slot
-constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kOneBytes + 2 * kBiasBBytes + (int)sizeof(Misc);
+constexpr int kSmemBytes = 2 * kABytes + kNst * kStageBytes + kOneBytes + kSlots * kBiasBBytes + (int)sizeof(Misc);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // ---- TMEM store: 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread ------------------------------------
@@ -121,17 +123,18 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   uint8_t* As = smem;                                   // [2][64 KB] layer-1 operands (double buffered)
   uint8_t* Ws = smem + 2 * kABytes;                     // weight ring
   uint8_t* A_one = Ws + kNst * kStageBytes;
-  uint8_t* B_bias = A_one + kOneBytes;                  // [2][8 KB]
-  Misc* m = reinterpret_cast<Misc*>(B_bias + 2 * kBiasBBytes);
+  uint8_t* B_bias = A_one + kOneBytes;                  // [kSlots][8 KB]
+  Misc* m = reinterpret_cast<Misc*>(B_bias + kSlots * kBiasBBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < (kOneBytes + 2 * kBiasBBytes) / 16; i += kThreads) {      // zero, then 1.0 | 1.0 in K columns 0, 1 of every A row
+  for (int i = tid; i < (kOneBytes + kSlots * kBiasBBytes) / 16; i += kThreads) {      // zero, then 1.0 | 1.0 in K columns 0, 1 of every A row
     const bool one = i < kRows;                          // 16-byte piece i < 128 of A_one = (row i, K 0..7)
     st_shared_v4(A_one + i * 16, one ? 0x3F803F80u : 0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();                              // these tiles are read by the tensor core (async proxy)
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); mbar_init(&m->slot_free[b], kEpiThreads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&m->a_full[b], kRoleThreads); mbar_init(&m->a_empty[b], 1); }
+    for (int b = 0; b < kSlots; ++b) mbar_init(&m->slot_free[b], kEpiThreads);
     for (int s = 0; s < kNst; ++s) { mbar_init(&m->w_full[s], 1); mbar_init(&m->w_empty[s], 1); }
     mbar_init(&m->acc_full, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&m->hand[q], kQuarterThreads);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           if (L == 1) {      // + per-ray bias: [1 1 0 ..] x [hi lo 0 ..]^T into both chains
             if (elect_one()) {
               const uint64_t ad = make_smem_desc(smem_u32(A_one), kChunkA, 128);
-              const uint64_t bd = make_smem_desc(smem_u32(B_bias) + buf * kBiasBBytes, 256 * 16, 128);
+              const uint64_t bd = make_smem_desc(smem_u32(B_bias) + (uint32_t)(it % kSlots) * kBiasBBytes, 256 * 16, 128);
               mma_bf16_ss(dx, ad, bd, idesc, 1);
               mma_bf16_ss(dy, ad, bd + (uint64_t)((128 * 16) >> 4), idesc, 1);
             }
@@ -301,14 +304,18 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       if (tid == 0) stamp(0, it, 0);
+      const int sl = (int)(it % kSlots);
       if (use > 0) {      // one polling warp, the rest of the gather group blocks in a named barrier (see the epilogue warps)
-        if (warp == 0) { mbar_wait(&m->a_empty[buf], (use - 1) & 1); mbar_wait(&m->slot_free[buf], (use - 1) & 1); }
+        if (warp == 0) {
+          mbar_wait(&m->a_empty[buf], (use - 1) & 1);
+          if (it >= kSlots) mbar_wait(&m->slot_free[sl], (uint32_t)(it / kSlots - 1) & 1);
+        }
         named_bar_sync(5, kRoleThreads);
       }
       if (tid == 0) stamp(0, it, 1);
       uint8_t* Aq = As + buf * kABytes;
       uint8_t* a_row = Aq + r * 16;
-      RaySlot* slot = &m->slot[buf];
+      RaySlot* slot = &m->slot[sl];
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           for (int j = 0; j < kPeDir; ++j) b = fmaf(__ldg(w + j * 256), ped[j], b);
           uint32_t hi, lo;
           split_bf16x2(b, 0.f, hi, lo);                   // low halves: bf16 hi / lo of b
-          *reinterpret_cast<uint32_t*>(B_bias + buf * kBiasBBytes + col * 16) = (hi & 0xffffu) | (lo << 16);     // K column 0: hi, 1: lo
+          *reinterpret_cast<uint32_t*>(B_bias + sl * kBiasBBytes + col * 16) = (hi & 0xffffu) | (lo << 16);     // K column 0: hi, 1: lo
         }
       }
       named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
@@ -395,8 +402,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
     const bool has_bias1 = a.mlp.color1_b != nullptr;
     uint32_t n_use = 0;                            // completed accumulator uses (3 per ray)
     for (int64_t it = 0; it < n_my; ++it) {
-      const int buf = (int)(it & 1);
-      RaySlot* slot = &m->slot[buf];
+      const int sl = (int)(it % kSlots);
+      RaySlot* slot = &m->slot[sl];
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
       float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
       const bool st0 = (ew == 0 && lane == 0);
@@ -536,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       }
       named_bar_sync(2, kEpiThreads);               // headp / red / wtot free for the next ray
       if (st0) stamp(2, it, 7);
-      mbar_arrive(&m->slot_free[buf]);              // slot[buf] (z, bias) may be rewritten by the gather warps
+      mbar_arrive(&m->slot_free[sl]);               // slot[sl] (z, bias operand) may be rewritten by the gather warps
     }
   }
   tc_fence_before();
