@@ -195,6 +195,17 @@ def normalize_ccw(ccw, scale):
     return c / torch.sum(c, -1, keepdim=True)
 
 
+def get_rays(H, W, K, c2w):
+    """utils/rays.py:8-22 (HALF_PIX = 0.5): full-image camera rays [H, W, 3, 2] of pose c2w [3|4, 4] (eval-path ray generation)."""
+    dev = c2w.device
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="xy")
+    dirs = torch.stack([(i + (0.5 - float(K[0][2]))) / float(K[0][0]), -(j + (0.5 - float(K[1][2]))) / float(K[1][1]),
+                        -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return torch.stack([rays_o, rays_d], -1)
+
+
 def build_ray_batch(H, W, focal, rays, near=0., far=1., ndc=True):
     """render() prologue (renderer.py:423-446): rays [R,3,2] -> ray_batch [R,11]."""
     r = rays.detach().to(torch.float32).contiguous().reshape(-1, 3, 2)
@@ -204,11 +215,74 @@ def build_ray_batch(H, W, focal, rays, near=0., far=1., ndc=True):
     return out
 
 
+def init_reference_parameters(args, device="cuda", seed=None):
+    """The parameters `NeRFAll(args, ...)` creates in the reference for mode = c2f (renderer.py:49-82; voxnerf.py:40-118): same
+    state_dict names, shapes and initialisation -- VM planes / lines 0.1 * randn (init_one_svd), nn.Linear default init
+    (U(-1/sqrt(in), 1/sqrt(in))), biases only with --rgb_add_bias."""
+    g = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+    P = {}
+
+    def lin(name, out_c, in_c, bias=False):
+        b = 1.0 / (in_c ** 0.5)
+        P[name + ".weight"] = ((torch.rand(out_c, in_c, generator=g) * 2 - 1) * b).to(device)
+        if bias:
+            P[name + ".bias"] = ((torch.rand(out_c, generator=g) * 2 - 1) * b).to(device)
+
+    amin, amax = (torch.as_tensor(t, dtype=torch.float32).cpu() for t in args.bounding_box)
+    pe_pts = 3 + 6 * args.multires
+    pe_dir = (3 + 6 * args.multires_views) if args.use_viewdirs else 0
+    fields = [("mlp_coarse.", args.coarse_n_voxels, args.coarse_app_n_comp, args.coarse_app_dim, args.coarse_app_dim + pe_pts,
+               args.coarse_num_layers, args.coarse_hidden_dim, args.kernel_feat_cnl, args.coarse_num_layers_color)]
+    if args.N_importance > 0:
+        fields.append(("mlp_fine.", args.fine_n_voxels, args.fine_app_n_comp, args.fine_app_dim,
+                       args.coarse_app_dim + args.fine_app_dim + pe_pts, args.fine_num_layers, args.fine_hidden_dim,
+                       args.fine_geo_feat_dim, args.fine_num_layers_color))
+    for pre, n_vox, n_comp, app_dim, in_ch, n_layers, hidden, geo, n_layers_color in fields:
+        voxel = ((amax - amin).prod() / n_vox).pow(1 / 3)                   # voxnerf.py:87-89
+        gs = ((amax - amin) / voxel).long().tolist()
+        for i, ((m0, m1), v) in enumerate((((0, 1), 2), ((0, 2), 1), ((1, 2), 0))):
+            P[pre + f"app_plane.{i}"] = (0.1 * torch.randn((1, n_comp[i], gs[m1], gs[m0]), generator=g)).to(device)
+            P[pre + f"app_line.{i}"] = (0.1 * torch.randn((1, n_comp[i], gs[v], 1), generator=g)).to(device)
+        lin(pre + "basis_mat", app_dim, sum(n_comp))
+        for l in range(n_layers):                                              # voxnerf.py:49-62
+            lin(pre + f"sigma_net.{l}", (1 + geo) if l == n_layers - 1 else hidden, in_ch if l == 0 else hidden)
+        for l in range(n_layers_color):                                        # voxnerf.py:68-80
+            lin(pre + f"color_net.{l}", 3 if l == n_layers_color - 1 else hidden, (pe_dir + geo) if l == 0 else hidden, bias=args.rgb_add_bias)
+    return P
+
+
 class NeRFAll:
     """Drop-in for the reference façade (mode = c2f or nerf -- detected from the parameter names --, kernel_type = RBK or
-    none).  `params`: reference state_dict."""
+    none).  Two constructor shapes:
+      NeRFAll(params, aabb_min, aabb_max, kernel_ptnum=5, precision=..., ...)   `params`: a reference state_dict
+      NeRFAll(args, kernelsnet=None, awpnet=None, precision=..., device=...)    the reference's own signature (renderer.py:15):
+          `args` is the option namespace (bounding_box, *_n_voxels, kernel_ptnum, kernel_use_awp, render_rmnearplane ...); the PDRF
+          fields are created with the reference's initialisation, `kernelsnet` / `awpnet` are objects with a `state_dict()` (the
+          reference's nn.Modules) or plain dicts.  Either way the object then offers the nn.Module surface run_nerf.py uses:
+          parameters() / named_parameters() / state_dict() / load_state_dict() / get_parameters() / train() / eval() / zero_grad()."""
 
-    def __init__(self, params, aabb_min, aabb_max, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False):
+    def __init__(self, params, aabb_min=None, aabb_max=None, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False,
+                 awpnet=None, device="cuda", seed=None):
+        if not isinstance(params, dict):                     # reference signature: (args, kernelsnet, awpnet)
+            args, kernelsnet = params, aabb_min
+            awpnet = aabb_max if aabb_max is not None else awpnet
+            if getattr(args, "mode", "c2f") != "c2f":
+                raise NotImplementedError("NeRFAll(args, ...): mode = nerf models are built from a state_dict (NeRFAll(params, ...))")
+            if getattr(args, "kernel_type", "RBK") not in ("RBK", "none"):
+                raise NotImplementedError(f"kernel_type {args.kernel_type!r}: the DSK / PBE blur kernels are not built (DESIGN.md section 7)")
+            P = init_reference_parameters(args, device=device, seed=seed)
+            for pre, mod in (("kernelsnet.", kernelsnet), ("awpnet.", awpnet)):
+                if mod is not None:
+                    sd = mod if isinstance(mod, dict) else mod.state_dict()
+                    P.update({pre + k: v.detach().to(device) for k, v in sd.items()})
+            for v in P.values():
+                if v.is_floating_point():
+                    v.requires_grad_(True)
+            self.args = args
+            params = P
+            aabb_min, aabb_max = ([float(x) for x in t] for t in args.bounding_box)
+            kernel_ptnum, render_rmnearplane = args.kernel_ptnum, args.render_rmnearplane
+            use_awp = bool(args.kernel_use_awp) and awpnet is not None
         self.params = {k: v for k, v in params.items() if isinstance(v, torch.Tensor)}
         self.mode = "nerf" if "mlp_coarse.pts_linears.0.weight" in self.params else "c2f"
         if self.mode == "nerf":
@@ -229,6 +303,52 @@ class NeRFAll:
         self._grad_names = sorted(k for k in self.params if k.startswith(("mlp_coarse.", "mlp_fine.", "kernelsnet."))
                                   and self.params[k].is_floating_point())
         self._packed_version = self._param_version()
+
+    # ---- nn.Module surface used by run_nerf.py (optimizer construction :243-274, checkpoints :282-295, 628-634) --------------
+    _BUFFERS = (".running_mean", ".running_var", ".num_batches_tracked")
+
+    def named_parameters(self):
+        return [(k, v) for k, v in self.params.items() if v.is_floating_point() and not k.endswith(self._BUFFERS)]
+
+    def parameters(self):
+        return [v for _, v in self.named_parameters()]
+
+    def get_parameters(self, type, match_re=None, not_match_re=None):
+        """renderer.py:108-127: "net" / "vol" parameter lists filtered by regular expressions on the names."""
+        import re
+        hit = lambda text, rx: len(re.findall(rx, text)) > 0
+        vol = lambda k: "app_plane" in k or "app_line" in k
+        return [v for k, v in self.named_parameters()
+                if (match_re is None or hit(k, match_re)) and (not_match_re is None or not hit(k, not_match_re))
+                and ((type == "net" and not vol(k)) or (type == "vol" and vol(k)))]
+
+    def state_dict(self):
+        return {k: v.detach() for k, v in self.params.items()}
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self.params if k not in sd]
+        unexpected = [k for k in sd if k not in self.params]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:4]}, unexpected {unexpected[:4]}")
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in self.params:
+                    self.params[k].copy_(v)
+        self.repack()
+        return missing, unexpected
+
+    def zero_grad(self, set_to_none=True):
+        for v in self.parameters():
+            if set_to_none:
+                v.grad = None
+            elif v.grad is not None:
+                v.grad.zero_()
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
 
     # ---- autograd plumbing (the reference trains through torch autograd, run_nerf.py:594) --------------------------------
     def _param_version(self):
@@ -269,6 +389,7 @@ class NeRFAll:
     # ---- renderer.py:129 ----------------------------------------------------------------------------------------------
     def render_rays(self, ray_batch, N_samples, retraw=False, lindisp=False, perturb=0., N_importance=0, white_bkgd=False,
                     raw_noise_std=0., pytest=False, force_naive=False, inference=False, **extra):
+        self._maybe_repack()      # parameters updated in place (optimizer.step()) since the last render
         return self.engine.render_rays(ray_batch, N_samples, retraw=retraw, lindisp=lindisp, perturb=perturb,
                                        N_importance=N_importance, white_bkgd=white_bkgd, raw_noise_std=raw_noise_std,
                                        pytest=pytest, force_naive=force_naive, inference=inference, is_train=self.training,
@@ -284,9 +405,15 @@ class NeRFAll:
     # ---- renderer.py:399 ----------------------------------------------------------------------------------------------
     def render(self, H, W, K, chunk, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False, c2w_staticcam=None,
                **kwargs):
-        if c2w is not None or c2w_staticcam is not None:
-            raise NotImplementedError("render(c2w=...) : use render_path for full images")
+        # (`c2w` is accepted and, as in the reference, not used: renderer.py:399-446 only ever reads `rays`)
         rb = build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc)
+        if c2w_staticcam is not None:       # renderer.py:428-431: camera rays from the static pose, view directions from `rays`
+            static = get_rays(H, W, K, torch.as_tensor(c2w_staticcam, dtype=torch.float32, device=rb.device)).reshape(-1, 3, 2)
+            if static.shape[0] != rb.shape[0]:
+                raise RuntimeError("c2w_staticcam: `rays` must cover the full H x W image")
+            rb_static = build_ray_batch(H, W, float(K[0][0]), static, near, far, ndc)
+            rb_static[:, 8:11] = rb[:, 8:11]
+            rb = rb_static
         return self._render_batch(rb, rays.shape[:-2], **kwargs)
 
     # ---- renderer.py:266 ----------------------------------------------------------------------------------------------
@@ -440,13 +567,7 @@ class NeRFAll:
         dev = self.engine.device
         for c2w in render_poses:
             c2w = torch.as_tensor(c2w, dtype=torch.float32, device=dev)
-            # get_rays (utils/rays.py:8-22): host-side ray generation, "next" scope of SURVEY 8(f)
-            i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="xy")
-            dirs = torch.stack([(i + (0.5 - float(K[0][2]))) / float(K[0][0]), -(j + (0.5 - float(K[1][2]))) / float(K[1][1]),
-                                -torch.ones_like(i)], -1)            # HALF_PIX = 0.5 (utils/rays.py:5)
-            rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
-            rays_o = c2w[:3, -1].expand(rays_d.shape)
-            rays = torch.stack([rays_o, rays_d], -1).reshape(-1, 3, 2)
+            rays = get_rays(H, W, K, c2w).reshape(-1, 3, 2)
             rb = build_ray_batch(H, W, float(K[0][0]), rays, near, far, ndc)
             rgb, depth, acc, _ = self._render_batch(rb, (H, W), **kw)
             rgbs.append(rgb)
