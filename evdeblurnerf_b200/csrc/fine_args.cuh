@@ -26,7 +26,7 @@ struct FineArgs {
 
 // fine_tc2.cu: second-generation tensor-core fine kernel (lean schedule, rays of <= 128 samples); wblob = the lean section of the
 // fine tensor-core blob ([layer][K-step][256 x 16] bf16, edn_pack_fine_tc)
-int launch_fine_tc2(const FineArgs& a, int grid_dtype, const uint8_t* wblob, cudaStream_t st);
+int launch_fine_tc2(const FineArgs& a, int grid_dtype, const uint8_t* wblob, const uint8_t* wgeo, cudaStream_t st);
 
 // fine_tc3.cu: bf16 x 3 tensor-core parity mode (EDN_TC32) and its blob section packer (scratch: 128 KB)
 int launch_fine_tc3(const FineArgs& a, int grid_dtype, const uint8_t* wblob, cudaStream_t st);

@@ -670,7 +670,10 @@ int launch_fine_tc(const FineArgs& a_in, int grid_dtype, cudaStream_t st) {
     }
   }
   static const bool force_v1 = [] { const char* e = getenv("EDN_TC_V1"); return e && e[0] == '1'; }();   // dev switch: round-1 kernel
-  if (lean && a.S <= kRows && !force_v1 && !ablate) return launch_fine_tc2(a, grid_dtype, blob + kOffLean, st);   // same lean weight stream
+  // fine_tc2: the lean weight stream; with depth_feature requested it adds the geo layer (sigma_net.1's geo columns: the second
+  // 64 KB layer of the full section, [K-step][128 x 16])
+  if (a.S <= kRows && !force_v1 && !ablate && !(fv && fv[0] == '1'))
+    return launch_fine_tc2(a, grid_dtype, blob + kOffLean, blob + kOffFull + 65536, st);
   const char* tr = getenv("EDN_TC_TRACE");
   if (tr && tr[0] == '1') {   // dev tooling: print the phase time line of CTA 0 (synchronises!)
     FineArgs b = a;

@@ -117,8 +117,13 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob, const int hslot) {
+// FEAT: depth_feature (the geo output of sigma_net.1, voxnerf.py:221) is emitted as well -- an extra N = 128 layer on the SAME A operand
+// as the folded second layer (geo = W_s1geo . relu(h1)), issued between layers 1 and 2 into ONE accumulator slot; its epilogue
+// streams the 128 fp32 columns to a.feat and leaves the A operand untouched.  wgeo: sigma_net.1's geo columns, [K-step][128 x 16] bf16.
+template <typename T, bool FEAT>
+__global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArgs a, const uint8_t* __restrict__ wblob,
+                                                                   const uint8_t* __restrict__ wgeo, const int hslot) {
+  constexpr int kRayStages = FEAT ? kStagesPerRay + 4 : kStagesPerRay;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                                   // [2][64 KB] layer-1 operands (double buffered)
   uint8_t* Ws = smem + 2 * kABytes;                     // weight ring
@@ -187,17 +192,20 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
     // =================================== weight stream =====================================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (n_my > 0) {      // converged warp, one elected lane issues (uniform operands: no per-lane retry loop around UBLKCP)
-      const uint32_t total = (uint32_t)n_my * kStagesPerRay;
+      const uint32_t total = (uint32_t)n_my * kRayStages;
       for (uint32_t g = 0; g < total; ++g) {
         const int s = g % kNst;
         const uint32_t use = g / kNst;
         if (use > 0) mbar_wait(&m->w_empty[s], (use - 1) & 1);
+        const uint32_t j = g % kRayStages;      // stage within the ray: lean layer 1 | (FEAT: geo, 4 stages) | lean layers 2, 3
+        const uint8_t* src = (!FEAT || j < 8) ? wblob + (size_t)j * kStageBytes
+                           : (j < 12 ? wgeo + (size_t)(j - 8) * kStageBytes : wblob + (size_t)(j - 4) * kStageBytes);
         if (elect_one()) {
           if (a.ablate & 2) {
             mbar_expect_tx(&m->w_full[s], 0);
           } else {
             mbar_expect_tx(&m->w_full[s], kStageBytes);
-            bulk_g2s(Ws + s * kStageBytes, wblob + (size_t)(g % kStagesPerRay) * kStageBytes, kStageBytes, &m->w_full[s]);
+            bulk_g2s(Ws + s * kStageBytes, src, kStageBytes, &m->w_full[s]);
           }
         }
         __syncwarp();
@@ -217,14 +225,16 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       const uint32_t idesc = make_idesc_bf16(128, kNsub);
       const uint32_t w_base = smem_u32(Ws);
       uint32_t g = 0;                       // ring stage counter
-      uint32_t n_layer = 0;                 // layers issued so far (3 per ray)
+      uint32_t n_layer = 0;                 // layers issued so far (3 per ray; 4 with FEAT)
+      uint32_t cs = 0;                      // accumulator slot counter: a layer takes slots cs % 3, (cs + 1) % 3 (the geo layer: one)
       for (int64_t it = 0; it < n_my; ++it) {
         const int buf = (int)(it & 1);
         const uint32_t a_in = smem_u32(As) + buf * kABytes;
         if (lane == 0) stamp(1, it, 0);
 #pragma unroll 1
         for (int L = 0; L < 3; ++L) {
-          const uint32_t dx = tmem + kColAcc + ((2 * n_layer) % 3) * 128, dy = tmem + kColAcc + ((2 * n_layer + 1) % 3) * 128;
+          const uint32_t dx = tmem + kColAcc + (cs % 3) * 128, dy = tmem + kColAcc + ((cs + 1) % 3) * 128;
+          cs += 2;
           const uint32_t a_tm = tmem + kColA;
           // Issue order of a layer (chain x -> slot dx = the spare one, chain y -> slot dy = the previous layer's x slot):
           //   after hand[0] (A' K 0..63):            x.K0-3
@@ -289,6 +299,32 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           __syncwarp();
           ++n_layer;
           if (lane == 0) stamp(1, it, 1 + L);
+          if (FEAT && L == 0) {
+            // ---- geo layer: [128 x 256] A (relu(h1), just written by the epilogue) x [256 -> 128], one chain, one slot -----------
+            const uint32_t dg = tmem + kColAcc + (cs % 3) * 128;
+            cs += 1;
+            const uint32_t hp2 = (n_layer - 1) & 1;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) mbar_wait(&m->hand[q], hp2);        // the whole A operand is written
+#pragma unroll 1
+            for (int st4 = 0; st4 < 4; ++st4) {
+              const int s = g % kNst;
+              mbar_wait(&m->w_full[s], (g / kNst) & 1);
+              tc_fence_after();
+              const uint64_t bd0 = make_smem_desc(w_base + s * kStageBytes, 128 * 16, 128);
+              if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  mma_bf16_ts(dg, a_tm + (st4 * 4 + i) * 8, bd0 + (uint64_t)((i * 4096) >> 4), idesc, (st4 | i) > 0);
+                mma_commit(&m->w_empty[s]);
+              }
+              __syncwarp();
+              ++g;
+            }
+            if (elect_one()) mma_commit(&m->acc_full);
+            __syncwarp();
+            ++n_layer;
+          }
         }
       }
     }
@@ -400,7 +436,8 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     const float near_thr = a.rmnearplane / 128.0f;
     const bool has_bias1 = a.mlp.color1_b != nullptr;
-    uint32_t n_use = 0;                            // completed accumulator uses (3 per ray)
+    uint32_t n_use = 0;                            // completed accumulator uses (3 per ray; 4 with FEAT)
+    uint32_t cs = 0;                               // accumulator slot counter, mirrors the MMA issuer's
     for (int64_t it = 0; it < n_my; ++it) {
       const int sl = (int)(it % kSlots);
       RaySlot* slot = &m->slot[sl];
@@ -460,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {       // quarters th (slot x) then th + 2 (slot y)
           const int tq = th + 2 * pass;
-          const uint32_t acc_q = lane_base + kColAcc + ((2 * n_use + pass) % 3) * 128 + th * 64;
+          const uint32_t acc_q = lane_base + kColAcc + ((cs + pass) % 3) * 128 + th * 64;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
@@ -485,7 +522,33 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         }
         if (tr_on) { a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 0] = t_ld; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 1] = t_pr; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 2] = t_st; }
         ++n_use;
+        cs += 2;
         if (st0) stamp(2, it, 2 + 2 * L);
+        if (FEAT && L == 0) {
+          // ---- geo layer: 128 fp32 columns of this row -> depth_feature [ray][r][128]; thread th streams columns 64 th .. 64 th + 63
+          if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
+          named_bar_sync(4, kEpiThreads);
+          tc_fence_after();
+          const uint32_t acc_g = lane_base + kColAcc + (cs % 3) * 128 + th * 64;
+          float* gout = (r < S) ? a.feat + ((size_t)ray * S + r) * 128 + th * 64 : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(acc_g + c * 32, v);
+            tmem_ld_wait();
+            if (gout) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(gout + c * 32 + i) =
+                    make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&m->hand[th]);               // the slot is drained; the A operand was not touched: both of this thread's quarters
+          mbar_arrive(&m->hand[th + 2]);
+          ++n_use;
+          cs += 1;
+        }
       }
       m->headp[th][r][0] = rr; m->headp[th][r][1] = rg_; m->headp[th][r][2] = rbl; m->headp[th][r][3] = sig_part;
       named_bar_sync(2, kEpiThreads);               // all four quarters' head partials visible
@@ -561,7 +624,7 @@ static __global__ void heads_stage_kernel(const float* __restrict__ sigma1_v, co
   for (int j = 0; j < 3; ++j) dst[256 + j * 256 + i] = color2_t[i * 4 + j];
 }
 
-int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, cudaStream_t st) {
+int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, const uint8_t* wgeo, cudaStream_t st) {
   FineArgs a = a_in;
   static float* stage = nullptr;
   static unsigned launch_no = 0;
@@ -579,8 +642,8 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
     EDN_CUDA_OK(cudaMallocManaged(&buf, 4 * 4 * 16 * sizeof(long long)));
     memset(buf, 0, 4 * 4 * 16 * sizeof(long long));
     a.trace = buf;
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
+    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    fine_fwd_tc2_kernel<__nv_bfloat16, false><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, wgeo, hslot);
     EDN_CUDA_OK(cudaStreamSynchronize(st));
     const long long t0 = buf[16];   // MMA role, it = 8, slot 0
     static const char* role[3] = {"gather", "mma", "epi"};
@@ -598,13 +661,15 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
     cudaFree(buf);
     return EDN_OK;
   }
-  if (grid_dtype == EDN_BF16) {
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<__nv_bfloat16><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
-  } else {
-    EDN_CUDA_OK(cudaFuncSetAttribute(fine_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    fine_fwd_tc2_kernel<float><<<gx, kThreads, kSmemBytes, st>>>(a, wblob, hslot);
-  }
+  auto launch = [&](auto kern) -> int {
+    EDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    kern<<<gx, kThreads, kSmemBytes, st>>>(a, wblob, wgeo, hslot);
+    return EDN_OK;
+  };
+  int rc;
+  if (grid_dtype == EDN_BF16) rc = a.feat ? launch(fine_fwd_tc2_kernel<__nv_bfloat16, true>) : launch(fine_fwd_tc2_kernel<__nv_bfloat16, false>);
+  else rc = a.feat ? launch(fine_fwd_tc2_kernel<float, true>) : launch(fine_fwd_tc2_kernel<float, false>);
+  if (rc) return rc;
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }
