@@ -562,7 +562,7 @@ extern "C" int64_t edn_awp_workspace_floats(int64_t n_rays, int32_t n_exposure, 
 namespace edn {
 int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
                 const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
-                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream) {
+                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream, bool keep_all) {
   EDN_REQUIRE(phase >= 0 && phase <= 2, "edn_awp_fwd: phase must be 0, 1 or 2");
   EDN_REQUIRE(p && depth_feature && z_vals && rays_d && view_feature && workspace && ccw, "edn_awp_fwd: null pointer");
   EDN_REQUIRE(n_exposure >= 1 && n_exposure <= kMaxE && n_samples >= 2 && n_samples <= kMaxS,
@@ -590,6 +590,22 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
     EDN_CUDA_OK(cudaFuncSetAttribute(awp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     const int64_t g1 = NE < (int64_t)num_sms() ? NE : (int64_t)num_sms();
     awp_sample_kernel<<<(unsigned)g1, kT, smem1, st>>>(a);
+  } else if (tf32) {
+    // EDN_BF16 precision: the five per-sample contractions on tcgen05, activations on chip (awp_tc.cu)
+    EDN_REQUIRE((reinterpret_cast<uintptr_t>(depth_feature) & 15) == 0, "edn_awp_fwd: depth_feature must be 16-byte aligned");
+    const int64_t M = NE * n_samples;
+    static const bool use_blas = [] { const char* e = getenv("EDN_AWP_BLAS"); return e && e[0] == '1'; }();   // dev switch: round-1 TF32 GEMM chain
+    if (use_blas) return awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, n_rays, n_exposure, n_samples, bn_eps, true,
+                                     false, phase, bn_rows_total, workspace, ccw, stream, keep_all);
+    int rc = awp_sample_mlp_tc(p, depth_feature, M, ws, keep_all ? 1 : 0, st);
+    if (rc) return rc;
+    if (n_samples <= 128) {
+      awp_integrate4_kernel<<<(unsigned)NE, 512, 0, st>>>(a, ws.act[3]);
+    } else {
+      const size_t smem_i = sizeof(float) * (size_t)(n_samples * (3 * 65 + 33 + 1));
+      EDN_CUDA_OK(cudaFuncSetAttribute(awp_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+      awp_integrate_kernel<<<(unsigned)NE, 128, smem_i, st>>>(a, ws.act[3]);
+    }
   } else {
     EDN_REQUIRE((reinterpret_cast<uintptr_t>(depth_feature) & 15) == 0, "edn_awp_fwd: depth_feature must be 16-byte aligned");
     cublasHandle_t h = blas_handle();
@@ -637,7 +653,7 @@ extern "C" int edn_awp_fwd(const edn_awp_params* p, const float* depth_feature, 
   EDN_REQUIRE(opt && (opt->precision == EDN_F32 || opt->precision == EDN_BF16), "edn_awp_fwd: bad options");
   return awp_forward(p, depth_feature, z_vals, rays_d, rays_d_stride, view_feature, n_rays, n_exposure, n_samples, bn_eps,
                      opt->precision == EDN_BF16 || opt->keep_activations, opt->precision == EDN_BF16, opt->phase, opt->bn_rows_total,
-                     workspace, ccw, stream);
+                     workspace, ccw, stream, opt->keep_activations != 0);
 }
 
 extern "C" int64_t edn_awp_stats_offset_floats(int64_t n_rays, int32_t n_exposure, int32_t n_samples) {

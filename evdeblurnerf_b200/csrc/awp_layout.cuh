@@ -42,7 +42,10 @@ inline AwpWs awp_ws_carve(float* w, int64_t N, int E, int S, bool gemm) {
 // GEMMs; phase / bn_rows as in edn_awp_options)
 int awp_forward(const edn_awp_params* p, const float* depth_feature, const float* z_vals, const float* rays_d, int32_t rays_d_stride,
                 const float* view_feature, int64_t n_rays, int32_t n_exposure, int32_t n_samples, float bn_eps, bool gemm_path,
-                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream);
+                bool tf32, int phase, int64_t bn_rows_total, float* workspace, float* ccw, void* stream, bool keep_all = true);
+
+// awp_tc.cu: the per-sample MLP + MAM.linear on tcgen05 (bf16 operands): fills ws.act[3], ws.xl and, with keep != 0, ws.act[0..2]
+int awp_sample_mlp_tc(const edn_awp_params* p, const float* depth_feature, int64_t M, const AwpWs& ws, int keep, cudaStream_t st);
 
 // Backward scratch that precedes the large buffers (awp_bwd.cu): ccw_tmp [NE], d_yn [NE][32], d_x [NE][32], bn_sums [64] doubles.
 struct AwpBwdHead { float* ccw_tmp; float* d_yn; float* d_x; double* bn_sums; float* next; };

@@ -133,23 +133,27 @@ __global__ void mse_kernel(const float* __restrict__ x, const float* __restrict_
   if (threadIdx.x == 0) out[0] = (float)(t / (double)n);
 }
 
-// ---- TV regulariser: sum of squared forward differences along H and W of one [C][H][W] tensor ---------------------------
-__global__ void tv_sums_kernel(const float* __restrict__ x, int C, int H, int W, double* __restrict__ acc /*[2]*/) {
+// ---- TV regulariser: sums of squared forward differences along H and W of [C][H][W] tensors -----------------------------------
+struct TvDims { int C[6], H[6], W[6]; };
+// all six tensors of a field in ONE launch: blockIdx.y = tensor (3 planes, 3 lines), grid-stride over its elements in blockIdx.x
+struct TvPtrs { const float* x[6]; };
+__global__ void tv_sums_all_kernel(const TvPtrs p, const TvDims d, double* __restrict__ acc /*[6][2]*/) {
   __shared__ double sh[32];
-  const int64_t n = (int64_t)C * H * W;
+  const int t = blockIdx.y;
+  const float* __restrict__ x = p.x[t];
+  const int H = d.H[t], W = d.W[t];
+  const int64_t n = (int64_t)d.C[t] * H * W;
   double hs = 0.0, ws = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
     const int h = (int)((i / W) % H);
     const float v = x[i];
-    if (h + 1 < H) { const float d = x[i + W] - v; hs += (double)(d * d); }
-    if (w + 1 < W) { const float d = x[i + 1] - v; ws += (double)(d * d); }
+    if (h + 1 < H) { const float dd = x[i + W] - v; hs += (double)(dd * dd); }
+    if (w + 1 < W) { const float dd = x[i + 1] - v; ws += (double)(dd * dd); }
   }
   const double th = block_sum(hs, sh), tw = block_sum(ws, sh);
-  if (threadIdx.x == 0) { atomicAdd(acc + 0, th); atomicAdd(acc + 1, tw); }
+  if (threadIdx.x == 0 && (th != 0.0 || tw != 0.0)) { atomicAdd(acc + 2 * t, th); atomicAdd(acc + 2 * t + 1, tw); }
 }
-
-struct TvDims { int C[6], H[6], W[6]; };
 __global__ void tv_finalize_kernel(const double* __restrict__ acc /*[6][2]*/, const TvDims d, float* __restrict__ out) {
   // TV_loss_app = sum_i 1e-2 * reg(plane_i) + 1e-3 * reg(line_i); reg = 2 * (h_tv / count_h + w_tv / count_w)
   float total = 0.f;
@@ -220,20 +224,25 @@ extern "C" int edn_tv_loss_app(const float* const planes_chw[3], const float* co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   EDN_CUDA_OK(cudaMemsetAsync(workspace, 0, 12 * sizeof(double), st));
   TvDims d;
+  TvPtrs ptrs;
+  int64_t n_max = 0;
   for (int i = 0; i < 6; ++i) {
     const bool plane = i < 3;
     const int k = plane ? i : i - 3;
     d.C[i] = n_comp[k];
     d.H[i] = plane ? plane_h[k] : line_len[k];
     d.W[i] = plane ? plane_w[k] : 1;
-    const float* x = plane ? planes_chw[k] : lines_chw[k];
-    EDN_REQUIRE(x != nullptr, "edn_tv_loss_app: null tensor %d", i);
+    ptrs.x[i] = plane ? planes_chw[k] : lines_chw[k];
+    EDN_REQUIRE(ptrs.x[i] != nullptr, "edn_tv_loss_app: null tensor %d", i);
     const int64_t n = (int64_t)d.C[i] * d.H[i] * d.W[i];
-    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
-    const int64_t cap = 4 * (int64_t)num_sms();
+    n_max = n > n_max ? n : n_max;
+  }
+  {
+    int64_t blocks = (n_max + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = 2 * (int64_t)num_sms();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    tv_sums_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, d.C[i], d.H[i], d.W[i], workspace + 2 * i);
+    tv_sums_all_kernel<<<dim3((unsigned)blocks, 6), 256, 0, st>>>(ptrs, d, workspace);
   }
   tv_finalize_kernel<<<1, 1, 0, st>>>(workspace, d, out);
   EDN_CUDA_OK(cudaGetLastError());
