@@ -577,13 +577,14 @@ def main():
     for name in ("r2_tc_kernels_ncu_summary.txt", "r1_tc_kernels_ncu_summary.txt"):
         try:
             txt = open(os.path.join(ROOT, "profiles", name)).read().split("=" * 100)
-            blk = next(b for b in txt if "fine_fwd_tc_kernel" in b)
+            want = {"bf16": ("fine_fwd_tc2_kernel", "fine_fwd_tc_kernel"), "tc32": ("fine_fwd_tc3_kernel",)}.get(args.precision, ())
+            blk = next(b for b in txt if any(w in b for w in want))
             unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
             tot = 0.0
             for key in ("dram__bytes_read.sum ", "dram__bytes_write.sum "):
                 ln = next(l for l in blk.splitlines() if l.startswith(key)).split()
                 tot += float(ln[1]) * unit[ln[2]]
-            traffic, traffic_src = (tot if args.precision == "bf16" else None), "profiles/" + name
+            traffic, traffic_src = tot, "profiles/" + name
             break
         except Exception:
             continue
@@ -595,7 +596,9 @@ def main():
         "config": workload_config(args.precision),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": rays_host.numel() * 4 + idx_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": 7 * args.steps,   # rbk_warp_ndc, coarse, sample_pdf_merge, fine, NaN/Inf guard, 2 x weighted_sum
+        # rbk_warp_ndc, coarse, sample_pdf_merge, fine, NaN/Inf guard, 2 x weighted_sum (+ heads_stage in front of the bf16 fine kernel);
+        # checked against profiles/r2_launches_bench_bf16.csv
+        "gpu_launches": (8 if args.precision == "bf16" else 7) * args.steps,
         "clocks": clocks,
         "kernels_ms": kern_ms,
         "numerical_errors": headline_errs,
