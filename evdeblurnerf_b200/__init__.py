@@ -6,7 +6,8 @@ csrc/libevdeblur_b200.so through the C ABI declared in include/evdeblur_b200.h. 
 from . import _lib  # noqa: F401
 from .engine import NerfRenderEngine, RenderEngine, PackedField  # noqa: F401
 from .renderer import NeRFAll, RigidBlurringModel, build_ray_batch, weighted_sum  # noqa: F401
+from .dsk import BlurModel  # noqa: F401
 from .losses import TonemappingTransform, egm_loss, img2mse, mse2psnr, tv_loss_app, edi_prior_image  # noqa: F401
 
-__all__ = ["RenderEngine", "PackedField", "NeRFAll", "RigidBlurringModel", "build_ray_batch", "weighted_sum",
+__all__ = ["RenderEngine", "PackedField", "NeRFAll", "RigidBlurringModel", "BlurModel", "build_ray_batch", "weighted_sum",
            "TonemappingTransform", "egm_loss", "img2mse", "mse2psnr", "tv_loss_app", "edi_prior_image"]

@@ -52,6 +52,21 @@ class RbkGrads(C.Structure):
                                            "w_linear_b")]
 
 
+DSK_MAX_HIDDEN = 4
+_DSK_PTRS = [("img_embed", C.c_void_p), ("pattern_pos", C.c_void_p), ("pattern_trans", C.c_void_p),
+             ("lin_w", C.c_void_p * DSK_MAX_HIDDEN), ("lin_b", C.c_void_p * DSK_MAX_HIDDEN),
+             ("out0_w", C.c_void_p), ("out0_b", C.c_void_p), ("out1_w", C.c_void_p), ("out1_b", C.c_void_p)]
+
+
+class DskParams(C.Structure):
+    _fields_ = _DSK_PTRS + [(n, C.c_int32) for n in ("n_img", "n_pt", "embed", "in_embed", "spatial_embed", "num_hidden", "wide",
+                                                      "short_cut", "isglobal", "optim_sv_trans")] + [("kernel_hwindow", C.c_float)]
+
+
+class DskGrads(C.Structure):
+    _fields_ = list(_DSK_PTRS)
+
+
 class CrfGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3")]
 
@@ -140,6 +155,11 @@ SIGNATURES = {
     "edn_awp_fwd": (C.c_int, [C.POINTER(AwpParams), _P, _P, _P, _I32, _P, _I64, _I32, _I32, _F, C.POINTER(AwpOptions), _P, _P, _P]),
     "edn_rbk_warp_ndc_fwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
     "edn_build_ray_batch": (C.c_int, [_P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P]),
+    "edn_build_ray_batch_bwd": (C.c_int, [_P, _I64, _I32, _I32, _F, _I32, _P, _P, _P]),
+    "edn_dsk_workspace_floats": (C.c_int64, [C.POINTER(DskParams), _I64]),
+    "edn_dsk_rays_fwd": (C.c_int, [C.POINTER(DskParams), _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
+    "edn_dsk_rays_bwd": (C.c_int, [C.POINTER(DskParams), _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _P, _P, _P,
+                                   C.POINTER(DskGrads), _P, _P]),
     "edn_weighted_sum": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),
     "edn_crf_fwd": (C.c_int, [C.POINTER(CrfParams), _P, _P, _I32, _I32, _I64, _P, _P]),
     "edn_egm_loss_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _F, _P, _P]),

@@ -206,6 +206,7 @@ class RenderSubRaysFn(torch.autograd.Function):
         ctx.saved = {"ray_batch": rb, "z_vals0": out["z_vals0"] if Ni > 0 else out["z_vals"], "z_vals": out["z_vals"] if Ni > 0 else None,
                      "noise0": rand.get("noise0"), "noise1": rand.get("noise1")}
         ctx.rays = _c(rays)
+        ctx.rays_grad = kn is None and isinstance(rays, torch.Tensor) and rays.requires_grad      # rays from a learned kernel (DSK)
         ctx.idx = images_idx.reshape(-1).to(torch.int64).contiguous() if images_idx is not None else None
         zero3, zero1 = torch.zeros((R, 3), device=dev), torch.zeros((R,), device=dev)
         empty = torch.zeros((0,), device=dev)
@@ -243,11 +244,19 @@ class RenderSubRaysFn(torch.autograd.Function):
                                            ptr(d_rb), ptr(_c(d_weight)) if d_weight is not None and d_weight.numel() else None,
                                            ptr(_c(d_img_embed)) if d_img_embed is not None else None,
                                            C.byref(g), ptr(ws), stream_ptr()), "edn_rbk_warp_ndc_bwd")
+        d_rays = None
+        if ctx.rays_grad:          # explicit rays that carry a graph: d ray_batch -> d rays (their rows come first)
+            H, W, focal, ndc = ctx.geom
+            R = ctx.rays.reshape(-1, 3, 2).shape[0]
+            d_rays = torch.empty((R, 3, 2), dtype=torch.float32, device=d_rb.device)
+            check(lib.edn_build_ray_batch_bwd(ptr(ctx.rays), R, int(H), int(W), float(focal), 1 if ndc else 0, ptr(_c(d_rb[:R])),
+                                              ptr(d_rays), stream_ptr()), "edn_build_ray_batch_bwd")
+            d_rays = d_rays.reshape(ctx.rays.shape)
         out = []
         for nm in ctx.names:
             gr = named.get(nm)
             out.append(gr)
-        return (None,) * 12 + tuple(out)
+        return (None,) * 5 + (d_rays,) + (None,) * 6 + tuple(out)
 
 
 _AWP_FIELDS = (   # (struct field, index | None, state_dict name, transposed)

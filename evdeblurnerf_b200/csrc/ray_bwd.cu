@@ -73,6 +73,33 @@ __device__ Dual dcos(const Dual& a) {
   return r;
 }
 
+// ray_batch row (o, d, viewdirs = out[0..8]) of a ray (wo, wd): view-direction normalisation + NDC projection, same arithmetic as
+// ray_batch_kernel / rbk_warp_ndc_kernel (renderer.py:423-446, utils/rays.py:104-145).
+__device__ void finish_ray_dual(const Dual wo[3], const Dual wd[3], float Hf, float Wf, float focal, int ndc, Dual out[9]) {
+  const Dual nrm = dsqrt(wd[0] * wd[0] + wd[1] * wd[1] + wd[2] * wd[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out[6 + i] = wd[i] / nrm;
+  if (ndc) {
+    const float near = 1.0f;
+    const Dual t = -(Dual(near) + wo[2]) / wd[2];
+    Dual oo[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) oo[i] = wo[i] + t * wd[i];
+    const Dual ox_oz = oo[0] / oo[2], oy_oz = oo[1] / oo[2];
+    const float sx = -1.f / (Wf / (2.f * focal)), sy = -1.f / (Hf / (2.f * focal));
+    out[0] = Dual(sx) * ox_oz;
+    out[1] = Dual(sy) * oy_oz;
+    out[2] = Dual(1.f) + Dual(2.f * near) / oo[2];
+    out[3] = Dual(sx) * (wd[0] / wd[2] - ox_oz);
+    out[4] = Dual(sy) * (wd[1] / wd[2] - oy_oz);
+    out[5] = Dual(1.f) - out[2];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { out[i] = wo[i]; out[3 + i] = wd[i]; }
+  }
+}
+
+
 // ray_batch row (o, d, viewdirs = out[0..8]) of the sub-ray warped by (rot, trn): same arithmetic as rbk_warp_ndc_kernel.
 __device__ void warp_ray_dual(const Dual rot[3], const Dual trn[3], const float o[3], const float d[3], float Hf, float Wf, float focal,
                               int ndc, Dual out[9]) {
@@ -102,27 +129,7 @@ __device__ void warp_ray_dual(const Dual rot[3], const Dual trn[3], const float 
     wo[i] = ro + p;
     wd[i] = (re + p) - wo[i];
   }
-  const Dual nrm = dsqrt(wd[0] * wd[0] + wd[1] * wd[1] + wd[2] * wd[2]);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) out[6 + i] = wd[i] / nrm;
-  if (ndc) {
-    const float near = 1.0f;
-    const Dual t = -(Dual(near) + wo[2]) / wd[2];
-    Dual oo[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) oo[i] = wo[i] + t * wd[i];
-    const Dual ox_oz = oo[0] / oo[2], oy_oz = oo[1] / oo[2];
-    const float sx = -1.f / (Wf / (2.f * focal)), sy = -1.f / (Hf / (2.f * focal));
-    out[0] = Dual(sx) * ox_oz;
-    out[1] = Dual(sy) * oy_oz;
-    out[2] = Dual(1.f) + Dual(2.f * near) / oo[2];
-    out[3] = Dual(sx) * (wd[0] / wd[2] - ox_oz);
-    out[4] = Dual(sy) * (wd[1] / wd[2] - oy_oz);
-    out[5] = Dual(1.f) - out[2];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { out[i] = wo[i]; out[3 + i] = wd[i]; }
-  }
+  finish_ray_dual(wo, wd, Hf, Wf, focal, ndc, out);
 }
 
 // one thread per (ray, motion): d r, d v [N][3M] (component-major, motion-minor; before the rv_window scale is undone)
@@ -159,6 +166,30 @@ __global__ void rbk_warp_bwd_kernel(const float* __restrict__ rays, const float*
   for (int j = 0; j < 3; ++j) {
     d_r[n * 3 * M + j * M + mi] = gin[j];
     d_v[n * 3 * M + j * M + mi] = gin[3 + j];
+  }
+}
+
+// edn_build_ray_batch_bwd: one thread per ray, the 6 tangent lanes seed (o, d) themselves
+__global__ void ray_batch_bwd_kernel(const float* __restrict__ rays, int64_t R, int H, int W, float focal, int ndc,
+                                     const float* __restrict__ d_rb, float* __restrict__ d_rays) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= R) return;
+  Dual wo[3], wd[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    wo[i] = Dual(rays[n * 6 + 2 * i]); wo[i].d[i] = 1.f;
+    wd[i] = Dual(rays[n * 6 + 2 * i + 1]); wd[i].d[3 + i] = 1.f;
+  }
+  Dual out[9];
+  finish_ray_dual(wo, wd, (float)H, (float)W, focal, ndc, out);
+  const float* g = d_rb + n * 11;
+  const float gq[9] = {g[0], g[1], g[2], g[3], g[4], g[5], g[8], g[9], g[10]};
+#pragma unroll
+  for (int k = 0; k < kT; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s = fmaf(gq[q], out[q].d[k], s);
+    d_rays[n * 6 + 2 * (k % 3) + (k / 3)] = s;
   }
 }
 
@@ -292,6 +323,16 @@ extern "C" int edn_weighted_sum_bwd(const float* x, const float* w, const float*
   if (n <= 0) return n == 0 ? EDN_OK : EDN_E_INVALID;
   weighted_sum_bwd_kernel<<<blocks_for(n * n_exposure, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, d_out, n, n_exposure,
                                                                                                                channels, d_x, d_w);
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
+
+extern "C" int edn_build_ray_batch_bwd(const float* rays, int64_t n_rays, int32_t H, int32_t W, float focal, int32_t ndc,
+                                       const float* d_ray_batch, float* d_rays, void* stream) {
+  using namespace edn;
+  EDN_REQUIRE(rays && d_ray_batch && d_rays, "edn_build_ray_batch_bwd: null pointer");
+  if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
+  ray_batch_bwd_kernel<<<blocks_for(n_rays, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rays, n_rays, H, W, focal, ndc, d_ray_batch, d_rays);
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;
 }

@@ -1,4 +1,4 @@
-"""Host mirror of the reference renderer façade `NeRFAll` (networks/renderer.py:14-626), mode = c2f, kernel_type = RBK.
+"""Host mirror of the reference renderer façade `NeRFAll` (networks/renderer.py:14-626), mode = c2f | nerf, kernel_type = RBK | DSK | none.
 
 Same method names, argument order and return structure as the reference so that `run_nerf.py`'s call sites
 (`nerf(H, W, K, chunk, rays=..., rays_info=..., **render_kwargs)`) keep working; every arithmetic
@@ -252,8 +252,9 @@ def init_reference_parameters(args, device="cuda", seed=None):
 
 
 class NeRFAll:
-    """Drop-in for the reference façade (mode = c2f or nerf -- detected from the parameter names --, kernel_type = RBK or
-    none).  Two constructor shapes:
+    """Drop-in for the reference façade (mode = c2f or nerf, kernel_type = RBK, DSK or none -- all detected from the parameter
+    names; `kernel_cfg` carries the DSK options the shapes cannot tell: in_embed, spatial_embed, kernel_hwindow, random_hwindow).
+    Two constructor shapes:
       NeRFAll(params, aabb_min, aabb_max, kernel_ptnum=5, precision=..., ...)   `params`: a reference state_dict
       NeRFAll(args, kernelsnet=None, awpnet=None, precision=..., device=...)    the reference's own signature (renderer.py:15):
           `args` is the option namespace (bounding_box, *_n_voxels, kernel_ptnum, kernel_use_awp, render_rmnearplane ...); the PDRF
@@ -262,14 +263,17 @@ class NeRFAll:
           parameters() / named_parameters() / state_dict() / load_state_dict() / get_parameters() / train() / eval() / zero_grad()."""
 
     def __init__(self, params, aabb_min=None, aabb_max=None, kernel_ptnum=5, precision="fp32", render_rmnearplane=0, use_awp=False,
-                 awpnet=None, device="cuda", seed=None):
+                 awpnet=None, device="cuda", seed=None, kernel_cfg=None):
         if not isinstance(params, dict):                     # reference signature: (args, kernelsnet, awpnet)
             args, kernelsnet = params, aabb_min
             awpnet = aabb_max if aabb_max is not None else awpnet
             if getattr(args, "mode", "c2f") != "c2f":
                 raise NotImplementedError("NeRFAll(args, ...): mode = nerf models are built from a state_dict (NeRFAll(params, ...))")
-            if getattr(args, "kernel_type", "RBK") not in ("RBK", "none"):
-                raise NotImplementedError(f"kernel_type {args.kernel_type!r}: the DSK / PBE blur kernels are not built (DESIGN.md section 7)")
+            if getattr(args, "kernel_type", "RBK") not in ("RBK", "DSK", "none"):
+                raise NotImplementedError(f"kernel_type {args.kernel_type!r}: the PBE two-stage blur kernel is not built (DESIGN.md section 8)")
+            if getattr(args, "kernel_type", "RBK") == "DSK":      # run_nerf.py:184-203 option names
+                kernel_cfg = dict(in_embed=getattr(args, "kernel_rand_embed", 3), spatial_embed=getattr(args, "kernel_spatial_embed", 0),
+                                  kernel_hwindow=getattr(args, "kernel_hwindow", 10), random_hwindow=getattr(args, "kernel_random_hwindow", 0.25))
             P = init_reference_parameters(args, device=device, seed=seed)
             for pre, mod in (("kernelsnet.", kernelsnet), ("awpnet.", awpnet)):
                 if mod is not None:
@@ -293,6 +297,11 @@ class NeRFAll:
         if "kernelsnet.r_linear.weight" in self.params:
             self.kernelsnet = RigidBlurringModel(self.params, kernel_ptnum - 1)
         self.kernel_type, self.use_awp = "RBK", bool(use_awp)
+        if "kernelsnet.pattern_pos" in self.params:           # deformable sparse kernel (pdrf/blurmodel.py)
+            from .dsk import BlurModel
+            self.kernelsnet, self.kernel_type = BlurModel(self.params, kernel_ptnum, **(kernel_cfg or {})), "DSK"
+            if self.use_awp:
+                raise NotImplementedError("kernel_use_awp with kernel_type = DSK is not built")
         self.awpnet = (AdaptiveWeightProposal(self.params, kernel_ptnum - 1,
                                               precision=_lib.EDN_BF16 if precision == "bf16" else _lib.EDN_F32) if self.use_awp else None)
         if self.use_awp and self.mode != "c2f":
@@ -430,10 +439,12 @@ class NeRFAll:
         kwargs.pop("use_viewdirs", None)
         other_loss, other_tensors = {}, {}
         self._maybe_repack()
+        if self.kernel_type == "DSK" and not force_baseline:
+            return self._forward_dsk(H, W, K, rays, rays_info, return_pts0_rgb, N_importance, ndc, near, far, kwargs, want_tv)
         if self._wants_grad():
             return self._forward_with_grad(H, W, K, rays, rays_info, force_baseline, return_pts0_rgb, N_importance, ndc, near, far,
                                            kwargs, want_tv)
-        if self.kernelsnet is not None and not force_baseline:
+        if self.kernelsnet is not None and self.kernel_type == "RBK" and not force_baseline:
             k = self.kernelsnet.warp(H, W, float(K[0][0]), rays, rays_info["images_idx"], near, far, ndc, want_new_rays=False)
             weight1 = k["weight"]
             N, E = weight1.shape
@@ -484,7 +495,7 @@ class NeRFAll:
                            want_tv=True, naive_rays=None):
         """Training branch of forward() (renderer.py:277-378) with outputs attached to the autograd graph."""
         other_loss, other_tensors = {}, {}
-        blur = self.kernelsnet is not None and not force_baseline
+        blur = self.kernelsnet is not None and self.kernel_type == "RBK" and not force_baseline
         if naive_rays:
             kwargs = dict(kwargs, extra_rays=torch.cat([r.reshape(-1, 3, 2) for r in naive_rays], 0))
         rgb, depth, acc, rgb0, depth0, acc0, weight1, feat, rb, img_embed = self._render_sub_rays(
@@ -526,10 +537,36 @@ class NeRFAll:
             return rgb_b, rgb1, other_loss, other_tensors, naive_out
         return rgb_b, rgb1, other_loss, other_tensors
 
+    def _forward_dsk(self, H, W, K, rays, rays_info, return_pts0_rgb, N_importance, ndc, near, far, kwargs, want_tv=True):
+        """renderer.py:301-378 with kernel_type = DSK, no AWP: kernel rays -> render of the N * num_pt rays -> per-point weighted sums;
+        `align` joins the extra losses.  With parameters that require grad the three stages are autograd nodes (DskRaysFn ->
+        RenderSubRaysFn, which returns d rays -> WeightedSumFn)."""
+        other_loss, other_tensors = {}, {}
+        new_rays, weight1, align, _ = self.kernelsnet(H, W, K, rays, rays_info, noise=kwargs.pop("dsk_noise", None))
+        N, E = weight1.shape
+        sub = new_rays.reshape(-1, 3, 2)
+        if self._wants_grad():
+            rgb, _, _, rgb0 = self._render_sub_rays(H, W, K, sub, None, near, far, ndc, kwargs, blur=False)[:4]
+        else:
+            rgb, _, _, extras = self._render_batch(build_ray_batch(H, W, float(K[0][0]), sub, near, far, ndc), (N * E,), **kwargs)
+            rgb0 = extras.get("rgb0")
+        rgb_b = weighted_sum(rgb, weight1)
+        rgb1 = weighted_sum(rgb0, weight1) if N_importance > 0 else None
+        if self.mode == "c2f" and want_tv:
+            other_loss["TV"] = self.tv_loss(N_importance > 0)
+        other_loss["align"] = align.reshape(1, 1)
+        if return_pts0_rgb:
+            other_tensors["stage1_rgb_pts0"] = rgb.reshape(N, E, 3)[:, 0]
+            if N_importance > 0:
+                other_tensors["stage1_rgb1_pts0"] = rgb0.reshape(N, E, 3)[:, 0]
+        return rgb_b, rgb1, other_loss, other_tensors
+
     def render_blurred(self, H, W, K, rays, images_idx, near=0., far=1., ndc=True, **kwargs):
         """The render part of the training forward (renderer.py:303-343 without the loss terms): blur-kernel warp ->
         NDC ray batch -> c2f render of the N*E sub-rays -> exposure-weighted sum.  Returns (rgb [N,3], rgb0 [N,3] | None)."""
         self._maybe_repack()
+        if self.kernel_type == "DSK":
+            raise NotImplementedError("render_blurred takes RBK rays; with kernel_type = DSK call forward(rays_info=...) (pixel coordinates + poses)")
         if self._wants_grad():
             rgb, _, _, rgb0, _, _, weight1 = self._render_sub_rays(H, W, K, rays, images_idx, near, far, ndc, kwargs)[:7]
             if self.kernelsnet is None:

@@ -98,7 +98,7 @@ class Trainer:
     def __init__(self, state, crf_state, aabb_min, aabb_max, kernel_ptnum=5, precision="bf16", lrate=5e-4, lrate_decay=250,
                  lrate_warmup_iters=0, lrate_warmup_factor=1.0, colornet_weightdecay=0.0, tv_loss_weight=1e-2,
                  event_loss_weight=0.0, crf_kwargs=None, render_kwargs=None, device=None, process_group=None, seed=0,
-                 use_awp=False, awp_fine_loss_weight=None, schedule=None, check_numerics_every=100):
+                 use_awp=False, awp_fine_loss_weight=None, schedule=None, check_numerics_every=100, kernel_cfg=None):
         if not torch.cuda.is_available():
             raise RuntimeError("evdeblurnerf_b200.Trainer needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if device is not None else "cuda")
@@ -111,11 +111,13 @@ class Trainer:
         self.flat = FlatParams({**trainable, **crf_train}, dev)
         P = {k: self.flat.views[k] for k in trainable}
         Pc = {k[4:]: self.flat.views[k] for k in crf_train}
-        self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision, use_awp=use_awp).train()
+        self.nerf = NeRFAll(P, aabb_min, aabb_max, kernel_ptnum=kernel_ptnum, precision=precision, use_awp=use_awp,
+                            kernel_cfg=kernel_cfg).train()
         if use_awp:     # BatchNorm statistics over the WHOLE batch, as on one GPU (SURVEY 8(e) caveat 1)
             self.nerf.awpnet.sync_bn, self.nerf.awpnet.group = True, process_group
         self.awp_fine_loss_weight = awp_fine_loss_weight
-        self.fuse_event_renders = True      # one render + one backward for the blurred rays and both event ray sets
+        # one render + one backward for the blurred rays and both event ray sets (RBK; the DSK rays come out of their own autograd node)
+        self.fuse_event_renders = self.nerf.kernel_type != "DSK"
         self.crf = TonemappingTransform(Pc, **(crf_kwargs or dict(map_type_rgb="gamma", map_type_event="learn" if Pc else "gamma",
                                                                   extra_features_event=2)))
         self.hp = dict(lrate=lrate, decay=lrate_decay, warm_it=lrate_warmup_iters, warm_f=lrate_warmup_factor,
@@ -134,7 +136,7 @@ class Trainer:
         # kernel_awp_use_coarse_to_fine_opt, use_pts0_prior, pts0_target_{weight,weight_end,weight_steps,weight_scheduler,
         # start_iter,end_iter}, blur_loss_after, event_egm_{weight,weight_end,weight_steps,weight_scheduler}, clip_grads_norm,
         # tone_mapping_start_learn_iter, add_event_egm_startiter, add_event_egm_stages, event_egm_use_color_weights,
-        # event_egm_color_weights_start_iter, kernel_awp_fine_loss_start_ratio
+        # event_egm_color_weights_start_iter, kernel_awp_fine_loss_start_ratio, kernel_align_weight, align_start_iter, align_end_iter
         sc = dict(kernel_start_iter=0, kernel_start_warmup_mode="step", kernel_start_warmup_iters=1, N_iters=200000,
                   kernel_awp_use_coarse_to_fine_opt=False, use_pts0_prior=None, pts0_target_weight=0.1, pts0_target_weight_end=1.0,
                   pts0_target_weight_steps=None, pts0_target_weight_scheduler="constant", pts0_target_start_iter=-1,
@@ -142,7 +144,7 @@ class Trainer:
                   event_egm_weight_end=event_loss_weight, event_egm_weight_steps=None, event_egm_weight_scheduler="constant",
                   clip_grads_norm=None, tone_mapping_start_learn_iter=0, add_event_egm_startiter=None,
                   add_event_egm_stages=("stage0", "stage1"), event_egm_use_color_weights=None, event_egm_color_weights_start_iter=-1,
-                  kernel_awp_fine_loss_start_ratio=0.1)
+                  kernel_awp_fine_loss_start_ratio=0.1, kernel_align_weight=0.0, align_start_iter=0, align_end_iter=1e10)
         unknown = set(schedule or {}) - set(sc)
         if unknown:
             raise ValueError(f"unknown schedule keys {sorted(unknown)}")
@@ -219,6 +221,8 @@ class Trainer:
                 loss = self.w_kernel(g) * loss + (1 - self.w_kernel(g)) * pts0_loss
         if self.hp["tv_w"] > 0 and extra_loss.get("TV") is not None:
             loss = loss + extra_loss["TV"] * self.hp["tv_w"]
+        if "align" in extra_loss and sc["align_start_iter"] <= i <= sc["align_end_iter"]:      # run_nerf.py:502-504 (DSK kernels)
+            loss = loss + extra_loss["align"].reshape(()) * sc["kernel_align_weight"]
         if events:
             feat = batch.get("ev_extra_feat")
             cmask = batch.get("ev_color_map")

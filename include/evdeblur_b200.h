@@ -299,6 +299,58 @@ int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, const int64
 int edn_weighted_sum_bwd(const float* x, const float* w, const float* d_out, int64_t n, int32_t n_exposure, int64_t channels,
                          float* d_x, float* d_w, void* stream);
 
+/* Backward of edn_build_ray_batch (renderer.py:423-446, utils/rays.py:104-145): d_ray_batch [R][11] -> d_rays [R][3][2]
+ * (overwritten).  Lets gradients reach rays that come from a learned blur kernel other than RBK (the DSK rays below). */
+int edn_build_ray_batch_bwd(const float* rays, int64_t n_rays, int32_t H, int32_t W, float focal, int32_t ndc,
+                            const float* d_ray_batch, float* d_rays, void* stream);
+
+/* ---- deformable sparse kernel (DSK) ---------------------------------------------------------------------------------------- */
+
+/* BlurModel parameters with kernel_type = DSK, use_pattern_pos = True, depth_embed = 0 (networks/pdrf/blurmodel.py:9-107), fp32,
+ * nn.Linear layout [out][in]: img_embed = img_embed.img_embed [n_img][embed]; pattern_pos [n_pat][n_pt][2] (n_pat = 1 when
+ * isglobal, else n_img); pattern_trans [n_pat][n_pt][2] or NULL (optim_trans); lin_w[l] / lin_b[l] = linears.{2l}
+ * ([wide][in_cnl] for l = 0, then [wide][wide]), l < num_hidden <= EDN_DSK_MAX_HIDDEN; out0 = linears1.0 ([wide][wide], or
+ * [wide][in_cnl + wide] when short_cut: input columns first); out1 = linears1.2 ([3][wide], or [5][wide] when optim_sv_trans).
+ * in_cnl = (2 + 4 in_embed) + embed + (spatial_embed ? 2 + 4 spatial_embed : 0). */
+#define EDN_DSK_MAX_HIDDEN 4
+typedef struct edn_dsk_params {
+  const float* img_embed;
+  const float* pattern_pos;
+  const float* pattern_trans;
+  const float* lin_w[EDN_DSK_MAX_HIDDEN]; const float* lin_b[EDN_DSK_MAX_HIDDEN];
+  const float* out0_w; const float* out0_b;
+  const float* out1_w; const float* out1_b;
+  int32_t n_img, n_pt, embed, in_embed, spatial_embed, num_hidden, wide, short_cut, isglobal, optim_sv_trans;
+  float kernel_hwindow;
+} edn_dsk_params;
+
+typedef struct edn_dsk_grads {
+  float* img_embed;
+  float* pattern_pos;
+  float* pattern_trans;
+  float* lin_w[EDN_DSK_MAX_HIDDEN]; float* lin_b[EDN_DSK_MAX_HIDDEN];
+  float* out0_w; float* out0_b;
+  float* out1_w; float* out1_b;
+} edn_dsk_grads;
+
+/* BlurModel.forward, kernel_type = DSK (pdrf/blurmodel.py:109-224): canonical kernel positions (+ noise [N][n_pt][2] =
+ * randn * random_hwindow, or NULL) -> PE | view embedding | PE(pixel position) -> MLP -> position offsets, optional origin
+ * offsets, softmax weights -> rays through the offset pixels with the per-ray camera poses [N][3][4].
+ *   rays_x, rays_y [N] pixel coordinates; images_idx [N] int64; fx, fy, cx, cy = K[0][0], K[1][1], K[0][2], K[1][2]
+ * outputs: new_rays [N][n_pt][3][2], weight [N][n_pt], align [1] (blurmodel.py:190-191).
+ * workspace: edn_dsk_workspace_floats(p, n_rays) floats. */
+int64_t edn_dsk_workspace_floats(const edn_dsk_params* p, int64_t n_rays);
+int edn_dsk_rays_fwd(const edn_dsk_params* p, const float* rays_x, const float* rays_y, const int64_t* images_idx,
+                     const float* poses, const float* noise, int64_t n_rays, int32_t H, int32_t W, float fx, float fy, float cx,
+                     float cy, float* new_rays, float* weight, float* align, float* workspace, void* stream);
+
+/* Backward of edn_dsk_rays_fwd: d_new_rays [N][n_pt][3][2] (or NULL), d_weight [N][n_pt] (or NULL), d_align device scalar (or
+ * NULL) -> ACCUMULATES the parameter gradients into `grads` (same layouts as edn_dsk_params).  Same workspace size. */
+int edn_dsk_rays_bwd(const edn_dsk_params* p, const float* rays_x, const float* rays_y, const int64_t* images_idx,
+                     const float* poses, const float* noise, int64_t n_rays, int32_t H, int32_t W, float fx, float fy, float cx,
+                     float cy, const float* d_new_rays, const float* d_weight, const float* d_align, const edn_dsk_grads* grads,
+                     float* workspace, void* stream);
+
 /* ---- adaptive weight proposal -------------------------------------------------------------------------------------------- */
 
 /* AdaptiveWeightProposal weights (networks/dpnerf/awp.py:37-47, mam.py:13-65), fp32:

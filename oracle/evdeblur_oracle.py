@@ -460,6 +460,74 @@ def forward_train(P, cfg, H, W, focal, rays, images_idx, E, n_samples, n_importa
 
 
 # --------------------------------------------------------------------------------------------------------------
+# f3  Deformable sparse kernel (DSK)                                          networks/pdrf/blurmodel.py:9-224
+# --------------------------------------------------------------------------------------------------------------
+def dsk_forward(P, cfg, H, W, K, rays_x, rays_y, images_idx, poses, noise=None, prefix="kernelsnet."):
+    """BlurModel.forward with kernel_type = DSK (blurmodel.py:109-224).  cfg: num_pt, kernel_hwindow, in_embed, spatial_embed,
+    num_hidden, short_cut, isglobal, optim_trans, optim_sv_trans.  rays_x / rays_y [N,1] pixel coordinates, poses [N,3,4],
+    K = 3x3 intrinsics; noise [N,P,2] = randn_like(pt_pos) * random_hwindow (blurmodel.py:125-127) or None.
+    Returns new_rays [N,P,3,2], weight [N,P], align (scalar)."""
+    npt, hw = int(cfg["num_pt"]), float(cfg["kernel_hwindow"])
+    idx = images_idx.reshape(-1).long()
+    N = idx.shape[0]
+    emb = P[prefix + "img_embed.img_embed"][idx]                                       # blurmodel.py:119
+    pt_pos = P[prefix + "pattern_pos"]
+    pt_pos = pt_pos.expand(N, -1, -1) if cfg.get("isglobal") else pt_pos[idx]        # blurmodel.py:122-124
+    pt_pos = torch.tanh(pt_pos) * hw
+    if noise is not None:
+        pt_pos = pt_pos + noise
+    input_pos = pt_pos
+    if int(cfg.get("in_embed", 0)) > 0:
+        pt_pos = posenc(pt_pos * (math.pi / hw), int(cfg["in_embed"]))              # blurmodel.py:130-132
+    x = torch.cat([pt_pos, emb[:, None].expand(N, npt, emb.shape[-1])], -1)
+    if int(cfg.get("spatial_embed", 0)) > 0:                                           # blurmodel.py:149-155
+        sp = torch.cat([rays_x / (W / 2 / math.pi) - math.pi, rays_y / (H / 2 / math.pi) - math.pi], -1)
+        sp = posenc(sp, int(cfg["spatial_embed"]))
+        x = torch.cat([x, sp[:, None].expand(N, npt, sp.shape[-1])], -1)
+    h = x
+    for l in range(int(cfg["num_hidden"])):                                          # linears: Linear + ReLU, num_hidden times
+        h = torch.relu(h @ P[prefix + f"linears.{2 * l}.weight"].t() + P[prefix + f"linears.{2 * l}.bias"])
+    if cfg.get("short_cut"):
+        h = torch.cat([x, h], -1)
+    h = torch.relu(h @ P[prefix + "linears1.0.weight"].t() + P[prefix + "linears1.0.bias"])
+    out = h @ P[prefix + "linears1.2.weight"].t() + P[prefix + "linears1.2.bias"]
+    if cfg.get("optim_sv_trans"):
+        delta_trans, delta_pos, wl = out[..., 0:2], out[..., 2:4], out[..., 4]
+    else:
+        delta_pos, wl = out[..., 0:2], out[..., 2]
+        delta_trans = None
+    if cfg.get("optim_trans"):                                                        # blurmodel.py:174-176
+        pt = P[prefix + "pattern_trans"]
+        delta_trans = pt.expand(N, -1, -1) if cfg.get("isglobal") else pt[idx]
+    if delta_trans is None:
+        delta_trans = torch.zeros_like(delta_pos)
+    delta_trans = delta_trans * 0.01
+    new_xy = delta_pos + input_pos
+    align = new_xy[:, 0, :].abs().mean() + delta_trans[:, 0, :].abs().mean() * 10    # blurmodel.py:190-191
+    weight = torch.softmax(wl, -1)
+    rx = (rays_x - K[0, 2] + new_xy[..., 0]) / K[0, 0]                                 # blurmodel.py:199-200
+    ry = -(rays_y - K[1, 2] + new_xy[..., 1]) / K[1, 1]
+    dirs = torch.stack([rx - delta_trans[..., 0], ry - delta_trans[..., 1], -torch.ones_like(rx)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * poses[:, None, :3, :3], -1)
+    tr = torch.stack([delta_trans[..., 0], delta_trans[..., 1], torch.zeros_like(rx), torch.ones_like(rx)], -1)
+    rays_o = torch.sum(tr[..., None, :] * poses[:, None], -1)
+    return torch.stack([rays_o, rays_d], -1), weight, align
+
+
+def forward_train_dsk(P, cfg, dsk_cfg, H, W, K, rays_x, rays_y, images_idx, poses, n_samples, n_importance, noise=None):
+    """NeRFAll.forward, kernel_type = DSK, no AWP (renderer.py:301-378): DSK rays -> render -> per-point weighted sums."""
+    new_rays, weight, align = dsk_forward(P, dsk_cfg, H, W, K, rays_x, rays_y, images_idx, poses, noise)
+    N, npt = weight.shape
+    rb = build_ray_batch(H, W, float(K[0, 0]), new_rays.reshape(-1, 3, 2))
+    ret = render_rays(P, cfg, rb, n_samples, n_importance)
+    out = {"new_rays": new_rays, "weight": weight, "align": align, "render": ret,
+           "rgb": torch.sum(ret["rgb_map"].reshape(N, npt, 3) * weight[..., None], 1)}
+    if n_importance > 0:
+        out["rgb1"] = torch.sum(ret["rgb0"].reshape(N, npt, 3) * weight[..., None], 1)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
 # a17  TV regulariser                                networks/pdrf/voxnerf.py:126-130, 306-324; renderer.py:361-365
 # --------------------------------------------------------------------------------------------------------------
 def tv_reg(x):
