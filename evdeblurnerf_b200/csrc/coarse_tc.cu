@@ -11,6 +11,8 @@
 //                     into color_net.0 (64 -> 64, + view-dir bias), color_net.1 (64 -> 64): 3 stages;
 //     full (feature_map requested): basis_mat (96 -> 32), sigma_net 96 -> 64 -> 16, color_net 16 -> 64 -> 64: 5 stages.
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 
 #include "coarse_args.cuh"
 #include "common.cuh"
@@ -395,6 +397,336 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
   if (warp == kRowWarps) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ======================================================================================================================================
+// Second-generation coarse kernel (lean schedule, S a multiple of 32): the VM gather is DECOUPLED from the MLP chain.
+//   warps 0-15  producer (setmaxnreg 88): sample placement + PE + per-ray view-direction bias + VM gather of the NEXT tile of either
+//               group straight into that group's A tile -- as soon as the tile's first MMA stage has retired (a_free), i.e. while the
+//               group's epilogue warps are still two stages and a compositing away from finishing the previous tile;
+//   warps 16-23 epilogue (64 registers): two groups x 4 warps, ONE thread per row: TMEM -> ReLU -> bf16 -> the group's 16 KB
+//               activation buffer (next stage's A operand), fp32 sigma / rgb heads, warp-shuffle compositing;
+//   warps 24-25 MMA issuers (one per group, converged warp + elect.sync), warps 26-27 idle donors (24 registers).
+// TMEM: per group TWO 64-column accumulators (tile parity), so stage 1 of the next tile runs under the last epilogue of this one.
+// Round 1's kernel kept every row warp on gather -> wait -> epilogue -> wait ...; its top stall was the long scoreboard of the gather.
+constexpr int kV2GatherWarps = 16, kV2EpiWarps = 8;
+constexpr int kV2WarpMma = kV2GatherWarps + kV2EpiWarps;
+constexpr int kV2Threads = (kV2GatherWarps + kV2EpiWarps + 4) * 32;     // 896
+constexpr int kV2ProdThreads = kV2GatherWarps * 32;
+constexpr int kV2ABytes = 20 * kChunkA;              // [g 96 | PE 64] = 20 chunks of 8 columns
+constexpr int kV2ActBytes = 8 * kChunkA;             // 64 hidden columns
+constexpr int kV2WBytes = kWBytes - kOffL1;          // the lean section of the blob
+constexpr uint32_t kV2TmemCols = 256;                // 2 groups x 2 tile parities x 64 columns
+
+struct alignas(16) GroupMisc2 {
+  float z[2][kRows];                      // tile parity
+  alignas(16) float bias[2][kMaxRpt][64];
+  float sig[kRows];
+  float w[kRows];
+  float rgb[kRows * 3];
+  float red[4][8];
+  float wtot[4];
+};
+struct Misc2 {
+  uint64_t a_full[2], a_free[2], act_full[2], acc[2], tile_done[2], bar_w;
+  GridDev grid;
+  uint32_t tmem_base, pad[3];
+  alignas(16) float wdir[kPeDir][64];
+  alignas(16) float b0[64];
+  alignas(16) float b1[64];
+  alignas(16) float wsig[64];
+  alignas(16) float wrgb[64][4];
+  GroupMisc2 grp[2];
+};
+constexpr int kV2SmemBytes = 2 * kV2ABytes + 2 * kV2ActBytes + kV2WBytes + (int)sizeof(Misc2);
+static_assert(kV2SmemBytes <= 232448, "shared memory budget");
+static_assert(offsetof(Misc2, wdir) % 16 == 0 && offsetof(Misc2, grp) % 16 == 0 && offsetof(GroupMisc2, bias) % 16 == 0, "alignment");
+
+template <typename T>
+__global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const CoarseArgs a, const uint8_t* __restrict__ blob, const int ablate, long long* __restrict__ trace) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* As = smem;                                   // [2 groups][40 KB]
+  uint8_t* Act = smem + 2 * kV2ABytes;                  // [2 groups][16 KB]
+  uint8_t* Wsm = Act + 2 * kV2ActBytes;
+  Misc2* m = reinterpret_cast<Misc2*>(Wsm + kV2WBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.n_samples;
+  const int rpt = kRows / S;
+  const int64_t n_tiles = (a.n_rays + rpt - 1) / rpt;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int64_t n_my = (n_pairs > (int64_t)blockIdx.x) ? (n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&m->a_full[q], kV2ProdThreads); mbar_init(&m->a_free[q], 1); mbar_init(&m->act_full[q], kRows);
+      mbar_init(&m->acc[q], 1); mbar_init(&m->tile_done[q], kRows);
+    }
+    mbar_init(&m->bar_w, 1);
+    fence_barrier_init();
+    m->grid = a.grid;
+  }
+  if (warp == kV2WarpMma) tmem_alloc(&m->tmem_base, kV2TmemCols);
+  if (ablate) {      // dev ablations leave parts of the operand tiles unwritten: start from zeros
+    for (int i = tid; i < 2 * kV2ABytes / 16; i += kV2Threads) st_shared_v4(As + i * 16, 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  for (int i = tid; i < kPeDir * 64; i += kV2Threads) m->wdir[i / 64][i % 64] = __ldg(a.mlp.color0_t + (15 + i / 64) * 64 + i % 64);
+  for (int i = tid; i < 64; i += kV2Threads) {
+    m->b0[i] = a.mlp.color0_b ? __ldg(a.mlp.color0_b + i) : 0.f;
+    m->b1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
+    m->wsig[i] = __ldg(a.mlp.sigma1_t + i * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m->wrgb[i][j] = __ldg(a.mlp.color2_t + i * 4 + j);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = m->tmem_base;
+
+  if (warp >= kV2WarpMma) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    const int q = warp - kV2WarpMma;
+    if (q < 2 && n_my > 0) {
+      // =================================== MMA issuer of group q ==========================================================
+      if (q == 0 && elect_one()) { mbar_expect_tx(&m->bar_w, kV2WBytes); bulk_g2s(Wsm, blob + kOffL1, kV2WBytes, &m->bar_w); }
+      __syncwarp();
+      const uint32_t aq = smem_u32(As) + q * kV2ABytes, actq = smem_u32(Act) + q * kV2ActBytes, wb = smem_u32(Wsm);
+      mbar_wait(&m->bar_w, 0);
+      for (int64_t it = 0; it < n_my; ++it) {
+        const uint32_t d_tmem = tmem + q * 128 + (uint32_t)(it & 1) * 64;
+        mbar_wait(&m->a_full[q], (uint32_t)it & 1); tc_fence_after();
+        if (elect_one()) {
+          issue_layer(d_tmem, aq, wb, 10, 64, 2048);                       // [g 96 | PE 64] -> 64
+          mma_commit(&m->acc[q]);
+          mma_commit(&m->a_free[q]);                                        // the producer may refill this group's A tile
+        }
+        __syncwarp();
+        mbar_wait(&m->act_full[q], 0); tc_fence_after();
+        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL2 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q]); }
+        __syncwarp();
+        mbar_wait(&m->act_full[q], 1); tc_fence_after();
+        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL3 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q]); }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp < kV2GatherWarps) {
+    // =================================== producer warps ======================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    const int gwarp = warp & 3, gi = warp >> 2;
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int par = (int)(it & 1);
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        auto stamp = [&](int k) { if (trace && blockIdx.x == 0 && tid == 0 && it >= 8 && it < 12) trace[((it - 8) * 2 + q) * 8 + k] = clock64(); };
+        stamp(0);
+        if (it > 0) {      // one polling warp, the rest blocks in a named barrier
+          if (warp == 0) {
+            mbar_wait(&m->a_free[q], (uint32_t)(it - 1) & 1);
+            if (it >= 2) mbar_wait(&m->tile_done[q], (uint32_t)(it - 2) & 1);
+          }
+          named_bar_sync(5, kV2ProdThreads);
+        }
+        stamp(1);
+        const int64_t tile = 2 * ((int64_t)blockIdx.x + it * gridDim.x) + q;
+        uint8_t* Aq = As + q * kV2ABytes;
+        GroupMisc2* gm = &m->grp[q];
+        if (ablate & 2) {
+        } else if (warp < 4) {
+          // ---- sample depth + PE(pts) of row r -> A chunks 12..19 ------------------------------------------------------------
+          const int r = warp * 32 + lane;
+          const int lr = min(r / S, rpt - 1), sm = (r / S < rpt) ? r - lr * S : S - 1;
+          const int64_t ray = min(tile * rpt + lr, a.n_rays - 1);
+          const float* rb = a.ray_batch + ray * 11;
+          const float zv = place_sample(a, ray, sm, __ldg(rb + 6), __ldg(rb + 7));
+          gm->z[par][r] = zv;
+          float pe[64];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            pe[i] = __fadd_rn(__ldg(rb + i), __fmul_rn(__ldg(rb + 3 + i), zv));
+            fast_sincos(pe[i], &pe[3 + i], &pe[6 + i]);
+          }
+#pragma unroll
+          for (int f = 1; f < kPeFreqPts; ++f) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float sp = pe[3 + 6 * (f - 1) + i], cp = pe[6 + 6 * (f - 1) + i];
+              pe[3 + 6 * f + i] = 2.0f * sp * cp;
+              pe[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+            }
+          }
+          pe[63] = 0.f;
+          uint8_t* a_row = Aq + r * 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(a_row + (12 + j) * kChunkA, pack_bf16x2(pe[8 * j], pe[8 * j + 1]), pack_bf16x2(pe[8 * j + 2], pe[8 * j + 3]),
+                         pack_bf16x2(pe[8 * j + 4], pe[8 * j + 5]), pack_bf16x2(pe[8 * j + 6], pe[8 * j + 7]));
+        } else if (warp < 8) {
+          // ---- per-ray bias of color_net.0: b0 + W0[:, 15:42] . PE(viewdir), fp32 ---------------------------------------------
+#pragma unroll 1
+          for (int idx = (warp - 4) * 32 + lane; idx < rpt * 64; idx += kRows) {
+            const int br = idx >> 6, col = idx & 63;
+            const int64_t bray = min(tile * rpt + br, a.n_rays - 1);
+            const float* rb2 = a.ray_batch + bray * 11;
+            float ped[kPeDir];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { ped[i] = __ldg(rb2 + 8 + i); fast_sincos(ped[i], &ped[3 + i], &ped[6 + i]); }
+#pragma unroll
+            for (int f = 1; f < kPeFreqDir; ++f) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const float sp = ped[3 + 6 * (f - 1) + i], cp = ped[6 + 6 * (f - 1) + i];
+                ped[3 + 6 * f + i] = 2.0f * sp * cp;
+                ped[6 + 6 * f + i] = fmaf(-2.0f * sp, sp, 1.0f);
+              }
+            }
+            float b = m->b0[col];
+#pragma unroll
+            for (int j = 0; j < kPeDir; ++j) b = fmaf(m->wdir[j][col], ped[j], b);
+            gm->bias[par][br][col] = b;
+          }
+        }
+        stamp(2);
+        // ---- VM gather: warp (gwarp, gi) handles points 32 gwarp + 8 gi .. + 7; the depth is recomputed (same function, same bits) ----
+        if (!(ablate & 1)) gather_points<T>(m->grid, Aq, 0, gwarp, lane, gi, gi + 1, [&](int pt, float (&p)[3]) {
+          const int plr = min(pt / S, rpt - 1), ps = (pt / S < rpt) ? pt - plr * S : S - 1;
+          const int64_t pray = min(tile * rpt + plr, a.n_rays - 1);
+          const float* rbp = a.ray_batch + pray * 11;
+          const float zp = place_sample(a, pray, ps, __ldg(rbp + 6), __ldg(rbp + 7));
+#pragma unroll
+          for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(__ldg(rbp + i), __fmul_rn(__ldg(rbp + 3 + i), zp));
+        });
+        stamp(3);
+        fence_proxy_async_smem();
+        mbar_arrive(&m->a_full[q]);
+      }
+    }
+  } else {
+    // =================================== epilogue warps: group q, ONE thread per row ============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    const int ew = warp - kV2GatherWarps;
+    const int q = ew >> 2, gwarp = ew & 3;
+    const int r = gwarp * 32 + lane;
+    GroupMisc2* gm = &m->grp[q];
+    uint8_t* act_row = Act + q * kV2ActBytes + r * 16;
+    const int bar_id = 1 + q;
+    uint32_t pacc = 0;
+    const int lr = min(r / S, rpt - 1), s = (r / S < rpt) ? r - lr * S : S - 1;
+    const bool row_valid = r < rpt * S;
+    const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
+    auto wait_acc = [&]() {
+      if (gwarp == 0) mbar_wait(&m->acc[q], pacc);
+      pacc ^= 1;
+      named_bar_sync(bar_id, kRows);
+      tc_fence_after();
+    };
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int par = (int)(it & 1);
+      const int64_t tile = 2 * ((int64_t)blockIdx.x + it * gridDim.x) + q;
+      const int64_t ray_raw = tile * rpt + lr;
+      const bool live = row_valid && ray_raw < a.n_rays;
+      const int64_t ray = ray_raw < a.n_rays ? ray_raw : a.n_rays - 1;
+      const float* rb = a.ray_batch + ray * 11;
+      const uint32_t taddr_row = tmem + ((uint32_t)(gwarp * 32) << 16) + q * 128 + (uint32_t)par * 64;
+      // global operands of the compositing, loaded a whole MLP chain ahead of their use
+      const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+      const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+      const bool is_last = (s == S - 1);
+      const float nz = (a.noise && !is_last) ? __ldg(a.noise + ray * (S - 1) + s) : 0.f;
+      auto estamp = [&](int k) { if (trace && blockIdx.x == 0 && r == 0 && it >= 8 && it < 12) trace[64 + ((it - 8) * 2 + q) * 8 + k] = clock64(); };
+      estamp(0);
+      // ---- stage 1: [g | PE] -> 64, ReLU; sigma head = fp32 dot with sigma_net.1 row 0 -----------------------------------------
+      wait_acc();
+      estamp(1);
+      float sg = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols<32>(taddr_row, 32 * h, true, nullptr, act_row, f, true);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sg = fmaf(f[i], m->wsig[32 * h + i], sg);
+      }
+      rows_signal(&m->act_full[q]);
+      estamp(2);
+      // ---- stage 2: color_net.0 (+ per-ray view-direction bias), ReLU ----------------------------------------------------------------
+      wait_acc();
+      estamp(3);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols<32>(taddr_row, 32 * h, true, gm->bias[par][lr], act_row, f, true);
+      }
+      rows_signal(&m->act_full[q]);
+      estamp(4);
+      // ---- stage 3: color_net.1, ReLU -> rgb head (fp32) ---------------------------------------------------------------------------
+      wait_acc();
+      estamp(5);
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols<32>(taddr_row, 32 * h, true, m->b1, act_row, f, false);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(&m->wrgb[32 * h + i][0]);
+          c0 = fmaf(f[i], w.x, c0); c1 = fmaf(f[i], w.y, c1); c2 = fmaf(f[i], w.z, c2);
+        }
+      }
+      tc_fence_before();
+      estamp(6);
+      // ---- compositing (voxnerf.py:153-201): per-row alpha, warp-shuffle transmittance scan, per-ray sums -----------------------------
+      const float zv = gm->z[par][r];
+      const float z_next = gm->z[par][min(r + 1, kRows - 1)];
+      const float alpha = row_valid ? alpha_of_sample(sg, zv, z_next, nz, dnorm, mask_near, a.rmnearplane / 128.0f, is_last) : 0.f;
+      float cr = sigmoidf_(c0 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 0) : 0.f));
+      float cg = sigmoidf_(c1 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 1) : 0.f));
+      float cb = sigmoidf_(c2 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 2) : 0.f));
+      float t = 1.0f - alpha;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, t, dlt);
+        if (lane >= dlt) t *= y;
+      }
+      float Tr = __shfl_up_sync(0xffffffffu, t, 1);
+      if (lane == 0) Tr = 1.0f;
+      if (lane == 31) gm->wtot[gwarp] = t;
+      named_bar_sync(bar_id, kRows);
+      const int wpr = S >> 5, first = (gwarp / wpr) * wpr;       // warps per ray, first warp of this row's ray
+      for (int w2 = first; w2 < gwarp; ++w2) Tr *= gm->wtot[w2];
+      const float wgt = alpha * Tr;
+      if (a.flags & EDN_FLAG_RELU_RGB) { cr = fmaxf(cr, 0.f); cg = fmaxf(cg, 0.f); cb = fmaxf(cb, 0.f); }
+      float red[5] = {wgt * cr, wgt * cg, wgt * cb, wgt * zv, wgt};
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], off);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) gm->red[gwarp][i] = red[i];
+      }
+      named_bar_sync(bar_id, kRows);
+      if (r < rpt * 5) {
+        const int rr = r / 5, i = r % 5;
+        const int64_t r2 = tile * rpt + rr;
+        if (r2 < a.n_rays) {
+          float sum = 0.f;
+          for (int w2 = rr * wpr; w2 < (rr + 1) * wpr; ++w2) sum += gm->red[w2][i];
+          if (i < 3) a.rgb[r2 * 3 + i] = sum; else if (i == 3) a.depth[r2] = sum; else a.acc[r2] = sum;
+        }
+      }
+      if (live) {
+        a.z_vals[ray * S + s] = zv;
+        a.weights[ray * S + s] = wgt;
+      }
+      named_bar_sync(bar_id, kRows);          // red[] / wtot[] are rewritten by the next tile
+      mbar_arrive(&m->tile_done[q]);
+      estamp(7);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kV2WarpMma) tmem_dealloc(tmem, kV2TmemCols);
+}
+
 // C[M][N] = A[M][K] . B[K][N] (row-major fp32): weight folding at pack time only
 __global__ void fold_matmul_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ Cm, int ldc,
                                    int M, int K, int N) {
@@ -424,6 +756,35 @@ int launch_coarse_tc(const CoarseArgs& a, int grid_dtype, cudaStream_t st) {
   const unsigned gx = (unsigned)(n_pairs < (int64_t)num_sms() ? n_pairs : (int64_t)num_sms());
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob);
   const bool lean = a.feat == nullptr;            // the geo feature_map only exists in the full schedule
+  static const bool force_v1 = getenv("EDN_COARSE_V1") != nullptr;      // dev switch: round 1's coupled kernel
+  static const int ablate = getenv("EDN_COARSE_ABLATE") ? atoi(getenv("EDN_COARSE_ABLATE")) : 0;   // dev timing ablations: 1 no gather, 2 no PE / bias
+  if (lean && (a.n_samples & 31) == 0 && !force_v1) {
+    static const bool want_trace = getenv("EDN_COARSE_TRACE") != nullptr;      // dev: clock64 time line of CTA 0, tiles 8..11 of each group
+    long long* trace = nullptr;
+    if (want_trace) { EDN_CUDA_OK(cudaMalloc(&trace, 128 * sizeof(long long))); EDN_CUDA_OK(cudaMemsetAsync(trace, 0, 128 * sizeof(long long), st)); }
+    if (grid_dtype == EDN_BF16) {
+      EDN_CUDA_OK(cudaFuncSetAttribute(coarse_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes));
+      coarse_fwd_tc2_kernel<__nv_bfloat16><<<gx, kV2Threads, kV2SmemBytes, st>>>(a, blob, ablate, trace);
+    } else {
+      EDN_CUDA_OK(cudaFuncSetAttribute(coarse_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes));
+      coarse_fwd_tc2_kernel<float><<<gx, kV2Threads, kV2SmemBytes, st>>>(a, blob, ablate, trace);
+    }
+    EDN_CUDA_OK(cudaGetLastError());
+    if (trace) {
+      long long h[128];
+      EDN_CUDA_OK(cudaStreamSynchronize(st));
+      EDN_CUDA_OK(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(trace);
+      const long long t0 = h[0];
+      for (int role = 0; role < 2; ++role)
+        for (int i = 0; i < 8; ++i) {
+          printf("[coarse2 %s it=%d q=%d]", role ? "epi " : "prod", 8 + i / 2, i & 1);
+          for (int k = 0; k < (role ? 8 : 4); ++k) printf(" s%d=%lld", k, h[role * 64 + i * 8 + k] - t0);
+          printf("\n");
+        }
+    }
+    return EDN_OK;
+  }
   if (grid_dtype == EDN_BF16)
     return lean ? launch_variant<__nv_bfloat16, true>(a, blob, gx, st) : launch_variant<__nv_bfloat16, false>(a, blob, gx, st);
   return lean ? launch_variant<float, true>(a, blob, gx, st) : launch_variant<float, false>(a, blob, gx, st);
