@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <type_traits>
 #include "common.cuh"
 #include "fine_args.cuh"
 #include "tc_common.cuh"
@@ -445,111 +446,101 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
       float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
       const bool st0 = (ew == 0 && lane == 0);
       if (st0) stamp(2, it, 0);
-#pragma unroll 1
-      for (int L = 0; L < 3; ++L) {
-        // ONE warp polls the mbarrier, the other 15 block in a named barrier: a polling warp re-issues its try_wait loop every ~35
+      // One layer's epilogue; L, the pass (accumulator slot x / y) and the 32-column chunk are COMPILE-TIME constants, so the head
+      // weights' constant-bank offsets are immediates off one uniform base and there is no per-chunk branching (the run-time-L
+      // version spent ~60 % of the epilogue's issue slots on uniform address arithmetic, branches and dead ablation code).
+      auto layer = [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        // ONE warp polls the mbarrier, the others block in a named barrier: a polling warp re-issues its try_wait loop every ~35
         // cycles, and sixteen of them took ~40 % of the SM's issue slots from the warps doing the work (ncu source page, round 2)
         if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
         named_bar_sync(4, kEpiThreads);
         if (st0) stamp(2, it, 1 + 2 * L);
         tc_fence_after();
-        // 32 accumulator columns [col0, col0 + 32) of this thread's row
-        auto process = [&](const uint32_t (&v)[32], const int tq, const int c) {
-          const int col0 = tq * 64 + c * 32;
-          float f[32];
+        const float* __restrict__ cwq = cw + th * 64;          // this thread's first quarter; the second one is 128 columns on
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (L == 2 && has_bias1) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = s_bias1[(col0 + i) >> 2];
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-            }
-          }
-          if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (constant-bank operands, 4 accumulators)
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              s0 = fmaf(fmaxf(f[i], 0.f), cw[col0 + i], s0); s1 = fmaf(fmaxf(f[i + 1], 0.f), cw[col0 + i + 1], s1);
-              s2 = fmaf(fmaxf(f[i + 2], 0.f), cw[col0 + i + 2], s2); s3 = fmaf(fmaxf(f[i + 3], 0.f), cw[col0 + i + 3], s3);
-            }
-            sig_part += (s0 + s1) + (s2 + s3);
-          }
-          if (L < 2) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(f[2 * i], f[2 * i + 1]);
-            if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + (col0 >> 1), pk);   // in place: the layer's MMAs are complete
-          } else {             // rgb head: fp32 dot of relu(h3) with color_net.2 (constant-bank operands, 2 accumulators per channel)
-            float r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = fmaxf(f[i], 0.f), x1 = fmaxf(f[i + 1], 0.f);
-              r0 = fmaf(x0, cw[256 + col0 + i], r0); r1 = fmaf(x1, cw[256 + col0 + i + 1], r1);
-              g0 = fmaf(x0, cw[512 + col0 + i], g0); g1 = fmaf(x1, cw[512 + col0 + i + 1], g1);
-              b0 = fmaf(x0, cw[768 + col0 + i], b0); b1 = fmaf(x1, cw[768 + col0 + i + 1], b1);
-            }
-            rr += r0 + r1; rg_ += g0 + g1; rbl += b0 + b1;
-          }
-        };
-        long long t_ld = 0, t_pr = 0, t_st = 0;
-        const bool tr_on = st0 && a.trace && blockIdx.x == 0 && it >= 8 && it < 12;
-#pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {       // quarters th (slot x) then th + 2 (slot y)
           const int tq = th + 2 * pass;
           const uint32_t acc_q = lane_base + kColAcc + ((cs + pass) % 3) * 128 + th * 64;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            long long c0 = tr_on ? clock64() : 0;
-            if (a.ablate & 4) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0u;
-            } else {
-              tmem_ld32(acc_q + c * 32, v);
-              tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            const int cc = pass * 128 + c * 32;       // compile-time offset of the chunk relative to column 64 th
+            uint32_t v[32];
+            tmem_ld32(acc_q + c * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (L == 2 && has_bias1) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = s_bias1[(th * 64 + cc + i) >> 2];
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
             }
-            long long c1 = tr_on ? clock64() : 0;
-            process(v, tq, c);
-            if (tr_on) { const long long c2 = clock64(); t_ld += c1 - c0; t_pr += c2 - c1; }
+            if (L == 0) {        // sigma head: fp32 dot of relu(h1) with sigma_net.1 row 0 (constant-bank operands, 4 accumulators)
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                s0 = fmaf(fmaxf(f[i], 0.f), cwq[cc + i], s0); s1 = fmaf(fmaxf(f[i + 1], 0.f), cwq[cc + i + 1], s1);
+                s2 = fmaf(fmaxf(f[i + 2], 0.f), cwq[cc + i + 2], s2); s3 = fmaf(fmaxf(f[i + 3], 0.f), cwq[cc + i + 3], s3);
+              }
+              sig_part += (s0 + s1) + (s2 + s3);
+            }
+            if (L < 2) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(f[2 * i], f[2 * i + 1]);
+              if (!(a.ablate & 8)) tmem_st16(lane_base + kColA + ((th * 64 + cc) >> 1), pk);   // in place: the layer's MMAs are complete
+            } else {             // rgb head: fp32 dot of relu(h3) with color_net.2 (constant-bank operands, 2 accumulators per channel)
+              float r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float x0 = fmaxf(f[i], 0.f), x1 = fmaxf(f[i + 1], 0.f);
+                r0 = fmaf(x0, cwq[256 + cc + i], r0); r1 = fmaf(x1, cwq[256 + cc + i + 1], r1);
+                g0 = fmaf(x0, cwq[512 + cc + i], g0); g1 = fmaf(x1, cwq[512 + cc + i + 1], g1);
+                b0 = fmaf(x0, cwq[768 + cc + i], b0); b1 = fmaf(x1, cwq[768 + cc + i + 1], b1);
+              }
+              rr += r0 + r1; rg_ += g0 + g1; rbl += b0 + b1;
+            }
           }
-          long long c2 = tr_on ? clock64() : 0;
           // quarter tq of the layer is done: its A' columns are written (and with quarter tq ^ 1 its accumulator slot is drained)
           if (L < 2) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&m->hand[tq]);
-          if (tr_on) t_st += clock64() - c2;
         }
-        if (tr_on) { a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 0] = t_ld; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 1] = t_pr; a.trace[(3 * 4 + (it - 8)) * 16 + L * 3 + 2] = t_st; }
         ++n_use;
         cs += 2;
         if (st0) stamp(2, it, 2 + 2 * L);
-        if (FEAT && L == 0) {
-          // ---- geo layer: 128 fp32 columns of this row -> depth_feature [ray][r][128]; thread th streams columns 64 th .. 64 th + 63
-          if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
-          named_bar_sync(4, kEpiThreads);
-          tc_fence_after();
-          const uint32_t acc_g = lane_base + kColAcc + (cs % 3) * 128 + th * 64;
-          float* gout = (r < S) ? a.feat + ((size_t)ray * S + r) * 128 + th * 64 : nullptr;
+      };
+      layer(std::integral_constant<int, 0>{});
+      if (FEAT) {
+        // ---- geo layer: 128 fp32 columns of this row -> depth_feature [ray][r][128]; thread th streams columns 64 th .. 64 th + 63
+        if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
+        named_bar_sync(4, kEpiThreads);
+        tc_fence_after();
+        const uint32_t acc_g = lane_base + kColAcc + (cs % 3) * 128 + th * 64;
+        float* gout = (r < S) ? a.feat + ((size_t)ray * S + r) * 128 + th * 64 : nullptr;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(acc_g + c * 32, v);
-            tmem_ld_wait();
-            if (gout) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(acc_g + c * 32, v);
+          tmem_ld_wait();
+          if (gout) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(gout + c * 32 + i) =
-                    make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-            }
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(gout + c * 32 + i) =
+                  make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
           }
-          tc_fence_before();
-          mbar_arrive(&m->hand[th]);               // the slot is drained; the A operand was not touched: both of this thread's quarters
-          mbar_arrive(&m->hand[th + 2]);
-          ++n_use;
-          cs += 1;
         }
+        tc_fence_before();
+        mbar_arrive(&m->hand[th]);               // the slot is drained; the A operand was not touched: both of this thread's quarters
+        mbar_arrive(&m->hand[th + 2]);
+        ++n_use;
+        cs += 1;
       }
+      layer(std::integral_constant<int, 1>{});
+      layer(std::integral_constant<int, 2>{});
       m->headp[th][r][0] = rr; m->headp[th][r][1] = rg_; m->headp[th][r][2] = rbl; m->headp[th][r][3] = sig_part;
       named_bar_sync(2, kEpiThreads);               // all four quarters' head partials visible
       if (th == 0) {
@@ -653,11 +644,6 @@ int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, 
         for (int k = 0; k < 8; ++k) if (buf[(r * 4 + i) * 16 + k]) fprintf(stderr, " s%d=%lld", k, buf[(r * 4 + i) * 16 + k] - t0);
         fprintf(stderr, "\n");
       }
-    for (int i = 0; i < 4; ++i) {
-      fprintf(stderr, "[trace2 epi-split it=%d] (ld, process, st+arrive) per layer:", 8 + i);
-      for (int k = 0; k < 9; ++k) fprintf(stderr, " %lld%s", buf[(3 * 4 + i) * 16 + k], k % 3 == 2 ? " |" : "");
-      fprintf(stderr, "\n");
-    }
     cudaFree(buf);
     return EDN_OK;
   }
