@@ -78,7 +78,7 @@ struct Misc {
   uint64_t w_full[kNst], w_empty[kNst];
   uint64_t acc_full, hand[4];           // hand[q]: the epilogue finished quarter q of a layer (A' K 64q..64q+63 written; q = 1 / 3: slot x / y drained)
   GridDev grids[2];
-  uint32_t tmem_base, pad[3];
+  uint32_t tmem_base, round_ctr[2], pad[1];      // round_ctr[buf]: next gather round of the ray going into A_in[buf] (work stealing)
   alignas(16) float bias1[256];
   RaySlot slot[kSlots];
   alignas(16) float headp[4][kRows][4];   // per column quarter: partial rgb (xyz) / sigma (w) heads
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
   for (int i = tid; i < 256; i += kThreads) {
     m->bias1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
   }
-  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
+  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; m->round_ctr[0] = 0; m->round_ctr[1] = 0; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
         if (warp == 0) {
           mbar_wait(&m->a_empty[buf], (use - 1) & 1);
           if (it >= kSlots) mbar_wait(&m->slot_free[sl], (uint32_t)(it / kSlots - 1) & 1);
+          if (lane == 0) m->round_ctr[buf] = 0;      // every warp is past its last pull from this counter (two rays ago)
         }
         named_bar_sync(5, kRoleThreads);
       }
@@ -409,15 +410,24 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc2_kernel(const FineArg
           *reinterpret_cast<uint32_t*>(B_bias + sl * kBiasBBytes + col * 16) = (hi & 0xffffu) | (lo << 16);     // K column 0: hi, 1: lo
         }
       }
-      named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
       if (tid == 0) stamp(0, it, 2);
       if (!(a.ablate & 1)) {      // lean A layout: coarse-grid products in chunks 0..11, fine-grid products in chunks 12..23
-        const float* z_s = slot->z;
-        gather_points<T>(m->grids[half], Aq, half ? 12 : 0, gwarp, lane, 2 * gsub, 2 * gsub + 2, [&](int pt, float (&p)[3]) {
-          const float zv = z_s[pt];
+        // 32 rounds per ray (grid x row group x 8-point group), PULLED from a shared counter: the warps that just did the PE / bias
+        // work take fewer rounds than the others (a fixed 2 rounds per warp left half of the warps 3 k cycles short every ray).
+        // The depths come straight from global memory (the z[] copy in shared memory is for the epilogue), so no barrier is needed.
+        const float* z_g = a.z_vals + ray * S;
+        for (;;) {
+          int k = 0;
+          if (lane == 0) k = (int)atomicAdd(&m->round_ctr[buf], 1u);
+          k = __shfl_sync(0xffffffffu, k, 0);
+          if (k >= 32) break;
+          const int hk = k >> 4, gk = (k >> 2) & 3, gik = k & 3;
+          gather_points<T>(m->grids[hk], Aq, hk ? 12 : 0, gk, lane, gik, gik + 1, [&](int pt, float (&p)[3]) {
+            const float zv = __ldg(z_g + min(pt, S - 1));
 #pragma unroll
-          for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
-        });
+            for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+          });
+        }
       }
       fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&m->a_full[buf]);
