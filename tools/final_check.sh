@@ -26,7 +26,10 @@ ncu --set full --clock-control none --import-source on -k regex:"fine_fwd_tc3" -
 python tools/ncu_summary.py $O/r2_tc_kernels.ncu-rep > $O/r2_tc_kernels_ncu_summary.txt; python tools/ncu_summary.py $O/r2_tc3_kernel.ncu-rep >> $O/r2_tc_kernels_ncu_summary.txt
 # fine kernel: phase trace + timing ablations
 python tools/dev_trace.py 2>&1 | grep trace2 > $O/r2_fine_tc2_phase_trace.txt
-ABL="0 1 2 3 4 8 12 15 16 48" bash tools/dev_ablate.sh > $O/r2_fine_tc2_ablation.txt 2>&1; cat $O/r2_fine_tc2_ablation.txt
+ABL="0 1 2 3 8 16 48" bash tools/dev_ablate.sh > $O/r2_fine_tc2_ablation.txt 2>&1; cat $O/r2_fine_tc2_ablation.txt
+# coarse kernel: producer / epilogue time line of CTA 0 and timing ablations (1 no gather, 2 no PE / bias; outputs invalid)
+EDN_COARSE_TRACE=1 python bench.py --steps 1 --warmup 3 --no-train --no-cpu-baseline 2>/dev/null | grep coarse2 | tail -16 > $O/r2_coarse_tc2_phase_trace.txt
+ABL="0 1 2 3" bash tools/dev_coarse.sh > $O/r2_coarse_tc2_ablation.txt 2>&1; cat $O/r2_coarse_tc2_ablation.txt
 # sweep (config 5), one GPU
 python tools/sweep.py > $O/r2_sweep.jsonl 2>/dev/null; wc -l $O/r2_sweep.jsonl
 # memcheck over smoke (the three precisions + the backward)
