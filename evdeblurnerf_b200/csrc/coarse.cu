@@ -209,6 +209,7 @@ extern "C" int edn_render_coarse_fwd(const edn_vm_grid* grid, const edn_field_ml
   a.z_vals = z_vals; a.weights = weights; a.rgb = rgb; a.depth = depth; a.acc = acc; a.feat = feat;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == EDN_BF16) return launch_coarse_tc(a, grid->dtype, st);
+  if (precision == EDN_TC32) return launch_coarse_tc3(a, grid->dtype, st);
   EDN_REQUIRE(precision == EDN_F32, "edn_render_coarse_fwd: bad precision %d", precision);
   const int rpb = kCoarseThreads / n_samples;
   const int64_t n_groups = (n_rays + rpb - 1) / rpb;

@@ -41,5 +41,6 @@ __device__ __forceinline__ float place_sample(const CoarseArgs& a, int64_t ray, 
 
 
 int launch_coarse_tc(const CoarseArgs& a, int grid_dtype, cudaStream_t st);   // coarse_tc.cu
+int launch_coarse_tc3(const CoarseArgs& a, int grid_dtype, cudaStream_t st);  // coarse_tc.cu: bf16 x 3 parity kernel (EDN_TC32)
 
 }  // namespace edn

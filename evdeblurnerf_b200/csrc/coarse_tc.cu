@@ -727,6 +727,314 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
   if (warp == kV2WarpMma) tmem_dealloc(tmem, kV2TmemCols);
 }
 
+// ======================================================================================================================================
+// Tensor-core PARITY coarse kernel (precision EDN_TC32, lean schedule): fine_tc3.cu's "bf16 x 3" recipe on the coarse pass.  Every GEMM
+// operand (gathered products, PE, activations AND weights) is split into bf16 hi + bf16 lo, every K-step issues three MMAs (hi.hi +
+// lo.hi + hi.lo) into one fp32 TMEM accumulator; everything around the GEMMs is the fp32 SIMT kernel's arithmetic (fp32 grids and
+// taps, sincosf positional encodings, fp32 heads, bit-exact sample placement).  One group per CTA (two A tiles + two activation
+// buffers + 72 KB of split weights fill the shared memory), the v2 roles: 16 producer warps, 4 epilogue warps (one thread per row),
+// 1 MMA warp; two 64-column TMEM accumulators by tile parity.
+constexpr int kT3EpiWarps = 4;
+constexpr int kT3WarpMma = kV2GatherWarps + kT3EpiWarps;                  // 20
+constexpr int kT3Threads = (kV2GatherWarps + kT3EpiWarps + 4) * 32;       // 768 (a whole warpgroup for the MMA warp: setmaxnreg)
+constexpr int kT3WBytes = 2 * kV2WBytes;             // [L1 hi | L1 lo | L2 hi | L2 lo | L3 hi | L3 lo]
+constexpr int kT3OffL1 = 0, kT3OffL2 = 2 * 20480, kT3OffL3 = kT3OffL2 + 2 * 8192;
+constexpr uint32_t kT3TmemCols = 128;
+
+struct Misc3 {
+  uint64_t a_full, a_free, act_full, acc, tile_done, bar_w;
+  GridDev grid;
+  uint32_t tmem_base, pad[3];
+  alignas(16) float wdir[kPeDir][64];
+  alignas(16) float b0[64];
+  alignas(16) float b1[64];
+  alignas(16) float wsig[64];
+  alignas(16) float wrgb[64][4];
+  GroupMisc2 grp;
+};
+constexpr int kT3SmemBytes = 2 * kV2ABytes + 2 * kV2ActBytes + kT3WBytes + (int)sizeof(Misc3);
+static_assert(kT3SmemBytes <= 232448, "shared memory budget");
+static_assert(offsetof(Misc3, wdir) % 16 == 0 && offsetof(Misc3, grp) % 16 == 0, "alignment");
+
+// 32 accumulator columns -> (+bias) -> ReLU -> f[]; optionally the hi / lo split -> the two activation tiles
+__device__ __forceinline__ void epi_cols_split(uint32_t taddr, int col0, const float* bias_s, uint8_t* hi_row, uint8_t* lo_row, float (&f)[32],
+                                               bool store) {
+  uint32_t v[32];
+  tmem_ld32(taddr + col0, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (bias_s) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
+      f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  if (store) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16x2(f[8 * j + 2 * i], f[8 * j + 2 * i + 1], hi[i], lo[i]);
+      st_shared_v4(hi_row + (col0 / 8 + j) * kChunkA, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(lo_row + (col0 / 8 + j) * kChunkA, lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// hi.hi + lo.hi + hi.lo per K-step (N = 64)
+__device__ __forceinline__ void issue_layer3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ksteps) {
+  const uint32_t idesc = make_idesc_bf16(128, 64);
+  for (int j = 0; j < ksteps; ++j) {
+    const uint64_t ah = make_smem_desc(a_hi + 2 * j * kChunkA, kChunkA, 128), al = make_smem_desc(a_lo + 2 * j * kChunkA, kChunkA, 128);
+    const uint64_t bh = make_smem_desc(b_hi + j * 2048, 64u * 16u, 128), bl = make_smem_desc(b_lo + j * 2048, 64u * 16u, 128);
+    mma_bf16_ss(d_tmem, ah, bh, idesc, j > 0);
+    mma_bf16_ss(d_tmem, al, bh, idesc, 1);
+    mma_bf16_ss(d_tmem, ah, bl, idesc, 1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const CoarseArgs a, const uint8_t* __restrict__ blob3) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* A_hi = smem;
+  uint8_t* A_lo = smem + kV2ABytes;
+  uint8_t* Act_hi = smem + 2 * kV2ABytes;
+  uint8_t* Act_lo = Act_hi + kV2ActBytes;
+  uint8_t* Wsm = Act_lo + kV2ActBytes;
+  Misc3* m = reinterpret_cast<Misc3*>(Wsm + kT3WBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.n_samples;
+  const int rpt = kRows / S;
+  const int64_t n_tiles = (a.n_rays + rpt - 1) / rpt;
+  const int64_t n_my = (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    mbar_init(&m->a_full, kV2ProdThreads); mbar_init(&m->a_free, 1); mbar_init(&m->act_full, kRows);
+    mbar_init(&m->acc, 1); mbar_init(&m->tile_done, kRows); mbar_init(&m->bar_w, 1);
+    fence_barrier_init();
+    m->grid = a.grid;
+  }
+  if (warp == kT3WarpMma) tmem_alloc(&m->tmem_base, kT3TmemCols);
+  for (int i = tid; i < kPeDir * 64; i += kT3Threads) m->wdir[i / 64][i % 64] = __ldg(a.mlp.color0_t + (15 + i / 64) * 64 + i % 64);
+  for (int i = tid; i < 64; i += kT3Threads) {
+    m->b0[i] = a.mlp.color0_b ? __ldg(a.mlp.color0_b + i) : 0.f;
+    m->b1[i] = a.mlp.color1_b ? __ldg(a.mlp.color1_b + i) : 0.f;
+    m->wsig[i] = __ldg(a.mlp.sigma1_t + i * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m->wrgb[i][j] = __ldg(a.mlp.color2_t + i * 4 + j);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = m->tmem_base;
+  GroupMisc2* gm = &m->grp;
+
+  if (warp >= kT3WarpMma) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == kT3WarpMma && n_my > 0) {
+      // =================================== MMA issuer ==========================================================================
+      if (elect_one()) { mbar_expect_tx(&m->bar_w, kT3WBytes); bulk_g2s(Wsm, blob3, kT3WBytes, &m->bar_w); }
+      __syncwarp();
+      const uint32_t ah = smem_u32(A_hi), al = smem_u32(A_lo), ch = smem_u32(Act_hi), cl = smem_u32(Act_lo), wb = smem_u32(Wsm);
+      mbar_wait(&m->bar_w, 0);
+      for (int64_t it = 0; it < n_my; ++it) {
+        const uint32_t d_tmem = tmem + (uint32_t)(it & 1) * 64;
+        mbar_wait(&m->a_full, (uint32_t)it & 1); tc_fence_after();
+        if (elect_one()) {
+          issue_layer3(d_tmem, ah, al, wb + kT3OffL1, wb + kT3OffL1 + 20480, 10);
+          mma_commit(&m->acc);
+          mma_commit(&m->a_free);
+        }
+        __syncwarp();
+        mbar_wait(&m->act_full, 0); tc_fence_after();
+        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL2, wb + kT3OffL2 + 8192, 4); mma_commit(&m->acc); }
+        __syncwarp();
+        mbar_wait(&m->act_full, 1); tc_fence_after();
+        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL3, wb + kT3OffL3 + 8192, 4); mma_commit(&m->acc); }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp < kV2GatherWarps) {
+    // =================================== producer warps ======================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");      // pool: 768 x 80 = 61440 >= 512 x 88 + 128 x 80 + 128 x 24
+    const int gwarp = warp & 3, gi = warp >> 2;
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int par = (int)(it & 1);
+      if (it > 0) {
+        if (warp == 0) {
+          mbar_wait(&m->a_free, (uint32_t)(it - 1) & 1);
+          if (it >= 2) mbar_wait(&m->tile_done, (uint32_t)(it - 2) & 1);
+        }
+        named_bar_sync(5, kV2ProdThreads);
+      }
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      if (warp < 4) {
+        // ---- sample depth + PE(pts) of row r (the fp32 kernel's arithmetic: sincosf(p 2^f)) -> A chunks 12..19, hi / lo -----------
+        const int r = warp * 32 + lane;
+        const int lr = min(r / S, rpt - 1), sm = (r / S < rpt) ? r - lr * S : S - 1;
+        const int64_t ray = min(tile * rpt + lr, a.n_rays - 1);
+        const float* rb = a.ray_batch + ray * 11;
+        const float zv = place_sample(a, ray, sm, __ldg(rb + 6), __ldg(rb + 7));
+        gm->z[par][r] = zv;
+        float pe[64];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pe[i] = __fadd_rn(__ldg(rb + i), __fmul_rn(__ldg(rb + 3 + i), zv));
+#pragma unroll
+        for (int f = 0; f < kPeFreqPts; ++f) {
+          const float fr = (float)(1 << f);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sincosf(pe[i] * fr, &pe[3 + 6 * f + i], &pe[6 + 6 * f + i]);
+        }
+        pe[63] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_bf16x2(pe[8 * j + 2 * i], pe[8 * j + 2 * i + 1], hi[i], lo[i]);
+          st_shared_v4(A_hi + r * 16 + (12 + j) * kChunkA, hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(A_lo + r * 16 + (12 + j) * kChunkA, lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else if (warp < 8) {
+        // ---- per-ray bias of color_net.0: b0 + W0[:, 15:42] . PE(viewdir), the fp32 kernel's arithmetic ------------------------------
+#pragma unroll 1
+        for (int idx = (warp - 4) * 32 + lane; idx < rpt * 64; idx += kRows) {
+          const int br = idx >> 6, col = idx & 63;
+          const int64_t bray = min(tile * rpt + br, a.n_rays - 1);
+          const float* rb2 = a.ray_batch + bray * 11;
+          const float vd[3] = {__ldg(rb2 + 8), __ldg(rb2 + 9), __ldg(rb2 + 10)};
+          float b = m->b0[col];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) b = fmaf(m->wdir[i][col], vd[i], b);
+#pragma unroll 1
+          for (int f = 0; f < kPeFreqDir; ++f) {
+            const float fr = (float)(1 << f);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              float sn, cs;
+              sincosf(vd[i] * fr, &sn, &cs);
+              b = fmaf(m->wdir[3 + 6 * f + i][col], sn, b);
+              b = fmaf(m->wdir[6 + 6 * f + i][col], cs, b);
+            }
+          }
+          gm->bias[par][br][col] = b;
+        }
+      }
+      gather_points_split<T>(m->grid, A_hi, A_lo, 0, gwarp, lane, gi, gi + 1, [&](int pt, float (&p)[3]) {
+        const int plr = min(pt / S, rpt - 1), ps = (pt / S < rpt) ? pt - plr * S : S - 1;
+        const int64_t pray = min(tile * rpt + plr, a.n_rays - 1);
+        const float* rbp = a.ray_batch + pray * 11;
+        const float zp = place_sample(a, pray, ps, __ldg(rbp + 6), __ldg(rbp + 7));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(__ldg(rbp + i), __fmul_rn(__ldg(rbp + 3 + i), zp));
+      });
+      fence_proxy_async_smem();
+      mbar_arrive(&m->a_full);
+    }
+  } else {
+    // =================================== epilogue warps: ONE thread per row =====================================================
+    const int gwarp = warp - kV2GatherWarps;      // (stays at the launch allocation of 80 registers)
+    const int r = gwarp * 32 + lane;
+    uint8_t* hi_row = Act_hi + r * 16;
+    uint8_t* lo_row = Act_lo + r * 16;
+    uint32_t pacc = 0;
+    const int lr = min(r / S, rpt - 1), s = (r / S < rpt) ? r - lr * S : S - 1;
+    const bool row_valid = r < rpt * S;
+    const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
+    auto wait_acc = [&]() {
+      if (gwarp == 0) mbar_wait(&m->acc, pacc);
+      pacc ^= 1;
+      named_bar_sync(1, kRows);
+      tc_fence_after();
+    };
+    for (int64_t it = 0; it < n_my; ++it) {
+      const int par = (int)(it & 1);
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      const int64_t ray_raw = tile * rpt + lr;
+      const bool live = row_valid && ray_raw < a.n_rays;
+      const int64_t ray = ray_raw < a.n_rays ? ray_raw : a.n_rays - 1;
+      const float* rb = a.ray_batch + ray * 11;
+      const uint32_t taddr_row = tmem + ((uint32_t)(gwarp * 32) << 16) + (uint32_t)par * 64;
+      const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+      const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+      const bool is_last = (s == S - 1);
+      const float nz = (a.noise && !is_last) ? __ldg(a.noise + ray * (S - 1) + s) : 0.f;
+      wait_acc();
+      float sg = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols_split(taddr_row, 32 * h, nullptr, hi_row, lo_row, f, true);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sg = fmaf(f[i], m->wsig[32 * h + i], sg);
+      }
+      rows_signal(&m->act_full);
+      wait_acc();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols_split(taddr_row, 32 * h, gm->bias[par][lr], hi_row, lo_row, f, true);
+      }
+      rows_signal(&m->act_full);
+      wait_acc();
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+        epi_cols_split(taddr_row, 32 * h, m->b1, hi_row, lo_row, f, false);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(&m->wrgb[32 * h + i][0]);
+          c0 = fmaf(f[i], w.x, c0); c1 = fmaf(f[i], w.y, c1); c2 = fmaf(f[i], w.z, c2);
+        }
+      }
+      tc_fence_before();
+      const float zv = gm->z[par][r];
+      const float z_next = gm->z[par][min(r + 1, kRows - 1)];
+      gm->sig[r] = row_valid ? alpha_of_sample(sg, zv, z_next, nz, dnorm, mask_near, a.rmnearplane / 128.0f, is_last) : 0.f;
+      gm->rgb[3 * r + 0] = sigmoidf_(c0 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 0) : 0.f));
+      gm->rgb[3 * r + 1] = sigmoidf_(c1 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 1) : 0.f));
+      gm->rgb[3 * r + 2] = sigmoidf_(c2 + (a.mlp.color2_b ? __ldg(a.mlp.color2_b + 2) : 0.f));
+      named_bar_sync(1, kRows);
+      // one thread per ray composites in sample order: the fp32 kernel's summation order (parity mode)
+      if (r < rpt) {
+        const int64_t r2 = tile * rpt + r;
+        if (r2 < a.n_rays) {
+          float out[5];
+          composite_from_alpha(gm->sig + r * S, gm->rgb + 3 * r * S, gm->z[par] + r * S, S, (a.flags & EDN_FLAG_RELU_RGB) != 0, gm->w + r * S, out);
+          a.rgb[r2 * 3 + 0] = out[0]; a.rgb[r2 * 3 + 1] = out[1]; a.rgb[r2 * 3 + 2] = out[2];
+          a.depth[r2] = out[3];
+          a.acc[r2] = out[4];
+        }
+      }
+      named_bar_sync(1, kRows);
+      if (live) {
+        a.z_vals[ray * S + s] = zv;
+        a.weights[ray * S + s] = gm->w[r];
+      }
+      named_bar_sync(1, kRows);
+      mbar_arrive(&m->tile_done);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kT3WarpMma) tmem_dealloc(tmem, kT3TmemCols);
+}
+
+// [K][N] fp32 layer -> bf16 hi (split = 0) or lo = bf16(w - hi) (split = 1) in the UMMA K-major layout of tc::pack_layer_kernel
+__global__ void pack_layer_split_generic_kernel(const float* __restrict__ wt, int ld, int K, int N, int split, __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int k = i / N, n = i - k * N;
+  const float w = wt[(size_t)k * ld + n];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  dst[(size_t)(k / 16) * (N * 16) + ((k % 16) / 8) * (N * 8) + n * 8 + (k % 8)] = split ? __float2bfloat16_rn(w - __bfloat162float(hi)) : hi;
+}
+
 // C[M][N] = A[M][K] . B[K][N] (row-major fp32): weight folding at pack time only
 __global__ void fold_matmul_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ Cm, int ldc,
                                    int M, int K, int N) {
@@ -747,6 +1055,25 @@ int launch_variant(const CoarseArgs& a, const uint8_t* blob, unsigned gx, cudaSt
 }
 
 }  // namespace
+
+int launch_coarse_tc3(const CoarseArgs& a, int grid_dtype, cudaStream_t st) {
+  EDN_REQUIRE(a.n_samples >= 32 && a.n_samples <= kRows, "edn_render_coarse_fwd(tc32): n_samples must be in [32,128], got %d", a.n_samples);
+  EDN_REQUIRE(a.mlp.tc_blob != nullptr, "edn_render_coarse_fwd(tc32): edn_field_mlp.tc_blob is NULL (call edn_pack_coarse_tc)");
+  EDN_REQUIRE(a.feat == nullptr, "edn_render_coarse_fwd(tc32): feature_map is emitted by the fp32 path only");
+  const int rpt = kRows / a.n_samples;
+  const int64_t n_tiles = (a.n_rays + rpt - 1) / rpt;
+  const unsigned gx = (unsigned)(n_tiles < (int64_t)num_sms() ? n_tiles : (int64_t)num_sms());
+  const uint8_t* blob3 = reinterpret_cast<const uint8_t*>(a.mlp.tc_blob) + kWBytes;
+  if (grid_dtype == EDN_BF16) {
+    EDN_CUDA_OK(cudaFuncSetAttribute(coarse_fwd_tc3_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    coarse_fwd_tc3_kernel<__nv_bfloat16><<<gx, kT3Threads, kT3SmemBytes, st>>>(a, blob3);
+  } else {
+    EDN_CUDA_OK(cudaFuncSetAttribute(coarse_fwd_tc3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    coarse_fwd_tc3_kernel<float><<<gx, kT3Threads, kT3SmemBytes, st>>>(a, blob3);
+  }
+  EDN_CUDA_OK(cudaGetLastError());
+  return EDN_OK;
+}
 
 int launch_coarse_tc(const CoarseArgs& a, int grid_dtype, cudaStream_t st) {
   EDN_REQUIRE(a.n_samples >= 32 && a.n_samples <= kRows, "edn_render_coarse_fwd(bf16): n_samples must be in [32,128], got %d", a.n_samples);
@@ -792,7 +1119,7 @@ int launch_coarse_tc(const CoarseArgs& a, int grid_dtype, cudaStream_t st) {
 
 }  // namespace edn
 
-extern "C" int64_t edn_coarse_tc_blob_bytes(void) { return edn::kWBytes; }
+extern "C" int64_t edn_coarse_tc_blob_bytes(void) { return edn::kWBytes + edn::kT3WBytes; }      // bf16 schedules + the bf16 x 3 (tc32) section
 extern "C" int64_t edn_coarse_tc_pack_workspace_floats(void) { return 160 * 64 + 64 * 64; }
 
 extern "C" int edn_pack_coarse_tc(const edn_field_mlp* mlp, const float* basis_t, float* workspace, void* blob, void* stream) {
@@ -819,6 +1146,16 @@ extern "C" int edn_pack_coarse_tc(const edn_field_mlp* mlp, const float* basis_t
     const int total = src[L].K * src[L].N;
     tc::pack_layer_kernel<<<(total + 255) / 256, 256, 0, st>>>(src[L].wt, src[L].ld, src[L].kv, src[L].nv, src[L].K, src[L].N, src[L].rot,
                                                                reinterpret_cast<__nv_bfloat16*>(b + src[L].off));
+  }
+  // bf16 x 3 section (precision EDN_TC32): the three lean layers as hi / lo pairs, right behind the bf16 schedules
+  {
+    const float* lw[3] = {f1, f2, mlp->color1_t};
+    const int lk[3] = {160, 64, 64};
+    const int loff[3] = {kT3OffL1, kT3OffL2, kT3OffL3};
+    for (int L = 0; L < 3; ++L)
+      for (int split = 0; split < 2; ++split)
+        pack_layer_split_generic_kernel<<<(lk[L] * 64 + 255) / 256, 256, 0, st>>>(
+            lw[L], 64, lk[L], 64, split, reinterpret_cast<__nv_bfloat16*>(b + kWBytes + loff[L] + split * lk[L] * 64 * 2));
   }
   EDN_CUDA_OK(cudaGetLastError());
   return EDN_OK;

@@ -234,7 +234,7 @@ class RenderEngine(SamplerHost):
         self.params = {k: v.detach().float().contiguous() for k, v in P.items() if k.startswith(("mlp_coarse.", "mlp_fine."))}
         grid_dtype = self.prec_code
         self.coarse = PackedField(P, "mlp_coarse.", self.aabb_min, self.aabb_max, True, grid_dtype)
-        if self.prec_code == EDN_BF16:
+        if self.prec_code == EDN_BF16 or self.precision == "tc32":
             self.coarse.pack_tensor_core_operands()
         self.fine = None
         if "mlp_fine.sigma_net.0.weight" in P:
@@ -266,8 +266,11 @@ class RenderEngine(SamplerHost):
             return EDN_TC32 if (n_total <= 128 and not want_feat) else EDN_F32
         return self.prec_code
 
-    def _coarse_precision(self, n_samples):
-        # the tensor-core coarse kernel tiles 128 rows = floor(128 / n_samples) rays; other sample counts use the SIMT kernel
+    def _coarse_precision(self, n_samples, want_feat=False):
+        # the tensor-core coarse kernels tile 128 rows = floor(128 / n_samples) rays; other sample counts use the SIMT kernel, and so
+        # does the parity mode when the coarse feature_map is requested (the bf16 x 3 kernel runs the folded schedule)
+        if self.precision == "tc32":
+            return EDN_TC32 if (32 <= n_samples <= 128 and not want_feat) else EDN_F32
         return EDN_BF16 if (self.prec_code == EDN_BF16 and 32 <= n_samples <= 128) else EDN_F32
 
     def _linspace(self, n):
@@ -346,7 +349,7 @@ class RenderEngine(SamplerHost):
         tv = self._linspace(Nc)
         check(self._launch("coarse", lambda: lib.edn_render_coarse_fwd(
             C.byref(self.coarse.grid), C.byref(self.coarse.mlp), ptr(rb), ptr(tv), ptr(t_rand), ptr(noise0), R, Nc,
-            flags | FLAG_RELU_RGB, self.rmnearplane, self._coarse_precision(Nc), ptr(z0), ptr(w0), ptr(rgb0), ptr(depth0),
+            flags | FLAG_RELU_RGB, self.rmnearplane, self._coarse_precision(Nc, feat0 is not None), ptr(z0), ptr(w0), ptr(rgb0), ptr(depth0),
             ptr(acc0), ptr(feat0),
             stream_ptr())), "edn_render_coarse_fwd")
         if Ni <= 0:

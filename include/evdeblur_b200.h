@@ -28,7 +28,7 @@ enum {
   EDN_E_UNSUPPORTED = -3
 };
 
-/* precision / storage codes.  EDN_TC32 (edn_render_fine_fwd only): the tensor-core PARITY mode -- bf16 x 3 operand splitting
+/* precision / storage codes.  EDN_TC32 (edn_render_coarse_fwd without feature_map, edn_render_fine_fwd): the tensor-core PARITY mode -- bf16 x 3 operand splitting
  * (hi.hi + lo.hi + hi.lo into fp32 TMEM accumulators), fp32 everywhere else: fp32-grade results on tcgen05. */
 enum { EDN_F32 = 0, EDN_BF16 = 1, EDN_TC32 = 2 };
 
