@@ -27,10 +27,11 @@ namespace {
 using namespace tc;
 
 constexpr int kRows = 128;
-constexpr int kGatherWarps = 8, kEpiWarps = 8;
+constexpr int kGatherWarps = 16, kEpiWarps = 8;
 constexpr int kWarpMma = kGatherWarps + kEpiWarps, kWarpLoad = kWarpMma + 1;
-constexpr int kThreads = (kGatherWarps + kEpiWarps + 2) * 32;      // 576
-constexpr int kRoleThreads = 256;
+constexpr int kThreads = (kGatherWarps + kEpiWarps + 4) * 32;      // 896 = 7 warpgroups (setmaxnreg: gather 88, epilogue 64, rest 24)
+constexpr int kGatherThreads = kGatherWarps * 32;                   // 512
+constexpr int kRoleThreads = 256;                                   // epilogue threads
 constexpr int kNst = 4;
 constexpr int kStageBytes = 16384;         // 2 K-steps x (256 rows x 16 x 2 B) of the hi OR the lo weights
 constexpr int kKstepBytes = 8192;
@@ -48,7 +49,7 @@ struct Misc {
   uint64_t w_full[kNst], w_empty[kNst];
   uint64_t acc_full, act;
   GridDev grids[2];
-  uint32_t tmem_base, pad[3];
+  uint32_t tmem_base, round_ctr[2], pad[1];     // round_ctr[ray parity]: the one being reset is never the one being pulled from
   alignas(16) float wsig[256];
   alignas(16) float wrgb[3][256];
   alignas(16) float bias1[256];
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&m->a_full, kRoleThreads); mbar_init(&m->a_empty, 1);
+    mbar_init(&m->a_full, kGatherThreads); mbar_init(&m->a_empty, 1);
     for (int b = 0; b < 2; ++b) mbar_init(&m->slot_free[b], kRoleThreads);
     for (int s = 0; s < kNst; ++s) { mbar_init(&m->w_full[s], 1); mbar_init(&m->w_empty[s], 1); }
     mbar_init(&m->acc_full, 1); mbar_init(&m->act, kRoleThreads);
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
 #pragma unroll
     for (int j = 0; j < 3; ++j) m->wrgb[j][i] = __ldg(a.mlp.color2_t + i * 4 + j);
   }
-  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; }
+  if (tid == 32) { m->grids[0] = a.gc; m->grids[1] = a.gf; m->round_ctr[0] = 0; m->round_ctr[1] = 0; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -107,8 +108,11 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
   const int S = a.S;
   const int64_t n_my = (a.n_rays > (int64_t)blockIdx.x) ? (a.n_rays - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == kWarpLoad) {
+  if (warp > kWarpLoad) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle warps of the donor warpgroup
+  } else if (warp == kWarpLoad) {
     // =================================== weight stream =====================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (n_my > 0) {
       const uint32_t total = (uint32_t)n_my * kStagesPerRay;
       for (uint32_t g = 0; g < total; ++g) {
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
     __syncwarp();
   } else if (warp == kWarpMma) {
     // =================================== MMA issuer (converged warp, one elected lane issues) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (n_my > 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256);
       const uint32_t w_base = smem_u32(Ws), a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
@@ -176,24 +181,27 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
     }
     __syncwarp();
   } else if (warp < kGatherWarps) {
-    // =================================== gather warps: TWO threads per sample row ===========================================
-    const int half = warp >> 2, gwarp = warp & 3;
-    const int r = gwarp * 32 + lane;
+    // =================================== gather warps ==========================================================================
+    // warps 0-3: depth + PE of the 128 rows, warps 4-7: the per-ray view-direction bias; then ALL 16 warps pull the 32 gather rounds
+    // (grid x row group x 8-point group) of the ray from a shared counter (the depths come from global memory: no barrier needed).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    const int r = (warp & 3) * 32 + lane;
     for (int64_t it = 0; it < n_my; ++it) {
       const int buf = (int)(it & 1);
       if (it > 0) {
         if (warp == 0) {
           mbar_wait(&m->a_empty, (uint32_t)(it - 1) & 1);
           if (it > 1) mbar_wait(&m->slot_free[buf], (uint32_t)((it >> 1) - 1) & 1);
+          if (it > 1 && lane == 0) m->round_ctr[buf] = 0;      // last pulled from two rays ago: every warp is past it
         }
-        named_bar_sync(5, kRoleThreads);
+        named_bar_sync(5, kGatherThreads);
       }
       RaySlot* slot = &m->slot[buf];
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
       const float* rb = a.ray_batch + ray * 11;
       const float o[3] = {__ldg(rb + 0), __ldg(rb + 1), __ldg(rb + 2)};
       const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
-      if (half == 0) {
+      if (warp < 4) {
         const float zv = a.z_vals[ray * S + min(r, S - 1)];
         slot->z[r] = zv;
         // PE(pts) (embedding.py:92-98; the fp32 path's arithmetic: sincosf(p * 2^f)) -> A chunks 24..31, hi / lo split
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
           st_shared_v4(A_hi + r * 16 + (24 + j) * kChunkA, hi[0], hi[1], hi[2], hi[3]);
           st_shared_v4(A_lo + r * 16 + (24 + j) * kChunkA, lo[0], lo[1], lo[2], lo[3]);
         }
-      } else {
+      } else if (warp < 8) {
         // per-ray bias of color_net.0: b0 + W0[:, 128:155] . PE(viewdir), the fp32 path's arithmetic (fine_f32.cu)
         const float vd[3] = {__ldg(rb + 8), __ldg(rb + 9), __ldg(rb + 10)};
 #pragma unroll 1
@@ -238,20 +246,27 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
           slot->bias[col] = b;
         }
       }
-      named_bar_sync(1, kRoleThreads);            // z[] visible to the whole gather group
       {
-        const float* z_s = slot->z;
-        gather_points_split<T>(m->grids[half], A_hi, A_lo, half ? 12 : 0, gwarp, lane, 0, 4, [&](int pt, float (&p)[3]) {
-          const float zv = z_s[pt];
+        const float* z_g = a.z_vals + ray * S;
+        for (;;) {
+          int k = 0;
+          if (lane == 0) k = (int)atomicAdd(&m->round_ctr[buf], 1u);
+          k = __shfl_sync(0xffffffffu, k, 0);
+          if (k >= 32) break;
+          const int hk = k >> 4, gk = (k >> 2) & 3, gik = k & 3;
+          gather_points_split<T>(m->grids[hk], A_hi, A_lo, hk ? 12 : 0, gk, lane, gik, gik + 1, [&](int pt, float (&p)[3]) {
+            const float zv = __ldg(z_g + min(pt, S - 1));
 #pragma unroll
-          for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
-        });
+            for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], zv));
+          });
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(&m->a_full);
     }
   } else {
     // =================================== epilogue warps: TWO threads per sample row ============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int ew = warp - kGatherWarps;
     const int half = ew >> 2, gwarp = ew & 3;
     const int r = gwarp * 32 + lane;
