@@ -407,6 +407,17 @@ __global__ void __launch_bounds__(kThreads, 1) coarse_fwd_tc_kernel(const Coarse
 //   warps 24-25 MMA issuers (one per group, converged warp + elect.sync), warps 26-27 idle donors (24 registers).
 // TMEM: per group TWO 64-column accumulators (tile parity), so stage 1 of the next tile runs under the last epilogue of this one.
 // Round 1's kernel kept every row warp on gather -> wait -> epilogue -> wait ...; its top stall was the long scoreboard of the gather.
+// Bounded wait until a shared-memory tile counter reaches `need` (a protocol bug traps instead of hanging).  Used where a 1-bit
+// mbarrier phase parity would be ambiguous: the epilogue may finish tile k - 1 before the producer asks for tile k - 2 (a slow producer,
+// e.g. perturbed sample placement), and an mbarrier two phases ahead looks exactly like one that has not completed.
+__device__ __forceinline__ void wait_tile_count(const uint32_t* ctr, uint32_t need) {
+  uint32_t spins = 0;
+  while (*reinterpret_cast<const volatile uint32_t*>(ctr) < need) {
+    if (++spins > (1u << 24)) __trap();
+  }
+  __threadfence_block();
+}
+
 constexpr int kV2GatherWarps = 16, kV2EpiWarps = 8;
 constexpr int kV2WarpMma = kV2GatherWarps + kV2EpiWarps;
 constexpr int kV2Threads = (kV2GatherWarps + kV2EpiWarps + 4) * 32;     // 896
@@ -426,9 +437,9 @@ struct alignas(16) GroupMisc2 {
   float wtot[4];
 };
 struct Misc2 {
-  uint64_t a_full[2], a_free[2], act_full[2], acc[2], tile_done[2], bar_w;
+  uint64_t a_full[2], a_free[2], act_full[2], acc[2][2], bar_w;      // acc[group][tile parity]
   GridDev grid;
-  uint32_t tmem_base, pad[3];
+  uint32_t tmem_base, tiles_done[2], pad[1];                            // tiles_done[group]: tiles whose epilogue has finished
   alignas(16) float wdir[kPeDir][64];
   alignas(16) float b0[64];
   alignas(16) float b1[64];
@@ -457,11 +468,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
   if (tid == 0) {
     for (int q = 0; q < 2; ++q) {
       mbar_init(&m->a_full[q], kV2ProdThreads); mbar_init(&m->a_free[q], 1); mbar_init(&m->act_full[q], kRows);
-      mbar_init(&m->acc[q], 1); mbar_init(&m->tile_done[q], kRows);
+      mbar_init(&m->acc[q][0], 1); mbar_init(&m->acc[q][1], 1);
     }
     mbar_init(&m->bar_w, 1);
     fence_barrier_init();
     m->grid = a.grid;
+    m->tiles_done[0] = 0; m->tiles_done[1] = 0;
   }
   if (warp == kV2WarpMma) tmem_alloc(&m->tmem_base, kV2TmemCols);
   if (ablate) {      // dev ablations leave parts of the operand tiles unwritten: start from zeros
@@ -495,15 +507,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
         mbar_wait(&m->a_full[q], (uint32_t)it & 1); tc_fence_after();
         if (elect_one()) {
           issue_layer(d_tmem, aq, wb, 10, 64, 2048);                       // [g 96 | PE 64] -> 64
-          mma_commit(&m->acc[q]);
+          mma_commit(&m->acc[q][it & 1]);
           mma_commit(&m->a_free[q]);                                        // the producer may refill this group's A tile
         }
         __syncwarp();
         mbar_wait(&m->act_full[q], 0); tc_fence_after();
-        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL2 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q]); }
+        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL2 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q][it & 1]); }
         __syncwarp();
         mbar_wait(&m->act_full[q], 1); tc_fence_after();
-        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL3 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q]); }
+        if (elect_one()) { issue_layer(d_tmem, actq, wb + (kOffL3 - kOffL1), 4, 64, 2048); mma_commit(&m->acc[q][it & 1]); }
         __syncwarp();
       }
     }
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
         if (it > 0) {      // one polling warp, the rest blocks in a named barrier
           if (warp == 0) {
             mbar_wait(&m->a_free[q], (uint32_t)(it - 1) & 1);
-            if (it >= 2) mbar_wait(&m->tile_done[q], (uint32_t)(it - 2) & 1);
+            if (it >= 2) wait_tile_count(&m->tiles_done[q], (uint32_t)(it - 1));      // tiles 0 .. it - 2 of this group are composited
           }
           named_bar_sync(5, kV2ProdThreads);
         }
@@ -608,18 +620,20 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
     GroupMisc2* gm = &m->grp[q];
     uint8_t* act_row = Act + q * kV2ActBytes + r * 16;
     const int bar_id = 1 + q;
-    uint32_t pacc = 0;
     const int lr = min(r / S, rpt - 1), s = (r / S < rpt) ? r - lr * S : S - 1;
     const bool row_valid = r < rpt * S;
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
+    uint32_t pbits = 0u;                   // bit p: phase parity of acc[q][p] (three completions per tile of parity p)
+    int cur_par = 0;
     auto wait_acc = [&]() {
-      if (gwarp == 0) mbar_wait(&m->acc[q], pacc);
-      pacc ^= 1;
+      if (gwarp == 0) mbar_wait(&m->acc[q][cur_par], (pbits >> cur_par) & 1u);
+      pbits ^= 1u << cur_par;
       named_bar_sync(bar_id, kRows);
       tc_fence_after();
     };
     for (int64_t it = 0; it < n_my; ++it) {
       const int par = (int)(it & 1);
+      cur_par = par;
       const int64_t tile = 2 * ((int64_t)blockIdx.x + it * gridDim.x) + q;
       const int64_t ray_raw = tile * rpt + lr;
       const bool live = row_valid && ray_raw < a.n_rays;
@@ -717,8 +731,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) coarse_fwd_tc2_kernel(const Coa
         a.z_vals[ray * S + s] = zv;
         a.weights[ray * S + s] = wgt;
       }
-      named_bar_sync(bar_id, kRows);          // red[] / wtot[] are rewritten by the next tile
-      mbar_arrive(&m->tile_done[q]);
+      named_bar_sync(bar_id, kRows);          // red[] / wtot[] are rewritten by the next tile; every thread is done with z[par] / TMEM
+      if (r == 0) { __threadfence_block(); atomicAdd(&m->tiles_done[q], 1u); }
       estamp(7);
     }
   }
@@ -742,9 +756,9 @@ constexpr int kT3OffL1 = 0, kT3OffL2 = 2 * 20480, kT3OffL3 = kT3OffL2 + 2 * 8192
 constexpr uint32_t kT3TmemCols = 128;
 
 struct Misc3 {
-  uint64_t a_full, a_free, act_full, acc, tile_done, bar_w;
+  uint64_t a_full, a_free, act_full, acc[2], bar_w;                    // acc[tile parity]
   GridDev grid;
-  uint32_t tmem_base, pad[3];
+  uint32_t tmem_base, tiles_done, pad[2];
   alignas(16) float wdir[kPeDir][64];
   alignas(16) float b0[64];
   alignas(16) float b1[64];
@@ -814,9 +828,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const Coa
 
   if (tid == 0) {
     mbar_init(&m->a_full, kV2ProdThreads); mbar_init(&m->a_free, 1); mbar_init(&m->act_full, kRows);
-    mbar_init(&m->acc, 1); mbar_init(&m->tile_done, kRows); mbar_init(&m->bar_w, 1);
+    mbar_init(&m->acc[0], 1); mbar_init(&m->acc[1], 1); mbar_init(&m->bar_w, 1);
     fence_barrier_init();
     m->grid = a.grid;
+    m->tiles_done = 0;
   }
   if (warp == kT3WarpMma) tmem_alloc(&m->tmem_base, kT3TmemCols);
   for (int i = tid; i < kPeDir * 64; i += kT3Threads) m->wdir[i / 64][i % 64] = __ldg(a.mlp.color0_t + (15 + i / 64) * 64 + i % 64);
@@ -846,15 +861,15 @@ __global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const Coa
         mbar_wait(&m->a_full, (uint32_t)it & 1); tc_fence_after();
         if (elect_one()) {
           issue_layer3(d_tmem, ah, al, wb + kT3OffL1, wb + kT3OffL1 + 20480, 10);
-          mma_commit(&m->acc);
+          mma_commit(&m->acc[it & 1]);
           mma_commit(&m->a_free);
         }
         __syncwarp();
         mbar_wait(&m->act_full, 0); tc_fence_after();
-        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL2, wb + kT3OffL2 + 8192, 4); mma_commit(&m->acc); }
+        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL2, wb + kT3OffL2 + 8192, 4); mma_commit(&m->acc[it & 1]); }
         __syncwarp();
         mbar_wait(&m->act_full, 1); tc_fence_after();
-        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL3, wb + kT3OffL3 + 8192, 4); mma_commit(&m->acc); }
+        if (elect_one()) { issue_layer3(d_tmem, ch, cl, wb + kT3OffL3, wb + kT3OffL3 + 8192, 4); mma_commit(&m->acc[it & 1]); }
         __syncwarp();
       }
     }
@@ -868,7 +883,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const Coa
       if (it > 0) {
         if (warp == 0) {
           mbar_wait(&m->a_free, (uint32_t)(it - 1) & 1);
-          if (it >= 2) mbar_wait(&m->tile_done, (uint32_t)(it - 2) & 1);
+          if (it >= 2) wait_tile_count(&m->tiles_done, (uint32_t)(it - 1));
         }
         named_bar_sync(5, kV2ProdThreads);
       }
@@ -941,18 +956,20 @@ __global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const Coa
     const int r = gwarp * 32 + lane;
     uint8_t* hi_row = Act_hi + r * 16;
     uint8_t* lo_row = Act_lo + r * 16;
-    uint32_t pacc = 0;
+    uint32_t pbits = 0u;                   // bit p: phase parity of acc[p]
+    int cur_par = 0;
     const int lr = min(r / S, rpt - 1), s = (r / S < rpt) ? r - lr * S : S - 1;
     const bool row_valid = r < rpt * S;
     const bool mask_near = !(a.flags & EDN_FLAG_TRAIN) && a.rmnearplane > 0.f;
     auto wait_acc = [&]() {
-      if (gwarp == 0) mbar_wait(&m->acc, pacc);
-      pacc ^= 1;
+      if (gwarp == 0) mbar_wait(&m->acc[cur_par], (pbits >> cur_par) & 1u);
+      pbits ^= 1u << cur_par;
       named_bar_sync(1, kRows);
       tc_fence_after();
     };
     for (int64_t it = 0; it < n_my; ++it) {
       const int par = (int)(it & 1);
+      cur_par = par;
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
       const int64_t ray_raw = tile * rpt + lr;
       const bool live = row_valid && ray_raw < a.n_rays;
@@ -1017,7 +1034,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) coarse_fwd_tc3_kernel(const Coa
         a.weights[ray * S + s] = gm->w[r];
       }
       named_bar_sync(1, kRows);
-      mbar_arrive(&m->tile_done);
+      if (r == 0) { __threadfence_block(); atomicAdd(&m->tiles_done, 1u); }
     }
   }
   tc_fence_before();
