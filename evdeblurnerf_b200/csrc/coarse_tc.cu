@@ -1,7 +1,11 @@
 // Coarse pass of render_rays on the tensor cores (tcgen05 + TMEM), bf16 operands / fp32 accumulation.
 // Replaces networks/renderer.py:157-188 + networks/pdrf/voxnerf.py:203-259,153-201 for the CRR coarse field.
+// Three kernels share this file's layouts and helpers:
+//   coarse_fwd_tc_kernel  (round 1; today: S not a multiple of 32, the full / feature_map schedule, EDN_COARSE_V1=1) -- described next;
+//   coarse_fwd_tc2_kernel (default, lean schedule): producer warps decoupled from the MLP chain, see its own header further down;
+//   coarse_fwd_tc3_kernel (precision EDN_TC32): the bf16 x 3 split-operand parity kernel.
 //
-// One persistent CTA per SM; two row groups, each renders one 128-row tile = floor(128 / Nc) rays x Nc coarse samples at a
+// Round-1 kernel: one persistent CTA per SM; two row groups, each renders one 128-row tile = floor(128 / Nc) rays x Nc coarse samples at a
 // time (2 rays for Nc = 64) with TWO threads per row (16 row warps: the halves split the gather and the epilogue
 // columns).  All weights are resident in shared memory; the small CTA footprint leaves L1 for the VM line tables.
 //   rows: bit-exact sample placement, PE -> A, cooperative VM gather -> 128x96 tile, layer epilogues

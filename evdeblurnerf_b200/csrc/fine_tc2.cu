@@ -5,17 +5,20 @@
 // What round 1's kernel (fine_tc.cu) was bound by: a ray group's VM gather, its three layer epilogues and its MMAs form ONE serial
 // chain, and shared memory (2 x 64 KB A operands + rings) / TMEM (2 x 256 accumulator columns) capped it at two such chains per SM.
 // Here the chain is cut in two and the hidden activations never touch shared memory:
-//   gather warps (8):   ray k+1: PE + view-direction bias + cooperative VM gather of both grids -> A_in[(k+1) & 1] (64 KB, UMMA
-//                       K-major layout) WHILE ray k is in the MLP: the gather is off the critical chain, double buffered.
-//   MMA issuer (1 thr): layer 1 reads A_in from shared memory (SS), layers 2 / 3 read their A operand from TENSOR MEMORY (TS): the
-//                       epilogue writes relu(acc) as packed bf16 straight back into TMEM (tcgen05.st), so shared memory holds only
-//                       layer-1 inputs and the weight ring.  Every layer is issued as four N = 64 quarters into four 64-column
-//                       accumulators, and the next layer's K-steps 4i..4i+3 only wait for quarter i's epilogue (K-chunk hand-over).
-//   epilogue warps (8): two threads per sample row; per quarter: tcgen05.ld 32 columns -> bias / ReLU -> sigma / rgb head partials ->
-//                       bf16x2 -> tcgen05.st into the next layer's A operand; finally sigma -> alpha compositing (warp-shuffle scan).
-//   weight stream (1 thr): the three layers' weights, quarter-major ([layer][quarter][K-step][64 x 16]), through a 4 x 16 KB ring
-//                       with cp.async.bulk (TMA engine); stages are released by tcgen05.commit.
-// TMEM map (512 columns): [0,128) A operand of layer 2, [128,256) A operand of layer 3, [256,512) four 64-column accumulators.
+//   gather warps (16):  ray k+1: PE + view-direction bias + cooperative VM gather of both grids -> A_in[(k+1) & 1] (64 KB, UMMA
+//                       K-major layout) WHILE ray k is in the MLP: the gather is off the critical chain, double buffered; the 32
+//                       gather rounds of a ray are pulled from a shared counter (work stealing).
+//   MMA issuer (1 warp, one elected lane): layer 1 reads A_in from shared memory (SS), layers 2 / 3 read their A operand from
+//                       TENSOR MEMORY (TS): the epilogue writes relu(acc) as packed bf16 straight back into TMEM (tcgen05.st), so
+//                       shared memory holds only layer-1 inputs and the weight ring.  Every layer is issued as two independent
+//                       N = 128 chains into two of three rotating 128-column accumulators; the next layer's K-steps 4i..4i+3 only
+//                       wait for quarter i of this layer's epilogue (hand[4]).  The per-ray bias rides on one extra K-step.
+//   epilogue warps (8): two threads per sample row (two 64-column quarters of every layer each); per 32-column chunk: tcgen05.ld ->
+//                       ReLU -> sigma / rgb head partials (constant-bank weights) -> bf16x2 -> tcgen05.st into the next layer's
+//                       A operand, everything indexed at compile time; finally sigma -> alpha compositing (warp-shuffle scan).
+//   weight stream (1 warp): the three layers' weights ([layer][K-step pair][256 x 16 x 2]) through a 3 x 16 KB ring with
+//                       cp.async.bulk (TMA engine); stages are released by tcgen05.commit.
+// TMEM map (512 columns): [0,128) the A operand of layers 2 / 3 (rewritten in place), [128,512) three 128-column accumulator slots.
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -34,9 +37,8 @@ using namespace tc;
 
 constexpr int kRows = 128;
 // Warp roles (7 warpgroups = 896 threads, launched at 72 registers per thread, then re-balanced with setmaxnreg):
-//   warps 0-7   gather   (2 warpgroups, raised to 96 registers: 18 sixteen-byte loads in flight per thread)
-//   warps 8-23  epilogue (4 warpgroups, 72 registers): FOUR threads per sample row, 64 columns of a layer each -- the epilogue is a
-//               per-warp dependent instruction stream (~5 cycles per instruction), so its latency halves with twice the warps
+//   warps 0-15  gather   (4 warpgroups, raised to 88 registers: two 6-load tap tasks in flight per lane)
+//   warps 16-23 epilogue (2 warpgroups, lowered to 64 registers): TWO threads per sample row
 //   warp 24 MMA issuer, warp 25 weight stream, warps 26-27 idle (the warpgroup drops to 24 registers and donates the rest)
 constexpr int kGatherWarps = 16, kEpiWarps = 8;
 constexpr int kWarpMma = kGatherWarps + kEpiWarps, kWarpLoad = kWarpMma + 1;

@@ -7,8 +7,8 @@
 // sum |a||w| -- fp32 SIMT grade -- while the contraction stays on the tensor cores.  Everything around the GEMMs is the fp32
 // parity path's arithmetic: fp32 VM planes, fp32 bilinear taps, sincosf positional encoding, fp32 heads / compositing.
 // Structure = fine_tc2.cu without the overlap tricks (this mode is judged on accuracy; it runs ~3x the MMAs):
-//   gather warps (8): PE + view bias + VM gather of both grids -> A_hi / A_lo (2 x 64 KB shared memory, single buffered: the gather
-//                     of ray k+1 overlaps layers 2, 3 of ray k);
+//   gather warps (16): PE + view bias + VM gather of both grids (work-stealing rounds) -> A_hi / A_lo (2 x 64 KB shared memory, single
+//                     buffered: the gather of ray k+1 overlaps layers 2, 3 of ray k);
 //   MMA warp:         layer 1 SS from shared memory, layers 2 / 3 TS from TMEM ([0,128) A_hi, [128,256) A_lo, [256,512) accumulator);
 //   epilogue warps (8): TMEM -> fp32 bias / ReLU / sigma, rgb heads -> hi / lo split -> TMEM; compositing;
 //   weight stream:    [layer][K-step pair][hi 16 KB | lo 16 KB] through a 4 x 16 KB ring (cp.async.bulk).
