@@ -15,6 +15,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fine_args.cuh"
@@ -284,12 +285,14 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
       const int64_t ray = (int64_t)blockIdx.x + it * gridDim.x;
       const float4* s_bias = reinterpret_cast<const float4*>(slot->bias);
       float sig_part = 0.f, rr = 0.f, rg_ = 0.f, rbl = 0.f;
-#pragma unroll 1
-      for (int L = 0; L < 3; ++L) {
+      // layer L and the column chunk are compile-time constants: straight-line epilogue code (this kernel's epilogue is serial with
+      // its MMAs, so every instruction saved here is kernel time)
+      auto layer = [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
         if (ew == 0) mbar_wait(&m->acc_full, n_use & 1);
         named_bar_sync(4, kRoleThreads);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col0 = q * 64 + half * 32;
           uint32_t v[32];
@@ -337,7 +340,10 @@ __global__ void __launch_bounds__(kThreads, 1) fine_fwd_tc3_kernel(const FineArg
         tc_fence_before();
         mbar_arrive(&m->act);
         ++n_use;
-      }
+      };
+      layer(std::integral_constant<int, 0>{});
+      layer(std::integral_constant<int, 1>{});
+      layer(std::integral_constant<int, 2>{});
       m->headp[half][r][0] = rr; m->headp[half][r][1] = rg_; m->headp[half][r][2] = rbl; m->headp[half][r][3] = sig_part;
       named_bar_sync(2, kRoleThreads);
       if (half == 0) {
