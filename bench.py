@@ -543,8 +543,8 @@ def main():
             ms = timed_steps(lambda i: nerf_p.render_blurred(H, W, KMAT, rays_dev, idx_dev, N_samples=NC, N_importance=NI, perturb=0., raw_noise_std=0.),
                              k2, w2, world, dev, before_each=flush_fn)
             extra["parity_mode"] = {"precision": "tc32", "ms_per_step": ms, "value": world * N_RAYS / (ms / 1e3), "unit": "rays/s",
-                                    "what": "same workload, fine pass on tcgen05 with bf16 x 3 split operands + fp32 TMEM accumulation (meets the 1e-4 "
-                                            "parity bar: tests/test_render_gpu.py runs in this precision), fp32 coarse pass",
+                                    "what": "same workload, coarse and fine passes on tcgen05 with bf16 x 3 split operands + fp32 TMEM accumulation "
+                                            "(meets the 1e-4 parity bar: tests/test_render_gpu.py runs in this precision)",
                                     "numerical_errors": nerf_p.engine.numerical_errors()}
             del nerf_p
             torch.cuda.empty_cache()
