@@ -186,8 +186,8 @@ class RenderEngine(SamplerHost):
     """Fused c2f renderer over a reference `NeRFAll.state_dict()`-style parameter dict.
 
     precision: "fp32" -> fp32 SIMT kernels everywhere (parity mode, 1e-4 rel against the reference);
-               "tc32" -> tensor-core parity mode: the fine pass's GEMMs on tcgen05 with bf16 x 3 split operands and fp32 TMEM
-                         accumulation (fp32-grade, same tolerances as "fp32") in both render passes; fp32 VM planes, fp32 backward;
+               "tc32" -> tensor-core parity mode: the GEMMs of both render passes on tcgen05 with bf16 x 3 split operands and
+                         fp32 TMEM accumulation (fp32-grade, same tolerances as "fp32"); fp32 VM planes, fp32 backward;
                "bf16" -> tcgen05 tensor-core fine pass with bf16 operands / fp32 accumulation and bf16 VM planes.
     """
 
