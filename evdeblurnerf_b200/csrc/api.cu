@@ -23,8 +23,31 @@ int check_cuda(cudaError_t e, const char* what) {
   return EDN_E_CUDA;
 }
 
+// The library keeps a little per-PROCESS device state (cuBLAS handle, cublasLt workspace, staging buffers of the tensor-core
+// launchers): one process per GPU, as the framework is run (torchrun).  The first call that touches such state binds the process to
+// its current device; a later call from another device fails loudly instead of reading the first device's buffers.
+int bind_device(const char* who) {
+  static int bound = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("%s: cudaGetDevice failed", who); return EDN_E_CUDA; }
+  if (bound < 0) bound = dev;
+  if (dev != bound) {
+    set_error("%s: this process is bound to CUDA device %d (one process per GPU); called with device %d current", who, bound, dev);
+    return EDN_E_UNSUPPORTED;
+  }
+  return EDN_OK;
+}
+
+// why blas_handle() returned NULL: the device binding (its message is kept) or cublasCreate
+int blas_unavailable() {
+  if (int rc = bind_device("cuBLAS handle")) return rc;
+  set_error("cublasCreate failed");
+  return EDN_E_CUDA;
+}
+
 cublasHandle_t blas_handle() {
   static cublasHandle_t h = nullptr;
+  if (bind_device("cuBLAS handle") != EDN_OK) return nullptr;
   if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
   return h;
 }

@@ -609,7 +609,7 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
   } else {
     EDN_REQUIRE((reinterpret_cast<uintptr_t>(depth_feature) & 15) == 0, "edn_awp_fwd: depth_feature must be 16-byte aligned");
     cublasHandle_t h = blas_handle();
-    if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+    if (!h) return blas_unavailable();
     if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
     const Gemm gemm{h, tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F};
     const int64_t M = NE * n_samples;

@@ -689,7 +689,7 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   float* gW0p = take(32 * 112);
 
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F};
 #define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)

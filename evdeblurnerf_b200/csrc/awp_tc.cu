@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 2) awp_sample_tc_kernel(const TcArgs
 // The five per-sample contractions of the AWP forward on tcgen05 (bf16 operands, fp32 accumulation): fills ws.act[3], ws.xl
 // (bias included) and, with keep != 0, ws.act[0..2] for the backward.
 int awp_sample_mlp_tc(const edn_awp_params* p, const float* depth_feature, int64_t M, const AwpWs& ws, int keep, cudaStream_t st) {
+  if (int rc = bind_device("edn_awp_fwd")) return rc;               // `blobs` below lives on the bound device
   static uint8_t* blobs = nullptr;
   static unsigned launch_no = 0;
   if (!blobs) EDN_CUDA_OK(cudaMalloc(&blobs, (size_t)kBlobSlots * kWBytes));

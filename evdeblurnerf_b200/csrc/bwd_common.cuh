@@ -7,7 +7,8 @@
 
 namespace edn {
 
-cublasHandle_t blas_handle();   // api.cu: process-wide cuBLAS handle (NULL if cublasCreate failed)
+cublasHandle_t blas_handle();   // api.cu: process-wide cuBLAS handle (NULL if cublasCreate failed or the process is bound to another device)
+int blas_unavailable();         // api.cu: sets the error text for a NULL handle, returns the status code
 
 // Row-major C[M,N] (+)= op(A) op(B).  !ta: A stored [M][K] (lda); ta: A stored [K][M].  !tb: B stored [K][N]; tb: B stored [N][K].
 template <typename T> struct CuType;

@@ -11,6 +11,7 @@ namespace edn {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int bind_device(const char* who);   // api.cu: one process per GPU -- binds on first use, EDN_E_UNSUPPORTED from another device
 
 #define EDN_CUDA_OK(expr)                                   \
   do {                                                      \

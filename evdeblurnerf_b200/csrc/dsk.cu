@@ -332,7 +332,7 @@ extern "C" int edn_dsk_rays_fwd(const edn_dsk_params* p, const float* rays_x, co
   EDN_REQUIRE(rays_x && rays_y && images_idx && poses && new_rays && weight && workspace, "edn_dsk_rays_fwd: null pointer");
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, CUBLAS_COMPUTE_32F};
@@ -357,7 +357,7 @@ extern "C" int edn_dsk_rays_bwd(const edn_dsk_params* p, const float* rays_x, co
   for (int l = 0; l < p->num_hidden; ++l) EDN_REQUIRE(g->lin_w[l] && g->lin_b[l], "edn_dsk_rays_bwd: null gradient buffer (hidden layer %d)", l);
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, CUBLAS_COMPUTE_32F};

@@ -604,7 +604,7 @@ int field_bwd_run(const FieldBwdCall& c) {
   if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;         // keep GEMM row counts well inside int range
 
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, c.ct};
 
@@ -835,7 +835,7 @@ extern "C" int edn_nerf_field_bwd(const edn_nerf_weights* w, const float* ray_ba
   chunk = chunk < n_rays ? chunk : n_rays;
   if (chunk * S > (1 << 22)) chunk = (1 << 22) / S;
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, precision == EDN_F32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32};

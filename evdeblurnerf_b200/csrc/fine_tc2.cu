@@ -629,6 +629,7 @@ static __global__ void heads_stage_kernel(const float* __restrict__ sigma1_v, co
 
 int launch_fine_tc2(const FineArgs& a_in, int grid_dtype, const uint8_t* wblob, const uint8_t* wgeo, cudaStream_t st) {
   FineArgs a = a_in;
+  if (int rc = bind_device("edn_render_fine_fwd")) return rc;      // `stage` below lives on the bound device
   static float* stage = nullptr;
   static unsigned launch_no = 0;
   if (!stage) EDN_CUDA_OK(cudaMalloc(&stage, sizeof(float) * kHeadSlots * kHeadFloats));

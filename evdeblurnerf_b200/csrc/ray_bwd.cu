@@ -261,7 +261,7 @@ extern "C" int edn_rbk_warp_ndc_bwd(const edn_rbk_params* p, const float* rays, 
                          g->v_linear_w && g->v_linear_b), "edn_rbk_warp_ndc_bwd: null r/v gradient buffer");
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
   cublasHandle_t h = blas_handle();
-  if (!h) { set_error("cublasCreate failed"); return EDN_E_CUDA; }
+  if (!h) return blas_unavailable();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return EDN_E_CUDA; }
   const Gemm gemm{h, CUBLAS_COMPUTE_32F};
