@@ -14,12 +14,13 @@ struct AwpWs {
   float* x;       // [N][E][32]    motion features
   float* y;       // [N][E][32]    convd output before BatchNorm
   double* stats;  // [32][2] + 2   BatchNorm batch sums; stats[64] = rows behind them (all-reduced together with the sums)
+  double* bn_part; // [64][64]     per-block partial sums of the two-level (deterministic) reduction behind `stats`
   float* act[4];  // [NE*S][64]    post-ReLU activations of sample_feature_embed_layer.l (GEMM path only)
 };
 
 inline int64_t awp_ws_floats(int64_t N, int E, int S, bool gemm) {
   const int64_t NE = N * E;
-  return NE * 64 + NE * 32 + NE * S * 32 + NE * S + 2 * NE * 32 + 2 * 66 + 8 /* alignment slack */ + (gemm ? 4 * NE * S * 64 : 0);
+  return NE * 64 + NE * 32 + NE * S * 32 + NE * S + 2 * NE * 32 + 2 * 66 + 2 * 64 * 64 + 8 /* alignment slack */ + (gemm ? 4 * NE * S * 64 : 0);
 }
 
 inline AwpWs awp_ws_carve(float* w, int64_t N, int E, int S, bool gemm) {
@@ -32,7 +33,8 @@ inline AwpWs awp_ws_carve(float* w, int64_t N, int E, int S, bool gemm) {
   a.x = w; w += NE * 32;
   a.y = w; w += NE * 32;
   a.stats = reinterpret_cast<double*>(w + (((uintptr_t)w & 7) ? 1 : 0));
-  w += 2 * 66 + 2;
+  a.bn_part = a.stats + 66;
+  w += 2 * 66 + 2 + 2 * 64 * 64;
   w += (4 - ((uintptr_t)w / 4) % 4) % 4;            // 16-byte align the GEMM operands
   if (gemm) for (int l = 0; l < 4; ++l) { a.act[l] = w; w += NE * S * 64; }
   return a;
