@@ -147,7 +147,8 @@ class BlurModel:
             new_rays, weight, align = DskRaysFn.apply(self, int(H), int(W), k4, rx, ry, idx, poses, noise, *ps)
         else:
             new_rays, weight, align = self.run(H, W, k4, rx, ry, idx, poses, noise)
-        extras = {"img_embed": self.tensors["img_embed.img_embed"][idx]} if return_img_embed else {}
+        # the view latents handed to AWP: a plain row gather of the parameter itself, so that AWP's gradient reaches it through autograd
+        extras = {"img_embed": self.params[self.prefix + "img_embed.img_embed"].to(torch.float32)[idx]} if return_img_embed else {}
         return new_rays, weight, align.reshape(()), extras
 
 

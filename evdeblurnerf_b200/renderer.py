@@ -300,8 +300,6 @@ class NeRFAll:
         if "kernelsnet.pattern_pos" in self.params:           # deformable sparse kernel (pdrf/blurmodel.py)
             from .dsk import BlurModel
             self.kernelsnet, self.kernel_type = BlurModel(self.params, kernel_ptnum, **(kernel_cfg or {})), "DSK"
-            if self.use_awp:
-                raise NotImplementedError("kernel_use_awp with kernel_type = DSK is not built")
         self.awpnet = (AdaptiveWeightProposal(self.params, kernel_ptnum - 1,
                                               precision=_lib.EDN_BF16 if precision == "bf16" else _lib.EDN_F32) if self.use_awp else None)
         if self.use_awp and self.mode != "c2f":
@@ -538,18 +536,27 @@ class NeRFAll:
         return rgb_b, rgb1, other_loss, other_tensors
 
     def _forward_dsk(self, H, W, K, rays, rays_info, return_pts0_rgb, N_importance, ndc, near, far, kwargs, want_tv=True):
-        """renderer.py:301-378 with kernel_type = DSK, no AWP: kernel rays -> render of the N * num_pt rays -> per-point weighted sums;
-        `align` joins the extra losses.  With parameters that require grad the three stages are autograd nodes (DskRaysFn ->
-        RenderSubRaysFn, which returns d rays -> WeightedSumFn)."""
+        """renderer.py:301-378 with kernel_type = DSK: kernel rays -> render of the N * num_pt rays -> per-point weighted sums (and,
+        with kernel_use_awp, AWP's weights over the points: renderer.py:310-343); `align` joins the extra losses.  With parameters
+        that require grad the stages are autograd nodes (DskRaysFn -> RenderSubRaysFn, which returns d rays -> AwpFn / WeightedSumFn)."""
         other_loss, other_tensors = {}, {}
-        new_rays, weight1, align, _ = self.kernelsnet(H, W, K, rays, rays_info, noise=kwargs.pop("dsk_noise", None))
+        new_rays, weight1, align, kex = self.kernelsnet(H, W, K, rays, rays_info, return_img_embed=self.use_awp,
+                                                        noise=kwargs.pop("dsk_noise", None))
         N, E = weight1.shape
         sub = new_rays.reshape(-1, 3, 2)
         if self._wants_grad():
-            rgb, _, _, rgb0 = self._render_sub_rays(H, W, K, sub, None, near, far, ndc, kwargs, blur=False)[:4]
+            rgb, _, _, rgb0, _, _, _, feat, rb, _ = self._render_sub_rays(H, W, K, sub, None, near, far, ndc, kwargs, blur=False)
+            z_vals = self.last_render["z_vals"]
         else:
-            rgb, _, _, extras = self._render_batch(build_ray_batch(H, W, float(K[0][0]), sub, near, far, ndc), (N * E,), **kwargs)
-            rgb0 = extras.get("rgb0")
+            rb = build_ray_batch(H, W, float(K[0][0]), sub, near, far, ndc)
+            rgb, _, _, extras = self._render_batch(rb, (N * E,), **kwargs)
+            rgb0, feat, z_vals = extras.get("rgb0"), extras.get("depth_feature"), extras.get("z_vals")
+        if self.use_awp:
+            ccw = self.awpnet(feat, z_vals, rb[:, 3:6], kex["img_embed"])
+            ccw = normalize_ccw(ccw, self.awpnet.ccw_fine_scale)
+            other_tensors["rgb_awp"] = weighted_sum(rgb, ccw)
+            other_tensors["ccw_fine"] = ccw
+            other_tensors["stage1_img_embed"] = kex["img_embed"]
         rgb_b = weighted_sum(rgb, weight1)
         rgb1 = weighted_sum(rgb0, weight1) if N_importance > 0 else None
         if self.mode == "c2f" and want_tv:

@@ -514,16 +514,23 @@ def dsk_forward(P, cfg, H, W, K, rays_x, rays_y, images_idx, poses, noise=None, 
     return torch.stack([rays_o, rays_d], -1), weight, align
 
 
-def forward_train_dsk(P, cfg, dsk_cfg, H, W, K, rays_x, rays_y, images_idx, poses, n_samples, n_importance, noise=None):
-    """NeRFAll.forward, kernel_type = DSK, no AWP (renderer.py:301-378): DSK rays -> render -> per-point weighted sums."""
+def forward_train_dsk(P, cfg, dsk_cfg, H, W, K, rays_x, rays_y, images_idx, poses, n_samples, n_importance, noise=None, use_awp=False):
+    """NeRFAll.forward, kernel_type = DSK (renderer.py:301-378): DSK rays -> render -> per-point weighted sums (+ the AWP branch)."""
     new_rays, weight, align = dsk_forward(P, dsk_cfg, H, W, K, rays_x, rays_y, images_idx, poses, noise)
     N, npt = weight.shape
     rb = build_ray_batch(H, W, float(K[0, 0]), new_rays.reshape(-1, 3, 2))
-    ret = render_rays(P, cfg, rb, n_samples, n_importance)
+    ret = render_rays(P, cfg, rb, n_samples, n_importance, want_feature=use_awp)
     out = {"new_rays": new_rays, "weight": weight, "align": align, "render": ret,
            "rgb": torch.sum(ret["rgb_map"].reshape(N, npt, 3) * weight[..., None], 1)}
     if n_importance > 0:
         out["rgb1"] = torch.sum(ret["rgb0"].reshape(N, npt, 3) * weight[..., None], 1)
+    if use_awp:                                                            # renderer.py:310-336 with a non-RBK kernel
+        emb = P["kernelsnet.img_embed.img_embed"][images_idx.reshape(-1).long()]
+        ccw = awp_forward(P, ret["depth_feature"], ret["z_vals"], rb[:, 3:6], emb, npt)
+        ccw = ccw + ccw * 0.05
+        ccw = ccw / torch.sum(ccw, -1, keepdim=True)
+        out["ccw_fine"] = ccw
+        out["rgb_awp"] = torch.sum(ret["rgb_map"].reshape(N, npt, 3) * ccw[..., None], 1)
     return out
 
 

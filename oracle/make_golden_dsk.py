@@ -142,6 +142,35 @@ def main():
                 "e2e.stage1_rgb_pts0": other["stage1_rgb_pts0"]})
     for k, v in kn.state_dict().items():
         out["e2e.param." + k] = v.detach()
+    # ---- the same with the AWP branch on (renderer.py:310-343 with a non-RBK kernel): rgb_awp from AWP's weights over the DSK points --
+    from networks.dpnerf.awp import AdaptiveWeightProposal
+    args2 = rh.blurfactory_args(E=NPT, coarse_n_voxels=18 * 18 * 12, fine_n_voxels=36 * 36 * 24, use_awp=True)
+    args2.kernel_type = "DSK"
+    torch.manual_seed(1)
+    awpnet = AdaptiveWeightProposal(input_ch=args2.fine_geo_feat_dim, num_motion=NPT - 1, use_origin=True, D_sam=4, W_sam=64, D_mot=1, W_mot=32,
+                                    dir_freq=2, rgb_freq=2, depth_freq=3, ray_dir_freq=2, view_feature_ch=32)
+    nerf2 = NeRFAll(args2, kn, awpnet)
+    sd2 = nerf2.state_dict()
+    loaded = 0
+    for k in sd2:
+        if k in small.files and tuple(small[k].shape) == tuple(sd2[k].shape) and not k.startswith("kernelsnet."):
+            sd2[k] = torch.from_numpy(small[k]); loaded += 1
+    nerf2.load_state_dict(sd2)
+    print("  e2e + AWP: tensors taken from params_small.npz:", loaded)
+    assert loaded >= 50
+    nerf2.train()
+    with torch.no_grad():
+        rgb_a, rgb1_a, _, other_a = nerf2(H, W, KMAT, chunk=32768, rays=torch.zeros(N, 3, 2), rays_info=info, force_naive=False,
+                                          return_pts0_rgb=True, retraw=True, N_samples=64, N_importance=64, perturb=0., raw_noise_std=0.,
+                                          ndc=True, near=0., far=1., use_viewdirs=True, lindisp=False, white_bkgd=False, inference=False)
+    P2 = {k: v.detach().clone() for k, v in nerf2.state_dict().items()}
+    with torch.no_grad():
+        mine2 = oc.forward_train_dsk(P2, CFG, oracle_cfg(cfg), H, W, KMAT, rays_x, rays_y, idx, poses, 64, 64, use_awp=True)
+    for a, b, nm in ((mine2["rgb"], rgb_a, "rgb"), (mine2["rgb1"], rgb1_a, "rgb1"), (mine2["rgb_awp"], other_a["rgb_awp"], "rgb_awp")):
+        err = (a - b).abs().max().item()
+        print(f"  e2e + AWP: oracle vs reference {nm}: max abs diff {err:.3e}")
+        assert err <= 5e-5, nm
+    out.update({"e2e.awp.rgb": rgb_a, "e2e.awp.rgb1": rgb1_a, "e2e.awp.rgb_awp": other_a["rgb_awp"], "e2e.awp.ccw_fine": mine2["ccw_fine"]})
     np.savez_compressed(os.path.join(OUT, "case9_dsk.npz"), **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
     print("wrote case9_dsk.npz", len(out), "arrays")
 

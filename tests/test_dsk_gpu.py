@@ -187,3 +187,64 @@ def test_trainer_steps_with_a_dsk_kernel_and_the_align_term():
     assert losses[-1] < losses[0], losses
     moved = [k for k, v in before.items() if float((tr.nerf.params[k].detach() - v).abs().max()) > 0]
     assert len(moved) == len(before), sorted(set(before) - set(moved))
+
+
+def awp_model(requires_grad):
+    from evdeblurnerf_b200 import NeRFAll
+    g = golden("case9_dsk")
+    P, _ = small_params()
+    P = {k: v for k, v in P.items() if not k.startswith("kernelsnet.")}
+    P.update({"kernelsnet." + k[len("e2e.param."):]: v for k, v in g.items() if k.startswith("e2e.param.")})
+    Pg = {k: v.cuda() for k, v in P.items()}
+    if requires_grad:
+        for k, v in Pg.items():
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+    nerf = NeRFAll(Pg, *AABB, kernel_ptnum=5, precision="fp32", use_awp=True,
+                   kernel_cfg=dict(in_embed=3, spatial_embed=0, kernel_hwindow=10, random_hwindow=0.0)).train()
+    io = {k[4:]: v for k, v in g.items() if k.startswith("e2e.") and not k.startswith("e2e.param.")}
+    return nerf, P, Pg, io
+
+
+def test_nerfall_dsk_with_awp_matches_the_reference():
+    """renderer.py:310-343 with a non-RBK kernel: AWP's weights over the DSK points -> rgb_awp (reference NeRFAll output)."""
+    nerf, _, _, io = awp_model(False)
+    with torch.no_grad():
+        rgb, rgb1, _, other = nerf(H, W, KMAT, chunk=32768, rays=torch.zeros(24, 3, 2).cuda(), rays_info=info_of(io), **KW)
+    assert_close(rgb, io["awp.rgb"], "blended rgb", rtol=1e-4, atol=2e-4)
+    assert_close(rgb1, io["awp.rgb1"], "blended rgb1", rtol=1e-4, atol=2e-5)
+    assert_close(other["ccw_fine"], io["awp.ccw_fine"], "ccw_fine", rtol=1e-4, atol=1e-5)
+    assert_close(other["rgb_awp"], io["awp.rgb_awp"], "rgb_awp", rtol=1e-4, atol=2e-4)
+
+
+def test_nerfall_dsk_with_awp_gradients_reach_every_tensor():
+    """The AWP term's gradient reaches the AWP net, the DSK view latents (through the row gather) and the fields; compared against
+    autograd on the oracle for the kernel-net and AWP tensors."""
+    nerf, P, Pg, io = awp_model(True)
+    gen = torch.Generator().manual_seed(41)
+    G = torch.randn(24, 3, generator=gen)
+    rgb, rgb1, _, other = nerf(H, W, KMAT, chunk=32768, rays=torch.zeros(24, 3, 2).cuda(), rays_info=info_of(io), **KW)
+    (other["rgb_awp"] * G.cuda()).sum().backward()
+    from util import oracle_fine_at
+    Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+    cfg = dict(num_pt=5, kernel_hwindow=10, in_embed=3, spatial_embed=0, num_hidden=3, short_cut=False, isglobal=False, optim_trans=False,
+               optim_sv_trans=False)
+    new_rays, weight, _ = oc.dsk_forward(Po, cfg, H, W, KMAT, io["rays_x"], io["rays_y"], io["images_idx"], io["poses"])
+    rb = oc.build_ray_batch(H, W, 400.0, new_rays.reshape(-1, 3, 2))
+    z = nerf.last_render["z_vals"].cpu()
+    f = oracle_fine_at(Po, rb, z, None)
+    emb = Po["kernelsnet.img_embed.img_embed"][io["images_idx"].reshape(-1).long()]
+    ccw = oc.awp_forward(Po, f["depth_feature"], z, rb[:, 3:6], emb, 5)
+    ccw = ccw + ccw * 0.05
+    ccw = ccw / ccw.sum(-1, keepdim=True)
+    o_awp = torch.sum(f["rgb_map"].reshape(24, 5, 3) * ccw[..., None], 1)
+    assert_close(other["rgb_awp"], o_awp, "rgb_awp vs oracle at the same depths", rtol=1e-4, atol=5e-5)
+    names = [k for k in Po if k.startswith(("kernelsnet.", "awpnet.")) and Po[k].is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    grads = torch.autograd.grad((o_awp * G).sum(), [Po[k] for k in names], allow_unused=True)
+    checked = 0
+    for k, ref in zip(names, grads):
+        if ref is None or float(ref.abs().max()) == 0.0 or k.endswith("MAM.linear.bias"):     # (BatchNorm cancels that bias: rounding noise)
+            continue
+        grad_close(Pg[k].grad, ref, "d " + k, tol=5e-3)
+        checked += 1
+    assert checked >= 25, checked
