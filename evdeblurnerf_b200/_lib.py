@@ -90,7 +90,7 @@ class AwpParams(C.Structure):
     _fields_ = [("sample_t", C.c_void_p * 4), ("sample_b", C.c_void_p * 4), ("motion_w", C.c_void_p * 2),
                 ("motion_b", C.c_void_p * 2)] + [(n, C.c_void_p) for n in (
                     "mam_linear_t", "mam_linear_b", "line_conv_att", "conva", "convb", "convc", "convn", "convl", "convd_w",
-                    "bn_weight", "bn_bias", "w_linear_w", "w_linear_b")]
+                    "bn_weight", "bn_bias", "w_linear_w", "w_linear_b")] + [("input_ch", C.c_int32)]
 
 
 class AwpOptions(C.Structure):

@@ -584,6 +584,10 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
               p->line_conv_att && p->conva && p->convb && p->convc && p->convn && p->convl && p->convd_w && p->bn_weight && p->bn_bias &&
               p->w_linear_w && p->w_linear_b, "edn_awp_fwd: null weight");
   if (n_rays <= 0) return n_rays == 0 ? EDN_OK : EDN_E_INVALID;
+  const int in_ch = p->input_ch > 0 ? p->input_ch : 128;
+  EDN_REQUIRE(in_ch % 4 == 0 && in_ch <= 1024, "edn_awp_fwd: input_ch must be a multiple of 4 up to 1024, got %d", in_ch);
+  EDN_REQUIRE(in_ch == 128 || gemm_path, "edn_awp_fwd: input_ch = %d runs the materialised path only: set keep_activations", in_ch);
+  if (in_ch != 128) tf32 = false;        // the tcgen05 sample MLP (awp_tc.cu) is built for the 128-channel c2f features
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t NE = n_rays * n_exposure;
   AwpArgs a{};
@@ -627,7 +631,7 @@ int awp_forward(const edn_awp_params* p, const float* depth_feature, const float
     const int64_t M = NE * n_samples;
     EDN_REQUIRE(M < (int64_t)1 << 31, "edn_awp_fwd: too many samples for one GEMM");
     const float* X = depth_feature;
-    int K = 128;
+    int K = in_ch;
     for (int l = 0; l < 4; ++l) {
       float* act = ws.act[l];
       const float* bias = p->sample_b[l];

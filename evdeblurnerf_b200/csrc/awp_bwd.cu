@@ -661,6 +661,7 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t N = n_rays, NE = n_rays * n_exposure, M = NE * n_samples;
   const int E = n_exposure, S = n_samples;
+  const int in_ch = p->input_ch > 0 ? p->input_ch : 128;
   const bool tf32 = precision == EDN_BF16;
   const AwpBwdHead head = awp_bwd_head(workspace, N, E, S);
   float* base = head.next;
@@ -751,7 +752,7 @@ extern "C" int edn_awp_bwd(const edn_awp_params* p, const float* depth_feature, 
   float* Dnext = Dn;
   for (int l = 3; l >= 0; --l) {
     const float* X = l > 0 ? a.ws.act[l - 1] : depth_feature;
-    const int K = l > 0 ? 64 : 128;
+    const int K = l > 0 ? 64 : in_ch;
     relu_mask_kernel<<<blocks_for(M * 16, 256), 256, 0, st>>>(D, a.ws.act[l], 64, 64, M);
     EDN_RC(gemm(true, false, K, 64, M, X, K, D, 64, 1.f, grads->sample_t[l], 64));
     colsum_kernel<<<blocks_for(M, 512), 64, 0, st>>>(D, 64, 64, M, grads->sample_b[l]);

@@ -103,9 +103,12 @@ class AdaptiveWeightProposal:
             self.keep.append(t)
             return t.data_ptr()
 
+        # depth_feature width = in-features of the first sample layer: 128 (c2f geo features) or 256 (mode = nerf, run_nerf.py:203-212)
+        self.input_ch = int(params[prefix + "sample_feature_embed_layer.0.weight"].shape[1])
         for l in range(4):
-            p.sample_t[l] = g(f"sample_feature_embed_layer.{l}.weight", True, (64, 128) if l == 0 else (64, 64))
+            p.sample_t[l] = g(f"sample_feature_embed_layer.{l}.weight", True, (64, self.input_ch) if l == 0 else (64, 64))
             p.sample_b[l] = g(f"sample_feature_embed_layer.{l}.bias")
+        p.input_ch = self.input_ch
         if (prefix + "sample_feature_embed_layer.4.weight") in params or (prefix + "motion_feature_embed_layer.2.weight") in params:
             raise RuntimeError("unsupported AWP depth")
         p.motion_w[0], p.motion_b[0] = g("motion_feature_embed_layer.0.weight", shape=(32, 111)), g("motion_feature_embed_layer.0.bias")
@@ -140,7 +143,9 @@ class AdaptiveWeightProposal:
         return dist.get_world_size(self.group) if (self.sync_bn and dist.is_available() and dist.is_initialized()) else 1
 
     def options(self, keep_activations=False, phase=0, bn_rows_total=0):
-        return _lib.AwpOptions(self.precision, 1 if keep_activations else 0, int(phase), int(bn_rows_total))
+        # widths other than 128 have no fused per-sample kernel: they always run the materialised (GEMM) path
+        keep = keep_activations or self.input_ch != 128
+        return _lib.AwpOptions(self.precision, 1 if keep else 0, int(phase), int(bn_rows_total))
 
     def _all_reduce_block(self, ws, offset_floats, n_doubles):
         import torch.distributed as dist
@@ -150,8 +155,8 @@ class AdaptiveWeightProposal:
     def run(self, depth_feature, z_vals, rays_d, view_feature, workspace=None, keep_activations=False):
         df, z = depth_feature.detach().float().contiguous(), z_vals.detach().float().contiguous()
         NE, S, Fd = df.shape
-        if Fd != 128:
-            raise RuntimeError("AWP: depth_feature must have 128 channels (mode = c2f)")
+        if Fd != self.input_ch:
+            raise RuntimeError(f"AWP: depth_feature has {Fd} channels, sample_feature_embed_layer.0 expects {self.input_ch}")
         E = self.E
         N = NE // E
         rd = rays_d.detach().float()
@@ -290,7 +295,7 @@ class NeRFAll:
         self.params = {k: v for k, v in params.items() if isinstance(v, torch.Tensor)}
         self.mode = "nerf" if "mlp_coarse.pts_linears.0.weight" in self.params else "c2f"
         if self.mode == "nerf":
-            self.engine = NerfRenderEngine(self.params, rmnearplane=render_rmnearplane)
+            self.engine = NerfRenderEngine(self.params, rmnearplane=render_rmnearplane, use_awp=bool(use_awp))
         else:
             self.engine = RenderEngine(self.params, aabb_min, aabb_max, precision=precision, rmnearplane=render_rmnearplane)
         self.kernelsnet = None
@@ -302,8 +307,6 @@ class NeRFAll:
             self.kernelsnet, self.kernel_type = BlurModel(self.params, kernel_ptnum, **(kernel_cfg or {})), "DSK"
         self.awpnet = (AdaptiveWeightProposal(self.params, kernel_ptnum - 1,
                                               precision=_lib.EDN_BF16 if precision == "bf16" else _lib.EDN_F32) if self.use_awp else None)
-        if self.use_awp and self.mode != "c2f":
-            raise NotImplementedError("kernel_use_awp with mode = nerf (256-channel depth_feature) is not built")
         self.training = True
         self.backward_chunk_rays = 8192     # rays per recompute chunk of the backward pass (workspace ~ 8.6 KB x samples)
         self.last_render = None

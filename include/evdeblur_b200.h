@@ -366,10 +366,13 @@ typedef struct edn_awp_params {
   const float* conva; const float* convb; const float* convc; const float* convn; const float* convl;
   const float* convd_w; const float* bn_weight; const float* bn_bias;
   const float* w_linear_w; const float* w_linear_b;
+  int32_t input_ch;   /* channels of depth_feature = in-features of sample_feature_embed_layer.0: 128 (c2f geo features; 0 means 128)
+                       * or 256 (mode = nerf, run_nerf.py:203-212).  Widths other than 128 run the materialised (GEMM) path: the
+                       * caller sets edn_awp_options.keep_activations. */
 } edn_awp_params;
 
 /* AdaptiveWeightProposal.forward (awp.py:79-117) in train mode (BatchNorm1d uses batch statistics, mam.py:24-27):
- * depth_feature [N*E][S][128], z_vals [N*E][S], rays_d rows of 3 floats with row stride rays_d_stride (e.g. ray_batch + 3,
+ * depth_feature [N*E][S][input_ch], z_vals [N*E][S], rays_d rows of 3 floats with row stride rays_d_stride (e.g. ray_batch + 3,
  * stride 11), view_feature [N][32] -> ccw [N][E].  workspace: edn_awp_workspace_floats() floats.
  * Options: see edn_awp_options below. */
 typedef struct edn_awp_options {

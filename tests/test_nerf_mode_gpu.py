@@ -140,3 +140,76 @@ def test_nerfall_nerf_mode_loss_backward(case5):
     (img2mse(rgb, target) + img2mse(rgb0, target)).backward()
     for k, v in Pg.items():
         assert v.grad is not None and float(v.grad.abs().max()) > 0, k
+
+
+def nerf_awp_model(requires_grad):
+    """mode = nerf + RBK + AWP on 256-channel features: case 5's MLP for both passes, kernel / AWP nets of case 10."""
+    from evdeblurnerf_b200 import NeRFAll
+    g5, g10 = golden("case5_nerf24"), golden("case10_nerf_awp")
+    P = {}
+    for k, v in g5.items():
+        if k.startswith("P.mlp_fine."):
+            P[k[2:]] = v
+            P["mlp_coarse." + k[len("P.mlp_fine."):]] = v.clone()
+    P.update({k[2:]: v for k, v in g10.items() if k.startswith("P.")})
+    Pg = {k: v.cuda() for k, v in P.items()}
+    if requires_grad:
+        for k, v in Pg.items():
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+    nerf = NeRFAll(Pg, *AABB, kernel_ptnum=5, precision="fp32", use_awp=True).train()
+    assert nerf.mode == "nerf" and nerf.awpnet.input_ch == 256
+    return nerf, P, Pg, g10
+
+
+NERF_KW = dict(force_naive=False, return_pts0_rgb=True, retraw=True, N_samples=64, N_importance=64, perturb=0., raw_noise_std=0.,
+               use_viewdirs=True, white_bkgd=False, inference=False, near=0., far=1.)
+KMAT_N = torch.tensor([[400.0, 0, 200.0], [0, 400.0, 200.0], [0, 0, 1.0]])
+
+
+def test_awp_on_nerf_mode_features_matches_the_reference():
+    """run_nerf.py:203-212 / networks/nerf.py:140-150: AWP with input_ch = netwidth (256) on the trunk features of mode = nerf."""
+    nerf, _, _, g = nerf_awp_model(False)
+    with torch.no_grad():
+        rgb, rgb1, _, other = nerf(400, 400, KMAT_N, chunk=32768, rays=g["rays"].cuda(), rays_info={"images_idx": g["images_idx"].cuda()}, **NERF_KW)
+    assert_close(rgb, g["rgb"], "blended rgb", rtol=1e-4, atol=2e-4)
+    assert_close(rgb1, g["rgb1"], "blended rgb1", rtol=1e-4, atol=2e-5)
+    assert_close(other["ccw_fine"], g["ccw_fine"], "ccw_fine", rtol=1e-4, atol=2e-5)
+    assert_close(other["rgb_awp"], g["rgb_awp"], "rgb_awp", rtol=1e-4, atol=2e-4)
+
+
+def test_awp_on_nerf_mode_features_gradients():
+    """Gradients of the AWP term: the AWP net against autograd on the oracle (its inputs taken from the CUDA forward), and the MLP
+    trunk receives a gradient through depth_feature."""
+    nerf, P, Pg, g = nerf_awp_model(True)
+    gen = torch.Generator().manual_seed(51)
+    G = torch.randn(12, 3, generator=gen)
+    rgb, rgb1, _, other = nerf(400, 400, KMAT_N, chunk=32768, rays=g["rays"].cuda(), rays_info={"images_idx": g["images_idx"].cuda()}, **NERF_KW)
+    (other["rgb_awp"] * G.cuda()).sum().backward()
+    lr = nerf.last_render
+    Po = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and k.startswith("awpnet.")) else v) for k, v in P.items()}
+    rb, z = lr["ray_batch"].detach().cpu(), lr["z_vals"].detach().cpu()
+    o, d, vd = rb[:, :3], rb[:, 3:6], rb[:, -3:]
+    raw, feat = oc.nerf_mlpforward(P, "mlp_fine.", o[:, None] + d[:, None] * z[..., None], vd)
+    rgb_s = oc.nerf_raw2outputs(raw, z, d)[0]
+    emb = lr["img_embed"].detach().cpu()
+    ccw = oc.awp_forward(Po, feat, z, d, emb, 5)
+    ccw = ccw + ccw * 0.05
+    ccw = ccw / ccw.sum(-1, keepdim=True)
+    o_awp = oc.rbk_weighted_sum(rgb_s, ccw)
+    assert_close(other["rgb_awp"], o_awp, "rgb_awp vs oracle", rtol=1e-4, atol=5e-5)
+    names = [k for k in Po if k.startswith("awpnet.") and Po[k].is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    grads = torch.autograd.grad((o_awp * G).sum(), [Po[k] for k in names], allow_unused=True)
+    checked = 0
+    for k, ref in zip(names, grads):
+        if ref is None or float(ref.abs().max()) == 0.0 or k.endswith("MAM.linear.bias"):
+            continue
+        b = ref
+        scale = float(b.abs().max())
+        if scale < 1e-8:          # (the softmax-over-samples logit weights here: gradients of ~1e-10, pure cancellation noise)
+            continue
+        assert_close(Pg[k].grad, b, "d " + k, rtol=2e-3, atol=2e-3 * scale)
+        checked += 1
+    assert checked >= 20, checked
+    gt = Pg["mlp_fine.pts_linears.7.weight"].grad
+    assert gt is not None and float(gt.abs().max()) > 0
