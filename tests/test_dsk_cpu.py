@@ -39,3 +39,24 @@ def test_oracle_dsk_matches_the_reference(name):
         ref = G[k]
         gr = torch.zeros_like(ref) if gr is None else gr
         assert torch.allclose(gr, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max() + 1e-12)), k
+
+
+def test_oracle_awp_on_nerf_mode_features_matches_the_reference():
+    """case 10 (oracle/make_golden_nerf_awp.py): the oracle's AWP restatement on the 256-channel trunk features of mode = nerf reproduces
+    the reference NeRFAll's ccw_fine / rgb_awp (MLP weights of case 5 for both passes, depths from the fixture)."""
+    g5, g = golden("case5_nerf24"), golden("case10_nerf_awp")
+    P = {k[2:]: v for k, v in g5.items() if k.startswith("P.mlp_fine.")}
+    P.update({k[2:]: v for k, v in g.items() if k.startswith("P.")})
+    new_rays, weight1, emb = oc.rbk_forward(P, g["rays"], g["images_idx"], 4)
+    rb = oc.build_ray_batch(400, 400, 400.0, new_rays.reshape(-1, 3, 2))
+    o, d, vd, z = rb[:, :3], rb[:, 3:6], rb[:, -3:], g["z_vals"]
+    with torch.no_grad():
+        raw, feat = oc.nerf_mlpforward(P, "mlp_fine.", o[:, None] + d[:, None] * z[..., None], vd)
+        assert torch.allclose(feat.double().sum(-1).float(), g["depth_feature_sum"], rtol=1e-4, atol=1e-3)
+        rgb_s = oc.nerf_raw2outputs(raw, z, d)[0]
+        ccw = oc.awp_forward(P, feat, z, d, emb, 5)
+        ccw = ccw + ccw * 0.05
+        ccw = ccw / ccw.sum(-1, keepdim=True)
+    assert torch.allclose(ccw, g["ccw_fine"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(oc.rbk_weighted_sum(rgb_s, ccw), g["rgb_awp"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(oc.rbk_weighted_sum(rgb_s, weight1), g["rgb"], rtol=1e-4, atol=1e-5)
