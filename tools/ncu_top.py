@@ -1,7 +1,8 @@
-"""Top stall sites of an ncu report (SASS view): python tools/ncu_top.py <report.ncu-rep> [N]"""
+"""Top stall sites of an ncu report (SASS view): python tools/ncu_top.py <report.ncu-rep> [N] [kernel-name regex]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *sel], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]; body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
