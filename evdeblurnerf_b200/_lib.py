@@ -39,6 +39,10 @@ class VmGridGrad(C.Structure):
     _fields_ = [("plane", C.c_void_p * 3), ("line", C.c_void_p * 3)]
 
 
+class FieldBwdMerge(C.Structure):
+    _fields_ = [("order", C.c_void_p), ("n_coarse", C.c_int32), ("moved", C.c_void_p)]
+
+
 class RbkParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("img_embed", "r_branch_w", "r_branch_b", "v_branch_w", "v_branch_b", "w_branch_w",
                                            "w_branch_b", "r_linear_w", "r_linear_b", "v_linear_w", "v_linear_b", "w_linear_w",
@@ -128,7 +132,7 @@ SIGNATURES = {
     "edn_field_bwd_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I64, _I32]),
     "edn_render_field_bwd": (C.c_int, [C.POINTER(VmGrid), C.POINTER(VmGrid), C.POINTER(FieldWeights), _P, _P, _P, _I64, _I32,
                                        _I32, _P, _P, _P, _P, _P, C.POINTER(FieldWeights), C.POINTER(VmGridGrad),
-                                       C.POINTER(VmGridGrad), _P, _P, _I64, _P]),
+                                       C.POINTER(VmGridGrad), _P, _P, _I64, C.POINTER(FieldBwdMerge), _P]),
     "edn_unpack_vm_plane_grad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "edn_rbk_bwd_workspace_floats": (C.c_int64, [_I64, _I32]),
     "edn_rbk_warp_ndc_bwd": (C.c_int, [C.POINTER(RbkParams), _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, C.POINTER(RbkGrads), _P, _P]),

@@ -197,6 +197,8 @@ class RenderSubRaysFn(torch.autograd.Function):
                 rand["noise0"] = eng._random((R, Nc - 1), 1, normal=True, scale=std)
             if Ni > 0 and "noise1" not in rand:
                 rand["noise1"] = eng._random((R, Nc + Ni - 1), 3, normal=True, scale=std)
+        if Ni > 0 and owner.mode == "c2f":
+            kw["want_indices"] = True            # the merged order lets the backward scatter every coarse position once
         out = owner.render_rays(rb, rand=rand, **kw)
         owner.last_render = dict(out, ray_batch=rb, img_embed=k.get("img_embed"), weight=weight)
         ctx.owner, ctx.kn, ctx.names = owner, kn, names
@@ -204,7 +206,7 @@ class RenderSubRaysFn(torch.autograd.Function):
         ctx.two_stage = Ni > 0
         ctx.white_bkgd = bool(kw.get("white_bkgd", False))
         ctx.saved = {"ray_batch": rb, "z_vals0": out["z_vals0"] if Ni > 0 else out["z_vals"], "z_vals": out["z_vals"] if Ni > 0 else None,
-                     "noise0": rand.get("noise0"), "noise1": rand.get("noise1")}
+                     "noise0": rand.get("noise0"), "noise1": rand.get("noise1"), "order": out.get("order") if Ni > 0 else None}
         ctx.rays = _c(rays)
         ctx.rays_grad = kn is None and isinstance(rays, torch.Tensor) and rays.requires_grad      # rays from a learned kernel (DSK)
         ctx.idx = images_idx.reshape(-1).to(torch.int64).contiguous() if images_idx is not None else None

@@ -71,7 +71,7 @@ class RenderGradients:
 
 
 def field_backward(engine, grads, fine, ray_batch, z_vals, noise, d_rgb, d_depth, d_acc, d_ray_batch, d_weights=None,
-                   d_feat=None, chunk_rays=2048):
+                   d_feat=None, chunk_rays=2048, merge=None):
     """Accumulates the gradients of one field's render pass (edn_render_field_bwd) into `grads` and `d_ray_batch`."""
     lib = _lib.load()
     P = engine.params
@@ -91,11 +91,14 @@ def field_backward(engine, grads, fine, ray_batch, z_vals, noise, d_rgb, d_depth
     keep = [f(t) for t in (ray_batch, z_vals, noise, d_rgb, d_depth, d_acc, d_weights, d_feat)]
     g0 = engine.coarse.grid
     g1 = engine.fine.grid if fine else None
+    mg = None
+    if merge is not None:          # (order [R][S] int64 | None, n_coarse, moved buffer): see edn_field_bwd_merge
+        mg = _lib.FieldBwdMerge(ptr(merge[0]) if fine else None, int(merge[1]), merge[2].data_ptr())
     check(engine._launch("field_bwd_fine" if fine else "field_bwd_coarse", lambda: lib.edn_render_field_bwd(
         C.byref(g0), C.byref(g1) if g1 is not None else None, C.byref(w), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), R, S,
         engine.prec_code, ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), ptr(keep[6]), ptr(keep[7]), C.byref(gw),
         C.byref(grads.grid_struct["mlp_coarse."]), C.byref(grads.grid_struct["mlp_fine."]) if fine else None,
-        ptr(d_ray_batch), ptr(ws), nbytes, stream_ptr())), "edn_render_field_bwd")
+        ptr(d_ray_batch), ptr(ws), nbytes, C.byref(mg) if mg is not None else None, stream_ptr())), "edn_render_field_bwd")
 
 
 def render_rays_backward(engine, saved, d_out, grads=None, chunk_rays=2048):
@@ -111,10 +114,19 @@ def render_rays_backward(engine, saved, d_out, grads=None, chunk_rays=2048):
     d_rb = torch.zeros_like(rb)
     two_stage = saved.get("z_vals") is not None and engine.fine is not None and saved["z_vals"].shape[1] != saved["z_vals0"].shape[1]
     if two_stage:
+        # the coarse positions inside the merged depths are scattered into the coarse grid ONCE: the fine call hands their d P rows to
+        # the coarse call (needs the merged order of the forward; without it both calls scatter their own rows)
+        merge = None
+        order = saved.get("order")
+        if order is not None:
+            R, Nc = saved["z_vals0"].shape
+            from ._lib import EDN_F32
+            moved = torch.empty((R * Nc * 96,), dtype=torch.float32 if engine.prec_code == EDN_F32 else torch.bfloat16, device=rb.device)
+            merge = (order.contiguous(), Nc, moved)
         field_backward(engine, grads, True, rb, saved["z_vals"], saved.get("noise1"), d_out.get("rgb_map"), d_out.get("depth_map"),
-                       d_out.get("acc_map"), d_rb, d_feat=d_out.get("depth_feature"), chunk_rays=chunk_rays)
+                       d_out.get("acc_map"), d_rb, d_feat=d_out.get("depth_feature"), chunk_rays=chunk_rays, merge=merge)
         field_backward(engine, grads, False, rb, saved["z_vals0"], saved.get("noise0"), d_out.get("rgb0"), d_out.get("depth0"),
-                       d_out.get("acc0"), d_rb, chunk_rays=chunk_rays)
+                       d_out.get("acc0"), d_rb, chunk_rays=chunk_rays, merge=merge)
     else:
         field_backward(engine, grads, False, rb, saved["z_vals0"], saved.get("noise0"), d_out.get("rgb_map"), d_out.get("depth_map"),
                        d_out.get("acc_map"), d_rb, d_feat=d_out.get("depth_feature"), chunk_rays=chunk_rays)

@@ -160,13 +160,15 @@ __global__ void __launch_bounds__(kOcts * 16) vm_products8_kernel(const GridDev 
 template <typename T, typename AT>
 __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g, const GradGrid gg, const float* __restrict__ rb,
                                                                  const float* __restrict__ z_vals, int64_t m0, int64_t Mc, int S,
-                                                                 const AT* __restrict__ dP, float* __restrict__ dpts) {
+                                                                 const AT* __restrict__ dP, float* __restrict__ dpts,
+                                                                 const int* __restrict__ row_list, const AT* __restrict__ dP2) {
   __shared__ float part[kVmThreads][3];      // per-thread coordinate-gradient contributions (no shared-memory atomics: fp32 ones are CAS loops)
   part[threadIdx.x][0] = 0.f; part[threadIdx.x][1] = 0.f; part[threadIdx.x][2] = 0.f;
   const int64_t t = (int64_t)blockIdx.x * kVmThreads + threadIdx.x;
-  const int64_t m = t / kQuads;
-  const int q = (int)(t % kQuads);
-  if (m < Mc) {
+  const int64_t li = t / kQuads;                  // logical row: with a row list (the fine positions of a merged-scatter call, Mc of
+  const int q = (int)(t % kQuads);                // them) the actual row of the chunk is row_list[li]
+  const int64_t m = (row_list && li < Mc) ? (int64_t)__ldg(row_list + li) : li;
+  if (li < Mc) {
     float p[3], n[3];
     sample_point(rb, z_vals, m0 + m, S, p);
     normalize_pt(g, p, n);
@@ -182,7 +184,11 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
     for (int k = 0; k < 4; ++k) { v[k] = load4<T>(plane + (size_t)tp.pt.off[k] * C + c); fma4(pl, v[k], tp.pt.w[k]); }
 #pragma unroll
     for (int k = 0; k < 2; ++k) { l[k] = load4<T>(line + (size_t)tp.lt.off[k] * C + c); fma4(ln, l[k], tp.lt.w[k]); }
-    const float4 dp = ldv4(dP + m * kAppComp + q * 4);
+    float4 dp = ldv4(dP + m * kAppComp + q * 4);
+    if (dP2) {
+      const float4 d2 = ldv4(dP2 + (m0 + m) * kAppComp + q * 4);
+      dp.x += d2.x; dp.y += d2.y; dp.z += d2.z; dp.w += d2.w;
+    }
     const float4 dpl = mul4(dp, ln), dln = mul4(dp, pl);
     float gx = 0.f, gy = 0.f, gv = 0.f;
 #pragma unroll
@@ -208,12 +214,39 @@ __global__ void __launch_bounds__(kVmThreads) vm_scatter_kernel(const GridDev g,
   __syncthreads();
   if (threadIdx.x < kSamplesPerBlock * 3) {
     const int s = threadIdx.x / 3, i = threadIdx.x % 3;
-    const int64_t mm = (int64_t)blockIdx.x * kSamplesPerBlock + s;
+    const int64_t ll = (int64_t)blockIdx.x * kSamplesPerBlock + s;
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < kQuads; ++q) acc += part[s * kQuads + q][i];
-    if (mm < Mc) dpts[mm * 4 + i] += acc * g.inv[i];            // n = (p - amin) * inv - 1
+    if (ll < Mc) {
+      const int64_t mm = row_list ? (int64_t)__ldg(row_list + ll) : ll;
+      dpts[mm * 4 + i] += acc * g.inv[i];            // n = (p - amin) * inv - 1
+    }
   }
+}
+
+// The fine pass samples the COARSE grid at all its merged depths, and Nc of them are the coarse pass's own positions: those rows of
+// d P (coarse-grid products) are moved here into [ray][coarse index][96] and added to the coarse pass's d P inside ITS scatter, so
+// every coarse position is scattered once instead of twice (a fifth of all reds of a c2f step).  One thread per 16-byte piece.
+// The rows that stay (the importance samples: order >= n_coarse, S - n_coarse per ray) are listed compactly in row_list, so the
+// fine call's coarse-grid scatter runs over full warps of live rows.
+template <typename AT>
+__global__ void move_rows_kernel(const AT* __restrict__ dP, const int64_t* __restrict__ order, int64_t m0, int64_t Mc, int S, int n_coarse,
+                                 AT* __restrict__ moved, int* __restrict__ row_list) {
+  constexpr int kPieces = kAppComp * (int)sizeof(AT) / 16;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = t / kPieces;
+  const int pc = (int)(t % kPieces);
+  if (m >= Mc) return;
+  const int64_t src = __ldg(order + m0 + m);
+  if (src >= n_coarse) {
+    if (pc == 0) row_list[(m / S) * (S - n_coarse) + (src - n_coarse)] = (int)m;      // chunks start at ray boundaries: m / S = local ray
+    return;
+  }
+  const int64_t ray = (m0 + m) / S;
+  const uint4* from = reinterpret_cast<const uint4*>(dP + m * kAppComp);
+  uint4* to = reinterpret_cast<uint4*>(moved + (ray * n_coarse + src) * kAppComp);
+  to[pc] = from[pc];
 }
 
 // Positional encodings (embedding.py:88-98): X0[:, nf : ldX) = [PE(pts) (63) | 0] (dirs = 0), SG[:, geo+1 : ldS) = [PE(viewdir) (27) | 0]
@@ -562,7 +595,7 @@ inline Dims make_dims(int n_grids, int hidden, int geo, int al) {
 inline int64_t bytes_per_sample(const Dims& d) {
   const int64_t act = (int64_t)kAppComp * d.ng /*P*/ + d.ldX /*X0*/ + d.hid * 3 /*H1 H2 H3*/ + d.ldS /*SG*/ + d.nr /*dRGB*/ + d.hid * 2 /*D1 D2*/ +
                       d.ldS /*dSG*/ + d.nf /*dXf*/ + kAppComp /*dP*/;
-  return act * d.esz + (int64_t)sizeof(float) * (d.ldX /*dX0*/ + d.nr /*RGB*/ + 4 /*dpts*/ + 3 /*alpha, T, d sigma*/);
+  return act * d.esz + (int64_t)sizeof(float) * (d.ldX /*dX0*/ + d.nr /*RGB*/ + 4 /*dpts*/ + 3 /*alpha, T, d sigma*/ + 1 /*row list*/);
 }
 inline int64_t weight_scratch_bytes(const Dims& d) {     // aligned weight copies (storage type) + fp32 gradients of the re-laid-out ones
   const int64_t relaid = (int64_t)d.hid * d.ldX + (int64_t)d.sgn * d.hid + (int64_t)d.hid * d.ldS + (int64_t)d.nr * d.hid;
@@ -583,6 +616,7 @@ struct FieldBwdCall {
   void* workspace; int64_t workspace_bytes;
   cudaStream_t st;
   cublasComputeType_t ct;
+  const int64_t* merge_order; int n_coarse; void* moved;      // edn_field_bwd_merge (NULL = every row scattered where it was computed)
 };
 
 template <typename AT>
@@ -649,6 +683,7 @@ int field_bwd_run(const FieldBwdCall& c) {
   float* al_ = takef(1);
   float* tr = takef(1);
   float* dsig = takef(1);
+  int* row_list = reinterpret_cast<int*>(takef(1));      // merged scatter: the chunk's rows that are not coarse positions
 
 #define EDN_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
   for (int64_t r0 = 0; r0 < n_rays; r0 += chunk) {
@@ -706,8 +741,20 @@ int field_bwd_run(const FieldBwdCall& c) {
     for (int g = 0; g < ng; ++g) {
       EDN_RC(gemm.run(true, false, kAppDim, kAppComp, M, dXf + 32 * g, D.nf, P[g], kAppComp, 1.f, grad_w->basis[g], kAppComp));
       EDN_RC(gemm.run(false, false, M, kAppComp, kAppDim, dXf + 32 * g, D.nf, Wb[g], kAppComp, 0.f, dP, kAppComp));
-      if (c.grids[g]->dtype == EDN_F32) vm_scatter_kernel<float, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
-      else vm_scatter_kernel<__nv_bfloat16, AT><<<blocks_for(M, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, M, S, dP, dpts);
+      // fine field, coarse grid (g == 0 of 2): the coarse positions' rows move to the coarse pass; coarse field: they are added back
+      const bool fine_call = ng == 2;
+      const int64_t* skip = (c.moved && fine_call && g == 0) ? c.merge_order : nullptr;
+      const AT* dP2 = (c.moved && !fine_call) ? reinterpret_cast<const AT*>(c.moved) : nullptr;
+      int64_t Ms = M;                   // rows the scatter walks
+      const int* rows = nullptr;
+      if (skip) {
+        constexpr int kPieces = kAppComp * (int)sizeof(AT) / 16;
+        move_rows_kernel<AT><<<blocks_for(M * kPieces, 256), 256, 0, st>>>(dP, skip, m0, M, S, c.n_coarse, reinterpret_cast<AT*>(c.moved), row_list);
+        Ms = Rc * (S - c.n_coarse);
+        rows = row_list;
+      }
+      if (c.grids[g]->dtype == EDN_F32) vm_scatter_kernel<float, AT><<<blocks_for(Ms, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, Ms, S, dP, dpts, rows, dP2);
+      else vm_scatter_kernel<__nv_bfloat16, AT><<<blocks_for(Ms, kSamplesPerBlock), kVmThreads, 0, st>>>(c.gd[g], c.gg[g], ray_batch, z_vals, m0, Ms, S, dP, dpts, rows, dP2);
     }
     ray_reduce_kernel<AT><<<blocks_for(Rc * 32, 256), 256, 0, st>>>(dpts, dSG, D.ldS, geo, ray_batch, z_vals, r0, Rc, S, c.d_ray_batch);
     EDN_CUDA_OK(cudaGetLastError());
@@ -738,7 +785,7 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
                                     const float* d_acc, const float* d_weights, const float* d_feat,
                                     const edn_field_weights* grad_w, const edn_vm_grid_grad* grad_grid0,
                                     const edn_vm_grid_grad* grad_grid1, float* d_ray_batch, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
+                                    int64_t workspace_bytes, const edn_field_bwd_merge* merge, void* stream) {
   using namespace edn;
   EDN_REQUIRE(grid0 && w && grad_w && grad_grid0 && ray_batch && z_vals && d_ray_batch && workspace, "edn_render_field_bwd: null pointer");
   EDN_REQUIRE(n_samples >= 2, "edn_render_field_bwd: n_samples must be >= 2");
@@ -770,6 +817,13 @@ extern "C" int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid*
   c.w = w; c.grad_w = grad_w; c.ray_batch = ray_batch; c.z_vals = z_vals; c.noise = noise; c.n_rays = n_rays; c.S = n_samples;
   c.d_rgb = d_rgb; c.d_depth = d_depth; c.d_acc = d_acc; c.d_weights = d_weights; c.d_feat = d_feat; c.d_ray_batch = d_ray_batch;
   c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.st = reinterpret_cast<cudaStream_t>(stream);
+  if (merge && merge->moved) {
+    EDN_REQUIRE(merge->n_coarse >= 1, "edn_render_field_bwd: merge.n_coarse must be >= 1");
+    EDN_REQUIRE(ng == 1 ? merge->n_coarse == n_samples : (merge->order != nullptr && merge->n_coarse < n_samples),
+                "edn_render_field_bwd: merge needs the merged order (fine field) / n_coarse == n_samples (coarse field)");
+    EDN_REQUIRE((reinterpret_cast<uintptr_t>(merge->moved) & 15) == 0, "edn_render_field_bwd: merge.moved must be 16-byte aligned");
+    c.merge_order = merge->order; c.n_coarse = merge->n_coarse; c.moved = merge->moved;
+  }
   // EDN_F32: fp32 activations, exact fp32 GEMMs (parity).  EDN_BF16: bf16 activations and GEMM operands, fp32 accumulation and fp32
   // weight gradients (the usual mixed-precision recipe: half the activation traffic, bf16 tensor-core GEMMs).
   c.ct = CUBLAS_COMPUTE_32F;

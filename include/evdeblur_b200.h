@@ -180,13 +180,24 @@ typedef struct edn_vm_grid_grad {
  * d_ray_batch [R][11] (columns o, d, viewdirs).  precision: EDN_F32 = fp32 GEMMs (parity), EDN_BF16 = TF32 tensor-core GEMMs.
  * The activations are recomputed chunk by chunk into `workspace`; edn_field_bwd_workspace_bytes gives the size for a chunk
  * of `chunk_rays` rays (any workspace holding >= 1 ray works; larger chunks run faster). */
+/* Optional merge of the two passes' coarse-grid scatters (NULL = off).  The fine pass samples the coarse grid at all merged depths;
+ * n_coarse of them per ray are the coarse pass's own positions (merged `order` < n_coarse, edn_sample_pdf_merge).  Fine-field call:
+ * `order` [R][S] given -> those rows of d P are written to moved[ray][order][96] (storage type of `precision`: fp32 / bf16) instead
+ * of being scattered.  Coarse-field call (n_coarse == n_samples, order ignored): `moved` is added to its own d P before the
+ * scatter.  Call the fine field first.  Same gradients, a third fewer coarse-grid reds. */
+typedef struct edn_field_bwd_merge {
+  const int64_t* order;
+  int32_t n_coarse;
+  void* moved;        /* [R][n_coarse][96] of the activation storage type, 16-byte aligned */
+} edn_field_bwd_merge;
+
 int64_t edn_field_bwd_workspace_bytes(int32_t n_grids, int32_t hidden, int32_t geo_feat, int64_t chunk_rays, int32_t n_samples);
 int edn_render_field_bwd(const edn_vm_grid* grid0, const edn_vm_grid* grid1, const edn_field_weights* w,
                          const float* ray_batch, const float* z_vals, const float* noise, int64_t n_rays, int32_t n_samples,
                          int32_t precision, const float* d_rgb, const float* d_depth, const float* d_acc,
                          const float* d_weights, const float* d_feat, const edn_field_weights* grad_w,
                          const edn_vm_grid_grad* grad_grid0, const edn_vm_grid_grad* grad_grid1, float* d_ray_batch,
-                         void* workspace, int64_t workspace_bytes, void* stream);
+                         void* workspace, int64_t workspace_bytes, const edn_field_bwd_merge* merge, void* stream);
 
 /* Channel-last gradient plane [H][W][C] -> += into the reference layout [1,C,H,W] (inverse of edn_pack_vm_plane). */
 int edn_unpack_vm_plane_grad(const float* src_hwc, float* dst_chw, int32_t C, int32_t H, int32_t W, int32_t accumulate, void* stream);

@@ -74,7 +74,10 @@ def test_coarse_field_backward_matches_autograd(bias):
     assert float(d_rb[:, 6:8].abs().max()) == 0.0
 
 
-def test_c2f_backward_matches_autograd():
+@pytest.mark.parametrize("merge", [False, True])
+def test_c2f_backward_matches_autograd(merge):
+    """merge = True: the merged order of the forward is handed to the backward, which then scatters every coarse position into the
+    coarse grid once (edn_field_bwd_merge) -- same gradients."""
     from evdeblurnerf_b200 import RenderEngine
     from evdeblurnerf_b200.backward import render_rays_backward
     R, Nc, Ni = 64, 32, 32
@@ -84,9 +87,10 @@ def test_c2f_backward_matches_autograd():
     noise0, noise1 = 0.5 * torch.randn(R, Nc - 1, generator=g), 0.5 * torch.randn(R, Nc + Ni - 1, generator=g)
     eng = RenderEngine({k: v.cuda() for k, v in P.items()}, *AABB, precision="fp32")
     rand = {"noise0": noise0.cuda(), "noise1": noise1.cuda()}
-    out = eng.render_rays(rb.cuda(), Nc, retraw=True, N_importance=Ni, rand=rand)
+    out = eng.render_rays(rb.cuda(), Nc, retraw=True, N_importance=Ni, rand=rand, want_indices=merge)
     ref, ref_rb = oracle_grads(P, rb, Nc, out["z_vals"].cpu(), cot, noise0=noise0, noise1=noise1)
-    saved = {"ray_batch": rb.cuda(), "z_vals0": out["z_vals0"], "z_vals": out["z_vals"], "noise0": rand["noise0"], "noise1": rand["noise1"]}
+    saved = {"ray_batch": rb.cuda(), "z_vals0": out["z_vals0"], "z_vals": out["z_vals"], "noise0": rand["noise0"], "noise1": rand["noise1"],
+             "order": out["order"] if merge else None}
     grads, d_rb = render_rays_backward(eng, saved, {k: v.cuda() for k, v in cot.items()}, chunk_rays=24)
     got = grads.finish()
     for k, gr in ref.items():
@@ -110,6 +114,16 @@ def test_backward_accumulates_and_chunking_is_invisible():
     for k in a:
         grad_close(a[k], b[k], "chunk " + k, tol=2e-5)
     grad_close(d1, d2, "chunk d_rb", tol=2e-5)
+    # the merged coarse-position scatter (edn_field_bwd_merge) is a re-association of the same sums, chunked or not
+    out_i = eng.render_rays(rb.cuda(), Nc, retraw=True, N_importance=Ni, want_indices=True)
+    assert torch.equal(out_i["z_vals"], out["z_vals"])
+    saved_m = dict(saved, order=out_i["order"])
+    for ch in (7, 4096):
+        g3, d3 = render_rays_backward(eng, saved_m, cot, chunk_rays=ch)
+        c3 = g3.finish()
+        for k in c3:
+            grad_close(c3[k], b[k], f"merged scatter (chunk {ch}) " + k, tol=2e-5)
+        grad_close(d3, d2, f"merged scatter (chunk {ch}) d_rb", tol=2e-5)
     acc = RenderGradients(eng)
     render_rays_backward(eng, saved, cot, grads=acc)
     render_rays_backward(eng, saved, cot, grads=acc)
@@ -169,7 +183,7 @@ def test_backward_error_paths_and_empty_batch():
     args = lambda gw_, ws_, n_: (C.byref(eng.coarse.grid), C.byref(eng.fine.grid), C.byref(w), saved["ray_batch"].data_ptr(),
                                  saved["z_vals"].data_ptr(), None, 8, 64, 0, None, None, None, None, None, C.byref(gw_),
                                  C.byref(g.grid_struct["mlp_coarse."]), C.byref(g.grid_struct["mlp_fine."]), d_rbuf.data_ptr(), ws_.data_ptr(), n_,
-                                 torch.cuda.current_stream().cuda_stream)
+                                 None, torch.cuda.current_stream().cuda_stream)
     with pytest.raises(RuntimeError, match="workspace too small"):
         _lib.check(lib.edn_render_field_bwd(*args(gw, ws, 1024)), "edn_render_field_bwd")
     gw.sigma0 = None
