@@ -687,3 +687,35 @@ def test_nccl_two_ranks_half_batch_equal_one_rank_full_batch(precision):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "NCCL_EQUIV_OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_one_process_drives_one_gpu_and_says_so():
+    """The library's per-process device state (cuBLAS handle, staging buffers) binds to the first device used; a call from a second
+    device in the same process fails with a message instead of touching the first device's memory (csrc/api.cu bind_device).  Runs in
+    a subprocess: the binding lasts for the life of the process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {os.path.join(root, 'oracle')!r})\n"
+        "import evdeblur_oracle as oc\n"
+        "from util import AABB, FOCAL, H, W, random_params, synthetic_rays\n"
+        "from evdeblurnerf_b200 import RenderEngine\n"
+        "P = random_params(3)\n"
+        "rays, _ = synthetic_rays(16, seed=1)\n"
+        "rb = oc.build_ray_batch(H, W, FOCAL, rays)\n"
+        "e0 = RenderEngine({k: v.to('cuda:0') for k, v in P.items()}, *AABB, precision='bf16', device='cuda:0')\n"
+        "e0.render_rays(rb.to('cuda:0'), 64, N_importance=64)\n"
+        "torch.cuda.synchronize()\n"
+        "torch.cuda.set_device(1)\n"
+        "try:\n"
+        "    e1 = RenderEngine({k: v.to('cuda:1') for k, v in P.items()}, *AABB, precision='bf16', device='cuda:1')\n"
+        "    e1.render_rays(rb.to('cuda:1'), 64, N_importance=64)\n"
+        "    print('NO_ERROR')\n"
+        "except RuntimeError as e:\n"
+        "    print('BOUND_OK' if 'one process per GPU' in str(e) else 'OTHER: ' + str(e))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "BOUND_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
